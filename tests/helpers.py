@@ -1,0 +1,36 @@
+"""Shared test plumbing: rebuild a golden case's inputs from seeds and load the reference's outputs."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import make_golden
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_case(name):
+    sub, w, fr, vol, t_rand, rk = make_golden.build_case(name)
+    g = dict(np.load(os.path.join(GOLDEN_DIR, f"render_{name}.npz")))
+    # the seeded generator must reproduce exactly what the fixture was made from
+    assert np.array_equal(g["rays_d"], fr.rays_d.numpy()) and np.array_equal(g["near"], fr.near.numpy())
+    assert np.array_equal(g["motion_scale_Rs"], fr.motion_scale_Rs.numpy())
+    assert float(g["emb_checksum"]) == w.embeddings.double().sum().item()
+    assert float(g["vol_checksum"]) == vol.double().sum().item()
+    if t_rand is not None:
+        assert np.array_equal(g["t_rand"], t_rand.numpy())
+    return sub, w, fr, vol, t_rand, rk, g
+
+
+def scatter_dense(idx, val, numel):
+    out = torch.zeros(numel, dtype=torch.float32)
+    out[torch.from_numpy(idx)] = torch.from_numpy(val)
+    return out
+
+
+def normwise_close(a, b, rel):
+    """max|a-b| <= rel * max|b| : the right yardstick for summed gradients, whose small entries are
+    cancellation noise in any summation order."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = np.abs(b).max()
+    return bool(np.abs(a - b).max() <= rel * scale + 1e-30)
