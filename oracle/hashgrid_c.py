@@ -99,7 +99,8 @@ def backward(grad, inputs, offsets, n_entries, C, S, H, *, level_scales=None, lb
 
 def input_backward(grad, dy_dx, B, D, C, L, lbc=False):
     gi = torch.empty(B, D, dtype=torch.float32)
-    lib().hg_input_backward(_p(grad.contiguous(), _f32p), _p(dy_dx.contiguous(), _f32p), _p(gi, _f32p), B, D, C, L, int(lbc))
+    grad, dy_dx = grad.contiguous().float(), dy_dx.contiguous().float()   # keep the temporaries alive across the call
+    lib().hg_input_backward(_p(grad, _f32p), _p(dy_dx, _f32p), _p(gi, _f32p), B, D, C, L, int(lbc))
     return gi
 
 
