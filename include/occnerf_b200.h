@@ -1,0 +1,168 @@
+/*
+ * occnerf_b200 -- C ABI of the B200-native OccNeRF per-ray rendering path.
+ *
+ * Every entry point takes raw DEVICE pointers (unless a parameter is suffixed `_host`), sizes and a
+ * CUDA stream (passed as void* so that this header needs no CUDA include), never allocates, and returns
+ * 0 on success or a non-zero OCCNERF_E* code; occnerf_last_error() gives the thread-local message.
+ * There is no CPU fallback anywhere behind this interface.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree tiangexiang/OccNeRF):
+ *   core/nets/occnerf/gridencoder/src/gridencoder.h:12-15 + bindings.cpp:5-9  -> occnerf_hashgrid_*
+ *   core/nets/occnerf/network.py:416-432,456,351-402 (_get_samples_along_ray, _stratified_sampling,
+ *       _sample_motion_fields)                                                -> occnerf_warp_*
+ *   core/nets/occnerf/knn.py:33-85,102-174 + network.py:236-255 (pykeops K-min) -> occnerf_knn
+ *   core/nets/occnerf/canonical_mlps/occnerf_mlp.py:146-167                   -> occnerf_sample_geometry
+ *   core/nets/occnerf/canonical_mlps/occnerf_mlp.py:110-126,175-178 (simple_agg) -> occnerf_aggregate_*
+ *   core/nets/occnerf/canonical_mlps/occnerf_mlp.py:183-199 (nn.Linear stacks) -> occnerf_sgemm, occnerf_mlp_*
+ *   core/nets/occnerf/embedders/hannw_fourier.py:27-45                        -> occnerf_hann_pe
+ *   core/nets/occnerf/network.py:320-348,486-499 (_raw2outputs, comp_loss)    -> occnerf_composite_*
+ *   core/nets/occnerf/network.py:502-517 (visibility counter)                 -> occnerf_visibility_hits
+ */
+#ifndef OCCNERF_B200_H
+#define OCCNERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *occnerf_stream_t; /* cudaStream_t */
+
+enum {
+    OCCNERF_OK = 0,
+    OCCNERF_EINVAL = 1,   /* bad argument / unsupported configuration */
+    OCCNERF_ECUDA = 2     /* a CUDA runtime call or kernel launch failed */
+};
+
+/* layout of the [.., L, C] feature axis of the hash grid */
+enum {
+    OCCNERF_LAYOUT_BLC = 0, /* [B, ld] rows, feature l*C+c at column l*C+c  (what grid.py:58 produces) */
+    OCCNERF_LAYOUT_LBC = 1  /* [L, B, C]  (what the reference kernels read/write, gridencoder.cu:99-197) */
+};
+
+/* sgemm epilogue flags */
+enum {
+    OCCNERF_GEMM_BIAS = 1,       /* += bias[j]                                            */
+    OCCNERF_GEMM_RELU = 2,       /* max(.,0)                                              */
+    OCCNERF_GEMM_ACCUM = 4,      /* += C (read-modify-write; with split_k>1 uses atomics)  */
+    OCCNERF_GEMM_RELUMASK = 8    /* *= (mask[i*ldmask+j] > 0)  (backward through a ReLU)   */
+};
+
+const char *occnerf_last_error(void);
+int occnerf_abi_version(void);
+
+/* ---- K1: ray sampling + 24-bone inverse-LBS warp (network.py:416-432,456,351-402) -------------------
+ * rays [N,8] = (o3,d3,near,far); t_lin [S] = linspace(0,1,S) as the host framework computes it;
+ * t_rand [N,S] or NULL (stratified jitter, network.py:423-432); Rs [nb,3,3], Ts [nb,3];
+ * vol [>=nb, vd,vh,vw] (only the first nb channels are read, network.py:363); bbox_min/scale [3].
+ * Outputs: z [N,S], x_skel [N,S,3], mask [N,S]; bins [N,S,nb,3] int32 (floor of the un-normalised voxel
+ * coordinate, x,y,z) or NULL. */
+int occnerf_warp_forward(const float *rays, const float *t_lin, const float *t_rand, const float *Rs,
+                         const float *Ts, const float *vol, const float *bbox_min, const float *bbox_scale,
+                         int N, int S, int nb, int vd, int vh, int vw, float *z, float *x_skel, float *mask,
+                         int32_t *bins, occnerf_stream_t stream);
+/* d(mask) -> g_vol [nb,vd,vh,vw] (accumulated; caller zeroes).  x_skel has no gradient consumer
+ * (network.py:225-299 uses it under no_grad only), Rs/Ts gradients are not produced. */
+int occnerf_warp_backward(const float *rays, const float *t_lin, const float *t_rand, const float *Rs,
+                          const float *Ts, const float *bbox_min, const float *bbox_scale, const float *g_mask,
+                          int N, int S, int nb, int vd, int vh, int vw, float *g_vol, occnerf_stream_t stream);
+
+/* ---- exact k-nearest-neighbour search (knn.py:33-85; network.py:236-255,265,508) --------------------
+ * queries [m,3]; supports4 [ns,4] = (x,y,z,unused); the support set is split into n_levels contiguous
+ * blocks level_begin_host[0..n_levels] (host array); support_gid [ns] maps a support row to the id written
+ * to the output (NULL = row index within its level).  out_idx [m, n_levels, k] int32, ascending distance,
+ * ties to the lower support row.  Distance = (dx*dx + dy*dy) + dz*dz in fp32, no contraction.
+ * query_sel [m] uint8 or NULL: rows with 0 are skipped (their output is left untouched).  k in {3,10}. */
+int occnerf_knn(const float *queries, int m, const float *supports4, const int32_t *support_gid,
+                const int32_t *level_begin_host, int n_levels, int k, const uint8_t *query_sel,
+                int32_t *out_idx, occnerf_stream_t stream);
+
+/* ---- per-sample surface geometry -> 4-D hash-grid input (occnerf_mlp.py:146-167) --------------------
+ * knn_idx rows have `knn_stride` int32 entries, the first 10 being the level-0 neighbours.
+ * enc_in [m,4] = (cos-weighted mean of the 3 nearest base vertices normalised to [0,1]^3, clamp((d+.2)/.5));
+ * dist[i*dist_stride] signed mean distance (inside vote in fp64); dist_stride = 5 writes raw[:,4] in place. */
+int occnerf_sample_geometry(const float *xyz, const int32_t *knn_idx, int knn_stride, const float *point_base,
+                            const float *point_norms, float bound, int m, float *enc_in, float *dist, int dist_stride,
+                            occnerf_stream_t stream);
+
+/* ---- multi-resolution hash grid (gridencoder.h:12-15; gridencoder.cu:50-369) -------------------------
+ * level_scales [L] = exp2f(l*S)*H-1 evaluated ON THE DEVICE exactly as gridencoder.cu:138 does. */
+int occnerf_hashgrid_level_scales(float S, uint32_t H, uint32_t L, float *level_scales, occnerf_stream_t stream);
+/* inputs [B,D] in [0,1]; embeddings [offsets[L], C]; offsets [L+1] int32 (device); outputs per `layout`
+ * (ld = row stride in floats for BLC); dy_dx [B, L*D*C] or NULL; cells [B,L,D] / slots [B,L,2^D] uint32 or
+ * NULL (integer cell coordinates and table slots, 0xFFFFFFFF where the sample is outside [0,1]^D). */
+int occnerf_hashgrid_forward(const float *inputs, const float *embeddings, const int32_t *offsets,
+                             const float *level_scales, float *outputs, int layout, int ld, uint32_t B, uint32_t D,
+                             uint32_t C, uint32_t L, float *dy_dx, uint32_t *cells, uint32_t *slots,
+                             occnerf_stream_t stream);
+/* grad per `layout`; grad_embeddings accumulated in place (caller zeroes, as grid.py:78 does). */
+int occnerf_hashgrid_backward(const float *grad, int layout, int ld, const float *inputs, const int32_t *offsets,
+                              const float *level_scales, float *grad_embeddings, uint32_t B, uint32_t D, uint32_t C,
+                              uint32_t L, occnerf_stream_t stream);
+/* grad_inputs[b,d] = sum_{l,c} grad[b,l,c] * dy_dx[b,l,d,c]  (gridencoder.cu:343-369) */
+int occnerf_hashgrid_input_backward(const float *grad, int layout, int ld, const float *dy_dx, float *grad_inputs,
+                                    uint32_t B, uint32_t D, uint32_t C, uint32_t L, occnerf_stream_t stream);
+
+/* ---- visibility-weighted neighbour aggregation (occnerf_mlp.py:110-126,175-178) ----------------------
+ * knn_idx [m,nn] int32 vertex ids (nn <= 64); point_counter [V]; feats [V,36] (35 features + 1 pad);
+ * writes X[i*ldx + 0..34] = sum_n softmax(att)_n * feats[idx_n], X[i*ldx + 35] = unbiased var(att). */
+int occnerf_aggregate_forward(const int32_t *knn_idx, const float *point_counter, const float *feats, int m, int nn,
+                              float *X, int ldx, occnerf_stream_t stream);
+/* g_feats [V,36] += att_n * gX[i*ldg + 0..34]  (att is detached in the reference, occnerf_mlp.py:123) */
+int occnerf_aggregate_backward(const int32_t *knn_idx, const float *point_counter, const float *gX, int ldg, int m,
+                               int nn, float *g_feats, occnerf_stream_t stream);
+
+/* ---- Hann-windowed positional encoding (hannw_fourier.py:27-45), window weights from the host ------- */
+int occnerf_hann_pe(const float *xyz, int m, const float *window_host, int multires, float *out, int ldo,
+                    occnerf_stream_t stream);
+
+/* ---- fp32 SIMT GEMM (the exact-fp32 MLP path): C[i,j] = epi( sum_r A[i*sAi + r*sAr] * B[r*sBr + j*sBj] )
+ * split_k > 1 partitions r over blockIdx.z and accumulates with atomics (C must be pre-zeroed or ACCUM). */
+int occnerf_sgemm(const float *A, long sAi, long sAr, const float *B, long sBr, long sBj, float *C, long ldc,
+                  const float *bias, const float *mask, long ldmask, int Mi, int Nj, int Kr, int flags, int split_k,
+                  occnerf_stream_t stream);
+/* out[j] (+)= sum_i A[i*lda + j] * (mask ? mask[i*ldmask+j] > 0 : 1)   (bias gradients) */
+int occnerf_colsum(const float *A, long lda, const float *mask, long ldmask, int Mi, int Nj, float *out,
+                   occnerf_stream_t stream);
+
+/* ---- fused canonical MLP on tcgen05/TMEM (occnerf_mlp.py:183-199) ------------------------------------
+ * Layer table (10 layers): pts 68->256,256,256,256 ; geo 256->65 ; rgb 131->256,256,256,256 ; out 256->3.
+ * occnerf_mlp_pack_weights re-lays the fp32 nn.Linear weights out as bf16 (hi[,lo]) UMMA operand images.
+ * n_pass = 1: bf16 x bf16 -> fp32 ; n_pass = 3: split-bf16 (hi*hi + hi*lo + lo*hi), fp32-grade accuracy. */
+typedef struct {
+    const float *w[10]; /* pts0..3, geo, rgb0..3, out : [out,in] row-major (nn.Linear.weight) */
+    const float *b[10];
+} occnerf_mlp_params;
+long occnerf_mlp_packed_bytes(int n_pass);
+int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, void *packed, occnerf_stream_t stream);
+/* X0 [m,68] = (agg35, var1, h32) -> raw [m, ldr] columns 0..3 = (rgb_pre3, sigma_pre1).
+ * act_save: NULL (inference) or bf16 buffer [9][m_pad][256] receiving the post-ReLU activations of the 8
+ * hidden layers and the geo output, for the backward pass. */
+int occnerf_mlp_forward_tc(const float *X0, int m, const void *packed, int n_pass, float *raw, int ldr, void *act_save,
+                           occnerf_stream_t stream);
+
+/* ---- alpha compositing (network.py:320-348) + completeness term (network.py:486-499) ----------------
+ * raw [N,S,5] = (rgb_pre3, sigma_pre, dist); mask, z [N,S]; rays [N,8]; bg [3] (0..255).
+ * Outputs rgb [N,3], acc [N], depth [N], term [N] int64 (argmax alpha, first maximum),
+ * weights [N,S] or NULL, comp [N,S] or NULL. */
+int occnerf_composite_forward(const float *raw, const float *mask, const float *z, const float *rays, const float *bg,
+                              int N, int S, float *rgb, float *acc, float *depth, int64_t *term, float *weights,
+                              float *comp, occnerf_stream_t stream);
+/* Transmittance is recomputed, nothing but the forward inputs is read.  g_comp may be NULL.
+ * Writes g_raw [N,S,5] (channel 4 = 0) and g_mask [N,S]. */
+int occnerf_composite_backward(const float *raw, const float *mask, const float *z, const float *rays, const float *bg,
+                               const float *g_rgb, const float *g_acc, const float *g_depth, const float *g_comp, int N,
+                               int S, float *g_raw, float *g_mask, occnerf_stream_t stream);
+
+/* ---- visibility counter update (network.py:502-517) --------------------------------------------------
+ * For rays with depth > thresh (only if more than one such ray) the canonical sample x_skel[ray, term[ray]]
+ * votes for its k nearest points of cloud4 [V,4]; hits [V] receives 1.0 for every voted point (else 0).
+ * scratch: >= (N*(k+4) + 4) * 4 bytes. */
+int occnerf_visibility_hits(const float *depth, const int64_t *term, const float *x_skel, int N, int S, float thresh,
+                            const float *cloud4, int V, int k, float *hits, void *scratch, occnerf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCCNERF_B200_H */

@@ -1,0 +1,95 @@
+"""ctypes binding of liboccnerf_b200.so -- the C ABI declared in include/occnerf_b200.h.
+
+PyTorch is only the plumbing here: tensors own the device memory, `torch.cuda.current_stream()` names the
+stream, and every call below hands raw pointers + sizes to the library.  There is no fallback: if the
+library cannot be loaded, or a tensor is not a contiguous CUDA tensor of the right dtype, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liboccnerf_b200.so")
+_lib = None
+
+_vp, _i, _l, _f, _u = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_uint32
+
+
+class MlpParams(C.Structure):
+    _fields_ = [("w", C.c_void_p * 10), ("b", C.c_void_p * 10)]
+
+
+_SIGNATURES = {
+    "occnerf_warp_forward": [_vp] * 8 + [_i] * 6 + [_vp] * 4 + [_vp],
+    "occnerf_warp_backward": [_vp] * 8 + [_i] * 6 + [_vp, _vp],
+    "occnerf_knn": [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "occnerf_sample_geometry": [_vp, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _vp],
+    "occnerf_hashgrid_level_scales": [_f, _u, _u, _vp, _vp],
+    "occnerf_hashgrid_forward": [_vp] * 5 + [_i, _i] + [_u] * 4 + [_vp] * 4,
+    "occnerf_hashgrid_backward": [_vp, _i, _i, _vp, _vp, _vp, _vp] + [_u] * 4 + [_vp],
+    "occnerf_hashgrid_input_backward": [_vp, _i, _i, _vp, _vp] + [_u] * 4 + [_vp],
+    "occnerf_aggregate_forward": [_vp, _vp, _vp, _i, _i, _vp, _i, _vp],
+    "occnerf_aggregate_backward": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "occnerf_hann_pe": [_vp, _i, _vp, _i, _vp, _i, _vp],
+    "occnerf_sgemm": [_vp, _l, _l, _vp, _l, _l, _vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp],
+    "occnerf_colsum": [_vp, _l, _vp, _l, _i, _i, _vp, _vp],
+    "occnerf_mlp_pack_weights": [C.POINTER(MlpParams), _i, _vp, _vp],
+    "occnerf_mlp_forward_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp],
+    "occnerf_composite_forward": [_vp] * 5 + [_i, _i] + [_vp] * 7,
+    "occnerf_composite_backward": [_vp] * 9 + [_i, _i] + [_vp] * 3,
+    "occnerf_visibility_hits": [_vp, _vp, _vp, _i, _i, _f, _vp, _i, _i, _vp, _vp, _vp],
+}
+EXPORTED = sorted(list(_SIGNATURES) + ["occnerf_last_error", "occnerf_abi_version", "occnerf_mlp_packed_bytes"])
+
+GEMM_BIAS, GEMM_RELU, GEMM_ACCUM, GEMM_RELUMASK = 1, 2, 4, 8
+LAYOUT_BLC, LAYOUT_LBC = 0, 1
+
+
+def load(build_if_missing: bool = True):
+    """Loads (building it first if absent and nvcc is present) the native library.  Raises if neither works."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise RuntimeError(f"{LIB_PATH} is missing; run `python -m occnerf_b200.build`")
+        from occnerf_b200 import build as _build
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = args, _i
+    lib.occnerf_last_error.restype = C.c_char_p
+    lib.occnerf_abi_version.restype = _i
+    lib.occnerf_mlp_packed_bytes.argtypes, lib.occnerf_mlp_packed_bytes.restype = [_i], _l
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise RuntimeError(f"{what} failed ({status}): {load().occnerf_last_error().decode()}")
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("occnerf_b200: expected a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("occnerf_b200: expected a contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"occnerf_b200: expected dtype {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args), name)

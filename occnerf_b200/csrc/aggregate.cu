@@ -1,0 +1,123 @@
+// Visibility-weighted aggregation of per-vertex features over the 4x10 multi-scale neighbours.
+//
+// Replaces CanonicalMLP.simple_agg and the (m,40,35) gather feeding it
+// (core/nets/occnerf/canonical_mlps/occnerf_mlp.py:110-126,175-178): the reference materialises
+// feats[knn_idxs] = 5.6 KB per sample in HBM; here one warp owns one sample, the 40 attention weights
+// live in registers/shared memory and each neighbour row (36 floats, 144 B, L2/L1 resident: the whole
+// table is 6890 x 144 B = 0.97 MB) is read with 9 x LDG.128 by one of three 9-lane groups.
+// Output goes straight into the MLP input row: X[0..34] = agg, X[35] = unbiased variance of the
+// normalised attention.
+//
+// Backward: att is detached upstream (occnerf_mlp.py:123), so only feats receives a gradient:
+// g_feats[idx_n] += att_n * gX[0..34] with red.global.add.v4.f32.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kMaxNN = 64;
+constexpr int kRowF4 = 9;   // 36 floats per feature row
+
+// attention weights of one sample -> shared (idx, w); returns the variance (valid in all lanes)
+__device__ __forceinline__ float attention(const int32_t *__restrict__ idx_row, const float *__restrict__ counter, int nn,
+                                           int lane, int *s_idx, float *s_w) {
+    const int n0 = lane, n1 = lane + 32;
+    const bool v0 = n0 < nn, v1 = n1 < nn;
+    const int i0 = v0 ? __ldg(idx_row + n0) : 0, i1 = v1 ? __ldg(idx_row + n1) : 0;
+    float a0 = v0 ? __ldg(counter + i0) : 0.f, a1 = v1 ? __ldg(counter + i1) : 0.f;
+    const float mn = warp_min(fminf(v0 ? a0 : INFINITY, v1 ? a1 : INFINITY));
+    a0 = __fadd_rn(a0, __fsub_rn(1.0f, mn));
+    a1 = __fadd_rn(a1, __fsub_rn(1.0f, mn));
+    const float mx = warp_max(fmaxf(v0 ? a0 : -INFINITY, v1 ? a1 : -INFINITY));
+    a0 = __fdiv_rn(a0, mx);
+    a1 = __fdiv_rn(a1, mx);
+    const float mean = warp_sum((v0 ? a0 : 0.f) + (v1 ? a1 : 0.f)) / (float)nn;
+    const float d0 = v0 ? a0 - mean : 0.f, d1 = v1 ? a1 - mean : 0.f;
+    const float var = warp_sum(d0 * d0 + d1 * d1) / (float)(nn - 1);
+    const float amax = warp_max(fmaxf(v0 ? a0 : -INFINITY, v1 ? a1 : -INFINITY));
+    const float e0 = v0 ? expf(a0 - amax) : 0.f, e1 = v1 ? expf(a1 - amax) : 0.f;
+    const float den = warp_sum(e0 + e1);
+    if (v0) { s_idx[n0] = i0; s_w[n0] = e0 / den; }
+    if (v1) { s_idx[n1] = i1; s_w[n1] = e1 / den; }
+    __syncwarp();
+    return var;
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+aggregate_fwd_kernel(const int32_t *__restrict__ knn_idx, const float *__restrict__ counter,
+                     const float4 *__restrict__ feats, int m, int nn, float *__restrict__ X, long ldx) {
+    __shared__ int s_idx[kWarps][kMaxNN];
+    __shared__ float s_w[kWarps][kMaxNN];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long q = (long)blockIdx.x * kWarps + wib;
+    if (q >= m) return;
+    const float var = attention(knn_idx + q * nn, counter, nn, lane, s_idx[wib], s_w[wib]);
+    const int grp = lane / kRowF4, col = lane - grp * kRowF4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grp < 3) {
+        for (int n = grp; n < nn; n += 3) {
+            const float w = s_w[wib][n];
+            const float4 f = __ldg(feats + (size_t)s_idx[wib][n] * kRowF4 + col);
+            acc.x = fmaf(w, f.x, acc.x); acc.y = fmaf(w, f.y, acc.y);
+            acc.z = fmaf(w, f.z, acc.z); acc.w = fmaf(w, f.w, acc.w);
+        }
+    }
+    // lanes 0..8 gather the partial sums of the other two 9-lane groups (both read before either is added)
+    const float4 p1 = make_float4(__shfl_down_sync(OCC_FULL, acc.x, kRowF4), __shfl_down_sync(OCC_FULL, acc.y, kRowF4),
+                                  __shfl_down_sync(OCC_FULL, acc.z, kRowF4), __shfl_down_sync(OCC_FULL, acc.w, kRowF4));
+    const float4 p2 = make_float4(__shfl_down_sync(OCC_FULL, acc.x, 2 * kRowF4), __shfl_down_sync(OCC_FULL, acc.y, 2 * kRowF4),
+                                  __shfl_down_sync(OCC_FULL, acc.z, 2 * kRowF4), __shfl_down_sync(OCC_FULL, acc.w, 2 * kRowF4));
+    acc.x += p1.x + p2.x; acc.y += p1.y + p2.y; acc.z += p1.z + p2.z; acc.w += p1.w + p2.w;
+    if (lane < kRowF4) {
+        if (lane == kRowF4 - 1) acc.w = var;   // column 35 carries the variance
+        *reinterpret_cast<float4 *>(X + q * ldx + lane * 4) = acc;
+    }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+aggregate_bwd_kernel(const int32_t *__restrict__ knn_idx, const float *__restrict__ counter,
+                     const float *__restrict__ gX, long ldg, int m, int nn, float *__restrict__ g_feats) {
+    __shared__ int s_idx[kWarps][kMaxNN];
+    __shared__ float s_w[kWarps][kMaxNN];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long q = (long)blockIdx.x * kWarps + wib;
+    if (q >= m) return;
+    attention(knn_idx + q * nn, counter, nn, lane, s_idx[wib], s_w[wib]);
+    const int grp = lane / kRowF4, col = lane - grp * kRowF4;
+    if (grp >= 3) return;
+    float4 g = __ldg(reinterpret_cast<const float4 *>(gX + q * ldg) + col);
+    if (col == kRowF4 - 1) g.w = 0.f;   // column 35 is the variance slot, not a feature
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) return;
+    for (int n = grp; n < nn; n += 3) {
+        const float w = s_w[wib][n];
+        red_add_v4(g_feats + ((size_t)s_idx[wib][n] * kRowF4 + col) * 4, w * g.x, w * g.y, w * g.z, w * g.w);
+    }
+}
+
+}  // namespace
+
+extern "C" int occnerf_aggregate_forward(const int32_t *knn_idx, const float *point_counter, const float *feats, int m,
+                                         int nn, float *X, int ldx, occnerf_stream_t stream) {
+    OCC_CHECK_ARG(knn_idx && point_counter && feats && X, "aggregate_forward: null pointer");
+    OCC_CHECK_ARG(nn >= 2 && nn <= kMaxNN, "aggregate_forward: nn=%d outside [2,%d]", nn, kMaxNN);
+    OCC_CHECK_ARG(ldx >= 36 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)feats & 15) == 0,
+                  "aggregate_forward: X/feats must be 16-byte aligned with ldx %% 4 == 0 (ldx=%d)", ldx);
+    if (m <= 0) return OCCNERF_OK;
+    aggregate_fwd_kernel<<<occ_div_up(m, kWarps), kWarps * 32, 0, (cudaStream_t)stream>>>(
+        knn_idx, point_counter, (const float4 *)feats, m, nn, X, ldx);
+    OCC_LAUNCH_CHECK();
+    return OCCNERF_OK;
+}
+
+extern "C" int occnerf_aggregate_backward(const int32_t *knn_idx, const float *point_counter, const float *gX, int ldg,
+                                          int m, int nn, float *g_feats, occnerf_stream_t stream) {
+    OCC_CHECK_ARG(knn_idx && point_counter && gX && g_feats, "aggregate_backward: null pointer");
+    OCC_CHECK_ARG(nn >= 2 && nn <= kMaxNN, "aggregate_backward: nn=%d outside [2,%d]", nn, kMaxNN);
+    OCC_CHECK_ARG(ldg >= 36 && ldg % 4 == 0 && ((uintptr_t)gX & 15) == 0 && ((uintptr_t)g_feats & 15) == 0,
+                  "aggregate_backward: gX/g_feats must be 16-byte aligned with ldg %% 4 == 0 (ldg=%d)", ldg);
+    if (m <= 0) return OCCNERF_OK;
+    aggregate_bwd_kernel<<<occ_div_up(m, kWarps), kWarps * 32, 0, (cudaStream_t)stream>>>(knn_idx, point_counter, gX,
+                                                                                         ldg, m, nn, g_feats);
+    OCC_LAUNCH_CHECK();
+    return OCCNERF_OK;
+}

@@ -1,0 +1,216 @@
+// Exact k-nearest-neighbour search, per-sample surface geometry and the visibility vote.
+//
+// Replaces the pykeops `Kmin_argKmin` reductions the reference calls through core/nets/occnerf/knn.py:33-85
+// (network.py:236-255: 4 block-diagonal levels x k=10 per sample; :265 k=3 per vertex; :508 k=10 per
+// terminating ray) and the no_grad geometry block of canonical_mlps/occnerf_mlp.py:146-167.
+//
+// v1 is tiled brute force on the fp32 CUDA cores (tensor cores are reserved for the MLP): the support set is
+// streamed through shared memory in 2048-point tiles as float4 and read with warp-broadcast LDS.128; every
+// thread owns one query and a sorted register top-k per level.  The ranking key is
+// (dx*dx + dy*dy) + dz*dz with explicit round-to-nearest ops (no FMA contraction) and ties go to the lower
+// support row, which makes the neighbour ids bit-exact with the oracle.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTile = 2048;
+
+template <int K>
+__device__ __forceinline__ void topk_insert(float (&dk)[K], int (&ik)[K], float d, int idx) {
+    bool ins = false;
+    float cd = d;
+    int ci = idx;
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        ins = ins || (cd < dk[t]);
+        if (ins) {
+            const float td = dk[t];
+            const int ti = ik[t];
+            dk[t] = cd; ik[t] = ci;
+            cd = td; ci = ti;
+        }
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+knn_kernel(const float *__restrict__ queries, int m, const float4 *__restrict__ supports, const int32_t *__restrict__ gid,
+           int lv0, int lv1, int lv2, int lv3, int lv4, int n_levels, const uint8_t *__restrict__ query_sel,
+           int32_t *__restrict__ out) {
+    __shared__ float4 tile[kTile];
+    const int q = blockIdx.x * kThreads + threadIdx.x;
+    bool active = q < m;
+    if (active && query_sel) active = query_sel[q] != 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        qx = __ldg(queries + (size_t)q * 3 + 0);
+        qy = __ldg(queries + (size_t)q * 3 + 1);
+        qz = __ldg(queries + (size_t)q * 3 + 2);
+    }
+    const int begins[5] = {lv0, lv1, lv2, lv3, lv4};
+#pragma unroll 1
+    for (int lev = 0; lev < n_levels; ++lev) {
+        const int s0 = begins[lev], s1 = begins[lev + 1];
+        float dk[K];
+        int ik[K];
+#pragma unroll
+        for (int t = 0; t < K; ++t) { dk[t] = INFINITY; ik[t] = -1; }
+#pragma unroll 1
+        for (int base = s0; base < s1; base += kTile) {
+            const int n = min(kTile, s1 - base);
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += kThreads) tile[i] = __ldg(supports + base + i);
+            __syncthreads();
+            if (active) {
+#pragma unroll 4
+                for (int i = 0; i < n; ++i) {
+                    const float4 s = tile[i];
+                    const float dx = __fsub_rn(qx, s.x), dy = __fsub_rn(qy, s.y), dz = __fsub_rn(qz, s.z);
+                    const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    if (d < dk[K - 1]) topk_insert<K>(dk, ik, d, base + i);
+                }
+            }
+        }
+        if (active) {
+            int32_t *o = out + ((size_t)q * n_levels + lev) * K;
+#pragma unroll
+            for (int t = 0; t < K; ++t) {
+                int v = ik[t];
+                if (v >= 0) v = gid ? __ldg(gid + v) : v - s0;
+                o[t] = v;
+            }
+        }
+    }
+}
+
+// occnerf_mlp.py:146-167
+__global__ void __launch_bounds__(kThreads)
+sample_geometry_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ knn_idx, int knn_stride,
+                       const float *__restrict__ base, const float *__restrict__ norms, float bound, int m,
+                       float *__restrict__ enc_in, float *__restrict__ dist_out, int dist_stride) {
+    const int q = blockIdx.x * kThreads + threadIdx.x;
+    if (q >= m) return;
+    const float x = __ldg(xyz + (size_t)q * 3), y = __ldg(xyz + (size_t)q * 3 + 1), z = __ldg(xyz + (size_t)q * 3 + 2);
+    const int32_t *idx = knn_idx + (size_t)q * knn_stride;
+    int inside = 0;
+    float nsum = 0.f, asum = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+    const float inv2b = 2.0f * bound;
+#pragma unroll
+    for (int t = 0; t < 10; ++t) {
+        const int v = __ldg(idx + t);
+        const float bx = __ldg(base + (size_t)v * 3), by = __ldg(base + (size_t)v * 3 + 1), bz = __ldg(base + (size_t)v * 3 + 2);
+        const float nx = __ldg(norms + (size_t)v * 3), ny = __ldg(norms + (size_t)v * 3 + 1), nz = __ldg(norms + (size_t)v * 3 + 2);
+        const float dx = __fsub_rn(x, bx), dy = __fsub_rn(y, by), dz = __fsub_rn(z, bz);
+        const double dot = ((double)dx * (double)nx + (double)dy * (double)ny) + (double)dz * (double)nz;
+        inside += dot < 0.0;
+        const float dn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+        nsum = __fadd_rn(nsum, dn);
+        if (t < 3) {
+            // |cosine_similarity(dir, n)| with eps = 1e-8 on each norm, then the weighted mean of the
+            // neighbour positions normalised to [0,1]^3
+            const float nn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
+            const float dd = fmaxf(dn, 1e-8f), nd_ = fmaxf(nn, 1e-8f);
+            const float a = fabsf((dx / dd) * (nx / nd_) + (dy / dd) * (ny / nd_) + (dz / dd) * (nz / nd_));
+            asum += a;
+            px += a * (__fadd_rn(bx, bound) / inv2b);
+            py += a * (__fadd_rn(by, bound) / inv2b);
+            pz += a * (__fadd_rn(bz, bound) / inv2b);
+        }
+    }
+    float dist = nsum / 10.0f;
+    if (inside > 5) dist = -dist;
+    const float nd = fminf(fmaxf(__fdiv_rn(__fadd_rn(dist, 0.2f), 0.5f), 0.0f), 1.0f);
+    reinterpret_cast<float4 *>(enc_in)[q] = make_float4(px / asum, py / asum, pz / asum, nd);
+    dist_out[(size_t)q * dist_stride] = dist;
+}
+
+// network.py:502-517
+__global__ void vis_select_kernel(const float *__restrict__ depth, const int64_t *__restrict__ term,
+                                  const float *__restrict__ x_skel, int N, int S, float thresh, int *__restrict__ count,
+                                  uint8_t *__restrict__ sel, float *__restrict__ qpts) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    const bool s = __ldg(depth + r) > thresh;
+    sel[r] = s ? 1 : 0;
+    long t = (long)__ldg(term + r);
+    t = t < 0 ? 0 : (t >= S ? S - 1 : t);
+    const float *p = x_skel + ((size_t)r * S + t) * 3;
+    qpts[r * 3 + 0] = p[0]; qpts[r * 3 + 1] = p[1]; qpts[r * 3 + 2] = p[2];
+    if (s) atomicAdd(count, 1);
+}
+__global__ void vis_mark_kernel(const int *__restrict__ count, const uint8_t *__restrict__ sel,
+                                const int32_t *__restrict__ idx, int N, int k, float *__restrict__ hits) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N || *count <= 1 || !sel[r]) return;
+    for (int t = 0; t < k; ++t) {
+        const int v = idx[(size_t)r * k + t];
+        if (v >= 0) hits[v] = 1.0f;
+    }
+}
+
+int launch_knn(const float *queries, int m, const float *supports4, const int32_t *gid, const int32_t *lb, int n_levels,
+               int k, const uint8_t *query_sel, int32_t *out, cudaStream_t st) {
+    int b[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i <= n_levels; ++i) b[i] = lb[i];
+    const unsigned grid = occ_div_up(m, kThreads);
+    if (k == 10)
+        knn_kernel<10><<<grid, kThreads, 0, st>>>(queries, m, (const float4 *)supports4, gid, b[0], b[1], b[2], b[3], b[4],
+                                                  n_levels, query_sel, out);
+    else
+        knn_kernel<3><<<grid, kThreads, 0, st>>>(queries, m, (const float4 *)supports4, gid, b[0], b[1], b[2], b[3], b[4],
+                                                 n_levels, query_sel, out);
+    OCC_LAUNCH_CHECK();
+    return OCCNERF_OK;
+}
+
+}  // namespace
+
+extern "C" int occnerf_knn(const float *queries, int m, const float *supports4, const int32_t *support_gid,
+                           const int32_t *level_begin_host, int n_levels, int k, const uint8_t *query_sel,
+                           int32_t *out_idx, occnerf_stream_t stream) {
+    OCC_CHECK_ARG(queries && supports4 && level_begin_host && out_idx, "knn: null pointer");
+    OCC_CHECK_ARG(n_levels >= 1 && n_levels <= 4, "knn: n_levels=%d outside [1,4]", n_levels);
+    OCC_CHECK_ARG(k == 3 || k == 10, "knn: k=%d (supported: 3, 10)", k);
+    OCC_CHECK_ARG(((uintptr_t)supports4 & 15) == 0, "knn: supports4 must be 16-byte aligned");
+    for (int i = 0; i < n_levels; ++i)
+        OCC_CHECK_ARG(level_begin_host[i] <= level_begin_host[i + 1], "knn: level_begin not ascending");
+    if (m <= 0) return OCCNERF_OK;
+    return launch_knn(queries, m, supports4, support_gid, level_begin_host, n_levels, k, query_sel, out_idx,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int occnerf_sample_geometry(const float *xyz, const int32_t *knn_idx, int knn_stride, const float *point_base,
+                                       const float *point_norms, float bound, int m, float *enc_in, float *dist,
+                                       int dist_stride, occnerf_stream_t stream) {
+    OCC_CHECK_ARG(xyz && knn_idx && point_base && point_norms && enc_in && dist, "sample_geometry: null pointer");
+    OCC_CHECK_ARG(knn_stride >= 10 && bound > 0.f && dist_stride >= 1, "sample_geometry: knn_stride=%d bound=%f", knn_stride, bound);
+    OCC_CHECK_ARG(((uintptr_t)enc_in & 15) == 0, "sample_geometry: enc_in must be 16-byte aligned");
+    if (m <= 0) return OCCNERF_OK;
+    sample_geometry_kernel<<<occ_div_up(m, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        xyz, knn_idx, knn_stride, point_base, point_norms, bound, m, enc_in, dist, dist_stride);
+    OCC_LAUNCH_CHECK();
+    return OCCNERF_OK;
+}
+
+extern "C" int occnerf_visibility_hits(const float *depth, const int64_t *term, const float *x_skel, int N, int S,
+                                       float thresh, const float *cloud4, int V, int k, float *hits, void *scratch,
+                                       occnerf_stream_t stream) {
+    OCC_CHECK_ARG(depth && term && x_skel && cloud4 && hits && scratch, "visibility_hits: null pointer");
+    OCC_CHECK_ARG(k == 3 || k == 10, "visibility_hits: k=%d", k);
+    cudaStream_t st = (cudaStream_t)stream;
+    OCC_CUDA(cudaMemsetAsync(hits, 0, sizeof(float) * (size_t)V, st));
+    if (N <= 0) return OCCNERF_OK;
+    int *count = (int *)scratch;
+    uint8_t *sel = (uint8_t *)scratch + 16;
+    float *qpts = (float *)((uint8_t *)scratch + 16 + (size_t)4 * N);
+    int32_t *idx = (int32_t *)(qpts + (size_t)3 * N);
+    OCC_CUDA(cudaMemsetAsync(count, 0, 16, st));
+    vis_select_kernel<<<occ_div_up(N, 256), 256, 0, st>>>(depth, term, x_skel, N, S, thresh, count, sel, qpts);
+    OCC_LAUNCH_CHECK();
+    const int32_t lb[2] = {0, V};
+    if (int e = launch_knn(qpts, N, cloud4, nullptr, lb, 1, k, sel, idx, st)) return e;
+    vis_mark_kernel<<<occ_div_up(N, 256), 256, 0, st>>>(count, sel, idx, N, k, hits);
+    OCC_LAUNCH_CHECK();
+    return OCCNERF_OK;
+}

@@ -1,0 +1,453 @@
+"""Host-side mirror of the reference's model interface for the per-ray rendering path.
+
+`Network.forward / _render_rays / _query_mlp` keep the reference's signatures, argument meaning and return
+dictionaries (core/nets/occnerf/network.py:542-549, 435-447, 164-192); parameter names and shapes follow
+SURVEY.md appendix B so that reference checkpoints load with `load_state_dict`.  Behind them every stage is a
+CUDA kernel of liboccnerf_b200.so (occnerf_b200/ops.py); there is no eager-PyTorch or CPU path.
+
+Differences that are deliberate and visible to a caller:
+  * `torch.rand` jitter (network.py:429) can be injected (`t_rand=`) so that runs are reproducible;
+  * the in-place `point_counter[...] += 1` side effect (network.py:517) is applied by `apply_visibility()`
+    from the returned `hits` so that data-parallel ranks can sum their votes first;
+  * K-NN ids are int32 internally (the reference carries int64).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from occnerf_b200 import mlp as M
+from occnerf_b200 import ops
+
+f32, i32 = torch.float32, torch.int32
+
+
+# ----------------------------------------------------------------------------- parameter containers
+def _xavier_(lin: nn.Linear, relu: bool):
+    """`initseq` (core/utils/network_util.py:316-334)."""
+    nn.init.xavier_uniform_(lin.weight, gain=math.sqrt(2.0) if relu else 1.0)
+    nn.init.zeros_(lin.bias)
+
+
+def _stack(dims):
+    mods = []
+    for i, o in zip(dims[:-1], dims[1:]):
+        lin = nn.Linear(i, o)
+        _xavier_(lin, True)
+        mods += [lin, nn.ReLU(inplace=True)]
+    return nn.ModuleList(mods)
+
+
+class GridEncoder(nn.Module):
+    """Same constructor, parameters (`embeddings`, `offsets`) and forward contract as the reference's
+    gridencoder/grid.py:97-170 (hash grid type, align_corners=False)."""
+
+    def __init__(self, input_dim=3, num_levels=16, level_dim=2, per_level_scale=2, base_resolution=16,
+                 log2_hashmap_size=19, desired_resolution=None, gridtype="hash", align_corners=False):
+        super().__init__()
+        if gridtype != "hash" or align_corners:
+            raise ValueError("occnerf_b200.GridEncoder supports gridtype='hash', align_corners=False (what OccNeRF uses)")
+        if desired_resolution is not None:
+            per_level_scale = np.exp2(np.log2(desired_resolution / base_resolution) / (num_levels - 1))
+        self.input_dim, self.num_levels, self.level_dim = input_dim, num_levels, level_dim
+        self.per_level_scale, self.base_resolution = per_level_scale, base_resolution
+        self.log2_hashmap_size = log2_hashmap_size
+        self.output_dim = num_levels * level_dim
+        offsets, offset = [], 0
+        self.max_params = 2 ** log2_hashmap_size
+        for i in range(num_levels):
+            resolution = int(np.ceil(base_resolution * per_level_scale ** i))
+            params_in_level = min(self.max_params, (resolution + 1) ** input_dim)
+            params_in_level = int(np.ceil(params_in_level / 8) * 8)
+            offsets.append(offset)
+            offset += params_in_level
+        offsets.append(offset)
+        self.register_buffer("offsets", torch.from_numpy(np.array(offsets, dtype=np.int32)))
+        self.n_params = offsets[-1] * level_dim
+        self.embeddings = nn.Parameter(torch.empty(offset, level_dim))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.embeddings.data.uniform_(-1e-4, 1e-4)
+
+    def forward(self, inputs, bound=None):
+        if bound is not None:
+            inputs = (inputs + bound) / (2 * bound)
+        prefix = list(inputs.shape[:-1])
+        out = ops.grid_encode(inputs.reshape(-1, self.input_dim), self.embeddings, self.offsets, self.per_level_scale,
+                              self.base_resolution)
+        return out.view(prefix + [self.output_dim])
+
+
+class CanonicalMLP(nn.Module):
+    """Parameter layout of canonical_mlps/occnerf_mlp.py:32-83 (mlp_depth=4, mlp_width=256, skips=[])."""
+
+    def __init__(self, mlp_depth=4, mlp_width=256, bound=1.0, **_):
+        super().__init__()
+        assert mlp_depth == 4 and mlp_width == 256, "the fused kernels are built for the shipped 4x256 configuration"
+        self.bound = bound
+        self.encoder = GridEncoder(input_dim=4, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
+                                   desired_resolution=2048 * bound)
+        self.pts_linears = _stack([68, 256, 256, 256, 256])
+        self.geo_linear = nn.Sequential(nn.Linear(256, 65))
+        _xavier_(self.geo_linear[0], False)
+        self.rgb_linears = _stack([131, 256, 256, 256, 256])
+        self.output_linear = nn.Sequential(nn.Linear(256, 3))
+        _xavier_(self.output_linear[0], False)
+
+    def flat_params(self):
+        out = []
+        for i in (0, 2, 4, 6):
+            out += [self.pts_linears[i].weight, self.pts_linears[i].bias]
+        out += [self.geo_linear[0].weight, self.geo_linear[0].bias]
+        for i in (0, 2, 4, 6):
+            out += [self.rgb_linears[i].weight, self.rgb_linears[i].bias]
+        out += [self.output_linear[0].weight, self.output_linear[0].bias]
+        return out
+
+
+class NonRigidMotionMLP(nn.Module):
+    """Parameter layout of non_rigid_motion_mlps/mlp_offset.py:7-42."""
+
+    def __init__(self):
+        super().__init__()
+        mods = []
+        for di in (105, 128, 128, 128, 164, 128):
+            lin = nn.Linear(di, 128)
+            _xavier_(lin, True)
+            mods += [lin, nn.ReLU()]
+        last = nn.Linear(128, 3)
+        last.weight.data.uniform_(-1e-5, 1e-5)
+        last.bias.data.zero_()
+        mods.append(last)
+        self.block_mlps = nn.ModuleList(mods)
+
+    def flat(self):
+        lin = [self.block_mlps[i] for i in range(0, 14, 2)]
+        return [l.weight for l in lin], [l.bias for l in lin]
+
+
+class _Replicated(nn.Module):
+    """Keeps the `.module.` level that nn.DataParallel puts into the reference's state_dict keys
+    (network.py:68-72,142-146) without any of its behaviour."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+
+class HannEmbedder:
+    """Stand-in for the closure `get_non_rigid_embedder` returns (hannw_fourier.py:48-62): carries the window
+    weights; the encoding itself is evaluated inside the CUDA path."""
+
+    def __init__(self, window):
+        self.window = list(window)
+
+    def __call__(self, xyz):
+        return ops.hann_pe(xyz.reshape(-1, 3).contiguous(), self.window).view(*xyz.shape[:-1], 6 * len(self.window))
+
+
+@dataclass
+class RenderConfig:
+    """The cfg values that parameterise the path."""
+    N_samples: int = 128
+    perturb: float = 1.0
+    chunk: int = 32768
+    netchunk_per_gpu: int = 300000
+    total_bones: int = 24
+    non_rigid_kick_in_iter: int = 100000
+    non_rigid_full_band_iter: int = 200000
+    non_rigid_multires: int = 6
+    ignore_non_rigid_motions: bool = False
+    bgcolor: tuple = (0.0, 0.0, 0.0)
+    mlp_engine: str = "fp32"        # "fp32" (exact SIMT) | "tc3" (tcgen05 split-bf16) | "tc1" (tcgen05 bf16)
+
+
+# ----------------------------------------------------------------------------- differentiable stages
+class _WarpFn(torch.autograd.Function):
+    """vol -> (z, x_skel, mask); only mask carries a gradient (to vol), as in the reference."""
+
+    @staticmethod
+    def forward(ctx, vol, rays, t_rand, Rs, Ts, bmin, bscale, S):
+        vol_c = vol.detach().contiguous().float()
+        z, x_skel, mask = ops.warp_forward(rays, t_rand, Rs, Ts, vol_c, bmin, bscale, S)
+        ctx.save_for_backward(rays, t_rand if t_rand is not None else torch.empty(0, device=rays.device), Rs, Ts, bmin, bscale)
+        ctx.meta = (S, tuple(vol.shape), t_rand is not None)
+        ctx.mark_non_differentiable(z, x_skel)
+        return z, x_skel, mask
+
+    @staticmethod
+    def backward(ctx, _gz, _gx, g_mask):
+        rays, t_rand, Rs, Ts, bmin, bscale = ctx.saved_tensors
+        S, vol_shape, has_rand = ctx.meta
+        g_vol = ops.warp_backward(rays, t_rand if has_rand else None, Rs, Ts, bmin, bscale, g_mask.contiguous(), S, vol_shape)
+        return g_vol, None, None, None, None, None, None, None
+
+
+class _CompositeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, mask, z, rays, bg, want_comp):
+        raw_c, mask_c = raw.detach().contiguous(), mask.detach().contiguous()
+        rgb, acc, depth, term, _, comp = ops.composite_forward(raw_c, mask_c, z, rays, bg, want_comp=want_comp)
+        ctx.save_for_backward(raw_c, mask_c, z, rays, bg)
+        ctx.want_comp = want_comp
+        ctx.mark_non_differentiable(term)
+        if comp is None:
+            comp = torch.zeros(1, 1, device=raw.device)
+        return rgb, acc, depth, term, comp
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_acc, g_depth, _gt, g_comp):
+        raw, mask, z, rays, bg = ctx.saved_tensors
+        N = z.shape[0]
+        dev = z.device
+        g_rgb = g_rgb if g_rgb is not None else torch.zeros(N, 3, device=dev)
+        g_acc = g_acc if g_acc is not None else torch.zeros(N, device=dev)
+        g_depth = g_depth if g_depth is not None else torch.zeros(N, device=dev)
+        g_raw, g_mask = ops.composite_backward(raw, mask, z, rays, bg, g_rgb.float(), g_acc.float(), g_depth.float(),
+                                               g_comp.float() if (ctx.want_comp and g_comp is not None) else None)
+        return g_raw, g_mask, None, None, None, None
+
+
+class _QueryFn(torch.autograd.Function):
+    """Canonical query of one chunk of points: non-rigid offset -> multi-scale KNN -> surface geometry ->
+    attention aggregation + hash encode -> MLP  (network.py:225-299 + occnerf_mlp.py:142-199).
+    Differentiable w.r.t. the per-vertex feature table, the hash table and the 20 MLP tensors."""
+
+    @staticmethod
+    def forward(ctx, xyz, feats36, embeddings, net, nr_cond, nr_window, *mlp_params):
+        xyz = xyz.detach().contiguous().float()
+        m, dev = xyz.shape[0], xyz.device
+        st = net._static()
+        if nr_window is not None:
+            nw, nb = net.non_rigid_mlp.module.flat()
+            xyz = M.nonrigid_offsets(xyz, nr_cond, nr_window, nw, nb)
+        knn_idx = ops.knn(xyz, st["supports4"], st["level_begin"], 10, support_gid=st["support_gid"])
+        raw = torch.empty(m, 5, device=dev, dtype=f32)
+        enc_in, _ = ops.sample_geometry(xyz, knn_idx, st["point_base"], st["point_norms"], net.bound, raw=raw)
+        XB = torch.empty(m, M.XB_LD, device=dev, dtype=f32)
+        feats_c = feats36.detach().contiguous()
+        emb_c = embeddings.detach().contiguous()
+        counter = net.point_counter.detach().contiguous().float()
+        ops.aggregate_forward(knn_idx, counter, feats_c, XB.data_ptr() + 4 * M.X0_OFF, M.XB_LD)
+        enc = net.cnl_mlp.module.encoder
+        scales = ops.level_scales(float(np.log2(enc.per_level_scale)), enc.base_resolution, enc.num_levels, dev)
+        ops.hashgrid_forward(enc_in, emb_c, enc.offsets, scales, out_ptr=XB.data_ptr() + 4 * M.H_OFF, ld=M.XB_LD)
+        W = M.MlpWeights(mlp_params)
+        need_grad = any(ctx.needs_input_grad)
+        engine = net._engine()
+        saved = engine.forward(XB, raw, W, save=need_grad)
+        if need_grad:
+            ctx.state = dict(knn_idx=knn_idx, enc_in=enc_in, XB=XB, W=W, saved=saved, engine=engine, counter=counter,
+                             offsets=enc.offsets, scales=scales, emb_shape=tuple(embeddings.shape), V=feats36.shape[0])
+        ctx.mark_non_differentiable(knn_idx)
+        return raw, knn_idx
+
+    @staticmethod
+    def backward(ctx, g_raw, _gk):
+        s = ctx.state
+        g_raw = g_raw.contiguous().float()
+        gXB, g_params = s["engine"].backward(s["XB"], g_raw, s["W"], s["saved"])
+        g_emb = torch.zeros(s["emb_shape"], device=g_raw.device, dtype=f32)
+        ops.hashgrid_backward(gXB.data_ptr() + 4 * M.H_OFF, M.XB_LD, 0, s["enc_in"], s["offsets"], s["scales"], g_emb,
+                              s["emb_shape"][1])
+        g_feats = ops.aggregate_backward(s["knn_idx"], s["counter"], gXB.data_ptr() + 4 * M.X0_OFF, M.XB_LD, s["V"])
+        ctx.state = None
+        return (None, g_feats, g_emb, None, None, None, *g_params)
+
+
+# ----------------------------------------------------------------------------- the model
+class Network(nn.Module):
+    def __init__(self, cfg: RenderConfig | None = None):
+        super().__init__()
+        self.cfg = cfg or RenderConfig()
+        self.non_rigid_mlp = _Replicated(NonRigidMotionMLP())
+        self._cache = None
+        # set by generate_neural_points()
+        self.bound = None
+        self.fps_index = None
+        # optional per-frame prologue (pose refinement, motion basis, weight-volume decoder):
+        # callable(dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec, iter_val) -> (Rs, Ts, vol)
+        self.prologue = None
+
+    # -- per-subject state (network.py:90-146)
+    def generate_neural_points(self, vertices, normals, fps_index, bbox_min=None, bbox_max=None, point_dist=None,
+                               point_counter=None):
+        """`vertices`/`normals` are the T-pose SMPL vertices and their normals (the reference derives them from the
+        SMPL pkl + trimesh, network.py:92-98); `fps_index` the three farthest-point subsets (network.py:113-118)."""
+        verts = torch.as_tensor(vertices, dtype=f32)
+        V = verts.shape[0]
+        if bbox_min is None:
+            bbox_min, bbox_max = verts.min(0)[0] - 0.3, verts.max(0)[0] + 0.3
+        self.bound = float(torch.max(torch.abs(torch.cat([torch.as_tensor(bbox_min).reshape(-1), torch.as_tensor(bbox_max).reshape(-1)]))))
+        self.point_base = nn.Parameter(verts.clone(), requires_grad=False)
+        pd = point_dist if point_dist is not None else (torch.rand(V, 1) * 2 - 1) * 1e-4
+        self.point_dist = nn.Parameter(torch.as_tensor(pd, dtype=f32).clone(), requires_grad=True)
+        pcn = point_counter if point_counter is not None else torch.ones(V)
+        self.point_counter = nn.Parameter(torch.as_tensor(pcn, dtype=f32).clone(), requires_grad=False)
+        self.register_buffer("point_norms", torch.as_tensor(normals, dtype=f32).clone(), persistent=False)
+        self.fps_index = [torch.as_tensor(f, dtype=torch.int64).clone() for f in fps_index]
+        self.cnl_mlp = _Replicated(CanonicalMLP(bound=self.bound))
+        self._cache = None
+        return self
+
+    @property
+    def point_cloud(self):
+        return self.point_base + self.point_dist
+
+    def _static(self):
+        """Device-resident support arrays for the KNN (rebuilt when the module moves)."""
+        dev = self.point_base.device
+        if self._cache is None or self._cache["device"] != dev:
+            base = self.point_base.detach()
+            fps = [f.to(dev) for f in self.fps_index]
+            sup = torch.cat([base] + [base[f] for f in fps], 0)
+            gid = torch.cat([torch.arange(base.shape[0], device=dev)] + fps).to(i32)
+            lb = np.cumsum([0, base.shape[0]] + [int(f.shape[0]) for f in fps]).tolist()
+            self._cache = dict(device=dev, supports4=ops.to_float4(sup), support_gid=gid.contiguous(), level_begin=lb,
+                               base4=ops.to_float4(base), point_base=base.contiguous().float(),
+                               point_norms=self.point_norms.contiguous().float())
+        return self._cache
+
+    def _engine(self):
+        e = self.cfg.mlp_engine
+        if e == "fp32":
+            return M.MlpSimt()
+        from occnerf_b200 import mlp_tc
+        return mlp_tc.MlpTc(n_pass=3 if e == "tc3" else 1)
+
+    # -- per-vertex block (network.py:263-284 + occnerf_mlp.py:171-175), once per call instead of once per chunk
+    def vertex_features(self):
+        st = self._static()
+        V = self.point_base.shape[0]
+        pc = self.point_base + self.point_dist
+        kidx = ops.knn(pc.detach().contiguous(), st["base4"], [0, V], 3)[:, 0].long()
+        b = self.point_base[kidx]
+        direction = pc[:, None, :] - b
+        n = self.point_norms[kidx]
+        a = torch.abs(torch.nn.functional.cosine_similarity(direction, n, dim=-1))[..., None]
+        knn_base = (a * b).sum(1) / a.sum(1)
+        inside = ((direction * n).sum(-1) < 0).sum(1) > 1.5
+        dist = direction.norm(dim=-1).mean(1, keepdim=True)
+        dist = torch.where(inside[:, None], -dist, dist)
+        v_in = torch.cat([(knn_base + self.bound) / (2 * self.bound), torch.clamp((dist + 0.2) / 0.8, 0.0, 1.0)], -1)
+        hv = self.cnl_mlp.module.encoder(v_in)
+        feats36 = torch.cat([hv, pc, torch.zeros(V, 1, device=pc.device, dtype=pc.dtype)], -1)
+        return feats36, pc
+
+    # -- reference API: network.py:164-192
+    def _query_mlp(self, pos_xyz, rays_d, pos_embed_fn, non_rigid_pos_embed_fn, non_rigid_mlp_input, _feats36=None,
+                   _return_knn=False):
+        pos_flat = pos_xyz.reshape(-1, pos_xyz.shape[-1])
+        feats36 = _feats36 if _feats36 is not None else self.vertex_features()[0]
+        window, cond = None, None
+        if not self.cfg.ignore_non_rigid_motions:
+            if not hasattr(non_rigid_pos_embed_fn, "window"):
+                raise TypeError("non_rigid_pos_embed_fn must be the HannEmbedder returned by get_non_rigid_embedder()")
+            window = non_rigid_pos_embed_fn.window
+            if non_rigid_mlp_input is not None and bool((non_rigid_mlp_input != 0).any()):
+                cond = non_rigid_mlp_input.reshape(1, -1).float()
+        cm = self.cnl_mlp.module
+        chunk = self.cfg.netchunk_per_gpu
+        raws, knns = [], []
+        for i in range(0, pos_flat.shape[0], chunk):
+            raw, knn_idx = _QueryFn.apply(pos_flat[i:i + chunk], feats36, cm.encoder.embeddings, self, cond, window,
+                                          *cm.flat_params())
+            raws.append(raw)
+            knns.append(knn_idx)
+        raws_flat = raws[0] if len(raws) == 1 else torch.cat(raws, 0)
+        out = {"raws": raws_flat.reshape(list(pos_xyz.shape[:-1]) + [5])}
+        if _return_knn:
+            out["knn_idxs"] = knns[0] if len(knns) == 1 else torch.cat(knns, 0)
+        return out
+
+    def get_non_rigid_embedder(self, multires, is_identity, iter_val):
+        return HannEmbedder(ops.hann_window(iter_val, self.cfg.non_rigid_kick_in_iter, self.cfg.non_rigid_full_band_iter,
+                                            multires)), 6 * multires
+
+    # -- reference API: network.py:435-525
+    def _render_rays(self, ray_batch, motion_scale_Rs, motion_Ts, motion_weights_vol, cnl_bbox_min_xyz,
+                     cnl_bbox_scale_xyz, pos_embed_fn, non_rigid_pos_embed_fn, non_rigid_mlp_input=None, bgcolor=None,
+                     t_rand=None, _feats=None, **_):
+        cfg = self.cfg
+        S = cfg.N_samples
+        rays = ray_batch.contiguous().float()
+        N = rays.shape[0]
+        dev = rays.device
+        if cfg.perturb > 0.0 and t_rand is None:
+            t_rand = torch.rand(N, S, device=dev)
+        if cfg.perturb <= 0.0:
+            t_rand = None
+        Rs = motion_scale_Rs.reshape(-1, 3, 3).contiguous().float()
+        Ts = motion_Ts.reshape(-1, 3).contiguous().float()
+        z, x_skel, mask = _WarpFn.apply(motion_weights_vol, rays, t_rand.contiguous() if t_rand is not None else None, Rs, Ts,
+                                        cnl_bbox_min_xyz.contiguous().float(), cnl_bbox_scale_xyz.contiguous().float(), S)
+        feats36, pc = _feats if _feats is not None else self.vertex_features()
+        q = self._query_mlp(pos_xyz=x_skel, rays_d=None, pos_embed_fn=pos_embed_fn,
+                            non_rigid_pos_embed_fn=non_rigid_pos_embed_fn, non_rigid_mlp_input=non_rigid_mlp_input,
+                            _feats36=feats36)
+        raw = q["raws"]
+        bg = (bgcolor if bgcolor is not None else torch.tensor(cfg.bgcolor)).to(dev).float().contiguous()
+        rgb, acc, depth, term, comp = _CompositeFn.apply(raw, mask, z, rays, bg, self.training)
+        out = {"rgb": rgb, "alpha": acc, "depth": depth, "comp_loss": comp}
+        if self.training:
+            out["hits"] = ops.visibility_hits(depth.detach(), term, x_skel, ops.to_float4(pc.detach()))
+        return out
+
+    def _batchify_rays(self, rays_flat, **kwargs):
+        """network.py:307-317."""
+        t_rand = kwargs.pop("t_rand", None)
+        feats = self.vertex_features()
+        all_ret = {}
+        for i in range(0, rays_flat.shape[0], self.cfg.chunk):
+            tr = t_rand[i:i + self.cfg.chunk] if t_rand is not None else None
+            ret = self._render_rays(rays_flat[i:i + self.cfg.chunk], t_rand=tr, _feats=feats, **kwargs)
+            for k, v in ret.items():
+                all_ret.setdefault(k, []).append(v)
+        out = {}
+        for k, v in all_ret.items():
+            if k == "hits":
+                out[k] = torch.stack(v, 0).amax(0)
+            elif k == "comp_loss" and not self.training:
+                out[k] = v[0]
+            else:
+                out[k] = v[0] if len(v) == 1 else torch.cat(v, 0)
+        return out
+
+    def apply_visibility(self, hits):
+        """The reference's in-place `point_counter[knn_index] += 1.` (network.py:517)."""
+        with torch.no_grad():
+            self.point_counter += (hits > 0).to(self.point_counter.dtype)
+
+    # -- reference API: network.py:542-623
+    def forward(self, rays, dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec=None, near=None, far=None,
+                iter_val=1e7, **kwargs):
+        cfg = self.cfg
+        if self.prologue is None:
+            raise RuntimeError("Network.prologue is not set: the per-frame prologue (pose refinement, motion basis, "
+                               "weight-volume decoder) is outside the ray path; install occnerf_b200.prologue.Prologue "
+                               "or pass precomputed tensors to _batchify_rays()")
+        motion_scale_Rs, motion_Ts, vol = self.prologue(dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec, iter_val)
+        emb_fn, _ = self.get_non_rigid_embedder(cfg.non_rigid_multires, 0, iter_val)
+        if iter_val < cfg.non_rigid_kick_in_iter:
+            nr_in = None
+        else:
+            nr_in = dst_posevec[None, ...]
+        rays_o, rays_d = rays
+        rays_shape = rays_d.shape
+        rays_o = rays_o.reshape(-1, 3).float()
+        rays_d = rays_d.reshape(-1, 3).float()
+        packed = torch.cat([rays_o, rays_d, near, far], -1)
+        keep = {k: kwargs[k] for k in ("cnl_bbox_min_xyz", "cnl_bbox_scale_xyz", "bgcolor", "t_rand") if k in kwargs}
+        all_ret = self._batchify_rays(packed, pos_embed_fn=None, non_rigid_pos_embed_fn=emb_fn, non_rigid_mlp_input=nr_in,
+                                      motion_scale_Rs=motion_scale_Rs, motion_Ts=motion_Ts, motion_weights_vol=vol, **keep)
+        for k in list(all_ret):
+            if k == "comp_loss":
+                all_ret[k] = all_ret[k].reshape(-1)
+            elif k != "hits":
+                all_ret[k] = all_ret[k].reshape(list(rays_shape[:-1]) + list(all_ret[k].shape[1:]))
+        return all_ret

@@ -1,0 +1,252 @@
+"""Operator layer: one Python function per C-ABI entry point (tensors in, tensors out) plus the
+autograd.Function for the hash grid.  Everything below runs on the CUDA library; nothing here has a CPU path.
+
+Shapes follow the reference: N rays, S samples per ray, M = N*S samples,
+V vertices, k = 10 neighbours on 4 levels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from occnerf_b200 import _lib
+from occnerf_b200._lib import call, ptr, stream
+
+f32, i32, i64, u8 = torch.float32, torch.int32, torch.int64, torch.uint8
+
+_T_LIN = {}
+
+
+def t_lin(S: int, device) -> torch.Tensor:
+    """linspace(0,1,S) as the host framework computes it on the CPU (network.py:417), cached on the device."""
+    key = (S, str(device))
+    if key not in _T_LIN:
+        _T_LIN[key] = torch.linspace(0.0, 1.0, steps=S).to(device)
+    return _T_LIN[key]
+
+
+# ----------------------------------------------------------------------------- K1 warp
+def warp_forward(rays, t_rand, Rs, Ts, vol, bbox_min, bbox_scale, S, want_bins=False):
+    """rays (N,8) -> z (N,S), x_skel (N,S,3), mask (N,S) [, bins (N,S,nb,3) int32]."""
+    N, nb = rays.shape[0], Rs.shape[0]
+    dev = rays.device
+    z = torch.empty(N, S, device=dev, dtype=f32)
+    x_skel = torch.empty(N, S, 3, device=dev, dtype=f32)
+    mask = torch.empty(N, S, device=dev, dtype=f32)
+    bins = torch.empty(N, S, nb, 3, device=dev, dtype=i32) if want_bins else None
+    vd, vh, vw = vol.shape[-3:]
+    assert vol.shape[0] >= nb
+    call("occnerf_warp_forward", ptr(rays, f32), ptr(t_lin(S, dev), f32), ptr(t_rand, f32), ptr(Rs, f32), ptr(Ts, f32),
+         ptr(vol, f32), ptr(bbox_min, f32), ptr(bbox_scale, f32), N, S, nb, vd, vh, vw, ptr(z), ptr(x_skel), ptr(mask),
+         ptr(bins), stream())
+    return (z, x_skel, mask, bins) if want_bins else (z, x_skel, mask)
+
+
+def warp_backward(rays, t_rand, Rs, Ts, bbox_min, bbox_scale, g_mask, S, vol_shape):
+    """d mask (N,S) -> g_vol with the shape of the reference's motion_weights_vol (channels >= nb stay 0)."""
+    N, nb = rays.shape[0], Rs.shape[0]
+    g_vol = torch.zeros(vol_shape, device=rays.device, dtype=f32)
+    vd, vh, vw = vol_shape[-3:]
+    call("occnerf_warp_backward", ptr(rays, f32), ptr(t_lin(S, rays.device), f32), ptr(t_rand, f32), ptr(Rs, f32),
+         ptr(Ts, f32), ptr(bbox_min, f32), ptr(bbox_scale, f32), ptr(g_mask, f32), N, S, nb, vd, vh, vw, ptr(g_vol),
+         stream())
+    return g_vol
+
+
+# ----------------------------------------------------------------------------- KNN
+def to_float4(points: torch.Tensor) -> torch.Tensor:
+    out = torch.zeros(points.shape[0], 4, device=points.device, dtype=f32)
+    out[:, :3] = points
+    return out
+
+
+def knn(queries, supports4, level_begin, k, support_gid=None, query_sel=None, out=None):
+    """queries (m,3) -> (m, n_levels, k) int32 neighbour ids (see occnerf_knn in include/occnerf_b200.h)."""
+    m, nl = queries.shape[0], len(level_begin) - 1
+    if out is None:
+        out = torch.empty(m, nl, k, device=queries.device, dtype=i32)
+    lb = (C.c_int32 * (nl + 1))(*[int(v) for v in level_begin])
+    call("occnerf_knn", ptr(queries, f32), m, ptr(supports4, f32), ptr(support_gid, i32), C.cast(lb, C.c_void_p), nl, k,
+         ptr(query_sel, u8), ptr(out, i32), stream())
+    return out
+
+
+def sample_geometry(xyz, knn_idx, point_base, point_norms, bound, raw=None):
+    """-> enc_in (m,4), dist.  With `raw` (m,5) given, dist is written into raw[:,4] in place and returned as a view."""
+    m = xyz.shape[0]
+    enc_in = torch.empty(m, 4, device=xyz.device, dtype=f32)
+    stride_knn = knn_idx.shape[1] * knn_idx.shape[2] if knn_idx.dim() == 3 else knn_idx.shape[1]
+    if raw is None:
+        dist = torch.empty(m, device=xyz.device, dtype=f32)
+        dptr, dstride = ptr(dist), 1
+    else:
+        assert raw.shape == (m, 5) and raw.is_contiguous()
+        dist = raw[:, 4]
+        dptr, dstride = raw.data_ptr() + 16, 5
+    call("occnerf_sample_geometry", ptr(xyz, f32), ptr(knn_idx, i32), stride_knn, ptr(point_base, f32),
+         ptr(point_norms, f32), float(bound), m, ptr(enc_in), dptr, dstride, stream())
+    return enc_in, dist
+
+
+# ----------------------------------------------------------------------------- hash grid
+_SCALES = {}
+
+
+def level_scales(S: float, H: int, L: int, device) -> torch.Tensor:
+    """Per-level scale table evaluated on the device with the reference's expression (gridencoder.cu:138)."""
+    key = (float(np.float32(S)), int(H), int(L), str(device))
+    if key not in _SCALES:
+        out = torch.empty(L, device=device, dtype=f32)
+        call("occnerf_hashgrid_level_scales", float(np.float32(S)), H, L, ptr(out), stream())
+        _SCALES[key] = out
+    return _SCALES[key]
+
+
+def hashgrid_forward(inputs, embeddings, offsets, scales, *, out=None, out_ptr=None, ld=None, layout=_lib.LAYOUT_BLC,
+                     want_dy_dx=False, want_cells=False):
+    B, D = inputs.shape
+    Cc, L = embeddings.shape[1], offsets.shape[0] - 1
+    dev = inputs.device
+    if out is None and out_ptr is None:
+        out = torch.empty((L, B, Cc) if layout == _lib.LAYOUT_LBC else (B, L * Cc), device=dev, dtype=f32)
+    if out_ptr is None:
+        out_ptr = ptr(out, f32)
+    if ld is None:
+        ld = L * Cc
+    dy_dx = torch.empty(B, L * D * Cc, device=dev, dtype=f32) if want_dy_dx else None
+    cells = torch.empty(B, L, D, device=dev, dtype=i32) if want_cells else None
+    slots = torch.empty(B, L, 1 << D, device=dev, dtype=i32) if want_cells else None
+    call("occnerf_hashgrid_forward", ptr(inputs, f32), ptr(embeddings, f32), ptr(offsets, i32), ptr(scales, f32), out_ptr,
+         layout, ld, B, D, Cc, L, ptr(dy_dx), ptr(cells), ptr(slots), stream())
+    return out, dy_dx, cells, slots
+
+
+def hashgrid_backward(grad_ptr, ld, layout, inputs, offsets, scales, g_emb, Cc):
+    B, D = inputs.shape
+    L = offsets.shape[0] - 1
+    call("occnerf_hashgrid_backward", grad_ptr, layout, ld, ptr(inputs, f32), ptr(offsets, i32), ptr(scales, f32),
+         ptr(g_emb, f32), B, D, Cc, L, stream())
+    return g_emb
+
+
+def hashgrid_input_backward(grad_ptr, ld, layout, dy_dx, B, D, Cc, L):
+    g_in = torch.empty(B, D, device=dy_dx.device, dtype=f32)
+    call("occnerf_hashgrid_input_backward", grad_ptr, layout, ld, ptr(dy_dx, f32), ptr(g_in), B, D, Cc, L, stream())
+    return g_in
+
+
+class _GridEncode(torch.autograd.Function):
+    """Differentiable hash-grid encode with the reference's semantics (gridencoder/grid.py:24-90):
+    inputs (B,D) in [0,1] -> (B, L*C); gradients to the table always, to the inputs iff they require grad."""
+
+    @staticmethod
+    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution):
+        inputs = inputs.contiguous().float()
+        S = float(np.log2(per_level_scale))
+        scales = level_scales(S, base_resolution, offsets.shape[0] - 1, inputs.device)
+        need_in = inputs.requires_grad
+        out, dy_dx, _, _ = hashgrid_forward(inputs.detach(), embeddings.detach().contiguous(), offsets, scales,
+                                            want_dy_dx=need_in)
+        ctx.save_for_backward(inputs.detach(), offsets, scales, dy_dx if need_in else torch.empty(0, device=inputs.device))
+        ctx.meta = (tuple(embeddings.shape), need_in)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        inputs, offsets, scales, dy_dx = ctx.saved_tensors
+        (n_emb, Cc), need_in = ctx.meta
+        g = g.contiguous()
+        B, D = inputs.shape
+        L = offsets.shape[0] - 1
+        g_emb = torch.zeros(n_emb, Cc, device=g.device, dtype=f32)
+        hashgrid_backward(ptr(g, f32), L * Cc, _lib.LAYOUT_BLC, inputs, offsets, scales, g_emb, Cc)
+        g_in = hashgrid_input_backward(ptr(g, f32), L * Cc, _lib.LAYOUT_BLC, dy_dx, B, D, Cc, L) if need_in else None
+        return g_in, g_emb, None, None, None
+
+
+grid_encode = _GridEncode.apply
+
+
+# ----------------------------------------------------------------------------- aggregation
+def aggregate_forward(knn_idx, point_counter, feats36, X_ptr, ldx):
+    m = knn_idx.shape[0]
+    nn = knn_idx.numel() // max(m, 1)
+    call("occnerf_aggregate_forward", ptr(knn_idx, i32), ptr(point_counter, f32), ptr(feats36, f32), m, nn, X_ptr, ldx,
+         stream())
+
+
+def aggregate_backward(knn_idx, point_counter, gX_ptr, ldg, V):
+    m = knn_idx.shape[0]
+    nn = knn_idx.numel() // max(m, 1)
+    g_feats = torch.zeros(V, 36, device=knn_idx.device, dtype=f32)
+    call("occnerf_aggregate_backward", ptr(knn_idx, i32), ptr(point_counter, f32), gX_ptr, ldg, m, nn, ptr(g_feats),
+         stream())
+    return g_feats
+
+
+# ----------------------------------------------------------------------------- fp32 GEMM helpers
+def sgemm(A_ptr, sAi, sAr, B_ptr, sBr, sBj, C_ptr, ldc, Mi, Nj, Kr, *, bias=None, mask_ptr=None, ldmask=0, relu=False,
+          accum=False, split_k=1):
+    flags = (_lib.GEMM_BIAS if bias is not None else 0) | (_lib.GEMM_RELU if relu else 0) | \
+            (_lib.GEMM_ACCUM if accum else 0) | (_lib.GEMM_RELUMASK if mask_ptr is not None else 0)
+    call("occnerf_sgemm", A_ptr, sAi, sAr, B_ptr, sBr, sBj, C_ptr, ldc, ptr(bias, f32) if bias is not None else None,
+         mask_ptr, ldmask, Mi, Nj, Kr, flags, split_k, stream())
+
+
+def colsum(A_ptr, lda, Mi, Nj, out, mask_ptr=None, ldmask=0):
+    call("occnerf_colsum", A_ptr, lda, mask_ptr, ldmask, Mi, Nj, ptr(out, f32), stream())
+
+
+def hann_window(iter_val, kick_in_iter, full_band_iter, multires=6):
+    """Window weights of hannw_fourier.py:27-33 evaluated in fp32 like the reference's tensor arithmetic."""
+    t = torch.clamp(torch.tensor(float(iter_val)) - torch.tensor(float(kick_in_iter)), min=0.0)
+    alpha = multires * t / (full_band_iter - torch.tensor(float(kick_in_iter)))
+    w = [(1.0 - torch.cos(math.pi * torch.clamp(alpha - j, min=0.0, max=1.0))) / 2.0 for j in range(multires)]
+    return [float(v) for v in w]
+
+
+def hann_pe(xyz, window, out=None):
+    m, mr = xyz.shape[0], len(window)
+    if out is None:
+        out = torch.empty(m, 6 * mr, device=xyz.device, dtype=f32)
+    w = (C.c_float * mr)(*window)
+    call("occnerf_hann_pe", ptr(xyz, f32), m, C.cast(w, C.c_void_p), mr, ptr(out, f32), out.shape[1], stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- K4 compositing
+def composite_forward(raw, mask, z, rays, bg, want_weights=False, want_comp=False):
+    N, S = z.shape
+    dev = z.device
+    rgb = torch.empty(N, 3, device=dev, dtype=f32)
+    acc = torch.empty(N, device=dev, dtype=f32)
+    depth = torch.empty(N, device=dev, dtype=f32)
+    term = torch.empty(N, device=dev, dtype=i64)
+    weights = torch.empty(N, S, device=dev, dtype=f32) if want_weights else None
+    comp = torch.empty(N, S, device=dev, dtype=f32) if want_comp else None
+    call("occnerf_composite_forward", ptr(raw, f32), ptr(mask, f32), ptr(z, f32), ptr(rays, f32), ptr(bg, f32), N, S,
+         ptr(rgb), ptr(acc), ptr(depth), ptr(term), ptr(weights), ptr(comp), stream())
+    return rgb, acc, depth, term, weights, comp
+
+
+def composite_backward(raw, mask, z, rays, bg, g_rgb, g_acc, g_depth, g_comp=None):
+    N, S = z.shape
+    g_raw = torch.empty(N, S, 5, device=z.device, dtype=f32)
+    g_mask = torch.empty(N, S, device=z.device, dtype=f32)
+    call("occnerf_composite_backward", ptr(raw, f32), ptr(mask, f32), ptr(z, f32), ptr(rays, f32), ptr(bg, f32),
+         ptr(g_rgb.contiguous(), f32), ptr(g_acc.contiguous(), f32), ptr(g_depth.contiguous(), f32),
+         ptr(g_comp.contiguous(), f32) if g_comp is not None else None, N, S, ptr(g_raw), ptr(g_mask), stream())
+    return g_raw, g_mask
+
+
+def visibility_hits(depth, term, x_skel, cloud4, k=10, thresh=0.5):
+    N, S = x_skel.shape[0], x_skel.shape[1]
+    V = cloud4.shape[0]
+    hits = torch.empty(V, device=depth.device, dtype=f32)
+    scratch = torch.empty(N * (k + 4) + 4, device=depth.device, dtype=i32)
+    call("occnerf_visibility_hits", ptr(depth, f32), ptr(term, i64), ptr(x_skel, f32), N, S, float(thresh), ptr(cloud4, f32),
+         V, k, ptr(hits), ptr(scratch), stream())
+    return hits

@@ -426,3 +426,37 @@ def make_frame(subject: Subject, mode: str = "patch", img: int = 512, n_patches:
         motion_scale_Rs=mRs, motion_Ts=mTs, dst_posevec=torch.from_numpy(pose[3:] + 1e-2),
         cnl_bbox_min_xyz=torch.from_numpy(cmin.copy()), cnl_bbox_scale_xyz=torch.from_numpy((2.0 / (cmax - cmin)).astype(np.float32)),
         bgcolor=torch.zeros(3), ray_mask=hit, img_hw=(img, img))
+
+
+def network_from_synthetic(subject: Subject, weights: NetWeights, cfg=None, device="cuda"):
+    """An occnerf_b200.network.Network carrying the synthetic per-subject state and the given parameters
+    (the counterpart of oracle/ref_shim.build_reference_network for the CUDA path)."""
+    from occnerf_b200.network import Network
+    net = Network(cfg)
+    net.generate_neural_points(subject.point_base, subject.point_norms, subject.fps_index, subject.bbox_min,
+                               subject.bbox_max, point_dist=subject.point_dist, point_counter=subject.point_counter)
+    assert abs(net.bound - subject.bound) < 1e-6
+    net.bound = subject.bound
+    m = net.cnl_mlp.module
+    with torch.no_grad():
+        assert torch.equal(m.encoder.offsets, weights.offsets), "hash-grid level table differs from the reference's"
+        m.encoder.embeddings.copy_(weights.embeddings)
+        for i, li in enumerate((0, 2, 4, 6)):
+            m.pts_linears[li].weight.copy_(weights.pts_w[i]); m.pts_linears[li].bias.copy_(weights.pts_b[i])
+            m.rgb_linears[li].weight.copy_(weights.rgb_w[i]); m.rgb_linears[li].bias.copy_(weights.rgb_b[i])
+        m.geo_linear[0].weight.copy_(weights.geo_w); m.geo_linear[0].bias.copy_(weights.geo_b)
+        m.output_linear[0].weight.copy_(weights.out_w); m.output_linear[0].bias.copy_(weights.out_b)
+        nr = net.non_rigid_mlp.module
+        for i, li in enumerate(range(0, 14, 2)):
+            nr.block_mlps[li].weight.copy_(weights.nr_w[i]); nr.block_mlps[li].bias.copy_(weights.nr_b[i])
+    return net.to(device)
+
+
+def frame_to(frame: Frame, device):
+    """Moves the tensor fields of a Frame to `device` (numpy fields stay on the host)."""
+    import dataclasses
+    kw = {}
+    for f in dataclasses.fields(frame):
+        v = getattr(frame, f.name)
+        kw[f.name] = v.to(device) if torch.is_tensor(v) else v
+    return Frame(**kw)

@@ -40,7 +40,7 @@ LOSS_W = dict(rgb=(1.0, 2.0, 3.0), alpha=0.5, depth=0.25, comp=1.0)
 
 def scalar_loss(out):
     """A fixed linear functional of the outputs so that every output gets a non-trivial upstream gradient."""
-    rgbw = torch.tensor(LOSS_W["rgb"], dtype=out["rgb"].dtype)
+    rgbw = torch.tensor(LOSS_W["rgb"], dtype=out["rgb"].dtype, device=out["rgb"].device)
     loss = (out["rgb"] * rgbw).sum() + out["alpha"].sum() * LOSS_W["alpha"] + out["depth"].sum() * LOSS_W["depth"]
     if out["comp_loss"].numel() > 1:
         loss = loss + out["comp_loss"].mean() * LOSS_W["comp"]

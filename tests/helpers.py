@@ -34,3 +34,21 @@ def normwise_close(a, b, rel):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     scale = np.abs(b).max()
     return bool(np.abs(a - b).max() <= rel * scale + 1e-30)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def report(name, **vals):
+    """Appends a line to gpurun_out/parity.log so that a GPU run leaves its measured errors behind."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "parity.log"), "a") as f:
+        f.write(name + " " + " ".join(f"{k}={v:.3e}" if isinstance(v, float) else f"{k}={v}" for k, v in vals.items()) + "\n")
+
+
+def maxabs(a, b):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max()) if a.size else 0.0

@@ -1,0 +1,140 @@
+"""GPU: the whole per-ray path through the reference-shaped interface (Network._render_rays / _query_mlp) against
+the golden fixtures written by the UNMODIFIED reference, and stage by stage against the oracle.
+
+Tolerances: BASELINE.json asks for rgb/alpha/depth within 1e-3 absolute of the reference's fp32 path; the fp32
+engine is held to 2e-5 here.  Integer outputs (term, visibility hits, neighbour ids) are exact."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from occnerf_b200 import synthetic as S
+from occnerf_b200.network import RenderConfig
+from oracle import make_golden, occnerf_oracle as O
+from tests.helpers import dev, load_case, maxabs, normwise_close, report
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["fp32"]
+
+
+def _net(sub, w, rk, engine="fp32"):
+    cfg = RenderConfig(perturb=1.0 if rk.get("perturb", 0.0) else 0.0, mlp_engine=engine)
+    net = S.network_from_synthetic(sub, w, cfg, device=dev())
+    net.train(rk["training"])
+    return net
+
+
+def _render(net, fr, vol, t_rand, iter_val):
+    d = dev()
+    frd = S.frame_to(fr, d)
+    emb_fn, _ = net.get_non_rigid_embedder(6, 0, iter_val)
+    nr_in = frd.dst_posevec[None] if iter_val >= net.cfg.non_rigid_kick_in_iter else None
+    packed = torch.cat([frd.rays_o, frd.rays_d, frd.near, frd.far], -1)
+    return net._batchify_rays(packed, pos_embed_fn=None, non_rigid_pos_embed_fn=emb_fn, non_rigid_mlp_input=nr_in,
+                              motion_scale_Rs=frd.motion_scale_Rs[None], motion_Ts=frd.motion_Ts[None], motion_weights_vol=vol,
+                              cnl_bbox_min_xyz=frd.cnl_bbox_min_xyz, cnl_bbox_scale_xyz=frd.cnl_bbox_scale_xyz,
+                              bgcolor=frd.bgcolor, t_rand=t_rand.to(d) if t_rand is not None else None)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", list(make_golden.CASES))
+def test_render_matches_reference_golden(name, engine):
+    sub, w, fr, vol, t_rand, rk, g = load_case(name)
+    net = _net(sub, w, rk, engine)
+    vol_d = vol.to(dev()).requires_grad_(True)
+    out = _render(net, fr, vol_d, t_rand, rk["iter_val"])
+    tol = 2e-5 if engine == "fp32" else 1e-3
+    errs = {k: maxabs(out[k], g[k]) for k in ("rgb", "alpha", "depth")}
+    report(f"render_golden[{name},{engine}]", **errs)
+    for k, e in errs.items():
+        assert e < tol, (k, e)
+    if not rk["training"]:
+        return
+    assert maxabs(out["comp_loss"], g["comp_loss"]) < (1e-5 if engine == "fp32" else 1e-3)
+    assert np.array_equal(out["hits"].cpu().numpy(), g["counter_delta"]), "visibility votes differ"
+    make_golden.scalar_loss({k: out[k] for k in ("rgb", "alpha", "depth", "comp_loss")}).backward()
+    m = net.cnl_mlp.module
+    rel = 1e-3 if engine == "fp32" else 2e-2
+    ge = m.encoder.embeddings.grad.reshape(-1).cpu().numpy()
+    offs = w.offsets.tolist()
+    l2 = np.array([m.encoder.embeddings.grad[a:b].double().norm().item() for a, b in zip(offs[:-1], offs[1:])])
+    gv = vol_d.grad.reshape(-1).cpu().numpy()
+    checks = {
+        "g_emb": normwise_close(ge[g["g_emb_idx"]], g["g_emb_val"], rel),
+        "g_emb_level_l2": bool(np.allclose(l2, g["g_emb_level_l2"], rtol=2 * rel)),
+        "g_vol": normwise_close(gv[g["g_vol_idx"]], g["g_vol_val"], rel),
+        "g_vol_l2": bool(np.isclose(vol_d.grad.double().norm().item(), float(g["g_vol_l2"]), rtol=rel)),
+        "g_point_dist": normwise_close(net.point_dist.grad.cpu().numpy(), g["g_point_dist"], rel),
+    }
+    for i, li in enumerate((0, 2, 4, 6)):
+        sl = (slice(None, None, 8), slice(None, None, 8)) if i else (slice(None), slice(None))
+        checks[f"g_pts_w{i}"] = normwise_close(m.pts_linears[li].weight.grad.cpu().numpy()[sl], g[f"g_pts_w{i}"], rel)
+        checks[f"g_rgb_w{i}"] = normwise_close(m.rgb_linears[li].weight.grad.cpu().numpy()[sl], g[f"g_rgb_w{i}"], rel)
+        checks[f"g_pts_b{i}"] = normwise_close(m.pts_linears[li].bias.grad.cpu().numpy(), g[f"g_pts_b{i}"], rel)
+        checks[f"g_rgb_b{i}"] = normwise_close(m.rgb_linears[li].bias.grad.cpu().numpy(), g[f"g_rgb_b{i}"], rel)
+    checks["g_geo_w"] = normwise_close(m.geo_linear[0].weight.grad.cpu().numpy(), g["g_geo_w"], rel)
+    checks["g_geo_b"] = normwise_close(m.geo_linear[0].bias.grad.cpu().numpy(), g["g_geo_b"], rel)
+    checks["g_out_w"] = normwise_close(m.output_linear[0].weight.grad.cpu().numpy(), g["g_out_w"], rel)
+    checks["g_out_b"] = normwise_close(m.output_linear[0].bias.grad.cpu().numpy(), g["g_out_b"], rel)
+    bad = [k for k, ok in checks.items() if not ok]
+    report(f"render_golden_grads[{name},{engine}]", failed=",".join(bad) or "none")
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_query_stages_against_oracle(engine):
+    """_query_mlp on the golden canonical points: neighbour ids exact; encoder input, aggregate and raw close."""
+    sub, w, fr, vol, t_rand, rk, g = load_case("train_dense")
+    net = _net(sub, w, rk, engine)
+    net.cfg.ignore_non_rigid_motions = True
+    xyz = torch.from_numpy(g["x_skel"]).reshape(-1, 3)[:4096].contiguous()
+    with torch.no_grad():
+        out = net._query_mlp(xyz.to(dev()).reshape(32, 128, 3), None, None, None, None, _return_knn=True)
+        raw_o, aux = O.query_canonical(xyz, sub, w, return_aux=True)
+    assert torch.equal(out["knn_idxs"].cpu().long(), aux["knn_idxs"])
+    e = maxabs(out["raws"].reshape(-1, 5), raw_o)
+    report(f"query_vs_oracle[{engine}]", raw=e)
+    assert e < (5e-5 if engine == "fp32" else 2e-2)
+    assert maxabs(out["raws"].reshape(-1, 5)[:, 4], raw_o[:, 4]) < 1e-6      # signed distance channel is engine independent
+
+
+def test_nonrigid_full_band_against_oracle():
+    """Non-rigid offset MLP with the window fully open and a non-zero pose condition (render-time regime)."""
+    from occnerf_b200 import mlp as M, ops
+    sub = S.make_subject(seed=0)
+    w = S.make_weights(sub.bound, seed=3, nonzero_bias=True)
+    w.nr_w[6] = w.nr_w[6] * 1e4                       # visible offsets
+    gen = torch.Generator().manual_seed(2)
+    xyz = torch.rand(5000, 3, generator=gen) * 2 - 1
+    cond = torch.randn(1, 69, generator=gen) * 0.2
+    for it in (10000000, 150000, 500):
+        window = ops.hann_window(it, 100000, 200000)
+        d = dev()
+        got = M.nonrigid_offsets(xyz.to(d), cond.to(d) if it >= 100000 else None, window, [t.to(d) for t in w.nr_w], [t.to(d) for t in w.nr_b])
+        pe = O.hann_pe(xyz, it, 100000, 200000)
+        c = cond if it >= 100000 else torch.zeros(1, 69)
+        want = xyz + O.non_rigid_offsets(xyz, c, pe, w.nr_w, w.nr_b)
+        e = maxabs(got, want)
+        report(f"nonrigid[{it}]", xyz=e, offset_scale=float((want - xyz).abs().max()))
+        assert e < 2e-6
+
+
+def test_full_size_step_runs_and_is_finite():
+    """BASELINE config 2: 6 x 32 x 32 rays, 128 samples, forward + backward through the public interface."""
+    sub = S.make_subject(seed=0)
+    w = S.make_weights(sub.bound, seed=0)
+    fr = S.make_frame(sub, mode="patch", n_patches=6, patch=32, seed=0)
+    vol = S.make_motion_weights_vol(sub.priors, seed=0).to(dev()).requires_grad_(True)
+    net = _net(sub, w, dict(training=True, perturb=1.0))
+    out = _render(net, fr, vol, None, 500)
+    assert out["rgb"].shape == (6144, 3) and out["comp_loss"].shape == (6144, 128)
+    loss = make_golden.scalar_loss({k: out[k] for k in ("rgb", "alpha", "depth", "comp_loss")})
+    loss.backward()
+    for p in [vol, net.point_dist] + list(net.cnl_mlp.parameters()):
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all())
+    assert float(out["alpha"].min()) >= 0.0 and float(out["alpha"].max()) <= 1.0 + 1e-5
+    before = net.point_counter.clone()
+    net.apply_visibility(out["hits"])
+    assert float((net.point_counter - before).sum()) == float(out["hits"].sum())
