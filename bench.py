@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the OccNeRF per-ray rendering path (BASELINE.json metric: rays/s at 128 samples/ray, fwd+bwd).
+
+    python bench.py --gpus N --steps K --warmup W [--engine fp32|tc3|tc1] [--impl reference]
+
+Workload (BASELINE.json configs[1]): one ZJU-Mocap-387-shaped training step = 6 patches of 32x32 rays
+(6144 rays, 786 432 samples), synthetic SMPL-like subject, random-init network, stratified jitter,
+forward + backward through `Network._batchify_rays` (value) and through `Network.forward` with host buffers
+(e2e).  N > 1: every rank renders its own 6144 rays (weak scaling) and the gradients that leave the path
+(hash table, MLP, point_dist, weight volume) are all-reduced with NCCL; no data-path collective.
+
+`--impl reference` times the reference's algorithm on the host cores: the oracle restatement
+(oracle/occnerf_oracle.py, CPU torch fp32 + the C hash grid; the reference itself cannot be imported on the
+GPU box), forward + backward on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S_SAMPLES = 128
+RAYS_PER_STEP = 6 * 32 * 32
+FLOP_MLP_FWD = 923136.0          # per sample
+FLOP_MLP_FWD_BWD = 2769408.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm / CPU baseline
+def cpu_reference(sample_rays: int, steps: int, warmup: int, seed: int = 0):
+    """Forward + backward of the oracle restatement on `sample_rays` rays of the bench workload, all host cores."""
+    from occnerf_b200 import synthetic as S
+    from oracle import hashgrid_c, make_golden, occnerf_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hashgrid_c.set_threads(cores)
+    sub = S.make_subject(seed=0)
+    w = S.make_weights(sub.bound, seed=0)
+    fr = S.make_frame(sub, mode="patch", n_patches=6, patch=32, seed=seed)
+    vol = S.make_motion_weights_vol(sub.priors, seed=0).requires_grad_(True)
+    for t in [w.embeddings, sub.point_dist, w.geo_w, w.geo_b, w.out_w, w.out_b] + w.pts_w + w.pts_b + w.rgb_w + w.rgb_b:
+        t.requires_grad_(True)
+    n = min(sample_rays, fr.rays_o.shape[0])
+    import dataclasses
+    sl = {f.name: (getattr(fr, f.name)[:n] if f.name in ("rays_o", "rays_d", "near", "far") else getattr(fr, f.name))
+          for f in dataclasses.fields(fr)}
+    frs = S.Frame(**sl)
+    t_rand = torch.rand(n, S_SAMPLES, generator=torch.Generator().manual_seed(1))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.render_rays(frs, vol, sub, w, iter_val=500, training=True, t_rand=t_rand)
+        make_golden.scalar_loss(out).backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        for t in [vol, w.embeddings]:
+            t.grad = None
+    hashgrid_c.set_threads(1)
+    ms = 1e3 * float(np.mean(times))
+    return {"value": n / (ms / 1e3), "ms_per_step": ms, "cores": cores, "sample": f"{n} of {RAYS_PER_STEP} rays x {S_SAMPLES} samples, fwd+bwd, {steps} timed repeats"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    r = cpu_reference(args.ref_rays, max(1, args.steps), max(0, min(args.warmup, 1)))
+    line = {"impl": "reference", "metric": "rays_per_sec_fwd_bwd_128spr", "value": r["value"], "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "zju387_train_step_6x32x32_rays_128spr_fwd_bwd", "rays_per_step": args.ref_rays, "samples_per_ray": S_SAMPLES},
+            "cpu_baseline": {"value": r["value"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+class Workload:
+    def __init__(self, device, rank, engine):
+        from occnerf_b200 import synthetic as S
+        from occnerf_b200.network import RenderConfig
+        self.S = S
+        sub = S.make_subject(seed=0)
+        w = S.make_weights(sub.bound, seed=0)
+        self.sub = sub
+        self.net = S.network_from_synthetic(sub, w, RenderConfig(perturb=1.0, mlp_engine=engine), device=device)
+        self.net.train(True)
+        self.net.install_prologue()
+        self.fr_host = S.make_frame(sub, mode="patch", n_patches=6, patch=32, seed=100 + rank)
+        self.fr = S.frame_to(self.fr_host, device)
+        self.vol = S.make_motion_weights_vol(sub.priors, seed=0).to(device).requires_grad_(True)
+        self.priors = sub.priors.to(device)
+        gen = torch.Generator().manual_seed(7 + rank)
+        self.target = torch.rand(RAYS_PER_STEP, 3, generator=gen).to(device)
+        self.device = device
+        self.iter_val = 500
+        self.emb_fn, _ = self.net.get_non_rigid_embedder(6, 0, self.iter_val)
+        self.packed = torch.cat([self.fr.rays_o, self.fr.rays_d, self.fr.near, self.fr.far], -1).contiguous()
+        path_params = [p for n, p in self.net.named_parameters() if p.requires_grad and not n.startswith(("mweight_vol_decoder", "pose_decoder", "non_rigid_mlp"))]
+        self.path_params = path_params
+        self.opt_path = torch.optim.Adam(path_params, lr=5e-4, fused=True)
+        self.opt_all = torch.optim.Adam([p for p in self.net.parameters() if p.requires_grad], lr=5e-4, fused=True)
+        # pinned host copies of everything `Network.forward` receives per frame (trainer.py:223-229)
+        h = self.fr_host
+        self.host = {k: v.pin_memory() for k, v in dict(rays_o=h.rays_o, rays_d=h.rays_d, near=h.near, far=h.far, dst_Rs=h.dst_Rs,
+                     dst_Ts=h.dst_Ts, cnl_gtfms=h.cnl_gtfms, priors=sub.priors, posevec=h.dst_posevec, bmin=h.cnl_bbox_min_xyz,
+                     bscale=h.cnl_bbox_scale_xyz, bg=h.bgcolor, target=self.target.cpu()).items()}
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.loss_host = torch.zeros(1).pin_memory()
+
+    def loss(self, out, target):
+        return 0.2 * torch.mean((out["rgb"] - target) ** 2) + out["comp_loss"].mean()
+
+    def grads_to_reduce(self):
+        return [p.grad for p in self.path_params if p.grad is not None] + ([self.vol.grad] if self.vol.grad is not None else [])
+
+    def step_device(self, world):
+        """One step with inputs resident in HBM: the ray path only (vol is a leaf)."""
+        net, fr = self.net, self.fr
+        out = net._batchify_rays(self.packed, pos_embed_fn=None, non_rigid_pos_embed_fn=self.emb_fn, non_rigid_mlp_input=None,
+                                 motion_scale_Rs=fr.motion_scale_Rs[None], motion_Ts=fr.motion_Ts[None], motion_weights_vol=self.vol,
+                                 cnl_bbox_min_xyz=fr.cnl_bbox_min_xyz, cnl_bbox_scale_xyz=fr.cnl_bbox_scale_xyz, bgcolor=fr.bgcolor)
+        self.loss(out, self.target).backward()
+        hits = out["hits"]
+        if world > 1:
+            import torch.distributed as dist
+            for g in self.grads_to_reduce():
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)
+            dist.all_reduce(hits, op=dist.ReduceOp.MAX)
+        torch.nn.utils.clip_grad_norm_(self.path_params, 1.0)
+        self.opt_path.step()
+        self.opt_path.zero_grad(set_to_none=True)
+        self.vol.grad = None
+        net.apply_visibility(hits)
+
+    def step_e2e(self, world):
+        """One step through the public API with host buffers: H2D of the frame, Network.forward, loss, backward,
+        all-reduce, optimizer, D2H of the loss."""
+        d = {k: v.to(self.device, non_blocking=True) for k, v in self.host.items()}
+        net = self.net
+        out = net.forward((d["rays_o"], d["rays_d"]), d["dst_Rs"], d["dst_Ts"], d["cnl_gtfms"], d["priors"], dst_posevec=d["posevec"],
+                          near=d["near"], far=d["far"], iter_val=self.iter_val, cnl_bbox_min_xyz=d["bmin"], cnl_bbox_scale_xyz=d["bscale"],
+                          bgcolor=d["bg"])
+        loss = self.loss({"rgb": out["rgb"], "comp_loss": out["comp_loss"]}, d["target"])
+        loss.backward()
+        params = [p for p in net.parameters() if p.requires_grad]
+        if world > 1:
+            import torch.distributed as dist
+            for p in params:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+            dist.all_reduce(out["hits"], op=dist.ReduceOp.MAX)
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        self.opt_all.step()
+        self.opt_all.zero_grad(set_to_none=True)
+        net.apply_visibility(out["hits"])
+        self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+
+def timed_loop(fn, steps, warmup, world, flush):
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        flush.fill_(1.0)                         # evict L2 (126 MB) between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps
+
+
+def kernel_table(profile, steps):
+    rows = []
+    for name, evs in profile.items():
+        ms = sum(a.elapsed_time(b) for a, b, _w in evs)
+        rows.append({"call": name, "ms_per_step": ms / steps, "launches_per_step": len(evs) / steps, "work_per_step": sum(w for _a, _b, w in evs) / steps})
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    return rows
+
+
+def roofline_for(row, peaks, M):
+    """Algorithmic work of one C call (SURVEY.md 8d / DESIGN.md) divided by its measured device time."""
+    name, ms = row["call"], row["ms_per_step"] / max(row["launches_per_step"], 1e-9)
+    per_launch_samples = M
+    hbm = {"occnerf_warp_forward": 20.25, "occnerf_warp_backward": 4.0, "occnerf_composite_forward": 28.0 + 28.0 / S_SAMPLES,
+           "occnerf_composite_backward": 52.0, "occnerf_hashgrid_forward": 144.0, "occnerf_hashgrid_backward": 128.0,
+           "occnerf_aggregate_forward": 160.0 + 144.0, "occnerf_aggregate_backward": 160.0 + 144.0, "occnerf_knn": 12.0 + 160.0,
+           "occnerf_sample_geometry": 12.0 + 40.0 + 20.0}
+    if name in ("occnerf_sgemm", "occnerf_mlp_forward_tc", "occnerf_mlp_backward_tc", "occnerf_mlp_wgrad_tc"):
+        flops = row["work_per_step"] / max(row["launches_per_step"], 1e-9)
+        ach = flops / (ms * 1e-3) / 1e12
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " bf16 dense (sustained)"}
+    bytes_ = hbm.get(name, 0.0) * per_launch_samples
+    ach = bytes_ / (ms * 1e-3) / 1e9
+    return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+            "traffic": None, "peak_source": peaks["source"] + " copy bandwidth"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default=os.environ.get("OCCNERF_ENGINE", "fp32"), choices=["fp32", "tc3", "tc1"])
+    ap.add_argument("--ref-rays", type=int, default=96, help="rays per step of the CPU reference arm / cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    from occnerf_b200 import _lib
+    _lib.load()
+    wl = Workload(device, rank, args.engine)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=device)
+    M = RAYS_PER_STEP * S_SAMPLES
+
+    # ---- value: ray path, inputs resident
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.PROFILE = {}
+    c0 = dict(_lib.COUNTERS)
+    for _ in range(args.warmup):
+        wl.step_device(world)
+    _lib.PROFILE, c0 = {}, dict(_lib.COUNTERS)
+    ms = timed_loop(lambda: wl.step_device(world), args.steps, 0, world, flush)
+    launches = (_lib.COUNTERS["launches"] - c0["launches"]) / args.steps
+    profile, _lib.PROFILE = _lib.PROFILE, None
+    clocks = sampler.stop()
+    table = kernel_table(profile, args.steps)
+    # ---- e2e: public API with host buffers
+    ms_e2e = timed_loop(lambda: wl.step_e2e(world), args.steps, args.warmup, world, flush)
+
+    if rank == 0:
+        peaks = load_peaks()
+        roof_all = [roofline_for(r, peaks, M) for r in table[:8]]
+        line = {
+            "metric": "rays_per_sec_fwd_bwd_128spr", "value": world * RAYS_PER_STEP / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "tc3": "bf16x3(split)->f32", "tc1": "bf16->f32"}[args.engine], "data": "synthetic",
+            "config": {"workload": "zju387_train_step_6x32x32_rays_128spr_fwd_bwd", "rays_per_step_per_gpu": RAYS_PER_STEP, "samples_per_ray": S_SAMPLES,
+                       "mlp_engine": args.engine, "l2": "256 MiB flush write between timed steps", "timing": "cuda events per step, max over ranks",
+                       "optimizer": "grad-clip + fused Adam (library) inside the step", "parallelism": f"dp{world}"},
+            "clocks": clocks,
+            "e2e": {"value": world * RAYS_PER_STEP / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": wl.h2d_bytes,
+                    "d2h_bytes_per_step": 4, "api": "Network.forward (prologue + ray path) + loss + backward + optimizer"},
+            "gpu_launches": launches,
+            "roofline": roof_all[0] if roof_all else None,
+            "kernels": [{"call": r["call"], "ms_per_step": round(r["ms_per_step"], 4), "launches_per_step": r["launches_per_step"]} for r in table],
+            "roofline_all": roof_all,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference(args.ref_rays, 2, 1)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": "rays/s", "cores": cb["cores"], "kind": "port", "sample": cb["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -91,5 +91,20 @@ def ptr(t, dtype=None):
     return t.data_ptr()
 
 
-def call(name: str, *args):
+# kernels launched per C call (for the bench's `gpu_launches` claim); entries not listed launch exactly one
+KERNELS_PER_CALL = {"occnerf_visibility_hits": 3}
+COUNTERS = {"calls": 0, "launches": 0}
+PROFILE = None   # set to {} to record (start_event, end_event, work) per C call on the current stream
+
+
+def call(name: str, *args, work: float = 0.0):
+    COUNTERS["calls"] += 1
+    COUNTERS["launches"] += KERNELS_PER_CALL.get(name, 1)
+    if PROFILE is None:
+        check(getattr(load(), name)(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(load(), name)(*args), name)
+    e1.record()
+    PROFILE.setdefault(name, []).append((e0, e1, work))

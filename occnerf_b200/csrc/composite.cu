@@ -210,6 +210,7 @@ composite_bwd_kernel(const float *__restrict__ raw, const float *__restrict__ ma
 extern "C" int occnerf_composite_forward(const float *raw, const float *mask, const float *z, const float *rays,
                                          const float *bg, int N, int S, float *rgb, float *acc, float *depth,
                                          int64_t *term, float *weights, float *comp, occnerf_stream_t stream) {
+    if (N == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(raw && mask && z && rays && bg && rgb && acc && depth && term, "composite_forward: null pointer");
     OCC_CHECK_ARG(N >= 0 && S >= 1, "composite_forward: bad N=%d S=%d", N, S);
     if (N == 0) return OCCNERF_OK;
@@ -223,6 +224,7 @@ extern "C" int occnerf_composite_backward(const float *raw, const float *mask, c
                                           const float *bg, const float *g_rgb, const float *g_acc,
                                           const float *g_depth, const float *g_comp, int N, int S, float *g_raw,
                                           float *g_mask, occnerf_stream_t stream) {
+    if (N == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(raw && mask && z && rays && bg && g_rgb && g_acc && g_depth && g_raw && g_mask,
                   "composite_backward: null pointer");
     OCC_CHECK_ARG(N >= 0 && S >= 1 && S <= 32 * kMaxChunks, "composite_backward: S=%d outside [1,%d]", S,

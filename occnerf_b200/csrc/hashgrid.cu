@@ -298,6 +298,8 @@ extern "C" int occnerf_hashgrid_forward(const float *inputs, const float *embedd
                                         const float *level_scales, float *outputs, int layout, int ld, uint32_t B,
                                         uint32_t D, uint32_t C, uint32_t L, float *dy_dx, uint32_t *cells,
                                         uint32_t *slots, occnerf_stream_t stream) {
+    if (B == 0 && D >= 2 && D <= 4) return OCCNERF_OK;
+    OCC_CHECK_ARG(D >= 2 && D <= 4, "hashgrid: unsupported D=%u C=%u (D in {2,3,4}, C in {1,2,4,8})", D, C);
     OCC_CHECK_ARG(inputs && embeddings && offsets && level_scales && outputs, "hashgrid_forward: null pointer");
     if (int e = check_layout(layout, ld, L, C)) return e;
     OCC_CHECK_ARG(C != 2 || layout == OCCNERF_LAYOUT_LBC || (ld % 2 == 0 && ((uintptr_t)outputs & 7) == 0),
@@ -312,6 +314,7 @@ extern "C" int occnerf_hashgrid_forward(const float *inputs, const float *embedd
 extern "C" int occnerf_hashgrid_backward(const float *grad, int layout, int ld, const float *inputs,
                                          const int32_t *offsets, const float *level_scales, float *grad_embeddings,
                                          uint32_t B, uint32_t D, uint32_t C, uint32_t L, occnerf_stream_t stream) {
+    if (B == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(grad && inputs && offsets && level_scales && grad_embeddings, "hashgrid_backward: null pointer");
     if (int e = check_layout(layout, ld, L, C)) return e;
     if (B == 0) return OCCNERF_OK;

@@ -212,6 +212,7 @@ extern "C" int occnerf_warp_forward(const float *rays, const float *t_lin, const
                                     const float *Ts, const float *vol, const float *bbox_min, const float *bbox_scale,
                                     int N, int S, int nb, int vd, int vh, int vw, float *z, float *x_skel, float *mask,
                                     int32_t *bins, occnerf_stream_t stream) {
+    if (N == 0) return OCCNERF_OK;
     if (int e = check_common(rays, t_lin, Rs, Ts, N, S, nb, vd, vh, vw)) return e;
     OCC_CHECK_ARG(vol && bbox_min && bbox_scale && z && x_skel && mask, "warp_forward: null pointer");
     const long M = (long)N * S;
@@ -226,6 +227,7 @@ extern "C" int occnerf_warp_backward(const float *rays, const float *t_lin, cons
                                      const float *Ts, const float *bbox_min, const float *bbox_scale,
                                      const float *g_mask, int N, int S, int nb, int vd, int vh, int vw, float *g_vol,
                                      occnerf_stream_t stream) {
+    if (N == 0) return OCCNERF_OK;
     if (int e = check_common(rays, t_lin, Rs, Ts, N, S, nb, vd, vh, vw)) return e;
     OCC_CHECK_ARG(bbox_min && bbox_scale && g_mask && g_vol, "warp_backward: null pointer");
     const long M = (long)N * S;

@@ -54,7 +54,8 @@ def _gemm(A, sAi, sAr, B, sBr, sBj, Cp, ldc, Mi, Nj, Kr, bias=None, mask=None, l
           split_k=1):
     flags = (_lib.GEMM_BIAS if bias else 0) | (_lib.GEMM_RELU if relu else 0) | (_lib.GEMM_ACCUM if accum else 0) | \
             (_lib.GEMM_RELUMASK if mask else 0)
-    call("occnerf_sgemm", A, sAi, sAr, B, sBr, sBj, Cp, ldc, bias, mask, ldmask, Mi, Nj, Kr, flags, split_k, stream())
+    call("occnerf_sgemm", A, sAi, sAr, B, sBr, sBj, Cp, ldc, bias, mask, ldmask, Mi, Nj, Kr, flags, split_k, stream(),
+         work=2.0 * Mi * Nj * Kr)
 
 
 class MlpSimt:

@@ -274,6 +274,29 @@ class Network(nn.Module):
         # callable(dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec, iter_val) -> (Rs, Ts, vol)
         self.prologue = None
 
+    def install_prologue(self, pose_kick_in_iter=2000000):
+        """Adds the reference's per-frame modules under their reference names (`mweight_vol_decoder`,
+        `pose_decoder`, `motion_basis_computer`; state_dict-compatible) and wires `forward` to them."""
+        from occnerf_b200 import prologue as P
+        self.motion_basis_computer = P.MotionBasisComputer()
+        self.mweight_vol_decoder = P.MotionWeightVolumeDecoder()
+        self.pose_decoder = P.BodyPoseRefiner()
+        dev = next(self.parameters()).device
+        for m in (self.mweight_vol_decoder, self.pose_decoder):
+            m.to(dev)
+
+        def run(dst_Rs, dst_Ts, cnl_gtfms, priors, dst_posevec, iter_val):
+            dst_Rs = dst_Rs[None]
+            if iter_val >= pose_kick_in_iter:
+                refined = self.pose_decoder(dst_posevec[None])["Rs"]
+                no_root = torch.matmul(dst_Rs[:, 1:].reshape(-1, 3, 3), refined.reshape(-1, 3, 3)).reshape(-1, 23, 3, 3)
+                dst_Rs = torch.cat([dst_Rs[:, 0:1], no_root], dim=1)
+            Rs, Ts = self.motion_basis_computer(dst_Rs, dst_Ts[None], cnl_gtfms[None])
+            return Rs, Ts, self.mweight_vol_decoder(motion_weights_priors=priors[None])[0]
+
+        self.prologue = run
+        return self
+
     # -- per-subject state (network.py:90-146)
     def generate_neural_points(self, vertices, normals, fps_index, bbox_min=None, bbox_max=None, point_dist=None,
                                point_counter=None):

@@ -236,9 +236,11 @@ def composite_backward(raw, mask, z, rays, bg, g_rgb, g_acc, g_depth, g_comp=Non
     N, S = z.shape
     g_raw = torch.empty(N, S, 5, device=z.device, dtype=f32)
     g_mask = torch.empty(N, S, device=z.device, dtype=f32)
+    # keep the (possibly freshly materialised) contiguous gradients alive until the launch has been issued
+    g_rgb, g_acc, g_depth = g_rgb.contiguous(), g_acc.contiguous(), g_depth.contiguous()
+    g_comp = g_comp.contiguous() if g_comp is not None else None
     call("occnerf_composite_backward", ptr(raw, f32), ptr(mask, f32), ptr(z, f32), ptr(rays, f32), ptr(bg, f32),
-         ptr(g_rgb.contiguous(), f32), ptr(g_acc.contiguous(), f32), ptr(g_depth.contiguous(), f32),
-         ptr(g_comp.contiguous(), f32) if g_comp is not None else None, N, S, ptr(g_raw), ptr(g_mask), stream())
+         ptr(g_rgb, f32), ptr(g_acc, f32), ptr(g_depth, f32), ptr(g_comp, f32), N, S, ptr(g_raw), ptr(g_mask), stream())
     return g_raw, g_mask
 
 

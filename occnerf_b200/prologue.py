@@ -1,0 +1,146 @@
+"""Per-frame prologue of `Network.forward` (network.py:558-597): pose refinement, motion basis, motion-weight
+volume decoder.  It runs once per frame and produces the ray path's inputs (`motion_scale_Rs`, `motion_Ts`,
+`motion_weights_vol`); SURVEY.md section 8(f) lists it as the NEXT row after the ray path, so for now it is
+plain library code (torch/cuDNN) with the reference's module and parameter names -- it is not claimed as a
+native kernel and is not inside the timed ray path of bench.py's `value`.
+
+  MotionBasisComputer         core/utils/network_util.py:138-200   (FK chain evaluated level by level of the SMPL tree)
+  MotionWeightVolumeDecoder   mweight_vol_decoders/deconv_vol_decoder.py:8-33 + network_util.py:12-50
+  BodyPoseRefiner             pose_decoders/mlp_delta_body_pose.py:35-41 (kick_in_iter = 2e6 in every shipped yaml)
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+SMPL_PARENT = {1: 0, 2: 0, 3: 0, 4: 1, 5: 2, 6: 3, 7: 4, 8: 5, 9: 6, 10: 7, 11: 8, 12: 9, 13: 9, 14: 9, 15: 12, 16: 13,
+               17: 14, 18: 16, 19: 17, 20: 18, 21: 19, 22: 20, 23: 21}
+
+
+def _tree_levels():
+    depth = {0: 0}
+    for i in range(1, 24):
+        depth[i] = depth[SMPL_PARENT[i]] + 1
+    levels = []
+    for d in range(1, max(depth.values()) + 1):
+        idx = [i for i in range(24) if depth[i] == d]
+        levels.append((idx, [SMPL_PARENT[i] for i in idx]))
+    return levels
+
+
+_LEVELS = _tree_levels()
+
+
+def _init_seq(seq):
+    """xavier-uniform with the gain of the following activation, zero bias (network_util.py:265-334)."""
+    mods = list(seq)
+    for i, m in enumerate(mods):
+        if isinstance(m, (nn.Linear, nn.ConvTranspose3d)):
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            gain = nn.init.calculate_gain("leaky_relu", 0.2) if isinstance(nxt, nn.LeakyReLU) else \
+                (math.sqrt(2.0) if isinstance(nxt, nn.ReLU) else 1.0)
+            nn.init.xavier_uniform_(m.weight, gain=gain)
+            nn.init.zeros_(m.bias)
+
+
+class MotionBasisComputer(nn.Module):
+    def forward(self, dst_Rs, dst_Ts, cnl_gtfms):
+        B = dst_Rs.shape[0]
+        G = torch.zeros(B, 24, 4, 4, dtype=dst_Rs.dtype, device=dst_Rs.device)
+        G[:, :, :3, :3] = dst_Rs
+        G[:, :, :3, 3] = dst_Ts
+        G[:, :, 3, 3] = 1.0
+        glob = [None] * 24
+        glob[0] = G[:, 0]
+        for idx, par in _LEVELS:
+            prod = torch.matmul(torch.stack([glob[p] for p in par], 1), G[:, idx])
+            for j, i in enumerate(idx):
+                glob[i] = prod[:, j]
+        dst = torch.stack(glob, 1).view(-1, 4, 4)
+        f = torch.matmul(cnl_gtfms.view(-1, 4, 4), torch.inverse(dst)).view(B, 24, 4, 4)
+        return f[:, :, :3, :3], f[:, :, :3, 3]
+
+
+class ConvDecoder3D(nn.Module):
+    def __init__(self, embedding_size=256, volume_size=32, voxel_channels=25):
+        super().__init__()
+        self.block_mlp = nn.Sequential(nn.Linear(embedding_size, 1024), nn.LeakyReLU(0.2))
+        block_conv, inc, outc = [], 1024, 512
+        for _ in range(int(np.log2(volume_size)) - 1):
+            block_conv += [nn.ConvTranspose3d(inc, outc, 4, 2, 1), nn.LeakyReLU(0.2)]
+            if inc == outc:
+                outc = inc // 2
+            else:
+                inc = outc
+        block_conv.append(nn.ConvTranspose3d(inc, voxel_channels, 4, 2, 1))
+        self.block_conv = nn.Sequential(*block_conv)
+        _init_seq(self.block_mlp)
+        _init_seq(self.block_conv)
+
+    def forward(self, embedding):
+        return self.block_conv(self.block_mlp(embedding).view(-1, 1024, 1, 1, 1))
+
+
+class MotionWeightVolumeDecoder(nn.Module):
+    def __init__(self, embedding_size=256, volume_size=32, total_bones=24):
+        super().__init__()
+        self.const_embedding = nn.Parameter(torch.randn(embedding_size))
+        self.decoder = ConvDecoder3D(embedding_size, volume_size, total_bones + 1)
+
+    def forward(self, motion_weights_priors, **_):
+        return F.softmax(self.decoder(self.const_embedding[None]) + torch.log(motion_weights_priors), dim=1)
+
+
+def rodrigues(rvec):
+    """network_util.py:98-127."""
+    theta = torch.sqrt(1e-5 + torch.sum(rvec ** 2, dim=1))
+    r = rvec / theta[:, None]
+    c, s = torch.cos(theta), torch.sin(theta)
+    x, y, z = r[:, 0], r[:, 1], r[:, 2]
+    return torch.stack((x ** 2 + (1. - x ** 2) * c, x * y * (1. - c) - z * s, x * z * (1. - c) + y * s,
+                        x * y * (1. - c) + z * s, y ** 2 + (1. - y ** 2) * c, y * z * (1. - c) - x * s,
+                        x * z * (1. - c) - y * s, y * z * (1. - c) + x * s, z ** 2 + (1. - z ** 2) * c), dim=1).view(-1, 3, 3)
+
+
+class BodyPoseRefiner(nn.Module):
+    def __init__(self, embedding_size=69, mlp_width=256, mlp_depth=4, total_bones=24):
+        super().__init__()
+        mods = [nn.Linear(embedding_size, mlp_width), nn.ReLU()]
+        for _ in range(mlp_depth - 1):
+            mods += [nn.Linear(mlp_width, mlp_width), nn.ReLU()]
+        self.total_bones = total_bones - 1
+        mods.append(nn.Linear(mlp_width, 3 * self.total_bones))
+        self.block_mlps = nn.Sequential(*mods)
+        _init_seq(self.block_mlps)
+        self.block_mlps[-1].weight.data.uniform_(-1e-5, 1e-5)
+        self.block_mlps[-1].bias.data.zero_()
+
+    def forward(self, pose_input):
+        return {"Rs": rodrigues(self.block_mlps(pose_input).view(-1, 3)).view(-1, self.total_bones, 3, 3)}
+
+
+class Prologue(nn.Module):
+    """callable(dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec, iter_val) -> (Rs, Ts, vol)
+    with the reference's control flow (network.py:558-597): pose refinement from `pose_kick_in_iter` on
+    (2 000 000 in every shipped yaml, i.e. never while training, always at render time where iter_val = 1e7)."""
+
+    def __init__(self, pose_kick_in_iter=2000000):
+        super().__init__()
+        self.motion_basis_computer = MotionBasisComputer()
+        self.mweight_vol_decoder = MotionWeightVolumeDecoder()
+        self.pose_decoder = BodyPoseRefiner()
+        self.pose_kick_in_iter = pose_kick_in_iter
+
+    def forward(self, dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec, iter_val):
+        dst_Rs = dst_Rs[None]
+        if iter_val >= self.pose_kick_in_iter:
+            refined = self.pose_decoder(dst_posevec[None])["Rs"]
+            no_root = torch.matmul(dst_Rs[:, 1:].reshape(-1, 3, 3), refined.reshape(-1, 3, 3)).reshape(-1, 23, 3, 3)
+            dst_Rs = torch.cat([dst_Rs[:, 0:1], no_root], dim=1)
+        Rs, Ts = self.motion_basis_computer(dst_Rs, dst_Ts[None], cnl_gtfms[None])
+        vol = self.mweight_vol_decoder(motion_weights_priors=motion_weights_priors[None])[0]
+        return Rs, Ts, vol

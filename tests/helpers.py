@@ -15,8 +15,9 @@ def load_case(name):
     # the seeded generator must reproduce exactly what the fixture was made from
     assert np.array_equal(g["rays_d"], fr.rays_d.numpy()) and np.array_equal(g["near"], fr.near.numpy())
     assert np.array_equal(g["motion_scale_Rs"], fr.motion_scale_Rs.numpy())
-    assert float(g["emb_checksum"]) == w.embeddings.double().sum().item()
-    assert float(g["vol_checksum"]) == vol.double().sum().item()
+    # (sums of 15.5 M values: the reduction order depends on the host's core count, so compare to 1e-9 relative)
+    assert np.isclose(float(g["emb_checksum"]), w.embeddings.double().sum().item(), rtol=1e-9, atol=1e-9)
+    assert np.isclose(float(g["vol_checksum"]), vol.double().sum().item(), rtol=1e-9, atol=1e-9)
     if t_rand is not None:
         assert np.array_equal(g["t_rand"], t_rand.numpy())
     return sub, w, fr, vol, t_rand, rk, g

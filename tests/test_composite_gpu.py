@@ -22,7 +22,7 @@ def test_forward_against_reference_golden(name):
     rgb, acc, depth, term, wts, comp = ops.composite_forward(*_cuda(raw, mask, z, rays, fr.bgcolor), want_weights=True, want_comp=True)
     errs = dict(rgb=maxabs(rgb, g["rgb"]), alpha=maxabs(acc, g["alpha"]), depth=maxabs(depth, g["depth"]), weights=maxabs(wts, g["weights"]))
     report(f"composite_golden[{name}]", **errs)
-    assert max(errs.values()) < 2e-6
+    assert max(errs[k] for k in ('rgb', 'alpha', 'weights')) < 2e-6 and errs['depth'] < 5e-6   # depth is O(6)
     assert np.array_equal(term.cpu().numpy().astype(np.int32), g["term"])
     if rk["training"]:
         assert maxabs(comp, g["comp_loss"]) < 1e-6

@@ -61,7 +61,8 @@ def test_backward_and_input_backward():
     x = _inputs(6000, seed=3)
     g = torch.randn(6000, 32, generator=torch.Generator().manual_seed(4))
     g_emb = torch.zeros_like(emb).to(d)
-    ops.hashgrid_backward(g.to(d).data_ptr(), 32, _lib.LAYOUT_BLC, x.to(d), offs.to(d), scales, g_emb, 2)
+    g_d, x_d = g.to(d), x.to(d)
+    ops.hashgrid_backward(g_d.data_ptr(), 32, _lib.LAYOUT_BLC, x_d, offs.to(d), scales, g_emb, 2)
     ref32, ref64 = hashgrid_c.backward(g, x, offs, emb.shape[0], 2, Sv, 16, level_scales=scales.cpu().contiguous(), want_f64=True)
     e = maxabs(g_emb, ref64) / float(ref64.abs().max())
     report("hashgrid_bwd", g_emb_rel_vs_f64=e, oracle_f32_rel_vs_f64=maxabs(ref32, ref64) / float(ref64.abs().max()))
@@ -69,7 +70,7 @@ def test_backward_and_input_backward():
     assert torch.equal((g_emb != 0).cpu(), ref64 != 0) or float((g_emb.cpu() - ref64.float()).abs().max()) < 1e-6
     # input gradient
     _o, dy_dx, _c, _s = ops.hashgrid_forward(x.to(d), emb.to(d), offs.to(d), scales, want_dy_dx=True)
-    gi = ops.hashgrid_input_backward(g.to(d).data_ptr(), 32, _lib.LAYOUT_BLC, dy_dx, 6000, 4, 2, 16)
+    gi = ops.hashgrid_input_backward(g_d.data_ptr(), 32, _lib.LAYOUT_BLC, dy_dx, 6000, 4, 2, 16)
     gi_o = hashgrid_c.input_backward(g, dy_dx.cpu(), 6000, 4, 2, 16)
     assert normwise_close(gi.cpu().numpy(), gi_o.numpy(), 1e-5)
 
@@ -112,7 +113,8 @@ def test_other_shapes_against_oracle(D, C):
     assert maxabs(out, r["out"]) < 1e-6
     g = torch.randn(3000, 8 * C, generator=gen)
     g_emb = torch.zeros_like(emb).to(d)
-    ops.hashgrid_backward(g.to(d).data_ptr(), 8 * C, 0, x.to(d), offs_t.to(d), sc, g_emb, C)
+    g_d, x_d = g.to(d), x.to(d)
+    ops.hashgrid_backward(g_d.data_ptr(), 8 * C, 0, x_d, offs_t.to(d), sc, g_emb, C)
     ref32, _ = hashgrid_c.backward(g, x, offs_t, emb.shape[0], C, Sv, 16, level_scales=sc.cpu().contiguous())
     assert normwise_close(g_emb.cpu().numpy(), ref32.numpy(), 1e-5)
 
