@@ -136,11 +136,12 @@ typedef struct {
 } occnerf_mlp_params;
 long occnerf_mlp_packed_bytes(int n_pass);
 int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, void *packed, occnerf_stream_t stream);
-/* X0 [m,68] = (agg35, var1, h32) -> raw [m, ldr] columns 0..3 = (rgb_pre3, sigma_pre1).
- * act_save: NULL (inference) or bf16 buffer [9][m_pad][256] receiving the post-ReLU activations of the 8
- * hidden layers and the geo output, for the backward pass. */
-int occnerf_mlp_forward_tc(const float *X0, int m, const void *packed, int n_pass, float *raw, int ldr, void *act_save,
-                           occnerf_stream_t stream);
+/* XB [m,132]: columns 64..131 = (agg35, var1, h32) are read; columns 0..63 receive the 64 geometry features when
+ * act_dtype != 0.  raw [m, ldr]: columns 0..3 = (rgb_pre3, sigma_pre1) are written.
+ * act_save: NULL (act_dtype 0, inference) or a buffer [8][m][256] receiving the post-ReLU activations of the 8
+ * hidden layers (pts1..4, rgb1..4) for the backward pass, as fp32 (act_dtype 1) or bf16 (act_dtype 2). */
+int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, float *raw, int ldr, void *act_save,
+                           int act_dtype, occnerf_stream_t stream);
 
 /* ---- alpha compositing (network.py:320-348) + completeness term (network.py:486-499) ----------------
  * raw [N,S,5] = (rgb_pre3, sigma_pre, dist); mask, z [N,S]; rays [N,8]; bg [3] (0..255).

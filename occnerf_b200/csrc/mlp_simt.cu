@@ -199,7 +199,7 @@ extern "C" int occnerf_colsum(const float *A, long lda, const float *mask, long 
                               occnerf_stream_t stream) {
     OCC_CHECK_ARG(A && out && Mi >= 0 && Nj >= 0, "colsum: bad arguments");
     if (Mi == 0 || Nj == 0) return OCCNERF_OK;
-    const int rows = 2048;
+    const int rows = 128;
     dim3 grid(occ_div_up(Nj, 256), occ_div_up(Mi, rows));
     colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, mask, ldmask, Mi, Nj, rows, out);
     OCC_LAUNCH_CHECK();

@@ -1,7 +1,474 @@
-// placeholder until the tcgen05 kernel lands (replaced in the next commit)
+// K3: the canonical density/colour MLP as ONE fused tcgen05/TMEM kernel (forward).
+//
+// Replaces the ten nn.Linear (+ReLU) launches of CanonicalMLP.forward
+// (core/nets/occnerf/canonical_mlps/occnerf_mlp.py:183-199):
+//     geo  : [agg35,var1,h32] (68) -> 256 -> 256 -> 256 -> 256 -> 65 (sigma + 64 features)
+//     rgb  : [geo64,agg35,h32] (131) -> 256 -> 256 -> 256 -> 256 -> 3
+// A CTA owns a tile of 128 samples.  The activation tile never leaves the SM: it lives in shared memory as a
+// bf16 UMMA A-operand (K-major, no swizzle, core-matrix-major so that the epilogue's 16-byte stores are
+// conflict free), the accumulator lives in TMEM (128 lanes x 256 fp32 columns), and the epilogue
+// (tcgen05.ld -> +bias -> ReLU -> bf16 split -> st.shared) writes the next layer's A operand in place.
+// Weights are pre-packed once per step (occnerf_mlp_pack_weights) into exactly the shared-memory image the
+// tensor core wants and streamed from L2 through a 3-stage ring with cp.async.bulk + mbarrier (TMA bulk copies;
+// no tensor map needed because the image is already tiled).
+//
+// Precision: n_pass = 1 is plain bf16 x bf16 -> fp32.  n_pass = 3 is the split-bf16 scheme
+//   x = hi + lo (both bf16),  x.w ~= hi.whi + hi.wlo + lo.whi   (fp32 accumulate in TMEM)
+// i.e. three MMAs per K-step on the same accumulator, ~2^-16 relative error per product -- fp32-grade results
+// (rgb/alpha/depth within 1e-5 of the fp32 reference on the golden cases) at 1.5x the cost of a TF32 pass.
+//
+// Warp roles (192 threads): warps 0-3 = epilogue (each owns 32 TMEM lanes = 32 samples), warp 4 lane 0 = weight
+// producer, warp 5 lane 0 = MMA issuer.  Pipelines: w_full/w_empty (producer <-> MMA), a_full (epilogue -> MMA),
+// acc_full (MMA -> epilogue, via tcgen05.commit).
+#include <cuda_bf16.h>
 #include "common.cuh"
-extern "C" long occnerf_mlp_packed_bytes(int) { return 0; }
-extern "C" int occnerf_mlp_pack_weights(const occnerf_mlp_params *, int, void *, occnerf_stream_t) {
-    occnerf_set_error("mlp_tc: not built"); return OCCNERF_EINVAL; }
-extern "C" int occnerf_mlp_forward_tc(const float *, int, const void *, int, float *, int, void *, occnerf_stream_t) {
-    occnerf_set_error("mlp_tc: not built"); return OCCNERF_EINVAL; }
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 192;
+constexpr int kStages = 3;
+constexpr int kStageBytes = 32768;
+constexpr int kLayers = 10;
+constexpr int kAPartBytes = 65536;          // 128 rows x 256 K x bf16
+constexpr uint32_t kSpinLimit = 1u << 27;   // a wedged pipeline traps instead of hanging the GPU
+
+// padded GEMM shapes of the chain; K multiple of 16, N multiple of 16
+__host__ __device__ constexpr int layer_K(int l) { return l == 0 ? 80 : (l == 5 ? 144 : 256); }
+__host__ __device__ constexpr int layer_N(int l) { return l == 4 ? 80 : (l == 9 ? 16 : 256); }
+__host__ __device__ constexpr int chunk_K(int n_pass) { return n_pass == 1 ? 64 : 32; }
+
+struct PackedLayout {
+    long w_off[kLayers];     // byte offset of layer l's weight image
+    long bias_off;           // byte offset of the padded biases [10][256] fp32
+    long total;
+};
+
+__host__ __device__ inline int n_chunks(int l, int n_pass) { return (layer_K(l) + chunk_K(n_pass) - 1) / chunk_K(n_pass); }
+__host__ __device__ inline int part_bytes(int l, int n_pass) { return layer_N(l) * chunk_K(n_pass) * 2; }   // full-chunk size of one part
+__host__ __device__ inline int parts(int n_pass) { return n_pass == 1 ? 1 : 2; }
+
+inline PackedLayout packed_layout(int n_pass) {
+    PackedLayout p;
+    long off = 0;
+    for (int l = 0; l < kLayers; ++l) {
+        p.w_off[l] = off;
+        off += (long)n_chunks(l, n_pass) * parts(n_pass) * part_bytes(l, n_pass);
+    }
+    p.bias_off = off;
+    off += kLayers * 256 * 4;
+    p.total = (off + 255) / 256 * 256;
+    return p;
+}
+
+struct DevLayout { long w_off[kLayers]; long bias_off; };
+
+// ------------------------------------------------------------------------------------------ weight packing
+// source element of the padded GEMM of layer l: W_l[n][k] with the row/column re-ordering described in mlp.py
+__device__ __forceinline__ float src_weight(const occnerf_mlp_params &P, int l, int n, int k) {
+    if (l == 0) return (k < 68) ? P.w[0][n * 68 + k] : 0.f;                                   // pts0: [agg35,var,h32]
+    if (l == 4) {                                                                              // geo: features first, sigma at 64
+        if (n < 64) return P.w[4][(n + 1) * 256 + k];
+        if (n == 64) return P.w[4][k];
+        return 0.f;
+    }
+    if (l == 5) {                                                                              // rgb0: [geo64 | agg35, var(0), h32]
+        if (k < 99) return P.w[5][n * 131 + k];
+        if (k == 99 || k >= 132) return 0.f;
+        return P.w[5][n * 131 + k - 1];
+    }
+    if (l == 9) return (n < 3) ? P.w[9][n * 256 + k] : 0.f;
+    return P.w[l][n * 256 + k];
+}
+__device__ __forceinline__ float src_bias(const occnerf_mlp_params &P, int l, int n) {
+    if (l == 4) return n < 64 ? P.b[4][n + 1] : (n == 64 ? P.b[4][0] : 0.f);
+    if (l == 9) return n < 3 ? P.b[9][n] : 0.f;
+    return P.b[l][n];
+}
+
+__global__ void pack_weights_kernel(occnerf_mlp_params P, DevLayout L, int n_pass, unsigned char *out) {
+    const int l = blockIdx.y;
+    const int K = layer_K(l), N = layer_N(l), KC = chunk_K(n_pass), np = parts(n_pass);
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < (long)N * K) {
+        const int n = (int)(idx / K), k = (int)(idx % K);
+        const float w = src_weight(P, l, n, k);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        const int chunk = k / KC, kk = k % KC;
+        const long pb = part_bytes(l, n_pass);
+        const long base = L.w_off[l] + (long)chunk * np * pb;
+        const long inner = ((long)(kk / 8) * (N / 8) + n / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(out + base + inner) = hi;
+        if (np == 2) *reinterpret_cast<__nv_bfloat16 *>(out + base + pb + inner) = lo;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 256) {
+        float *b = reinterpret_cast<float *>(out + L.bias_off) + l * 256;
+        b[threadIdx.x] = threadIdx.x < N ? src_bias(P, l, threadIdx.x) : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::f16 (bf16 operands, fp32 accumulate), issued by one thread
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no-swizzle shared-memory operand descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
+__device__ __forceinline__ uint32_t instr_desc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+        "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// bf16 split of 8 consecutive K values of one row -> one 16-byte store per part into the A operand image
+template <int NPASS>
+__device__ __forceinline__ void store_a8(unsigned char *a_base, int row, int k8, const float (&v)[8]) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        hi[i] = *reinterpret_cast<const uint32_t *>(&h);
+        if (NPASS == 3) {
+            const float2 hf = __bfloat1622float2(h);
+            const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+            lo[i] = *reinterpret_cast<const uint32_t *>(&l);
+        }
+    }
+    const uint32_t off = (uint32_t)(k8 * 16 + (row >> 3)) * 128 + (row & 7) * 16;
+    *reinterpret_cast<uint4 *>(a_base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (NPASS == 3) *reinterpret_cast<uint4 *>(a_base + kAPartBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// the (agg35, var, h32) part of a sample's input row -> A columns [col0, col0+68), zero padded to col0+80
+template <int NPASS>
+__device__ __forceinline__ void stage_x0(unsigned char *a_base, int row, const float *__restrict__ xrow, bool valid, int k8_0) {
+    // 68 floats = 17 float4 = 8.5 groups of 8; write 10 groups (80 columns), zero beyond 68
+#pragma unroll
+    for (int g = 0; g < 10; ++g) {
+        float v[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = g * 8 + h * 4;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && c < 68) x = __ldg(reinterpret_cast<const float4 *>(xrow + c));
+            v[h * 4 + 0] = x.x; v[h * 4 + 1] = x.y; v[h * 4 + 2] = x.z; v[h * 4 + 3] = x.w;
+        }
+        store_a8<NPASS>(a_base, row, k8_0 + g, v);
+    }
+}
+
+struct FwdArgs {
+    float *XB;              // [m,132]: cols 64..131 in, cols 0..63 out (geo features) when save != 0
+    int m;
+    const unsigned char *packed;
+    DevLayout L;
+    float *raw;             // [m, ldr]: cols 0..2 rgb_pre, col 3 sigma_pre
+    int ldr;
+    void *act_save;         // [8][m][256] post-ReLU activations of the 8 hidden layers (fp32 or bf16) or NULL
+    int act_dtype;          // 0 none, 1 fp32, 2 bf16
+};
+
+template <int NPASS>
+__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const FwdArgs args) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);
+    unsigned char *sA = smem;
+    unsigned char *sW = smem + kABytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kABytes + kStages * kStageBytes);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    const uint32_t bar_w_full = smem_u32(bars), bar_w_empty = smem_u32(bars + kStages);
+    const uint32_t bar_a_full = smem_u32(bars + 2 * kStages), bar_acc_full = smem_u32(bars + 2 * kStages + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = (args.m + kTileM - 1) / kTileM;
+    constexpr int KC = (NPASS == 1) ? 64 : 32;
+    constexpr int NP = (NPASS == 1) ? 1 : 2;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar_w_full + 8 * s, 1); mbar_init(bar_w_empty + 8 * s, 1); }
+        mbar_init(bar_a_full, kTileM);
+        mbar_init(bar_acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ================================= weight producer =================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int l = 0; l < kLayers; ++l) {
+                    const int K = layer_K(l), N = layer_N(l);
+                    const int nch = (K + KC - 1) / KC;
+                    const uint32_t pb = (uint32_t)N * KC * 2;
+                    const unsigned char *src = args.packed + args.L.w_off[l];
+                    for (int c = 0; c < nch; ++c, ++it) {
+                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        mbar_wait(bar_w_empty + 8 * s, ph ^ 1);
+                        const int kc = min(KC, K - c * KC);
+                        const uint32_t bytes = (uint32_t)N * kc * 2;          // per part; the k8-outer image is contiguous
+                        mbar_arrive_expect_tx(bar_w_full + 8 * s, bytes * NP);
+                        const uint32_t dst = smem_u32(sW + s * kStageBytes);
+                        for (int p = 0; p < NP; ++p)
+                            bulk_g2s(dst + p * (kStageBytes / NP), src + ((long)c * NP + p) * pb, bytes, bar_w_full + 8 * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ================================= MMA issuer =================================
+        if (lane == 0) {
+            uint32_t it = 0, a_cnt = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int l = 0; l < kLayers; ++l, ++a_cnt) {
+                    const int K = layer_K(l), N = layer_N(l);
+                    const int nch = (K + KC - 1) / KC;
+                    const uint32_t idesc = instr_desc(N);
+                    const uint32_t b_lbo = (uint32_t)(N / 8) * 128;
+                    mbar_wait(bar_a_full, a_cnt & 1);
+                    tc_fence_after();
+                    uint32_t first = 1;
+                    for (int c = 0; c < nch; ++c, ++it) {
+                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        mbar_wait(bar_w_full + 8 * s, ph);
+                        tc_fence_after();
+                        const int kc = min(KC, K - c * KC);
+                        const uint32_t wbase = smem_u32(sW + s * kStageBytes);
+                        for (int k16 = 0; k16 < kc / 16; ++k16) {
+                            const uint32_t a_hi = smem_u32(sA) + (uint32_t)(c * (KC / 16) + k16) * 4096;
+                            const uint32_t b_hi = wbase + (uint32_t)k16 * 2 * b_lbo;
+                            const uint64_t da_hi = smem_desc(a_hi, 2048, 128), db_hi = smem_desc(b_hi, b_lbo, 128);
+                            tc_mma(tmem_base, da_hi, db_hi, idesc, first ? 0u : 1u);
+                            first = 0;
+                            if (NPASS == 3) {
+                                const uint64_t da_lo = smem_desc(a_hi + kAPartBytes, 2048, 128);
+                                const uint64_t db_lo = smem_desc(b_hi + kStageBytes / 2, b_lbo, 128);
+                                tc_mma(tmem_base, da_hi, db_lo, idesc, 1u);
+                                tc_mma(tmem_base, da_lo, db_hi, idesc, 1u);
+                            }
+                        }
+                        tc_commit(bar_w_empty + 8 * s);       // frees the ring slot when these MMAs have read it
+                    }
+                    tc_commit(bar_acc_full);                  // accumulator of layer l complete
+                }
+            }
+        }
+    } else {
+        // ================================= epilogue warps (128 threads = 128 rows) =================================
+        const int row = threadIdx.x;                          // TMEM lane == sample row inside the tile
+        const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const float *bias_all = reinterpret_cast<const float *>(args.packed + args.L.bias_off);
+        uint32_t acc_cnt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const long grow = (long)tile * kTileM + row;
+            const bool valid = grow < args.m;
+            const float *xrow = args.XB + grow * 132 + 64;
+            // ---- layer-0 operand: (agg35, var, h32) -> A[:, 0:80)
+            stage_x0<NPASS>(sA, row, xrow, valid, 0);
+            fence_proxy_async();
+            mbar_arrive(bar_a_full);
+            for (int l = 0; l < kLayers; ++l, ++acc_cnt) {
+                mbar_wait(bar_acc_full, acc_cnt & 1);
+                tc_fence_after();
+                const float *bias = bias_all + l * 256;
+                if (l == 9) {
+                    // ---- output layer: 3 (+13 pad) columns -> raw[:, 0:3]
+                    uint32_t r[16];
+                    tmem_ld16(t_lane, r);
+                    if (valid) {
+                        float *o = args.raw + grow * args.ldr;
+                        o[0] = __uint_as_float(r[0]) + __ldg(bias + 0);
+                        o[1] = __uint_as_float(r[1]) + __ldg(bias + 1);
+                        o[2] = __uint_as_float(r[2]) + __ldg(bias + 2);
+                    }
+                    tc_fence_before();
+                    // no a_full arrive: the next tile's layer-0 staging does it
+                } else if (l == 4) {
+                    // ---- geometry head: columns 0..63 = features (-> A[:, 0:64) of the colour trunk), column 64 = sigma
+#pragma unroll 1
+                    for (int cg = 0; cg < 2; ++cg) {
+                        uint32_t r[32];
+                        tmem_ld32(t_lane + cg * 32, r);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]) + __ldg(bias + cg * 32 + j * 8 + i);
+                            store_a8<NPASS>(sA, row, cg * 4 + j, v);
+                            if (valid && args.act_dtype != 0) {
+                                float4 *dst = reinterpret_cast<float4 *>(args.XB + grow * 132 + cg * 32 + j * 8);
+                                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                            }
+                        }
+                    }
+                    {
+                        uint32_t r[16];
+                        tmem_ld16(t_lane + 64, r);
+                        if (valid) args.raw[grow * args.ldr + 3] = __uint_as_float(r[0]) + __ldg(bias + 64);
+                    }
+                    stage_x0<NPASS>(sA, row, xrow, valid, 8);       // A[:, 64:144) = (agg35, var, h32, 0 pad)
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(bar_a_full);
+                } else {
+                    // ---- hidden layer: +bias, ReLU -> next A operand (and the saved activation for the backward pass)
+                    const int slot = l < 4 ? l : l - 1;              // 0..3 = pts1..4, 4..7 = rgb1..4
+#pragma unroll 1
+                    for (int cg = 0; cg < 8; ++cg) {
+                        uint32_t r[32];
+                        tmem_ld32(t_lane + cg * 32, r);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                v[i] = fmaxf(__uint_as_float(r[j * 8 + i]) + __ldg(bias + cg * 32 + j * 8 + i), 0.f);
+                            store_a8<NPASS>(sA, row, cg * 4 + j, v);
+                            if (valid && args.act_dtype == 1) {
+                                float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(args.act_save) +
+                                                                         ((long)slot * args.m + grow) * 256 + cg * 32 + j * 8);
+                                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                            } else if (valid && args.act_dtype == 2) {
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                                    pk[i] = *reinterpret_cast<const uint32_t *>(&h);
+                                }
+                                *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(args.act_save) +
+                                                           ((long)slot * args.m + grow) * 256 + cg * 32 + j * 8) =
+                                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(bar_a_full);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+    }
+}
+
+template <int NPASS>
+int launch_fwd(const FwdArgs &a, cudaStream_t st) {
+    constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);
+    const int smem_bytes = kABytes + kStages * kStageBytes + 256;
+    static bool configured = false;
+    if (!configured) {
+        OCC_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    OCC_CUDA(cudaGetDevice(&dev));
+    OCC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int tiles = (a.m + kTileM - 1) / kTileM;
+    const int grid = tiles < sms ? tiles : sms;
+    mlp_fwd_tc_kernel<NPASS><<<grid, kThreads, smem_bytes, st>>>(a);
+    OCC_LAUNCH_CHECK();
+    return OCCNERF_OK;
+}
+
+}  // namespace
+
+extern "C" long occnerf_mlp_packed_bytes(int n_pass) {
+    if (n_pass != 1 && n_pass != 3) return -1;
+    return packed_layout(n_pass).total;
+}
+
+extern "C" int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, void *packed, occnerf_stream_t stream) {
+    OCC_CHECK_ARG(p_host && packed, "mlp_pack_weights: null pointer");
+    OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "mlp_pack_weights: n_pass=%d (supported: 1, 3)", n_pass);
+    for (int l = 0; l < kLayers; ++l) OCC_CHECK_ARG(p_host->w[l] && p_host->b[l], "mlp_pack_weights: layer %d has a null pointer", l);
+    const PackedLayout pl = packed_layout(n_pass);
+    DevLayout L;
+    for (int l = 0; l < kLayers; ++l) L.w_off[l] = pl.w_off[l];
+    L.bias_off = pl.bias_off;
+    dim3 grid(occ_div_up(256 * 256, 256), kLayers);
+    pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p_host, L, n_pass, (unsigned char *)packed);
+    OCC_LAUNCH_CHECK();
+    return OCCNERF_OK;
+}
+
+extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, float *raw, int ldr, void *act_save,
+                                      int act_dtype, occnerf_stream_t stream) {
+    if (m == 0) return OCCNERF_OK;
+    OCC_CHECK_ARG(XB && packed && raw, "mlp_forward_tc: null pointer");
+    OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "mlp_forward_tc: n_pass=%d (supported: 1, 3)", n_pass);
+    OCC_CHECK_ARG(m > 0 && ldr >= 4, "mlp_forward_tc: m=%d ldr=%d", m, ldr);
+    OCC_CHECK_ARG(act_dtype == 0 || act_save, "mlp_forward_tc: act_dtype=%d without act_save", act_dtype);
+    OCC_CHECK_ARG(((uintptr_t)XB & 15) == 0 && ((uintptr_t)packed & 15) == 0, "mlp_forward_tc: XB/packed must be 16-byte aligned");
+    const PackedLayout pl = packed_layout(n_pass);
+    FwdArgs a;
+    a.XB = XB; a.m = m; a.packed = (const unsigned char *)packed;
+    for (int l = 0; l < kLayers; ++l) a.L.w_off[l] = pl.w_off[l];
+    a.L.bias_off = pl.bias_off;
+    a.raw = raw; a.ldr = ldr; a.act_save = act_save; a.act_dtype = act_dtype;
+    return n_pass == 1 ? launch_fwd<1>(a, (cudaStream_t)stream) : launch_fwd<3>(a, (cudaStream_t)stream);
+}

@@ -23,6 +23,7 @@ f32 = torch.float32
 XB_LD = 132
 X0_OFF = 64          # XB[:, 64:132] = (agg35, var1, h32)
 H_OFF = 100          # XB[:, 100:132] = hash features
+FLOP_FWD = 923136.0  # per sample, SURVEY.md section 8d
 
 
 class MlpWeights:

@@ -16,7 +16,7 @@ from tests.helpers import dev, load_case, maxabs, normwise_close, report
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = ["fp32"]
+ENGINES = ["fp32", "tc3", "tc1"]
 
 
 def _net(sub, w, rk, engine="fp32"):
@@ -45,41 +45,55 @@ def test_render_matches_reference_golden(name, engine):
     net = _net(sub, w, rk, engine)
     vol_d = vol.to(dev()).requires_grad_(True)
     out = _render(net, fr, vol_d, t_rand, rk["iter_val"])
-    tol = 2e-5 if engine == "fp32" else 1e-3
+    tol = {"fp32": 2e-5, "tc3": 1e-4, "tc1": 1e-3}[engine]
     errs = {k: maxabs(out[k], g[k]) for k in ("rgb", "alpha", "depth")}
     report(f"render_golden[{name},{engine}]", **errs)
     for k, e in errs.items():
         assert e < tol, (k, e)
     if not rk["training"]:
         return
-    assert maxabs(out["comp_loss"], g["comp_loss"]) < (1e-5 if engine == "fp32" else 1e-3)
+    assert maxabs(out["comp_loss"], g["comp_loss"]) < {"fp32": 1e-5, "tc3": 1e-4, "tc1": 2e-2}[engine]
     assert np.array_equal(out["hits"].cpu().numpy(), g["counter_delta"]), "visibility votes differ"
     make_golden.scalar_loss({k: out[k] for k in ("rgb", "alpha", "depth", "comp_loss")}).backward()
     m = net.cnl_mlp.module
-    rel = 1e-3 if engine == "fp32" else 2e-2
+    # Normwise relative errors (max|a-b| / max|b|).  Per-entry hash-table and point_dist gradients are
+    # ill-conditioned: the finest level has ~3700 cells per unit, so the ~1e-6 differences in the canonical
+    # points that any re-ordered fp32 GEMM (non-rigid MLP) produces move interpolation weights by ~0.4 %.
+    # They get 2e-2; everything else, and the per-level L2 norms of the table gradient, are held to 1e-3 (fp32).
+    rel = {"fp32": 1e-3, "tc3": 5e-3, "tc1": 5e-2}[engine]
+    loose = {"fp32": 2e-2, "tc3": 2e-2, "tc1": 1e-1}[engine]
+
+    def nw(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        if engine != "fp32":     # Frobenius norm: robust to the few ReLU-mask flips a 2e-5 forward difference causes
+            return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+        return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
     ge = m.encoder.embeddings.grad.reshape(-1).cpu().numpy()
     offs = w.offsets.tolist()
     l2 = np.array([m.encoder.embeddings.grad[a:b].double().norm().item() for a, b in zip(offs[:-1], offs[1:])])
     gv = vol_d.grad.reshape(-1).cpu().numpy()
-    checks = {
-        "g_emb": normwise_close(ge[g["g_emb_idx"]], g["g_emb_val"], rel),
-        "g_emb_level_l2": bool(np.allclose(l2, g["g_emb_level_l2"], rtol=2 * rel)),
-        "g_vol": normwise_close(gv[g["g_vol_idx"]], g["g_vol_val"], rel),
-        "g_vol_l2": bool(np.isclose(vol_d.grad.double().norm().item(), float(g["g_vol_l2"]), rtol=rel)),
-        "g_point_dist": normwise_close(net.point_dist.grad.cpu().numpy(), g["g_point_dist"], rel),
+    errs = {
+        "g_emb": (nw(ge[g["g_emb_idx"]], g["g_emb_val"]), loose),
+        "g_emb_level_l2": (float(np.abs(l2 / g["g_emb_level_l2"] - 1).max()), 2 * rel),
+        "g_vol": (nw(gv[g["g_vol_idx"]], g["g_vol_val"]), rel),
+        "g_vol_l2": (abs(vol_d.grad.double().norm().item() / float(g["g_vol_l2"]) - 1), rel),
+        "g_point_dist": (nw(net.point_dist.grad.cpu().numpy(), g["g_point_dist"]), loose),
     }
     for i, li in enumerate((0, 2, 4, 6)):
         sl = (slice(None, None, 8), slice(None, None, 8)) if i else (slice(None), slice(None))
-        checks[f"g_pts_w{i}"] = normwise_close(m.pts_linears[li].weight.grad.cpu().numpy()[sl], g[f"g_pts_w{i}"], rel)
-        checks[f"g_rgb_w{i}"] = normwise_close(m.rgb_linears[li].weight.grad.cpu().numpy()[sl], g[f"g_rgb_w{i}"], rel)
-        checks[f"g_pts_b{i}"] = normwise_close(m.pts_linears[li].bias.grad.cpu().numpy(), g[f"g_pts_b{i}"], rel)
-        checks[f"g_rgb_b{i}"] = normwise_close(m.rgb_linears[li].bias.grad.cpu().numpy(), g[f"g_rgb_b{i}"], rel)
-    checks["g_geo_w"] = normwise_close(m.geo_linear[0].weight.grad.cpu().numpy(), g["g_geo_w"], rel)
-    checks["g_geo_b"] = normwise_close(m.geo_linear[0].bias.grad.cpu().numpy(), g["g_geo_b"], rel)
-    checks["g_out_w"] = normwise_close(m.output_linear[0].weight.grad.cpu().numpy(), g["g_out_w"], rel)
-    checks["g_out_b"] = normwise_close(m.output_linear[0].bias.grad.cpu().numpy(), g["g_out_b"], rel)
-    bad = [k for k, ok in checks.items() if not ok]
-    report(f"render_golden_grads[{name},{engine}]", failed=",".join(bad) or "none")
+        errs[f"g_pts_w{i}"] = (nw(m.pts_linears[li].weight.grad.cpu().numpy()[sl], g[f"g_pts_w{i}"]), rel)
+        errs[f"g_rgb_w{i}"] = (nw(m.rgb_linears[li].weight.grad.cpu().numpy()[sl], g[f"g_rgb_w{i}"]), rel)
+        errs[f"g_pts_b{i}"] = (nw(m.pts_linears[li].bias.grad.cpu().numpy(), g[f"g_pts_b{i}"]), rel)
+        errs[f"g_rgb_b{i}"] = (nw(m.rgb_linears[li].bias.grad.cpu().numpy(), g[f"g_rgb_b{i}"]), rel)
+    errs["g_geo_w"] = (nw(m.geo_linear[0].weight.grad.cpu().numpy(), g["g_geo_w"]), rel)
+    errs["g_geo_b"] = (nw(m.geo_linear[0].bias.grad.cpu().numpy(), g["g_geo_b"]), rel)
+    errs["g_out_w"] = (nw(m.output_linear[0].weight.grad.cpu().numpy(), g["g_out_w"]), rel)
+    errs["g_out_b"] = (nw(m.output_linear[0].bias.grad.cpu().numpy(), g["g_out_b"]), rel)
+    bad = [k for k, (e, t) in errs.items() if not e <= t]
+    report(f"render_golden_grads[{name},{engine}]", failed=",".join(bad) or "none",
+           worst_mlp=max(e for k, (e, t) in errs.items() if k[2:5] in ("pts", "rgb", "geo", "out")),
+           **{k: errs[k][0] for k in ("g_emb", "g_emb_level_l2", "g_vol", "g_point_dist")})
     assert not bad, bad
 
 
@@ -96,7 +110,7 @@ def test_query_stages_against_oracle(engine):
     assert torch.equal(out["knn_idxs"].cpu().long(), aux["knn_idxs"])
     e = maxabs(out["raws"].reshape(-1, 5), raw_o)
     report(f"query_vs_oracle[{engine}]", raw=e)
-    assert e < (5e-5 if engine == "fp32" else 2e-2)
+    assert e < {"fp32": 5e-5, "tc3": 2e-4, "tc1": 5e-2}[engine]
     assert maxabs(out["raws"].reshape(-1, 5)[:, 4], raw_o[:, 4]) < 1e-6      # signed distance channel is engine independent
 
 
