@@ -176,11 +176,13 @@ class Workload:
             for g in self.grads_to_reduce():
                 dist.all_reduce(g, op=dist.ReduceOp.AVG)
             dist.all_reduce(hits, op=dist.ReduceOp.MAX)
-        torch.nn.utils.clip_grad_norm_(self.path_params, 1.0)
-        self.opt_path.step()
-        self.opt_path.zero_grad(set_to_none=True)
-        self.vol.grad = None
-        net.apply_visibility(hits)
+        from occnerf_b200 import _lib
+        with _lib.region("lib:clip+adam+zero_grad"):
+            torch.nn.utils.clip_grad_norm_(self.path_params, 1.0)
+            self.opt_path.step()
+            self.opt_path.zero_grad(set_to_none=True)
+            self.vol.grad = None
+            net.apply_visibility(hits)
 
     def step_e2e(self, world):
         """One step through the public API with host buffers: H2D of the frame, Network.forward, loss, backward,

@@ -78,6 +78,18 @@ int occnerf_knn(const float *queries, int m, const float *supports4, const int32
                 const int32_t *level_begin_host, int n_levels, int k, const uint8_t *query_sel,
                 int32_t *out_idx, occnerf_stream_t stream);
 
+/* Cluster-pruned exact k-NN over a two-level hierarchy: the `nf` fine points are grouped around the `nc` points of a
+ * coarser level (OccNeRF: level 0 around level 2, level 1 around level 3; network.py:113-129).  One call returns the
+ * k-NN in BOTH levels, bit-identical to occnerf_knn on the same sets.
+ * fine4 [nf,4]: fine points sorted by cluster, .w = bit pattern of the point's original row in its level;
+ * centers4 [nc,4]: coarse points in their original order, .w = cluster radius (max member distance, inflated);
+ * cluster_ranges [nc,2] int32 = (begin, count) into fine4;  fine_gid [nf] / center_gid [nc]: original row -> output id
+ * (NULL = the row itself).  out_fine / out_center: row q at q*out_stride, k entries each.
+ * group_stride: queries are laid out [rays, group_stride]; a warp takes 32 consecutive rays at one sample index. */
+int occnerf_knn_hier(const float *queries, int m, int group_stride, const float *fine4, const float *centers4,
+                     const int32_t *cluster_ranges, int nf, int nc, const int32_t *fine_gid, const int32_t *center_gid,
+                     int k, int32_t *out_fine, int32_t *out_center, int out_stride, occnerf_stream_t stream);
+
 /* ---- per-sample surface geometry -> 4-D hash-grid input (occnerf_mlp.py:146-167) --------------------
  * knn_idx rows have `knn_stride` int32 entries, the first 10 being the level-0 neighbours.
  * enc_in [m,4] = (cos-weighted mean of the 3 nearest base vertices normalised to [0,1]^3, clamp((d+.2)/.5));
@@ -134,14 +146,23 @@ typedef struct {
     const float *w[10]; /* pts0..3, geo, rgb0..3, out : [out,in] row-major (nn.Linear.weight) */
     const float *b[10];
 } occnerf_mlp_params;
-long occnerf_mlp_packed_bytes(int n_pass);
-int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, void *packed, occnerf_stream_t stream);
+/* chain 0 = forward images (W, plus the padded biases), chain 1 = data-gradient images (W^T). */
+long occnerf_mlp_packed_bytes(int n_pass, int chain);
+int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, void *packed, occnerf_stream_t stream);
 /* XB [m,132]: columns 64..131 = (agg35, var1, h32) are read; columns 0..63 receive the 64 geometry features when
  * act_dtype != 0.  raw [m, ldr]: columns 0..3 = (rgb_pre3, sigma_pre1) are written.
  * act_save: NULL (act_dtype 0, inference) or a buffer [8][m][256] receiving the post-ReLU activations of the 8
  * hidden layers (pts1..4, rgb1..4) for the backward pass, as fp32 (act_dtype 1) or bf16 (act_dtype 2). */
 int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, float *raw, int ldr, void *act_save,
                            int act_dtype, occnerf_stream_t stream);
+
+/* Fused data-gradient chain (the transposed layers in reverse order, ReLU masks from the saved bf16 activations).
+ * g_raw [m,5] (d rgb_pre3, d sigma_pre, unused); act_bf16 [8][m][256] as saved by occnerf_mlp_forward_tc (act_dtype 2).
+ * Writes gXB [m,132] columns 64..131 = d(agg35, var1, h32) summed over both trunks, and g_save [9][m][256] bf16 =
+ * gradients w.r.t. the pre-activations of rgb3, rgb2, rgb1, rgb0, geo (columns 0..63 features, 64 sigma), pts3, pts2,
+ * pts1, pts0, which are the left operands of the weight-gradient GEMMs dW_l = G_l^T X_l. */
+int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, const void *act_bf16, float *gXB,
+                            void *g_save, occnerf_stream_t stream);
 
 /* ---- alpha compositing (network.py:320-348) + completeness term (network.py:486-499) ----------------
  * raw [N,S,5] = (rgb_pre3, sigma_pre, dist); mask, z [N,S]; rays [N,8]; bg [3] (0..255).

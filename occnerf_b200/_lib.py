@@ -26,6 +26,7 @@ _SIGNATURES = {
     "occnerf_warp_forward": [_vp] * 8 + [_i] * 6 + [_vp] * 4 + [_vp],
     "occnerf_warp_backward": [_vp] * 8 + [_i] * 6 + [_vp, _vp],
     "occnerf_knn": [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "occnerf_knn_hier": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp],
     "occnerf_sample_geometry": [_vp, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _vp],
     "occnerf_hashgrid_level_scales": [_f, _u, _u, _vp, _vp],
     "occnerf_hashgrid_forward": [_vp] * 5 + [_i, _i] + [_u] * 4 + [_vp] * 4,
@@ -36,8 +37,9 @@ _SIGNATURES = {
     "occnerf_hann_pe": [_vp, _i, _vp, _i, _vp, _i, _vp],
     "occnerf_sgemm": [_vp, _l, _l, _vp, _l, _l, _vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp],
     "occnerf_colsum": [_vp, _l, _vp, _l, _i, _i, _vp, _vp],
-    "occnerf_mlp_pack_weights": [C.POINTER(MlpParams), _i, _vp, _vp],
+    "occnerf_mlp_pack_weights": [C.POINTER(MlpParams), _i, _i, _vp, _vp],
     "occnerf_mlp_forward_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp],
+    "occnerf_mlp_backward_tc": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "occnerf_composite_forward": [_vp] * 5 + [_i, _i] + [_vp] * 7,
     "occnerf_composite_backward": [_vp] * 9 + [_i, _i] + [_vp] * 3,
     "occnerf_visibility_hits": [_vp, _vp, _vp, _i, _i, _f, _vp, _i, _i, _vp, _vp, _vp],
@@ -64,7 +66,7 @@ def load(build_if_missing: bool = True):
         fn.argtypes, fn.restype = args, _i
     lib.occnerf_last_error.restype = C.c_char_p
     lib.occnerf_abi_version.restype = _i
-    lib.occnerf_mlp_packed_bytes.argtypes, lib.occnerf_mlp_packed_bytes.restype = [_i], _l
+    lib.occnerf_mlp_packed_bytes.argtypes, lib.occnerf_mlp_packed_bytes.restype = [_i, _i], _l
     _lib = lib
     return lib
 
@@ -95,6 +97,27 @@ def ptr(t, dtype=None):
 KERNELS_PER_CALL = {"occnerf_visibility_hits": 3}
 COUNTERS = {"calls": 0, "launches": 0}
 PROFILE = None   # set to {} to record (start_event, end_event, work) per C call on the current stream
+
+
+class region:
+    """`with region("name"):` times a block of library (torch) work like a C call when profiling is on, so that the
+    bench's kernel table also shows what is NOT ours (cuBLAS weight gradients, optimizer, glue)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and hasattr(self, "e0"):
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.setdefault(self.name, []).append((self.e0, e1, 0.0))
+        return False
 
 
 def call(name: str, *args, work: float = 0.0):

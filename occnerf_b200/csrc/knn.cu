@@ -149,6 +149,121 @@ __global__ void vis_mark_kernel(const int *__restrict__ count, const uint8_t *__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Cluster-pruned exact search over a two-level hierarchy (fine level clustered around the points of a coarse level).
+// OccNeRF's multi-scale neighbourhoods are exactly that: level 2 (431 FPS points) are natural cluster centres for
+// level 0 (6890 vertices), level 3 (108) for level 1 (1723).  Per query:
+//   pass 1  distances to all centres  -> the coarse level's own k-NN (written out) and the nearest centre;
+//   seed    scan the nearest centre's members -> an upper bound U on the k-th fine distance;
+//   pass 2  every other cluster whose lower bound  |q-c| - r_c  can still beat U is scanned, the rest is skipped.
+// Lanes of a warp are 32 consecutive RAYS at the same sample index (group_stride = samples per ray), a few cm apart,
+// so they need the same handful of clusters: the loop over (cluster, member) is warp-uniform (broadcast LDS.128,
+// per-lane predicate) and only ~1/6 of the brute-force distance evaluations remain.
+// Exactness: member distances use the same arithmetic as the brute-force kernel; a cluster is skipped only if its
+// lower bound exceeds sqrt(U) by a margin (1e-5 relative + 1e-6) far above fp32 rounding, radii are inflated the same
+// way on the host, and ties are broken on (distance, original row) so the visiting order does not matter.
+template <int K>
+__device__ __forceinline__ void topk_insert_lex(float (&dk)[K], int (&ik)[K], float d, int idx) {
+    bool ins = false;
+    float cd = d;
+    int ci = idx;
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        ins = ins || (cd < dk[t]) || (cd == dk[t] && ci < ik[t]);
+        if (ins) {
+            const float td = dk[t];
+            const int ti = ik[t];
+            dk[t] = cd; ik[t] = ci;
+            cd = td; ci = ti;
+        }
+    }
+}
+
+__device__ __forceinline__ float dist2_rn(float qx, float qy, float qz, const float4 &s) {
+    const float dx = __fsub_rn(qx, s.x), dy = __fsub_rn(qy, s.y), dz = __fsub_rn(qz, s.z);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+constexpr int kHierThreads = 1024;   // one CTA per SM (the fine level fills most of shared memory) -> 32 warps/SM
+
+template <int K>
+__global__ void __launch_bounds__(kHierThreads)
+knn_hier_kernel(const float *__restrict__ queries, int m, int group_stride, const float4 *__restrict__ fine4,
+                const float4 *__restrict__ centers4, const int2 *__restrict__ ranges, int nf, int nc,
+                const int32_t *__restrict__ fine_gid, const int32_t *__restrict__ center_gid, int32_t *__restrict__ out_fine,
+                int32_t *__restrict__ out_center, int out_stride) {
+    extern __shared__ __align__(16) unsigned char hier_smem[];
+    float4 *s_fine = reinterpret_cast<float4 *>(hier_smem);
+    float4 *s_cent = s_fine + nf;
+    int2 *s_rng = reinterpret_cast<int2 *>(s_cent + nc);
+    for (int i = threadIdx.x; i < nf; i += kHierThreads) s_fine[i] = __ldg(fine4 + i);
+    for (int i = threadIdx.x; i < nc; i += kHierThreads) { s_cent[i] = __ldg(centers4 + i); s_rng[i] = __ldg(ranges + i); }
+    __syncthreads();
+    // warp -> (sample index j, block of 32 rays); lane -> ray
+    const long warp_global = ((long)blockIdx.x * kHierThreads + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long j = warp_global % group_stride, r0 = (warp_global / group_stride) * 32;
+    const long q = (r0 + lane) * group_stride + j;
+    const bool active = q < m;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) { qx = __ldg(queries + q * 3); qy = __ldg(queries + q * 3 + 1); qz = __ldg(queries + q * 3 + 2); }
+
+    float dk[K];
+    int ik[K];
+    // ---- pass 1: the coarse level itself
+#pragma unroll
+    for (int t = 0; t < K; ++t) { dk[t] = INFINITY; ik[t] = 0x7fffffff; }
+#pragma unroll 4
+    for (int c = 0; c < nc; ++c) {
+        const float d = dist2_rn(qx, qy, qz, s_cent[c]);
+        if (d < dk[K - 1]) topk_insert<K>(dk, ik, d, c);
+    }
+    const int seed = ik[0];
+    if (active) {
+        int32_t *o = out_center + q * out_stride;
+#pragma unroll
+        for (int t = 0; t < K; ++t) o[t] = (ik[t] == 0x7fffffff) ? -1 : (center_gid ? __ldg(center_gid + ik[t]) : ik[t]);
+    }
+    // ---- seed: members of the nearest centre (warp-uniform loop over the union of the lanes' seeds)
+#pragma unroll
+    for (int t = 0; t < K; ++t) { dk[t] = INFINITY; ik[t] = 0x7fffffff; }
+    {
+        unsigned todo = __ballot_sync(OCC_FULL, active);
+        while (todo) {
+            const int c = __shfl_sync(OCC_FULL, seed, __ffs(todo) - 1);
+            const bool need = active && seed == c;
+            const int2 rg = s_rng[c];
+            for (int i = rg.x; i < rg.x + rg.y; ++i) {
+                const float4 p = s_fine[i];
+                const float d = dist2_rn(qx, qy, qz, p);
+                const int row = __float_as_int(p.w);
+                if (need && (d < dk[K - 1] || (d == dk[K - 1] && row < ik[K - 1]))) topk_insert_lex<K>(dk, ik, d, row);
+            }
+            todo &= ~__ballot_sync(OCC_FULL, need);
+        }
+    }
+    // ---- pass 2: every other cluster that can still contain one of the k nearest
+#pragma unroll 2
+    for (int c = 0; c < nc; ++c) {
+        const float4 cc = s_cent[c];
+        const float lb = sqrtf(dist2_rn(qx, qy, qz, cc)) - cc.w;
+        const bool need = active && c != seed && !(lb > sqrtf(dk[K - 1]) * 1.00001f + 1e-6f);
+        if (!__any_sync(OCC_FULL, need)) continue;
+        const int2 rg = s_rng[c];
+        for (int i = rg.x; i < rg.x + rg.y; ++i) {
+            const float4 p = s_fine[i];
+            const float d = dist2_rn(qx, qy, qz, p);
+            const int row = __float_as_int(p.w);
+            if (need && (d < dk[K - 1] || (d == dk[K - 1] && row < ik[K - 1]))) topk_insert_lex<K>(dk, ik, d, row);
+        }
+    }
+    if (active) {
+        int32_t *o = out_fine + q * out_stride;
+#pragma unroll
+        for (int t = 0; t < K; ++t) o[t] = (ik[t] == 0x7fffffff) ? -1 : (fine_gid ? __ldg(fine_gid + ik[t]) : ik[t]);
+    }
+}
+
 int launch_knn(const float *queries, int m, const float *supports4, const int32_t *gid, const int32_t *lb, int n_levels,
                int k, const uint8_t *query_sel, int32_t *out, cudaStream_t st) {
     int b[5] = {0, 0, 0, 0, 0};
@@ -189,6 +304,29 @@ extern "C" int occnerf_sample_geometry(const float *xyz, const int32_t *knn_idx,
     if (m <= 0) return OCCNERF_OK;
     sample_geometry_kernel<<<occ_div_up(m, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         xyz, knn_idx, knn_stride, point_base, point_norms, bound, m, enc_in, dist, dist_stride);
+    OCC_LAUNCH_CHECK();
+    return OCCNERF_OK;
+}
+
+extern "C" int occnerf_knn_hier(const float *queries, int m, int group_stride, const float *fine4, const float *centers4,
+                                const int32_t *cluster_ranges, int nf, int nc, const int32_t *fine_gid,
+                                const int32_t *center_gid, int k, int32_t *out_fine, int32_t *out_center, int out_stride,
+                                occnerf_stream_t stream) {
+    if (m <= 0) return OCCNERF_OK;
+    OCC_CHECK_ARG(queries && fine4 && centers4 && cluster_ranges && out_fine && out_center, "knn_hier: null pointer");
+    OCC_CHECK_ARG(k == 10, "knn_hier: k=%d (supported: 10)", k);
+    OCC_CHECK_ARG(group_stride >= 1 && nf >= 1 && nc >= 1 && out_stride >= k, "knn_hier: bad sizes");
+    OCC_CHECK_ARG((((uintptr_t)fine4 | (uintptr_t)centers4) & 15) == 0 && ((uintptr_t)cluster_ranges & 7) == 0,
+                  "knn_hier: fine4/centers4 must be 16-byte and cluster_ranges 8-byte aligned");
+    const size_t smem = (size_t)(nf + nc) * 16 + (size_t)nc * 8;
+    OCC_CHECK_ARG(smem <= 220 * 1024, "knn_hier: %d + %d support points do not fit in shared memory", nf, nc);
+    OCC_CUDA(cudaFuncSetAttribute(knn_hier_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long rays = (m + group_stride - 1) / group_stride;
+    const long warps = ((rays + 31) / 32) * group_stride;
+    const unsigned grid = occ_div_up(warps * 32, kHierThreads);
+    knn_hier_kernel<10><<<grid, kHierThreads, smem, (cudaStream_t)stream>>>(
+        queries, m, group_stride, (const float4 *)fine4, (const float4 *)centers4, (const int2 *)cluster_ranges, nf, nc,
+        fine_gid, center_gid, out_fine, out_center, out_stride);
     OCC_LAUNCH_CHECK();
     return OCCNERF_OK;
 }

@@ -1,25 +1,24 @@
-// K3: the canonical density/colour MLP as ONE fused tcgen05/TMEM kernel (forward).
+// K3: the canonical density/colour MLP as fused tcgen05/TMEM kernels: forward chain and data-gradient chain.
 //
-// Replaces the ten nn.Linear (+ReLU) launches of CanonicalMLP.forward
+// Replaces the ten nn.Linear (+ReLU) launches of CanonicalMLP.forward and their autograd backward
 // (core/nets/occnerf/canonical_mlps/occnerf_mlp.py:183-199):
 //     geo  : [agg35,var1,h32] (68) -> 256 -> 256 -> 256 -> 256 -> 65 (sigma + 64 features)
 //     rgb  : [geo64,agg35,h32] (131) -> 256 -> 256 -> 256 -> 256 -> 3
-// A CTA owns a tile of 128 samples.  The activation tile never leaves the SM: it lives in shared memory as a
-// bf16 UMMA A-operand (K-major, no swizzle, core-matrix-major so that the epilogue's 16-byte stores are
-// conflict free), the accumulator lives in TMEM (128 lanes x 256 fp32 columns), and the epilogue
-// (tcgen05.ld -> +bias -> ReLU -> bf16 split -> st.shared) writes the next layer's A operand in place.
-// Weights are pre-packed once per step (occnerf_mlp_pack_weights) into exactly the shared-memory image the
-// tensor core wants and streamed from L2 through a 3-stage ring with cp.async.bulk + mbarrier (TMA bulk copies;
-// no tensor map needed because the image is already tiled).
+// A CTA owns a tile of 128 samples and walks a CHAIN of 10 GEMMs; the activation tile never leaves the SM:
+//  * A operand: bf16 in shared memory, K-major, SWIZZLE_NONE, core-matrix-major (each epilogue thread writes one
+//    16-byte chunk per 8 columns, conflict free), rewritten in place by the epilogue of the previous GEMM;
+//  * accumulators: two 256-column fp32 buffers in TMEM (ping-pong by chain position);
+//  * weights: pre-packed once per step (occnerf_mlp_pack_weights) into exactly the shared-memory image the tensor core
+//    wants and streamed from L2 through a 3 x 32 KB ring with cp.async.bulk + mbarrier complete_tx (UBLKCP);
+//  * fine-grained hand-off: the epilogue publishes the next A operand in 32-column groups (a_ready[g] mbarriers),
+//    so the MMAs of GEMM l+1 run while the epilogue of GEMM l is still draining TMEM -- tensor pipe and epilogue
+//    overlap inside one tile without a second activation buffer.
 //
-// Precision: n_pass = 1 is plain bf16 x bf16 -> fp32.  n_pass = 3 is the split-bf16 scheme
-//   x = hi + lo (both bf16),  x.w ~= hi.whi + hi.wlo + lo.whi   (fp32 accumulate in TMEM)
-// i.e. three MMAs per K-step on the same accumulator, ~2^-16 relative error per product -- fp32-grade results
-// (rgb/alpha/depth within 1e-5 of the fp32 reference on the golden cases) at 1.5x the cost of a TF32 pass.
+// Precision: n_pass = 1 is bf16 x bf16 -> fp32.  n_pass = 3 is split-bf16, x = hi + lo (both bf16),
+//   x.w ~= hi.whi + hi.wlo + lo.whi (three MMAs per K-step on one fp32 accumulator, ~2^-16 relative error per product).
 //
-// Warp roles (192 threads): warps 0-3 = epilogue (each owns 32 TMEM lanes = 32 samples), warp 4 lane 0 = weight
-// producer, warp 5 lane 0 = MMA issuer.  Pipelines: w_full/w_empty (producer <-> MMA), a_full (epilogue -> MMA),
-// acc_full (MMA -> epilogue, via tcgen05.commit).
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = 32 samples each), warp 4 lane 0 weight producer,
+// warp 5 lane 0 MMA issuer.  Every mbarrier wait has a spin limit that traps instead of hanging the GPU.
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -31,29 +30,33 @@ constexpr int kStages = 3;
 constexpr int kStageBytes = 32768;
 constexpr int kLayers = 10;
 constexpr int kAPartBytes = 65536;          // 128 rows x 256 K x bf16
-constexpr uint32_t kSpinLimit = 1u << 27;   // a wedged pipeline traps instead of hanging the GPU
+constexpr int kGroups = 8;                  // 32-column groups of the A operand
+constexpr uint32_t kSpinLimit = 1u << 27;
 
-// padded GEMM shapes of the chain; K multiple of 16, N multiple of 16
-__host__ __device__ constexpr int layer_K(int l) { return l == 0 ? 80 : (l == 5 ? 144 : 256); }
-__host__ __device__ constexpr int layer_N(int l) { return l == 4 ? 80 : (l == 9 ? 16 : 256); }
-__host__ __device__ constexpr int chunk_K(int n_pass) { return n_pass == 1 ? 64 : 32; }
+// padded GEMM shapes (K = contraction, N = output width; both multiples of 16)
+// forward chain : pts0, pts1-3, geo, rgb0, rgb1-3, out
+// backward chain: out^T, rgb3..1^T, rgb0^T, geo^T, pts3..1^T, pts0^T   (position d uses forward layer 9-d)
+__host__ __device__ inline int fwd_K(int l) { return l == 0 ? 80 : (l == 5 ? 144 : 256); }
+__host__ __device__ inline int fwd_N(int l) { return l == 4 ? 80 : (l == 9 ? 16 : 256); }
+__host__ __device__ inline int chain_K(int chain, int l) { return chain == 0 ? fwd_K(l) : fwd_N(9 - l); }
+__host__ __device__ inline int chain_N(int chain, int l) { return chain == 0 ? fwd_N(l) : fwd_K(9 - l); }
+__host__ __device__ inline int chunk_K(int n_pass) { return n_pass == 1 ? 64 : 32; }
+__host__ __device__ inline int parts(int n_pass) { return n_pass == 1 ? 1 : 2; }
 
 struct PackedLayout {
-    long w_off[kLayers];     // byte offset of layer l's weight image
-    long bias_off;           // byte offset of the padded biases [10][256] fp32
+    long w_off[kLayers];
+    long bias_off;
     long total;
 };
 
-__host__ __device__ inline int n_chunks(int l, int n_pass) { return (layer_K(l) + chunk_K(n_pass) - 1) / chunk_K(n_pass); }
-__host__ __device__ inline int part_bytes(int l, int n_pass) { return layer_N(l) * chunk_K(n_pass) * 2; }   // full-chunk size of one part
-__host__ __device__ inline int parts(int n_pass) { return n_pass == 1 ? 1 : 2; }
-
-inline PackedLayout packed_layout(int n_pass) {
+inline PackedLayout packed_layout(int n_pass, int chain) {
     PackedLayout p;
     long off = 0;
+    const int KC = chunk_K(n_pass);
     for (int l = 0; l < kLayers; ++l) {
         p.w_off[l] = off;
-        off += (long)n_chunks(l, n_pass) * parts(n_pass) * part_bytes(l, n_pass);
+        const int K = chain_K(chain, l), N = chain_N(chain, l);
+        off += (long)((K + KC - 1) / KC) * parts(n_pass) * N * KC * 2;
     }
     p.bias_off = off;
     off += kLayers * 256 * 4;
@@ -61,11 +64,9 @@ inline PackedLayout packed_layout(int n_pass) {
     return p;
 }
 
-struct DevLayout { long w_off[kLayers]; long bias_off; };
-
 // ------------------------------------------------------------------------------------------ weight packing
-// source element of the padded GEMM of layer l: W_l[n][k] with the row/column re-ordering described in mlp.py
-__device__ __forceinline__ float src_weight(const occnerf_mlp_params &P, int l, int n, int k) {
+// element [n][k] of the padded FORWARD GEMM of layer l, with the row/column re-ordering described in mlp.py
+__device__ __forceinline__ float fwd_weight(const occnerf_mlp_params &P, int l, int n, int k) {
     if (l == 0) return (k < 68) ? P.w[0][n * 68 + k] : 0.f;                                   // pts0: [agg35,var,h32]
     if (l == 4) {                                                                              // geo: features first, sigma at 64
         if (n < 64) return P.w[4][(n + 1) * 256 + k];
@@ -80,37 +81,38 @@ __device__ __forceinline__ float src_weight(const occnerf_mlp_params &P, int l, 
     if (l == 9) return (n < 3) ? P.w[9][n * 256 + k] : 0.f;
     return P.w[l][n * 256 + k];
 }
-__device__ __forceinline__ float src_bias(const occnerf_mlp_params &P, int l, int n) {
+__device__ __forceinline__ float fwd_bias(const occnerf_mlp_params &P, int l, int n) {
     if (l == 4) return n < 64 ? P.b[4][n + 1] : (n == 64 ? P.b[4][0] : 0.f);
     if (l == 9) return n < 3 ? P.b[9][n] : 0.f;
     return P.b[l][n];
 }
 
-__global__ void pack_weights_kernel(occnerf_mlp_params P, DevLayout L, int n_pass, unsigned char *out) {
+struct DevLayout { long w_off[kLayers]; long bias_off; };
+
+__global__ void pack_weights_kernel(occnerf_mlp_params P, DevLayout L, int n_pass, int chain, unsigned char *out) {
     const int l = blockIdx.y;
-    const int K = layer_K(l), N = layer_N(l), KC = chunk_K(n_pass), np = parts(n_pass);
+    const int K = chain_K(chain, l), N = chain_N(chain, l), KC = chunk_K(n_pass), np = parts(n_pass);
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < (long)N * K) {
         const int n = (int)(idx / K), k = (int)(idx % K);
-        const float w = src_weight(P, l, n, k);
+        const float w = chain == 0 ? fwd_weight(P, l, n, k) : fwd_weight(P, 9 - l, k, n);     // backward chain: W^T
         const __nv_bfloat16 hi = __float2bfloat16_rn(w);
         const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
         const int chunk = k / KC, kk = k % KC;
-        const long pb = part_bytes(l, n_pass);
+        const long pb = (long)N * KC * 2;
         const long base = L.w_off[l] + (long)chunk * np * pb;
         const long inner = ((long)(kk / 8) * (N / 8) + n / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2;
         *reinterpret_cast<__nv_bfloat16 *>(out + base + inner) = hi;
         if (np == 2) *reinterpret_cast<__nv_bfloat16 *>(out + base + pb + inner) = lo;
     }
-    if (blockIdx.x == 0 && threadIdx.x < 256) {
+    if (chain == 0 && blockIdx.x == 0 && threadIdx.x < 256) {
         float *b = reinterpret_cast<float *>(out + L.bias_off) + l * 256;
-        b[threadIdx.x] = threadIdx.x < N ? src_bias(P, l, threadIdx.x) : 0.f;
+        b[threadIdx.x] = threadIdx.x < N ? fwd_bias(P, l, threadIdx.x) : 0.f;
     }
 }
 
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -144,7 +146,7 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
     asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// K-major, no-swizzle shared-memory operand descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
+// K-major, no-swizzle shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout, version 1 = Blackwell)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
@@ -153,7 +155,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 __device__ __forceinline__ uint32_t instr_desc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
         "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -162,8 +164,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -191,11 +193,19 @@ __device__ __forceinline__ void store_a8(unsigned char *a_base, int row, int k8,
     *reinterpret_cast<uint4 *>(a_base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     if (NPASS == 3) *reinterpret_cast<uint4 *>(a_base + kAPartBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
+__device__ __forceinline__ uint4 pack_bf16x8(const float (&v)[8]) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        pk[i] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    return make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
 
-// the (agg35, var, h32) part of a sample's input row -> A columns [col0, col0+68), zero padded to col0+80
+// the (agg35, var, h32) part of a sample's input row -> A columns [8*k8_0, 8*k8_0 + 80), zero padded beyond 68
 template <int NPASS>
 __device__ __forceinline__ void stage_x0(unsigned char *a_base, int row, const float *__restrict__ xrow, bool valid, int k8_0) {
-    // 68 floats = 17 float4 = 8.5 groups of 8; write 10 groups (80 columns), zero beyond 68
 #pragma unroll
     for (int g = 0; g < 10; ++g) {
         float v[8];
@@ -210,40 +220,349 @@ __device__ __forceinline__ void stage_x0(unsigned char *a_base, int row, const f
     }
 }
 
-struct FwdArgs {
-    float *XB;              // [m,132]: cols 64..131 in, cols 0..63 out (geo features) when save != 0
+struct ChainArgs {
     int m;
+    int chain;                       // 0 forward, 1 backward
     const unsigned char *packed;
-    DevLayout L;
-    float *raw;             // [m, ldr]: cols 0..2 rgb_pre, col 3 sigma_pre
+    long w_off[kLayers];
+    long bias_off;
+    // forward
+    float *XB;                       // [m,132]: cols 64..131 in; cols 0..63 out (geo features) when act_dtype != 0
+    float *raw;                      // [m, ldr]: cols 0..2 rgb_pre, col 3 sigma_pre
     int ldr;
-    void *act_save;         // [8][m][256] post-ReLU activations of the 8 hidden layers (fp32 or bf16) or NULL
-    int act_dtype;          // 0 none, 1 fp32, 2 bf16
+    void *act_save;                  // [8][m][256] post-ReLU activations (fp32 / bf16) or NULL
+    int act_dtype;                   // 0 none, 1 fp32, 2 bf16
+    // backward
+    const float *g_raw;              // [m,5]
+    const __nv_bfloat16 *act;        // [8][m][256] bf16 (saved by the forward kernel)
+    float *gXB;                      // [m,132]: cols 64..131 written (d agg, d var, d h; both trunks summed)
+    __nv_bfloat16 *g_save;           // [9][m][256] bf16: gradients w.r.t. the pre-activations, for the weight gradients
 };
 
+struct Smem {
+    unsigned char *A, *W;
+    uint32_t bar_w_full, bar_w_empty, bar_a_ready, bar_acc_full;
+};
+
+// ---- weight producer: streams every K-chunk of every GEMM of every tile through the ring, running ahead freely
 template <int NPASS>
-__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const FwdArgs args) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);
-    unsigned char *sA = smem;
-    unsigned char *sW = smem + kABytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kABytes + kStages * kStageBytes);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
-    const uint32_t bar_w_full = smem_u32(bars), bar_w_empty = smem_u32(bars + kStages);
-    const uint32_t bar_a_full = smem_u32(bars + 2 * kStages), bar_acc_full = smem_u32(bars + 2 * kStages + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = (args.m + kTileM - 1) / kTileM;
+__device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem &sm, int num_tiles) {
     constexpr int KC = (NPASS == 1) ? 64 : 32;
     constexpr int NP = (NPASS == 1) ? 1 : 2;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int l = 0; l < kLayers; ++l) {
+            const int K = chain_K(args.chain, l), N = chain_N(args.chain, l);
+            const int nch = (K + KC - 1) / KC;
+            const uint32_t pb = (uint32_t)N * KC * 2;
+            const unsigned char *src = args.packed + args.w_off[l];
+            for (int c = 0; c < nch; ++c, ++it) {
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                mbar_wait(sm.bar_w_empty + 8 * s, ph ^ 1);
+                const int kc = min(KC, K - c * KC);
+                const uint32_t bytes = (uint32_t)N * kc * 2;       // per part; the k8-outer image is contiguous
+                mbar_arrive_expect_tx(sm.bar_w_full + 8 * s, bytes * NP);
+                const uint32_t dst = smem_u32(sm.W + s * kStageBytes);
+                for (int p = 0; p < NP; ++p)
+                    bulk_g2s(dst + p * (kStageBytes / NP), src + ((long)c * NP + p) * pb, bytes, sm.bar_w_full + 8 * s);
+            }
+        }
+    }
+}
+
+// ---- MMA issuer: GEMM l accumulates into TMEM buffer (l & 1); it consumes the A operand group by group as the
+//      epilogue of GEMM l-1 publishes it
+template <int NPASS>
+__device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base) {
+    constexpr int KC = (NPASS == 1) ? 64 : 32;
+    uint32_t it = 0, a_phase = 0;      // a_phase: one parity bit per A group
+    const uint32_t a_base = smem_u32(sm.A);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int l = 0; l < kLayers; ++l) {
+            const int K = chain_K(args.chain, l), N = chain_N(args.chain, l);
+            const int nch = (K + KC - 1) / KC;
+            const uint32_t idesc = instr_desc(N);
+            const uint32_t b_lbo = (uint32_t)(N / 8) * 128;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(l & 1) * 256;
+            uint32_t first = 1;
+            for (int c = 0; c < nch; ++c, ++it) {
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                mbar_wait(sm.bar_w_full + 8 * s, ph);
+                const int kc = min(KC, K - c * KC);
+                const uint32_t wbase = smem_u32(sm.W + s * kStageBytes);
+                for (int k16 = 0; k16 < kc / 16; ++k16) {
+                    const int t = c * (KC / 16) + k16;             // global K-step of this GEMM
+                    if ((t & 1) == 0) {                            // first step of a 32-column group: wait for the epilogue
+                        const int g = t >> 1;
+                        mbar_wait(sm.bar_a_ready + 8 * g, (a_phase >> g) & 1);
+                        a_phase ^= 1u << g;
+                    }
+                    tc_fence_after();
+                    const uint32_t a_hi = a_base + (uint32_t)t * 4096;
+                    const uint32_t b_hi = wbase + (uint32_t)k16 * 2 * b_lbo;
+                    const uint64_t da_hi = smem_desc(a_hi, 2048, 128), db_hi = smem_desc(b_hi, b_lbo, 128);
+                    tc_mma(d_tmem, da_hi, db_hi, idesc, first ? 0u : 1u);
+                    first = 0;
+                    if (NPASS == 3) {
+                        const uint64_t da_lo = smem_desc(a_hi + kAPartBytes, 2048, 128);
+                        const uint64_t db_lo = smem_desc(b_hi + kStageBytes / 2, b_lbo, 128);
+                        tc_mma(d_tmem, da_hi, db_lo, idesc, 1u);
+                        tc_mma(d_tmem, da_lo, db_hi, idesc, 1u);
+                    }
+                }
+                tc_commit(sm.bar_w_empty + 8 * s);       // frees the ring slot when these MMAs have read it
+            }
+            tc_commit(sm.bar_acc_full);                  // accumulator of GEMM l complete
+        }
+    }
+}
+
+// publish A groups [g0, g1) to the MMA issuer
+__device__ __forceinline__ void publish(const Smem &sm, int g0, int g1) {
+    tc_fence_before();
+    fence_proxy_async();
+    for (int g = g0; g < g1; ++g) mbar_arrive(sm.bar_a_ready + 8 * g);
+}
+
+// ---- forward epilogue
+template <int NPASS>
+__device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base, int warp) {
+    const int row = threadIdx.x;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float *bias_all = reinterpret_cast<const float *>(args.packed + args.bias_off);
+    uint32_t acc_cnt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long grow = (long)tile * kTileM + row;
+        const bool valid = grow < args.m;
+        const float *xrow = args.XB + grow * 132 + 64;
+        stage_x0<NPASS>(sm.A, row, xrow, valid, 0);                 // GEMM 0 operand: A[:, 0:80)
+        publish(sm, 0, 3);
+        for (int l = 0; l < kLayers; ++l, ++acc_cnt) {
+            mbar_wait(sm.bar_acc_full, acc_cnt & 1);
+            tc_fence_after();
+            const uint32_t t_acc = t_lane + (uint32_t)(l & 1) * 256;
+            const float *bias = bias_all + l * 256;
+            if (l == 9) {
+                uint32_t r[16];
+                tmem_ld16(t_acc, r);
+                if (valid) {
+                    float *o = args.raw + grow * args.ldr;
+                    o[0] = __uint_as_float(r[0]) + __ldg(bias + 0);
+                    o[1] = __uint_as_float(r[1]) + __ldg(bias + 1);
+                    o[2] = __uint_as_float(r[2]) + __ldg(bias + 2);
+                }
+                tc_fence_before();
+            } else if (l == 4) {
+                // geometry head: columns 0..63 = features (-> A[:, 0:64) of the colour trunk), column 64 = sigma
+#pragma unroll 1
+                for (int cg = 0; cg < 2; ++cg) {
+                    uint32_t r[32];
+                    tmem_ld32_issue(t_acc + cg * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]) + __ldg(bias + cg * 32 + j * 8 + i);
+                        store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
+                        if (valid && args.act_dtype != 0) {
+                            float4 *dst = reinterpret_cast<float4 *>(args.XB + grow * 132 + cg * 32 + j * 8);
+                            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        }
+                    }
+                    publish(sm, cg, cg + 1);
+                }
+                {
+                    uint32_t r[16];
+                    tmem_ld16(t_acc + 64, r);
+                    if (valid) args.raw[grow * args.ldr + 3] = __uint_as_float(r[0]) + __ldg(bias + 64);
+                }
+                stage_x0<NPASS>(sm.A, row, xrow, valid, 8);         // A[:, 64:144) = (agg35, var, h32, 0 pad)
+                publish(sm, 2, 5);
+            } else {
+                // hidden layer: +bias, ReLU -> next A operand (and the saved activation for the backward pass)
+                const int slot = l < 4 ? l : l - 1;                  // 0..3 = pts1..4, 4..7 = rgb1..4
+#pragma unroll 1
+                for (int cg = 0; cg < 8; ++cg) {
+                    uint32_t r[32];
+                    tmem_ld32_issue(t_acc + cg * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            v[i] = fmaxf(__uint_as_float(r[j * 8 + i]) + __ldg(bias + cg * 32 + j * 8 + i), 0.f);
+                        store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
+                        const long e = ((long)slot * args.m + grow) * 256 + cg * 32 + j * 8;
+                        if (valid && args.act_dtype == 1) {
+                            float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(args.act_save) + e);
+                            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        } else if (valid && args.act_dtype == 2) {
+                            *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(args.act_save) + e) = pack_bf16x8(v);
+                        }
+                    }
+                    publish(sm, cg, cg + 1);
+                }
+            }
+        }
+    }
+}
+
+// ---- backward (data-gradient) epilogue.  Chain position d: 0 out^T, 1..3 rgb3..1^T, 4 rgb0^T, 5 geo^T, 6..8 pts3..1^T, 9 pts0^T
+template <int NPASS>
+__device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base, int warp) {
+    const int row = threadIdx.x;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t acc_cnt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long grow = (long)tile * kTileM + row;
+        const bool valid = grow < args.m;
+        float g_sigma = 0.f;
+        {   // GEMM 0 operand: d raw[:, 0:3] in A[:, 0:16)
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (valid) {
+                const float *gr = args.g_raw + grow * 5;
+                v[0] = __ldg(gr + 0); v[1] = __ldg(gr + 1); v[2] = __ldg(gr + 2);
+                g_sigma = __ldg(gr + 3);
+            }
+            store_a8<NPASS>(sm.A, row, 0, v);
+            store_a8<NPASS>(sm.A, row, 1, z);
+            publish(sm, 0, 1);
+        }
+        for (int d = 0; d < kLayers; ++d, ++acc_cnt) {
+            mbar_wait(sm.bar_acc_full, acc_cnt & 1);
+            tc_fence_after();
+            const uint32_t t_acc = t_lane + (uint32_t)(d & 1) * 256;
+            if (d == 9) {
+                // pts0^T: 68 (+12 pad) columns, accumulated onto the colour trunk's share of d(agg,var,h)
+#pragma unroll 1
+                for (int cg = 0; cg < 3; ++cg) {
+                    uint32_t r[32];
+                    if (cg < 2) { tmem_ld32_issue(t_acc + cg * 32, r); tmem_ld_wait(); }
+                    else {
+                        uint32_t q[16];
+                        tmem_ld16(t_acc + 64, q);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = q[i];
+                    }
+                    if (valid) {
+                        float4 *dst = reinterpret_cast<float4 *>(args.gXB + grow * 132 + 64 + cg * 32);
+                        const int n4 = cg < 2 ? 8 : 1;               // 64 + 4 = 68 columns
+                        for (int i = 0; i < n4; ++i) {
+                            float4 o = dst[i];
+                            o.x += __uint_as_float(r[4 * i + 0]); o.y += __uint_as_float(r[4 * i + 1]);
+                            o.z += __uint_as_float(r[4 * i + 2]); o.w += __uint_as_float(r[4 * i + 3]);
+                            dst[i] = o;
+                        }
+                    }
+                }
+                tc_fence_before();
+            } else if (d == 4) {
+                // rgb0^T: columns 0..63 = d geo features (-> operand of geo^T together with d sigma), 64..131 = d(agg,var,h)
+#pragma unroll 1
+                for (int cg = 0; cg < 2; ++cg) {
+                    uint32_t r[32];
+                    tmem_ld32_issue(t_acc + cg * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
+                        store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
+                        if (valid) *reinterpret_cast<uint4 *>(args.g_save + ((long)4 * args.m + grow) * 256 + cg * 32 + j * 8) = pack_bf16x8(v);
+                    }
+                    publish(sm, cg, cg + 1);
+                }
+                {   // A[:, 64:80) = (d sigma, 0...)
+                    float v[8] = {g_sigma, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    store_a8<NPASS>(sm.A, row, 8, v);
+                    store_a8<NPASS>(sm.A, row, 9, z);
+                    if (valid) {
+                        __nv_bfloat16 *gs = args.g_save + ((long)4 * args.m + grow) * 256 + 64;
+                        *reinterpret_cast<uint4 *>(gs) = pack_bf16x8(v);
+                        *reinterpret_cast<uint4 *>(gs + 8) = pack_bf16x8(z);
+                    }
+                }
+#pragma unroll 1
+                for (int cg = 2; cg < 5; ++cg) {                     // columns 64..143 of the accumulator -> gXB[:, 64:132)
+                    uint32_t r[32];
+                    if (cg < 4) { tmem_ld32_issue(t_acc + cg * 32, r); tmem_ld_wait(); }
+                    else {
+                        uint32_t q[16];
+                        tmem_ld16(t_acc + 128, q);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = q[i];
+                    }
+                    if (valid) {
+                        float4 *dst = reinterpret_cast<float4 *>(args.gXB + grow * 132 + 64 + (cg - 2) * 32);
+                        const int n4 = cg < 4 ? 8 : 1;
+                        for (int i = 0; i < n4; ++i)
+                            dst[i] = make_float4(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1]),
+                                                 __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                    }
+                }
+                publish(sm, 2, 3);
+            } else {
+                // through a ReLU: G = acc * (saved activation > 0) -> next A operand, and saved for the weight gradient
+                const int slot = d < 4 ? 7 - d : 8 - d;              // d0..3 -> R4..R1 (slots 7..4); d5..8 -> H4..H1 (slots 3..0)
+                const int gslot = d;                                 // g_save: 0..3 rgb3..rgb0, 4 geo, 5..8 pts3..pts0
+                const __nv_bfloat16 *arow = args.act + ((long)slot * args.m + (valid ? grow : 0)) * 256;
+#pragma unroll 1
+                for (int cg = 0; cg < 8; ++cg) {
+                    uint32_t r[32];
+                    tmem_ld32_issue(t_acc + cg * 32, r);
+                    uint4 mk[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mk[j] = __ldg(reinterpret_cast<const uint4 *>(arow + cg * 32 + j * 8));
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t w[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            // bf16 > 0  <=>  sign bit clear and not zero (activations are post-ReLU, never negative)
+                            const uint32_t half = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
+                            v[i] = (valid && (half & 0x7FFFu) != 0u && (half & 0x8000u) == 0u) ? __uint_as_float(r[j * 8 + i]) : 0.f;
+                        }
+                        store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
+                        if (valid) *reinterpret_cast<uint4 *>(args.g_save + ((long)gslot * args.m + grow) * 256 + cg * 32 + j * 8) = pack_bf16x8(v);
+                    }
+                    publish(sm, cg, cg + 1);
+                }
+            }
+        }
+    }
+}
+
+template <int NPASS, int CHAIN>
+__global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_constant__ ChainArgs args) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kABytes + kStages * kStageBytes);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
+    Smem sm;
+    sm.A = smem;
+    sm.W = smem + kABytes;
+    sm.bar_w_full = smem_u32(bars);
+    sm.bar_w_empty = smem_u32(bars + kStages);
+    sm.bar_a_ready = smem_u32(bars + 2 * kStages);
+    sm.bar_acc_full = smem_u32(bars + 2 * kStages + kGroups);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = (args.m + kTileM - 1) / kTileM;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(bar_w_full + 8 * s, 1); mbar_init(bar_w_empty + 8 * s, 1); }
-        mbar_init(bar_a_full, kTileM);
-        mbar_init(bar_acc_full, 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(sm.bar_w_full + 8 * s, 1); mbar_init(sm.bar_w_empty + 8 * s, 1); }
+        for (int g = 0; g < kGroups; ++g) mbar_init(sm.bar_a_ready + 8 * g, kTileM);
+        mbar_init(sm.bar_acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -252,177 +571,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const FwdArgs a
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 4) {
-        // ================================= weight producer =================================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int l = 0; l < kLayers; ++l) {
-                    const int K = layer_K(l), N = layer_N(l);
-                    const int nch = (K + KC - 1) / KC;
-                    const uint32_t pb = (uint32_t)N * KC * 2;
-                    const unsigned char *src = args.packed + args.L.w_off[l];
-                    for (int c = 0; c < nch; ++c, ++it) {
-                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                        mbar_wait(bar_w_empty + 8 * s, ph ^ 1);
-                        const int kc = min(KC, K - c * KC);
-                        const uint32_t bytes = (uint32_t)N * kc * 2;          // per part; the k8-outer image is contiguous
-                        mbar_arrive_expect_tx(bar_w_full + 8 * s, bytes * NP);
-                        const uint32_t dst = smem_u32(sW + s * kStageBytes);
-                        for (int p = 0; p < NP; ++p)
-                            bulk_g2s(dst + p * (kStageBytes / NP), src + ((long)c * NP + p) * pb, bytes, bar_w_full + 8 * s);
-                    }
-                }
-            }
-        }
+        if (lane == 0) producer_loop<NPASS>(args, sm, num_tiles);
     } else if (warp == 5) {
-        // ================================= MMA issuer =================================
-        if (lane == 0) {
-            uint32_t it = 0, a_cnt = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int l = 0; l < kLayers; ++l, ++a_cnt) {
-                    const int K = layer_K(l), N = layer_N(l);
-                    const int nch = (K + KC - 1) / KC;
-                    const uint32_t idesc = instr_desc(N);
-                    const uint32_t b_lbo = (uint32_t)(N / 8) * 128;
-                    mbar_wait(bar_a_full, a_cnt & 1);
-                    tc_fence_after();
-                    uint32_t first = 1;
-                    for (int c = 0; c < nch; ++c, ++it) {
-                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                        mbar_wait(bar_w_full + 8 * s, ph);
-                        tc_fence_after();
-                        const int kc = min(KC, K - c * KC);
-                        const uint32_t wbase = smem_u32(sW + s * kStageBytes);
-                        for (int k16 = 0; k16 < kc / 16; ++k16) {
-                            const uint32_t a_hi = smem_u32(sA) + (uint32_t)(c * (KC / 16) + k16) * 4096;
-                            const uint32_t b_hi = wbase + (uint32_t)k16 * 2 * b_lbo;
-                            const uint64_t da_hi = smem_desc(a_hi, 2048, 128), db_hi = smem_desc(b_hi, b_lbo, 128);
-                            tc_mma(tmem_base, da_hi, db_hi, idesc, first ? 0u : 1u);
-                            first = 0;
-                            if (NPASS == 3) {
-                                const uint64_t da_lo = smem_desc(a_hi + kAPartBytes, 2048, 128);
-                                const uint64_t db_lo = smem_desc(b_hi + kStageBytes / 2, b_lbo, 128);
-                                tc_mma(tmem_base, da_hi, db_lo, idesc, 1u);
-                                tc_mma(tmem_base, da_lo, db_hi, idesc, 1u);
-                            }
-                        }
-                        tc_commit(bar_w_empty + 8 * s);       // frees the ring slot when these MMAs have read it
-                    }
-                    tc_commit(bar_acc_full);                  // accumulator of layer l complete
-                }
-            }
-        }
+        if (lane == 0) mma_loop<NPASS>(args, sm, num_tiles, tmem_base);
     } else {
-        // ================================= epilogue warps (128 threads = 128 rows) =================================
-        const int row = threadIdx.x;                          // TMEM lane == sample row inside the tile
-        const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const float *bias_all = reinterpret_cast<const float *>(args.packed + args.L.bias_off);
-        uint32_t acc_cnt = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const long grow = (long)tile * kTileM + row;
-            const bool valid = grow < args.m;
-            const float *xrow = args.XB + grow * 132 + 64;
-            // ---- layer-0 operand: (agg35, var, h32) -> A[:, 0:80)
-            stage_x0<NPASS>(sA, row, xrow, valid, 0);
-            fence_proxy_async();
-            mbar_arrive(bar_a_full);
-            for (int l = 0; l < kLayers; ++l, ++acc_cnt) {
-                mbar_wait(bar_acc_full, acc_cnt & 1);
-                tc_fence_after();
-                const float *bias = bias_all + l * 256;
-                if (l == 9) {
-                    // ---- output layer: 3 (+13 pad) columns -> raw[:, 0:3]
-                    uint32_t r[16];
-                    tmem_ld16(t_lane, r);
-                    if (valid) {
-                        float *o = args.raw + grow * args.ldr;
-                        o[0] = __uint_as_float(r[0]) + __ldg(bias + 0);
-                        o[1] = __uint_as_float(r[1]) + __ldg(bias + 1);
-                        o[2] = __uint_as_float(r[2]) + __ldg(bias + 2);
-                    }
-                    tc_fence_before();
-                    // no a_full arrive: the next tile's layer-0 staging does it
-                } else if (l == 4) {
-                    // ---- geometry head: columns 0..63 = features (-> A[:, 0:64) of the colour trunk), column 64 = sigma
-#pragma unroll 1
-                    for (int cg = 0; cg < 2; ++cg) {
-                        uint32_t r[32];
-                        tmem_ld32(t_lane + cg * 32, r);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float v[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]) + __ldg(bias + cg * 32 + j * 8 + i);
-                            store_a8<NPASS>(sA, row, cg * 4 + j, v);
-                            if (valid && args.act_dtype != 0) {
-                                float4 *dst = reinterpret_cast<float4 *>(args.XB + grow * 132 + cg * 32 + j * 8);
-                                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                            }
-                        }
-                    }
-                    {
-                        uint32_t r[16];
-                        tmem_ld16(t_lane + 64, r);
-                        if (valid) args.raw[grow * args.ldr + 3] = __uint_as_float(r[0]) + __ldg(bias + 64);
-                    }
-                    stage_x0<NPASS>(sA, row, xrow, valid, 8);       // A[:, 64:144) = (agg35, var, h32, 0 pad)
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(bar_a_full);
-                } else {
-                    // ---- hidden layer: +bias, ReLU -> next A operand (and the saved activation for the backward pass)
-                    const int slot = l < 4 ? l : l - 1;              // 0..3 = pts1..4, 4..7 = rgb1..4
-#pragma unroll 1
-                    for (int cg = 0; cg < 8; ++cg) {
-                        uint32_t r[32];
-                        tmem_ld32(t_lane + cg * 32, r);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float v[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                v[i] = fmaxf(__uint_as_float(r[j * 8 + i]) + __ldg(bias + cg * 32 + j * 8 + i), 0.f);
-                            store_a8<NPASS>(sA, row, cg * 4 + j, v);
-                            if (valid && args.act_dtype == 1) {
-                                float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(args.act_save) +
-                                                                         ((long)slot * args.m + grow) * 256 + cg * 32 + j * 8);
-                                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                            } else if (valid && args.act_dtype == 2) {
-                                uint32_t pk[4];
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                                    pk[i] = *reinterpret_cast<const uint32_t *>(&h);
-                                }
-                                *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(args.act_save) +
-                                                           ((long)slot * args.m + grow) * 256 + cg * 32 + j * 8) =
-                                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            }
-                        }
-                    }
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(bar_a_full);
-                }
-            }
-        }
+        if (CHAIN == 0) fwd_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
+        else bwd_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
-    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
-template <int NPASS>
-int launch_fwd(const FwdArgs &a, cudaStream_t st) {
+template <int NPASS, int CHAIN>
+int launch_chain(const ChainArgs &a, cudaStream_t st) {
     constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);
     const int smem_bytes = kABytes + kStages * kStageBytes + 256;
     static bool configured = false;
     if (!configured) {
-        OCC_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        OCC_CUDA(cudaFuncSetAttribute(mlp_chain_tc_kernel<NPASS, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured = true;
     }
     int dev = 0, sms = 148;
@@ -430,28 +597,38 @@ int launch_fwd(const FwdArgs &a, cudaStream_t st) {
     OCC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int tiles = (a.m + kTileM - 1) / kTileM;
     const int grid = tiles < sms ? tiles : sms;
-    mlp_fwd_tc_kernel<NPASS><<<grid, kThreads, smem_bytes, st>>>(a);
+    mlp_chain_tc_kernel<NPASS, CHAIN><<<grid, kThreads, smem_bytes, st>>>(a);
     OCC_LAUNCH_CHECK();
     return OCCNERF_OK;
 }
 
-}  // namespace
-
-extern "C" long occnerf_mlp_packed_bytes(int n_pass) {
-    if (n_pass != 1 && n_pass != 3) return -1;
-    return packed_layout(n_pass).total;
+void fill_layout(ChainArgs &a, int n_pass, int chain, const void *packed) {
+    const PackedLayout pl = packed_layout(n_pass, chain);
+    for (int l = 0; l < kLayers; ++l) a.w_off[l] = pl.w_off[l];
+    a.bias_off = pl.bias_off;
+    a.chain = chain;
+    a.packed = (const unsigned char *)packed;
 }
 
-extern "C" int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, void *packed, occnerf_stream_t stream) {
+}  // namespace
+
+extern "C" long occnerf_mlp_packed_bytes(int n_pass, int chain) {
+    if ((n_pass != 1 && n_pass != 3) || (chain != 0 && chain != 1)) return -1;
+    return packed_layout(n_pass, chain).total;
+}
+
+extern "C" int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, void *packed,
+                                        occnerf_stream_t stream) {
     OCC_CHECK_ARG(p_host && packed, "mlp_pack_weights: null pointer");
     OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "mlp_pack_weights: n_pass=%d (supported: 1, 3)", n_pass);
+    OCC_CHECK_ARG(chain == 0 || chain == 1, "mlp_pack_weights: chain=%d (0 forward, 1 backward)", chain);
     for (int l = 0; l < kLayers; ++l) OCC_CHECK_ARG(p_host->w[l] && p_host->b[l], "mlp_pack_weights: layer %d has a null pointer", l);
-    const PackedLayout pl = packed_layout(n_pass);
+    const PackedLayout pl = packed_layout(n_pass, chain);
     DevLayout L;
     for (int l = 0; l < kLayers; ++l) L.w_off[l] = pl.w_off[l];
     L.bias_off = pl.bias_off;
     dim3 grid(occ_div_up(256 * 256, 256), kLayers);
-    pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p_host, L, n_pass, (unsigned char *)packed);
+    pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p_host, L, n_pass, chain, (unsigned char *)packed);
     OCC_LAUNCH_CHECK();
     return OCCNERF_OK;
 }
@@ -462,13 +639,26 @@ extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int 
     OCC_CHECK_ARG(XB && packed && raw, "mlp_forward_tc: null pointer");
     OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "mlp_forward_tc: n_pass=%d (supported: 1, 3)", n_pass);
     OCC_CHECK_ARG(m > 0 && ldr >= 4, "mlp_forward_tc: m=%d ldr=%d", m, ldr);
-    OCC_CHECK_ARG(act_dtype == 0 || act_save, "mlp_forward_tc: act_dtype=%d without act_save", act_dtype);
-    OCC_CHECK_ARG(((uintptr_t)XB & 15) == 0 && ((uintptr_t)packed & 15) == 0, "mlp_forward_tc: XB/packed must be 16-byte aligned");
-    const PackedLayout pl = packed_layout(n_pass);
-    FwdArgs a;
-    a.XB = XB; a.m = m; a.packed = (const unsigned char *)packed;
-    for (int l = 0; l < kLayers; ++l) a.L.w_off[l] = pl.w_off[l];
-    a.L.bias_off = pl.bias_off;
-    a.raw = raw; a.ldr = ldr; a.act_save = act_save; a.act_dtype = act_dtype;
-    return n_pass == 1 ? launch_fwd<1>(a, (cudaStream_t)stream) : launch_fwd<3>(a, (cudaStream_t)stream);
+    OCC_CHECK_ARG(act_dtype >= 0 && act_dtype <= 2 && (act_dtype == 0 || act_save), "mlp_forward_tc: act_dtype=%d / act_save mismatch", act_dtype);
+    OCC_CHECK_ARG(((uintptr_t)XB & 15) == 0 && ((uintptr_t)packed & 15) == 0 && ((uintptr_t)act_save & 15) == 0,
+                  "mlp_forward_tc: XB/packed/act_save must be 16-byte aligned");
+    ChainArgs a = {};
+    a.m = m;
+    fill_layout(a, n_pass, 0, packed);
+    a.XB = XB; a.raw = raw; a.ldr = ldr; a.act_save = act_save; a.act_dtype = act_dtype;
+    return n_pass == 1 ? launch_chain<1, 0>(a, (cudaStream_t)stream) : launch_chain<3, 0>(a, (cudaStream_t)stream);
+}
+
+extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, const void *act_bf16,
+                                       float *gXB, void *g_save, occnerf_stream_t stream) {
+    if (m == 0) return OCCNERF_OK;
+    OCC_CHECK_ARG(g_raw && packed_bwd && act_bf16 && gXB && g_save, "mlp_backward_tc: null pointer");
+    OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "mlp_backward_tc: n_pass=%d (supported: 1, 3)", n_pass);
+    OCC_CHECK_ARG(((uintptr_t)gXB & 15) == 0 && ((uintptr_t)packed_bwd & 15) == 0 && ((uintptr_t)act_bf16 & 15) == 0 &&
+                  ((uintptr_t)g_save & 15) == 0, "mlp_backward_tc: buffers must be 16-byte aligned");
+    ChainArgs a = {};
+    a.m = m;
+    fill_layout(a, n_pass, 1, packed_bwd);
+    a.g_raw = g_raw; a.act = (const __nv_bfloat16 *)act_bf16; a.gXB = gXB; a.g_save = (__nv_bfloat16 *)g_save;
+    return n_pass == 1 ? launch_chain<1, 1>(a, (cudaStream_t)stream) : launch_chain<3, 1>(a, (cudaStream_t)stream);
 }

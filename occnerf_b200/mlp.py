@@ -145,12 +145,14 @@ class MlpSimt:
         return gXB, [grads[k] for k in MlpWeights.ORDER]
 
 
-def nonrigid_offsets(xyz, cond, window, nr_w, nr_b):
+def nonrigid_offsets(xyz, cond, window, nr_w, nr_b, const_off=None, return_const=False):
     """xyz (m,3) -> xyz + MLP([cond69, hann_pe36])  (mlp_offset.py:45-62), fp32, forward only (its output feeds
     no_grad code only).  When the Hann window is fully closed and the condition code is
     zero (every training iteration before kick_in_iter, network.py:579-583) every row of the MLP input is zero,
     so the offset is one constant 3-vector evaluated on a single row."""
     m, dev = xyz.shape[0], xyz.device
+    if const_off is not None:
+        return xyz + const_off
     w = [t.detach().contiguous() for t in nr_w]
     b = [t.detach().contiguous() for t in nr_b]
     zero_in = all(v == 0.0 for v in window) and cond is None
@@ -182,7 +184,7 @@ def nonrigid_offsets(xyz, cond, window, nr_w, nr_b):
     if zero_in:
         off = torch.empty(1, 3, device=dev, dtype=f32)
         _gemm(H[cur].data_ptr(), 128, 1, w[6].data_ptr(), 1, 128, off.data_ptr(), 3, 1, 3, 128, bias=b[6].data_ptr())
-        return xyz + off
+        return off if return_const else xyz + off
     out = xyz.clone()
     _gemm(H[cur].data_ptr(), 128, 1, w[6].data_ptr(), 1, 128, out.data_ptr(), 3, m, 3, 128, bias=b[6].data_ptr(), accum=True)
     return out

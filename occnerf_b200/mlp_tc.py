@@ -1,18 +1,22 @@
 """tcgen05/TMEM engine of the canonical MLP (csrc/mlp_tc.cu) behind the same interface as mlp.MlpSimt.
 
-forward : one fused kernel per chunk (occnerf_mlp_forward_tc), weights re-packed per call as bf16 (hi[,lo]) UMMA
-          operand images (occnerf_mlp_pack_weights; 0.5 M parameters, microseconds).
-backward: for now the exact-fp32 GEMM path of mlp.MlpSimt on the activations the fused forward saved (fp32), so a
-          training step is "tensor-core forward + fp32 backward" until the fused dgrad/wgrad kernels land.
+forward : one fused kernel per chunk (occnerf_mlp_forward_tc); weights re-packed per call as bf16 (hi[,lo]) UMMA
+          operand images (occnerf_mlp_pack_weights; 0.5 M parameters, microseconds); post-ReLU activations saved as bf16.
+backward: data gradients by the fused transposed chain (occnerf_mlp_backward_tc), which also leaves the bf16
+          pre-activation gradients G_l behind; the ten weight gradients dW_l = G_l^T X_l are plain [n,m]x[m,k]
+          GEMMs over the sample axis and go to the library (cuBLAS via torch.matmul, bf16 in / fp32 accumulate),
+          bias gradients are column sums.  A hand-written MN-major tcgen05 weight-gradient kernel is round-2 work.
 """
 from __future__ import annotations
+
+import ctypes
 
 import torch
 
 from occnerf_b200 import _lib, mlp as M
 from occnerf_b200._lib import call, stream
 
-f32 = torch.float32
+f32, bf16 = torch.float32, torch.bfloat16
 
 
 class MlpTc:
@@ -20,29 +24,58 @@ class MlpTc:
         assert n_pass in (1, 3)
         self.n_pass = n_pass
         self.name = f"tc{n_pass}"
-        self._simt = M.MlpSimt()
 
-    def pack(self, W: M.MlpWeights, device):
-        nbytes = _lib.load().occnerf_mlp_packed_bytes(self.n_pass)
+    def pack(self, W: M.MlpWeights, device, chain: int):
+        nbytes = _lib.load().occnerf_mlp_packed_bytes(self.n_pass, chain)
         packed = torch.empty(nbytes, device=device, dtype=torch.uint8)
         P = _lib.MlpParams()
         ws = W.pts_w + [W.geo_w] + W.rgb_w + [W.out_w]
         bs = W.pts_b + [W.geo_b] + W.rgb_b + [W.out_b]
         for i in range(10):
             P.w[i], P.b[i] = ws[i].data_ptr(), bs[i].data_ptr()
-        import ctypes
-        call("occnerf_mlp_pack_weights", ctypes.byref(P), self.n_pass, packed.data_ptr(), stream())
+        call("occnerf_mlp_pack_weights", ctypes.byref(P), self.n_pass, chain, packed.data_ptr(), stream())
         return packed
 
     def forward(self, XB, raw, W: M.MlpWeights, save: bool):
         m, dev = XB.shape[0], XB.device
-        packed = self.pack(W, dev)
-        acts = torch.empty(8, m, 256, device=dev, dtype=f32) if save else None
+        packed = self.pack(W, dev, 0)
+        acts = torch.empty(8, m, 256, device=dev, dtype=bf16) if save else None
         call("occnerf_mlp_forward_tc", XB.data_ptr(), m, packed.data_ptr(), self.n_pass, raw.data_ptr(), raw.shape[1],
-             acts.data_ptr() if save else None, 1 if save else 0, stream(), work=M.FLOP_FWD * m)
-        if not save:
-            return None
-        return {"acts": [acts[i] for i in range(8)], "w0": M._pad_rgb0(W.rgb_w[0]), "packed": packed}
+             acts.data_ptr() if save else None, 2 if save else 0, stream(), work=M.FLOP_FWD * m)
+        return {"acts": acts} if save else None
 
     def backward(self, XB, g_raw, W: M.MlpWeights, saved):
-        return self._simt.backward(XB, g_raw, W, saved)
+        m, dev = XB.shape[0], XB.device
+        acts = saved["acts"]
+        packed = self.pack(W, dev, 1)
+        gXB = torch.empty(m, M.XB_LD, device=dev, dtype=f32)
+        g_save = torch.empty(9, m, 256, device=dev, dtype=bf16)
+        call("occnerf_mlp_backward_tc", g_raw.data_ptr(), m, packed.data_ptr(), self.n_pass, acts.data_ptr(), gXB.data_ptr(),
+             g_save.data_ptr(), stream(), work=M.FLOP_FWD * m)
+        # ---- weight gradients: library GEMMs over the sample axis
+        with _lib.region("lib:wgrad(cuBLAS bf16)+bias sums"):
+            return gXB, self._wgrad(XB, g_raw, acts, g_save)
+
+    def _wgrad(self, XB, g_raw, acts, g_save):
+        Xb = XB.to(bf16)
+        g_out = g_raw[:, :3].to(bf16)
+
+        def dw(G, X):
+            return torch.matmul(G.t(), X).float()
+
+        def db(G):
+            return G.sum(0, dtype=f32)
+
+        grads = {}
+        grads["out_w"], grads["out_b"] = dw(g_out, acts[7]), g_raw[:, :3].sum(0)
+        for i, l in enumerate((3, 2, 1)):
+            grads[f"rgb_w{l}"], grads[f"rgb_b{l}"] = dw(g_save[i], acts[3 + l]), db(g_save[i])
+        g0 = dw(g_save[3], Xb)
+        grads["rgb_w0"], grads["rgb_b0"] = torch.cat([g0[:, :99], g0[:, 100:]], 1).contiguous(), db(g_save[3])
+        Gg = g_save[4][:, :65]
+        gw, gb = dw(Gg, acts[3]), db(Gg)
+        grads["geo_w"], grads["geo_b"] = torch.cat([gw[64:65], gw[:64]], 0).contiguous(), torch.cat([gb[64:65], gb[:64]], 0)
+        for i, l in enumerate((3, 2, 1)):
+            grads[f"pts_w{l}"], grads[f"pts_b{l}"] = dw(g_save[5 + i], acts[l - 1]), db(g_save[5 + i])
+        grads["pts_w0"], grads["pts_b0"] = dw(g_save[8], Xb[:, 64:132]), db(g_save[8])
+        return [grads[k] for k in M.MlpWeights.ORDER]

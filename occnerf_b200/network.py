@@ -165,6 +165,7 @@ class RenderConfig:
     ignore_non_rigid_motions: bool = False
     bgcolor: tuple = (0.0, 0.0, 0.0)
     mlp_engine: str = "fp32"        # "fp32" (exact SIMT) | "tc3" (tcgen05 split-bf16) | "tc1" (tcgen05 bf16)
+    knn_mode: str = "hier"          # "hier" (cluster-pruned exact search) | "brute" (tiled brute force); same ids
 
 
 # ----------------------------------------------------------------------------- differentiable stages
@@ -225,8 +226,14 @@ class _QueryFn(torch.autograd.Function):
         st = net._static()
         if nr_window is not None:
             nw, nb = net.non_rigid_mlp.module.flat()
-            xyz = M.nonrigid_offsets(xyz, nr_cond, nr_window, nw, nb)
-        knn_idx = ops.knn(xyz, st["supports4"], st["level_begin"], 10, support_gid=st["support_gid"])
+            xyz = M.nonrigid_offsets(xyz, nr_cond, nr_window, nw, nb, const_off=getattr(net, "_nr_const", None))
+        if net.cfg.knn_mode == "brute":
+            knn_idx = ops.knn(xyz, st["supports4"], st["level_begin"], 10, support_gid=st["support_gid"])
+        else:
+            knn_idx = torch.empty(m, 4, 10, device=dev, dtype=i32)
+            gs = max(1, int(getattr(net, "_group_stride", 1)))
+            ops.knn_hier(xyz, gs, *st["hier0"], knn_idx, 0, 2, None, st["gid2"])
+            ops.knn_hier(xyz, gs, *st["hier1"], knn_idx, 1, 3, st["gid1"], st["gid3"])
         raw = torch.empty(m, 5, device=dev, dtype=f32)
         enc_in, _ = ops.sample_geometry(xyz, knn_idx, st["point_base"], st["point_norms"], net.bound, raw=raw)
         XB = torch.empty(m, M.XB_LD, device=dev, dtype=f32)
@@ -333,7 +340,11 @@ class Network(nn.Module):
             lb = np.cumsum([0, base.shape[0]] + [int(f.shape[0]) for f in fps]).tolist()
             self._cache = dict(device=dev, supports4=ops.to_float4(sup), support_gid=gid.contiguous(), level_begin=lb,
                                base4=ops.to_float4(base), point_base=base.contiguous().float(),
-                               point_norms=self.point_norms.contiguous().float())
+                               point_norms=self.point_norms.contiguous().float(),
+                               # cluster hierarchies for the pruned exact search: level 0 around level 2, level 1 around level 3
+                               hier0=ops.build_knn_hierarchy(base, base[fps[1]]), gid2=fps[1].to(i32).contiguous(),
+                               hier1=ops.build_knn_hierarchy(base[fps[0]], base[fps[2]]), gid1=fps[0].to(i32).contiguous(),
+                               gid3=fps[2].to(i32).contiguous())
         return self._cache
 
     def _engine(self):
@@ -345,6 +356,11 @@ class Network(nn.Module):
 
     # -- per-vertex block (network.py:263-284 + occnerf_mlp.py:171-175), once per call instead of once per chunk
     def vertex_features(self):
+        from occnerf_b200 import _lib
+        with _lib.region("lib:vertex block glue (torch, V=6890)"):
+            return self._vertex_features()
+
+    def _vertex_features(self):
         st = self._static()
         V = self.point_base.shape[0]
         pc = self.point_base + self.point_dist
@@ -366,6 +382,7 @@ class Network(nn.Module):
     def _query_mlp(self, pos_xyz, rays_d, pos_embed_fn, non_rigid_pos_embed_fn, non_rigid_mlp_input, _feats36=None,
                    _return_knn=False):
         pos_flat = pos_xyz.reshape(-1, pos_xyz.shape[-1])
+        self._group_stride = pos_xyz.shape[-2] if pos_xyz.dim() >= 3 else 1     # samples per ray (warp = 32 rays at one depth)
         feats36 = _feats36 if _feats36 is not None else self.vertex_features()[0]
         window, cond = None, None
         if not self.cfg.ignore_non_rigid_motions:
@@ -374,6 +391,12 @@ class Network(nn.Module):
             window = non_rigid_pos_embed_fn.window
             if non_rigid_mlp_input is not None and bool((non_rigid_mlp_input != 0).any()):
                 cond = non_rigid_mlp_input.reshape(1, -1).float()
+        # closed Hann window + zero condition code (all of training before kick_in_iter): the offset is one constant
+        # 3-vector, evaluated once per call instead of once per chunk
+        self._nr_const = None
+        if window is not None and cond is None and all(v == 0.0 for v in window):
+            nw, nb = self.non_rigid_mlp.module.flat()
+            self._nr_const = M.nonrigid_offsets(pos_flat[:1].detach().contiguous().float(), None, window, nw, nb, return_const=True)
         cm = self.cnl_mlp.module
         chunk = self.cfg.netchunk_per_gpu
         raws, knns = [], []

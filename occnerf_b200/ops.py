@@ -74,6 +74,36 @@ def knn(queries, supports4, level_begin, k, support_gid=None, query_sel=None, ou
     return out
 
 
+def build_knn_hierarchy(fine: torch.Tensor, centers: torch.Tensor):
+    """Static acceleration structure for occnerf_knn_hier: assigns every fine point to its nearest centre and returns
+    (fine4 cluster-sorted with the original row in .w, centers4 with the inflated cluster radius in .w, ranges [nc,2])."""
+    nf, nc, dev = fine.shape[0], centers.shape[0], fine.device
+    diff = fine[:, None, :].float() - centers[None, :, :].float()
+    d = torch.sqrt((diff * diff).sum(-1))                              # (nf, nc), explicit differences (no matmul trick)
+    dmin, assign = d.min(1)
+    order = torch.argsort(assign, stable=True)
+    counts = torch.bincount(assign, minlength=nc)
+    begin = torch.cumsum(counts, 0) - counts
+    radius = torch.zeros(nc, device=dev, dtype=f32).scatter_reduce(0, assign, dmin, reduce="amax", include_self=True)
+    radius = radius * 1.00001 + 1e-6
+    fine4 = torch.empty(nf, 4, device=dev, dtype=f32)
+    fine4[:, :3] = fine[order].float()
+    fine4[:, 3] = order.to(i32).view(f32)
+    centers4 = torch.cat([centers.float(), radius[:, None]], 1).contiguous()
+    ranges = torch.stack([begin, counts], 1).to(i32).contiguous()
+    return fine4.contiguous(), centers4, ranges
+
+
+def knn_hier(queries, group_stride, fine4, centers4, ranges, out, fine_level, center_level, fine_gid=None, center_gid=None):
+    """Writes the k-NN in the fine and the centre level into out[:, fine_level, :] and out[:, center_level, :]."""
+    m, nl, k = out.shape
+    base = out.data_ptr()
+    call("occnerf_knn_hier", ptr(queries, f32), m, int(group_stride), ptr(fine4, f32), ptr(centers4, f32), ptr(ranges, i32),
+         fine4.shape[0], centers4.shape[0], ptr(fine_gid, i32), ptr(center_gid, i32), k, base + 4 * k * fine_level,
+         base + 4 * k * center_level, nl * k, stream())
+    return out
+
+
 def sample_geometry(xyz, knn_idx, point_base, point_norms, bound, raw=None):
     """-> enc_in (m,4), dist.  With `raw` (m,5) given, dist is written into raw[:,4] in place and returned as a view."""
     m = xyz.shape[0]

@@ -85,3 +85,31 @@ def test_sortedness_at_full_size():
     assert int(idx.min()) >= 0 and int(idx.max()) < base.shape[0]
     lvl3 = set(sub.fps_index[2].tolist())
     assert set(idx[:1000, 3].reshape(-1).tolist()) <= lvl3
+
+
+def test_hierarchical_search_is_bit_identical_to_brute_force():
+    """occnerf_knn_hier (cluster-pruned) must return exactly the ids of the brute-force kernel / oracle on all 4 levels,
+    for points on the body, far outside it, and with duplicated support points (ties)."""
+    sub = S.make_subject(seed=0)
+    d = dev()
+    base = sub.point_base.to(d).clone()
+    fps = [f.to(d) for f in sub.fps_index]
+    sup4, gid, lb = _subject_arrays(sub)
+    gen = torch.Generator().manual_seed(3)
+    sub_, w, fr, vol, t_rand, rk, g = load_case("train_dense")
+    near = torch.from_numpy(g["x_skel"]).reshape(-1, 3)
+    far = torch.rand(20000, 3, generator=gen) * 6 - 3
+    exact = sub.point_base[torch.randint(0, 6890, (3000,), generator=gen)]
+    zeros = torch.zeros(500, 3)
+    for S_ in (128, 1, 7):
+        q = torch.cat([near, far, exact, zeros], 0).contiguous().to(d)
+        ref = ops.knn(q, sup4, lb, 10, support_gid=gid)
+        out = torch.full((q.shape[0], 4, 10), -5, dtype=torch.int32, device=d)
+        h0 = ops.build_knn_hierarchy(base, base[fps[1]])
+        h1 = ops.build_knn_hierarchy(base[fps[0]], base[fps[2]])
+        ops.knn_hier(q, S_, *h0, out, 0, 2, None, fps[1].to(torch.int32).contiguous())
+        ops.knn_hier(q, S_, *h1, out, 1, 3, fps[0].to(torch.int32).contiguous(), fps[2].to(torch.int32).contiguous())
+        bad = (out != ref).any(-1)
+        assert not bool(bad.any()), (S_, int(bad.sum()), bad.nonzero()[:5].tolist())
+    ref_cpu = O.multiscale_knn(near[:4000], sub.point_base, sub.fps_index, 10)
+    assert torch.equal(out[:4000].cpu().long(), ref_cpu)

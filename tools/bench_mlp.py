@@ -25,4 +25,18 @@ for name, eng in [("tc1", mlp_tc.MlpTc(1)), ("tc3", mlp_tc.MlpTc(3))] + ([] if o
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         res[f"{name}_save{int(save)}"] = dict(ms=ms, tflops=m * M.FLOP_FWD / ms / 1e9)
+if not once:
+    g_raw = torch.randn(m, 5, device=d)
+    for name, eng in [("tc1", mlp_tc.MlpTc(1)), ("tc3", mlp_tc.MlpTc(3))]:
+        saved = eng.forward(XB, raw, W, save=True)
+        for _ in range(2): eng.backward(XB, g_raw, W, saved)
+        torch.cuda.synchronize()
+        from occnerf_b200 import _lib
+        _lib.PROFILE = {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3): eng.backward(XB, g_raw, W, saved)
+        e1.record(); torch.cuda.synchronize()
+        prof, _lib.PROFILE = _lib.PROFILE, None
+        res[f"{name}_bwd"] = dict(ms=e0.elapsed_time(e1) / 3, dgrad_ms=sum(a.elapsed_time(b) for a, b, _ in prof["occnerf_mlp_backward_tc"]) / 3)
 print(json.dumps(res, indent=1))
