@@ -151,18 +151,26 @@ long occnerf_mlp_packed_bytes(int n_pass, int chain);
 int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, void *packed, occnerf_stream_t stream);
 /* XB [m,132]: columns 64..131 = (agg35, var1, h32) are read; columns 0..63 receive the 64 geometry features when
  * act_dtype != 0.  raw [m, ldr]: columns 0..3 = (rgb_pre3, sigma_pre1) are written.
- * act_save: NULL (act_dtype 0, inference) or a buffer [8][m][256] receiving the post-ReLU activations of the 8
- * hidden layers (pts1..4, rgb1..4) for the backward pass, as fp32 (act_dtype 1) or bf16 (act_dtype 2). */
+ * act_save: NULL (act_dtype 0, inference) or a buffer [slots][slot_stride][256] receiving the post-ReLU activations of
+ * the 8 hidden layers (slots 0..3 = pts1..4, 4..7 = rgb1..4) for the backward pass: fp32 (act_dtype 1, 8 slots) or
+ * bf16 (act_dtype 2, 10 slots: slot 8 = input of pts0 (80 columns), slot 9 = input of rgb0 (144 columns)). */
 int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, float *raw, int ldr, void *act_save,
-                           int act_dtype, occnerf_stream_t stream);
+                           int act_dtype, long slot_stride, occnerf_stream_t stream);
 
 /* Fused data-gradient chain (the transposed layers in reverse order, ReLU masks from the saved bf16 activations).
- * g_raw [m,5] (d rgb_pre3, d sigma_pre, unused); act_bf16 [8][m][256] as saved by occnerf_mlp_forward_tc (act_dtype 2).
- * Writes gXB [m,132] columns 64..131 = d(agg35, var1, h32) summed over both trunks, and g_save [9][m][256] bf16 =
- * gradients w.r.t. the pre-activations of rgb3, rgb2, rgb1, rgb0, geo (columns 0..63 features, 64 sigma), pts3, pts2,
- * pts1, pts0, which are the left operands of the weight-gradient GEMMs dW_l = G_l^T X_l. */
+ * g_raw [m,5] (d rgb_pre3, d sigma_pre, unused); act_bf16 [10][slot_stride][256] as saved by occnerf_mlp_forward_tc.
+ * Writes gXB [m,132] columns 64..131 = d(agg35, var1, h32) summed over both trunks, and g_save [10][slot_stride][256]
+ * bf16 = gradients w.r.t. the pre-activations: slots 0..3 = rgb3, rgb2, rgb1, rgb0; 4 = geo (columns 0..63 features,
+ * 64 sigma); 5..8 = pts3, pts2, pts1, pts0; 9 = d raw[:, :3]. */
 int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, const void *act_bf16, float *gXB,
-                            void *g_save, occnerf_stream_t stream);
+                            void *g_save, long slot_stride, occnerf_stream_t stream);
+
+/* Weight and bias gradients dW_l = G_l^T X_l, db_l = colsum(G_l) of all 10 layers from the two bf16 buffers above
+ * (TMA + MN-major tcgen05, contraction over the sample axis).  slot_stride must be a multiple of 64 and the rows
+ * m..slot_stride-1 of every slot zero.  dW [10][256][256], dB [10][256] fp32 are ACCUMULATED (caller zeroes), in the
+ * padded/permuted layer layout of the fused kernels (see occnerf_b200/mlp_tc.py for the mapping back to nn.Linear). */
+int occnerf_mlp_wgrad_tc(const void *g_save, const void *act_bf16, int m, long slot_stride, float *dW, float *dB,
+                         occnerf_stream_t stream);
 
 /* ---- alpha compositing (network.py:320-348) + completeness term (network.py:486-499) ----------------
  * raw [N,S,5] = (rgb_pre3, sigma_pre, dist); mask, z [N,S]; rays [N,8]; bg [3] (0..255).

@@ -38,8 +38,9 @@ _SIGNATURES = {
     "occnerf_sgemm": [_vp, _l, _l, _vp, _l, _l, _vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp],
     "occnerf_colsum": [_vp, _l, _vp, _l, _i, _i, _vp, _vp],
     "occnerf_mlp_pack_weights": [C.POINTER(MlpParams), _i, _i, _vp, _vp],
-    "occnerf_mlp_forward_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp],
-    "occnerf_mlp_backward_tc": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp],
+    "occnerf_mlp_forward_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _l, _vp],
+    "occnerf_mlp_backward_tc": [_vp, _i, _vp, _i, _vp, _vp, _vp, _l, _vp],
+    "occnerf_mlp_wgrad_tc": [_vp, _vp, _i, _l, _vp, _vp, _vp],
     "occnerf_composite_forward": [_vp] * 5 + [_i, _i] + [_vp] * 7,
     "occnerf_composite_backward": [_vp] * 9 + [_i, _i] + [_vp] * 3,
     "occnerf_visibility_hits": [_vp, _vp, _vp, _i, _i, _f, _vp, _i, _i, _vp, _vp, _vp],

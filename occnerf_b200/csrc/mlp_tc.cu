@@ -205,7 +205,8 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&v)[8]) {
 
 // the (agg35, var, h32) part of a sample's input row -> A columns [8*k8_0, 8*k8_0 + 80), zero padded beyond 68
 template <int NPASS>
-__device__ __forceinline__ void stage_x0(unsigned char *a_base, int row, const float *__restrict__ xrow, bool valid, int k8_0) {
+__device__ __forceinline__ void stage_x0(unsigned char *a_base, int row, const float *__restrict__ xrow, bool valid, int k8_0,
+                                         __nv_bfloat16 *save_row = nullptr) {
 #pragma unroll
     for (int g = 0; g < 10; ++g) {
         float v[8];
@@ -217,11 +218,13 @@ __device__ __forceinline__ void stage_x0(unsigned char *a_base, int row, const f
             v[h * 4 + 0] = x.x; v[h * 4 + 1] = x.y; v[h * 4 + 2] = x.z; v[h * 4 + 3] = x.w;
         }
         store_a8<NPASS>(a_base, row, k8_0 + g, v);
+        if (save_row) *reinterpret_cast<uint4 *>(save_row + g * 8) = pack_bf16x8(v);
     }
 }
 
 struct ChainArgs {
     int m;
+    long slot_stride;                // rows per slot of act_save / act / g_save (>= m; a multiple of 64 for the wgrad kernel)
     int chain;                       // 0 forward, 1 backward
     const unsigned char *packed;
     long w_off[kLayers];
@@ -230,13 +233,14 @@ struct ChainArgs {
     float *XB;                       // [m,132]: cols 64..131 in; cols 0..63 out (geo features) when act_dtype != 0
     float *raw;                      // [m, ldr]: cols 0..2 rgb_pre, col 3 sigma_pre
     int ldr;
-    void *act_save;                  // [8][m][256] post-ReLU activations (fp32 / bf16) or NULL
+    void *act_save;                  // [8 or 10][slot_stride][256] post-ReLU activations (fp32 / bf16) or NULL;
+                                     // bf16 mode adds slot 8 = pts0 input (80 cols) and slot 9 = rgb0 input (144 cols)
     int act_dtype;                   // 0 none, 1 fp32, 2 bf16
     // backward
     const float *g_raw;              // [m,5]
     const __nv_bfloat16 *act;        // [8][m][256] bf16 (saved by the forward kernel)
     float *gXB;                      // [m,132]: cols 64..131 written (d agg, d var, d h; both trunks summed)
-    __nv_bfloat16 *g_save;           // [9][m][256] bf16: gradients w.r.t. the pre-activations, for the weight gradients
+    __nv_bfloat16 *g_save;           // [10][slot_stride][256] bf16: gradients w.r.t. the pre-activations (slot 9 = d raw[:, :3])
 };
 
 struct Smem {
@@ -335,7 +339,8 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
         const long grow = (long)tile * kTileM + row;
         const bool valid = grow < args.m;
         const float *xrow = args.XB + grow * 132 + 64;
-        stage_x0<NPASS>(sm.A, row, xrow, valid, 0);                 // GEMM 0 operand: A[:, 0:80)
+        __nv_bfloat16 *sv = (valid && args.act_dtype == 2) ? reinterpret_cast<__nv_bfloat16 *>(args.act_save) : nullptr;
+        stage_x0<NPASS>(sm.A, row, xrow, valid, 0, sv ? sv + (8 * args.slot_stride + grow) * 256 : nullptr);   // GEMM 0 operand: A[:, 0:80)
         publish(sm, 0, 3);
         for (int l = 0; l < kLayers; ++l, ++acc_cnt) {
             mbar_wait(sm.bar_acc_full, acc_cnt & 1);
@@ -369,6 +374,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                             float4 *dst = reinterpret_cast<float4 *>(args.XB + grow * 132 + cg * 32 + j * 8);
                             dst[0] = make_float4(v[0], v[1], v[2], v[3]);
                             dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                            if (sv) *reinterpret_cast<uint4 *>(sv + (9 * args.slot_stride + grow) * 256 + cg * 32 + j * 8) = pack_bf16x8(v);
                         }
                     }
                     publish(sm, cg, cg + 1);
@@ -378,7 +384,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                     tmem_ld16(t_acc + 64, r);
                     if (valid) args.raw[grow * args.ldr + 3] = __uint_as_float(r[0]) + __ldg(bias + 64);
                 }
-                stage_x0<NPASS>(sm.A, row, xrow, valid, 8);         // A[:, 64:144) = (agg35, var, h32, 0 pad)
+                stage_x0<NPASS>(sm.A, row, xrow, valid, 8, sv ? sv + (9 * args.slot_stride + grow) * 256 + 64 : nullptr);   // A[:, 64:144)
                 publish(sm, 2, 5);
             } else {
                 // hidden layer: +bias, ReLU -> next A operand (and the saved activation for the backward pass)
@@ -395,7 +401,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                         for (int i = 0; i < 8; ++i)
                             v[i] = fmaxf(__uint_as_float(r[j * 8 + i]) + __ldg(bias + cg * 32 + j * 8 + i), 0.f);
                         store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
-                        const long e = ((long)slot * args.m + grow) * 256 + cg * 32 + j * 8;
+                        const long e = ((long)slot * args.slot_stride + grow) * 256 + cg * 32 + j * 8;
                         if (valid && args.act_dtype == 1) {
                             float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(args.act_save) + e);
                             dst[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -430,6 +436,11 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
             }
             store_a8<NPASS>(sm.A, row, 0, v);
             store_a8<NPASS>(sm.A, row, 1, z);
+            if (valid) {
+                __nv_bfloat16 *gs = args.g_save + (9 * args.slot_stride + grow) * 256;
+                *reinterpret_cast<uint4 *>(gs) = pack_bf16x8(v);
+                *reinterpret_cast<uint4 *>(gs + 8) = pack_bf16x8(z);
+            }
             publish(sm, 0, 1);
         }
         for (int d = 0; d < kLayers; ++d, ++acc_cnt) {
@@ -473,7 +484,7 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
                         store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
-                        if (valid) *reinterpret_cast<uint4 *>(args.g_save + ((long)4 * args.m + grow) * 256 + cg * 32 + j * 8) = pack_bf16x8(v);
+                        if (valid) *reinterpret_cast<uint4 *>(args.g_save + (4 * args.slot_stride + grow) * 256 + cg * 32 + j * 8) = pack_bf16x8(v);
                     }
                     publish(sm, cg, cg + 1);
                 }
@@ -482,7 +493,7 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
                     store_a8<NPASS>(sm.A, row, 8, v);
                     store_a8<NPASS>(sm.A, row, 9, z);
                     if (valid) {
-                        __nv_bfloat16 *gs = args.g_save + ((long)4 * args.m + grow) * 256 + 64;
+                        __nv_bfloat16 *gs = args.g_save + (4 * args.slot_stride + grow) * 256 + 64;
                         *reinterpret_cast<uint4 *>(gs) = pack_bf16x8(v);
                         *reinterpret_cast<uint4 *>(gs + 8) = pack_bf16x8(z);
                     }
@@ -510,7 +521,7 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
                 // through a ReLU: G = acc * (saved activation > 0) -> next A operand, and saved for the weight gradient
                 const int slot = d < 4 ? 7 - d : 8 - d;              // d0..3 -> R4..R1 (slots 7..4); d5..8 -> H4..H1 (slots 3..0)
                 const int gslot = d;                                 // g_save: 0..3 rgb3..rgb0, 4 geo, 5..8 pts3..pts0
-                const __nv_bfloat16 *arow = args.act + ((long)slot * args.m + (valid ? grow : 0)) * 256;
+                const __nv_bfloat16 *arow = args.act + (slot * args.slot_stride + (valid ? grow : 0)) * 256;
 #pragma unroll 1
                 for (int cg = 0; cg < 8; ++cg) {
                     uint32_t r[32];
@@ -530,7 +541,7 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
                             v[i] = (valid && (half & 0x7FFFu) != 0u && (half & 0x8000u) == 0u) ? __uint_as_float(r[j * 8 + i]) : 0.f;
                         }
                         store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
-                        if (valid) *reinterpret_cast<uint4 *>(args.g_save + ((long)gslot * args.m + grow) * 256 + cg * 32 + j * 8) = pack_bf16x8(v);
+                        if (valid) *reinterpret_cast<uint4 *>(args.g_save + (gslot * args.slot_stride + grow) * 256 + cg * 32 + j * 8) = pack_bf16x8(v);
                     }
                     publish(sm, cg, cg + 1);
                 }
@@ -634,7 +645,7 @@ extern "C" int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_
 }
 
 extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, float *raw, int ldr, void *act_save,
-                                      int act_dtype, occnerf_stream_t stream) {
+                                      int act_dtype, long slot_stride, occnerf_stream_t stream) {
     if (m == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(XB && packed && raw, "mlp_forward_tc: null pointer");
     OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "mlp_forward_tc: n_pass=%d (supported: 1, 3)", n_pass);
@@ -645,12 +656,13 @@ extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int 
     ChainArgs a = {};
     a.m = m;
     fill_layout(a, n_pass, 0, packed);
-    a.XB = XB; a.raw = raw; a.ldr = ldr; a.act_save = act_save; a.act_dtype = act_dtype;
+    OCC_CHECK_ARG(act_dtype == 0 || slot_stride >= m, "mlp_forward_tc: slot_stride=%ld < m=%d", slot_stride, m);
+    a.XB = XB; a.raw = raw; a.ldr = ldr; a.act_save = act_save; a.act_dtype = act_dtype; a.slot_stride = slot_stride;
     return n_pass == 1 ? launch_chain<1, 0>(a, (cudaStream_t)stream) : launch_chain<3, 0>(a, (cudaStream_t)stream);
 }
 
 extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, const void *act_bf16,
-                                       float *gXB, void *g_save, occnerf_stream_t stream) {
+                                       float *gXB, void *g_save, long slot_stride, occnerf_stream_t stream) {
     if (m == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(g_raw && packed_bwd && act_bf16 && gXB && g_save, "mlp_backward_tc: null pointer");
     OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "mlp_backward_tc: n_pass=%d (supported: 1, 3)", n_pass);
@@ -659,6 +671,7 @@ extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *pa
     ChainArgs a = {};
     a.m = m;
     fill_layout(a, n_pass, 1, packed_bwd);
-    a.g_raw = g_raw; a.act = (const __nv_bfloat16 *)act_bf16; a.gXB = gXB; a.g_save = (__nv_bfloat16 *)g_save;
+    OCC_CHECK_ARG(slot_stride >= m, "mlp_backward_tc: slot_stride=%ld < m=%d", slot_stride, m);
+    a.g_raw = g_raw; a.act = (const __nv_bfloat16 *)act_bf16; a.gXB = gXB; a.g_save = (__nv_bfloat16 *)g_save; a.slot_stride = slot_stride;
     return n_pass == 1 ? launch_chain<1, 1>(a, (cudaStream_t)stream) : launch_chain<3, 1>(a, (cudaStream_t)stream);
 }

@@ -3,9 +3,8 @@
 forward : one fused kernel per chunk (occnerf_mlp_forward_tc); weights re-packed per call as bf16 (hi[,lo]) UMMA
           operand images (occnerf_mlp_pack_weights; 0.5 M parameters, microseconds); post-ReLU activations saved as bf16.
 backward: data gradients by the fused transposed chain (occnerf_mlp_backward_tc), which also leaves the bf16
-          pre-activation gradients G_l behind; the ten weight gradients dW_l = G_l^T X_l are plain [n,m]x[m,k]
-          GEMMs over the sample axis and go to the library (cuBLAS via torch.matmul, bf16 in / fp32 accumulate),
-          bias gradients are column sums.  A hand-written MN-major tcgen05 weight-gradient kernel is round-2 work.
+          pre-activation gradients G_l behind; the ten weight gradients dW_l = G_l^T X_l and the bias gradients come
+          from the MN-major tcgen05 kernel occnerf_mlp_wgrad_tc (csrc/mlp_wgrad.cu).
 """
 from __future__ import annotations
 
@@ -20,9 +19,10 @@ f32, bf16 = torch.float32, torch.bfloat16
 
 
 class MlpTc:
-    def __init__(self, n_pass: int = 3):
-        assert n_pass in (1, 3)
+    def __init__(self, n_pass: int = 3, wgrad: str = "tc"):
+        assert n_pass in (1, 3) and wgrad in ("tc", "lib")
         self.n_pass = n_pass
+        self.wgrad = wgrad      # "tc": hand-written tcgen05 kernel; "lib": cuBLAS (test cross-check only)
         self.name = f"tc{n_pass}"
 
     def pack(self, W: M.MlpWeights, device, chain: int):
@@ -39,24 +39,49 @@ class MlpTc:
     def forward(self, XB, raw, W: M.MlpWeights, save: bool):
         m, dev = XB.shape[0], XB.device
         packed = self.pack(W, dev, 0)
-        acts = torch.empty(8, m, 256, device=dev, dtype=bf16) if save else None
+        stride = (m + 63) // 64 * 64
+        acts = None
+        if save:
+            acts = torch.empty(10, stride, 256, device=dev, dtype=bf16)
+            if stride > m:
+                acts[:, m:].zero_()
         call("occnerf_mlp_forward_tc", XB.data_ptr(), m, packed.data_ptr(), self.n_pass, raw.data_ptr(), raw.shape[1],
-             acts.data_ptr() if save else None, 2 if save else 0, stream(), work=M.FLOP_FWD * m)
+             acts.data_ptr() if save else None, 2 if save else 0, stride, stream(), work=M.FLOP_FWD * m)
         return {"acts": acts} if save else None
 
     def backward(self, XB, g_raw, W: M.MlpWeights, saved):
         m, dev = XB.shape[0], XB.device
         acts = saved["acts"]
+        stride = acts.shape[1]
         packed = self.pack(W, dev, 1)
         gXB = torch.empty(m, M.XB_LD, device=dev, dtype=f32)
-        g_save = torch.empty(9, m, 256, device=dev, dtype=bf16)
+        g_save = torch.empty(10, stride, 256, device=dev, dtype=bf16)
+        if stride > m:
+            g_save[:, m:].zero_()
         call("occnerf_mlp_backward_tc", g_raw.data_ptr(), m, packed.data_ptr(), self.n_pass, acts.data_ptr(), gXB.data_ptr(),
-             g_save.data_ptr(), stream(), work=M.FLOP_FWD * m)
-        # ---- weight gradients: library GEMMs over the sample axis
-        with _lib.region("lib:wgrad(cuBLAS bf16)+bias sums"):
-            return gXB, self._wgrad(XB, g_raw, acts, g_save)
+             g_save.data_ptr(), stride, stream(), work=M.FLOP_FWD * m)
+        if self.wgrad == "lib":
+            with _lib.region("lib:wgrad(cuBLAS bf16)+bias sums"):
+                return gXB, self._wgrad_lib(XB, g_raw, acts[:, :m], g_save[:, :m])
+        dW = torch.zeros(10, 256, 256, device=dev, dtype=f32)
+        dB = torch.zeros(10, 256, device=dev, dtype=f32)
+        call("occnerf_mlp_wgrad_tc", g_save.data_ptr(), acts.data_ptr(), m, stride, dW.data_ptr(), dB.data_ptr(), stream(),
+             work=M.FLOP_FWD * m)
+        g = {}
+        g["pts_w0"], g["pts_b0"] = dW[0][:, :68].contiguous(), dB[0]
+        for l in (1, 2, 3):
+            g[f"pts_w{l}"], g[f"pts_b{l}"] = dW[l], dB[l]
+        g["geo_w"] = torch.cat([dW[4][64:65], dW[4][:64]], 0).contiguous()          # sigma row back to the front
+        g["geo_b"] = torch.cat([dB[4][64:65], dB[4][:64]], 0)
+        g["rgb_w0"] = torch.cat([dW[5][:, :99], dW[5][:, 100:132]], 1).contiguous()  # drop the variance column
+        g["rgb_b0"] = dB[5]
+        for l in (1, 2, 3):
+            g[f"rgb_w{l}"], g[f"rgb_b{l}"] = dW[5 + l], dB[5 + l]
+        g["out_w"], g["out_b"] = dW[9][:3].contiguous(), dB[9][:3].contiguous()
+        return gXB, [g[k] for k in M.MlpWeights.ORDER]
 
-    def _wgrad(self, XB, g_raw, acts, g_save):
+    def _wgrad_lib(self, XB, g_raw, acts, g_save):
+        """Library fallback-free alternative for cross-checking the hand-written kernel: the same GEMMs through cuBLAS."""
         Xb = XB.to(bf16)
         g_out = g_raw[:, :3].to(bf16)
 

@@ -106,3 +106,31 @@ def test_backward_against_torch(engine, rel):
     e_h = err(gXB[:, 100:132], h.grad)
     report(f"mlp_bwd[{engine}]", worst_param=worst, g_agg=e_agg, g_h=e_h)
     assert e_agg < rel and e_h < rel
+
+
+def test_wgrad_kernel_matches_library_gemm():
+    """occnerf_mlp_wgrad_tc (TMA + MN-major tcgen05) against cuBLAS on the very same bf16 operands."""
+    from occnerf_b200 import mlp_tc
+    m = 5000                                   # not a multiple of 64: exercises the zero-padded tail
+    w = _weights(seed=4)
+    agg, var, h = _inputs(m, seed=9)
+    d = dev()
+    XB = torch.zeros(m, 132, device=d)
+    XB[:, 64:99], XB[:, 99:100], XB[:, 100:] = agg.to(d), var.to(d), h.to(d)
+    W = _flat(w, d)
+    g_raw = torch.zeros(m, 5, device=d)
+    g_raw[:, :4] = torch.randn(m, 4, generator=torch.Generator().manual_seed(3)).to(d)
+    out = {}
+    for mode in ("tc", "lib"):
+        eng = mlp_tc.MlpTc(3, wgrad=mode)
+        raw = torch.zeros(m, 5, device=d)
+        XBc = XB.clone()                        # the forward writes the geometry features into columns 0..63
+        saved = eng.forward(XBc, raw, W, save=True)
+        out[mode] = eng.backward(XBc, g_raw, W, saved)
+    assert torch.equal(out["tc"][0][:, 64:], out["lib"][0][:, 64:])      # columns 0..63 of gXB are not produced
+    worst = 0.0
+    for nme, a, b in zip(M.MlpWeights.ORDER, out["tc"][1], out["lib"][1]):
+        e = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+        worst = max(worst, e)
+        assert a.shape == b.shape and e < 5e-3, (nme, e)      # cuBLAS returns bf16-rounded products
+    report("mlp_wgrad_tc_vs_cublas", worst=worst)
