@@ -269,9 +269,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("OCCNERF_ENGINE", "fp32"), choices=["fp32", "tc3", "tc1"])
+    ap.add_argument("--engine", default=os.environ.get("OCCNERF_ENGINE", "tc3"), choices=["fp32", "tc3", "tc1"])
     ap.add_argument("--ref-rays", type=int, default=96, help="rays per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true", help="device-resident steps only (no e2e, no CPU baseline): for ncu runs")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -306,6 +307,10 @@ def main():
     clocks = sampler.stop()
     table = kernel_table(profile, args.steps)
     # ---- e2e: public API with host buffers
+    if args.profile_mode:
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "ms_per_step": ms, "kernels": [(r["call"], round(r["ms_per_step"], 4)) for r in table]}))
+        return
     ms_e2e = timed_loop(lambda: wl.step_e2e(world), args.steps, args.warmup, world, flush)
 
     if rank == 0:

@@ -389,17 +389,19 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
             } else {
                 // hidden layer: +bias, ReLU -> next A operand (and the saved activation for the backward pass)
                 const int slot = l < 4 ? l : l - 1;                  // 0..3 = pts1..4, 4..7 = rgb1..4
-#pragma unroll 1
-                for (int cg = 0; cg < 8; ++cg) {
-                    uint32_t r[32];
-                    tmem_ld32_issue(t_acc + cg * 32, r);
-                    tmem_ld_wait();
+                // software pipeline over the eight 32-column groups: the TMEM load and the bias of group g+1 are in
+                // flight while group g is processed (4 epilogue warps per SM cannot hide those latencies by themselves)
+                auto load_bias = [&](int cg, float4 (&b)[8]) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) b[i] = __ldg(reinterpret_cast<const float4 *>(bias + cg * 32) + i);
+                };
+                auto process = [&](int cg, const uint32_t (&r)[32], const float4 (&b)[8]) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
+                        const float bj[8] = {b[2 * j].x, b[2 * j].y, b[2 * j].z, b[2 * j].w, b[2 * j + 1].x, b[2 * j + 1].y, b[2 * j + 1].z, b[2 * j + 1].w};
                         float v[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            v[i] = fmaxf(__uint_as_float(r[j * 8 + i]) + __ldg(bias + cg * 32 + j * 8 + i), 0.f);
+                        for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[j * 8 + i]) + bj[i], 0.f);
                         store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
                         const long e = ((long)slot * args.slot_stride + grow) * 256 + cg * 32 + j * 8;
                         if (valid && args.act_dtype == 1) {
@@ -411,6 +413,23 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                         }
                     }
                     publish(sm, cg, cg + 1);
+                };
+                uint32_t ra[32], rb[32];
+                float4 ba[8], bb[8];
+                tmem_ld32_issue(t_acc, ra);
+                load_bias(0, ba);
+#pragma unroll 1
+                for (int cg = 0; cg < 8; cg += 2) {
+                    tmem_ld_wait();
+                    tmem_ld32_issue(t_acc + (cg + 1) * 32, rb);
+                    load_bias(cg + 1, bb);
+                    process(cg, ra, ba);
+                    tmem_ld_wait();
+                    if (cg + 2 < 8) {
+                        tmem_ld32_issue(t_acc + (cg + 2) * 32, ra);
+                        load_bias(cg + 2, ba);
+                    }
+                    process(cg + 1, rb, bb);
                 }
             }
         }
@@ -522,14 +541,11 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
                 const int slot = d < 4 ? 7 - d : 8 - d;              // d0..3 -> R4..R1 (slots 7..4); d5..8 -> H4..H1 (slots 3..0)
                 const int gslot = d;                                 // g_save: 0..3 rgb3..rgb0, 4 geo, 5..8 pts3..pts0
                 const __nv_bfloat16 *arow = args.act + (slot * args.slot_stride + (valid ? grow : 0)) * 256;
-#pragma unroll 1
-                for (int cg = 0; cg < 8; ++cg) {
-                    uint32_t r[32];
-                    tmem_ld32_issue(t_acc + cg * 32, r);
-                    uint4 mk[4];
+                auto load_mask = [&](int cg, uint4 (&mk)[4]) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) mk[j] = __ldg(reinterpret_cast<const uint4 *>(arow + cg * 32 + j * 8));
-                    tmem_ld_wait();
+                };
+                auto process = [&](int cg, const uint32_t (&r)[32], const uint4 (&mk)[4]) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t w[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
@@ -544,6 +560,23 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
                         if (valid) *reinterpret_cast<uint4 *>(args.g_save + (gslot * args.slot_stride + grow) * 256 + cg * 32 + j * 8) = pack_bf16x8(v);
                     }
                     publish(sm, cg, cg + 1);
+                };
+                uint32_t ra[32], rb[32];
+                uint4 ma[4], mb[4];
+                tmem_ld32_issue(t_acc, ra);
+                load_mask(0, ma);
+#pragma unroll 1
+                for (int cg = 0; cg < 8; cg += 2) {
+                    tmem_ld_wait();
+                    tmem_ld32_issue(t_acc + (cg + 1) * 32, rb);
+                    load_mask(cg + 1, mb);
+                    process(cg, ra, ma);
+                    tmem_ld_wait();
+                    if (cg + 2 < 8) {
+                        tmem_ld32_issue(t_acc + (cg + 2) * 32, ra);
+                        load_mask(cg + 2, ma);
+                    }
+                    process(cg + 1, rb, mb);
                 }
             }
         }
