@@ -121,13 +121,11 @@ int occnerf_hashgrid_input_backward(const float *grad, int layout, int ld, const
  * writes X[i*ldx + 0..34] = sum_n softmax(att)_n * feats[idx_n], X[i*ldx + 35] = unbiased var(att). */
 int occnerf_aggregate_forward(const int32_t *knn_idx, const float *point_counter, const float *feats, int m, int nn,
                               float *X, int ldx, occnerf_stream_t stream);
-/* g_feats [V,36] += att_n * gX[i*ldg + 0..34]  (att is detached in the reference, occnerf_mlp.py:123) */
+/* g_feats [copies][V,36] += att_n * gX[i*ldg + 0..34]  (att is detached in the reference, occnerf_mlp.py:123).
+ * `copies` >= 1 privatised replicas spread the L2 reductions (CTA b adds into replica b % copies); the caller sums them. */
 int occnerf_aggregate_backward(const int32_t *knn_idx, const float *point_counter, const float *gX, int ldg, int m,
-                               int nn, float *g_feats, occnerf_stream_t stream);
-/* Same result, pre-reduced in shared memory (nn = 40 = 4 levels x 10 only): a warp takes 32 consecutive rays at one
- * sample index (group_stride = samples per ray) and accumulates into a private table before touching g_feats. */
-int occnerf_aggregate_backward2(const int32_t *knn_idx, const float *point_counter, const float *gX, int ldg, int m,
-                                int nn, int group_stride, float *g_feats, occnerf_stream_t stream);
+                               int nn, float *g_feats, int V, int copies, occnerf_stream_t stream);
+
 
 /* ---- Hann-windowed positional encoding (hannw_fourier.py:27-45), window weights from the host ------- */
 int occnerf_hann_pe(const float *xyz, int m, const float *window_host, int multires, float *out, int ldo,

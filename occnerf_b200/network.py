@@ -250,8 +250,7 @@ class _QueryFn(torch.autograd.Function):
         saved = engine.forward(XB, raw, W, save=need_grad)
         if need_grad:
             ctx.state = dict(knn_idx=knn_idx, enc_in=enc_in, XB=XB, W=W, saved=saved, engine=engine, counter=counter,
-                             offsets=enc.offsets, scales=scales, emb_shape=tuple(embeddings.shape), V=feats36.shape[0],
-                             group_stride=(0 if net.cfg.knn_mode == "brute" else max(1, int(getattr(net, "_group_stride", 1)))))
+                             offsets=enc.offsets, scales=scales, emb_shape=tuple(embeddings.shape), V=feats36.shape[0])
         ctx.mark_non_differentiable(knn_idx)
         return raw, knn_idx
 
@@ -263,8 +262,7 @@ class _QueryFn(torch.autograd.Function):
         g_emb = torch.zeros(s["emb_shape"], device=g_raw.device, dtype=f32)
         ops.hashgrid_backward(gXB.data_ptr() + 4 * M.H_OFF, M.XB_LD, 0, s["enc_in"], s["offsets"], s["scales"], g_emb,
                               s["emb_shape"][1])
-        g_feats = ops.aggregate_backward(s["knn_idx"], s["counter"], gXB.data_ptr() + 4 * M.X0_OFF, M.XB_LD, s["V"],
-                                         group_stride=s["group_stride"])
+        g_feats = ops.aggregate_backward(s["knn_idx"], s["counter"], gXB.data_ptr() + 4 * M.X0_OFF, M.XB_LD, s["V"])
         ctx.state = None
         return (None, g_feats, g_emb, None, None, None, *g_params)
 

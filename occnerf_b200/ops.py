@@ -208,18 +208,18 @@ def aggregate_forward(knn_idx, point_counter, feats36, X_ptr, ldx):
          stream())
 
 
-def aggregate_backward(knn_idx, point_counter, gX_ptr, ldg, V, group_stride=0):
-    """group_stride > 0 (samples per ray) selects the shared-memory pre-reducing kernel (4 x 10 neighbours only)."""
+AGG_BWD_COPIES = 64
+
+
+def aggregate_backward(knn_idx, point_counter, gX_ptr, ldg, V, copies=None):
+    """g_feats (V,36): one vector reduction per (sample, neighbour, column chunk) into `copies` privatised replicas."""
     m = knn_idx.shape[0]
     nn = knn_idx.numel() // max(m, 1)
-    g_feats = torch.zeros(V, 36, device=knn_idx.device, dtype=f32)
-    if group_stride > 0 and nn == 40:
-        call("occnerf_aggregate_backward2", ptr(knn_idx, i32), ptr(point_counter, f32), gX_ptr, ldg, m, nn, int(group_stride),
-             ptr(g_feats), stream())
-    else:
-        call("occnerf_aggregate_backward", ptr(knn_idx, i32), ptr(point_counter, f32), gX_ptr, ldg, m, nn, ptr(g_feats),
-             stream())
-    return g_feats
+    copies = AGG_BWD_COPIES if copies is None else copies
+    g_priv = torch.zeros(copies, V, 36, device=knn_idx.device, dtype=f32)
+    call("occnerf_aggregate_backward", ptr(knn_idx, i32), ptr(point_counter, f32), gX_ptr, ldg, m, nn, ptr(g_priv), V, copies,
+         stream())
+    return g_priv.sum(0) if copies > 1 else g_priv[0]
 
 
 # ----------------------------------------------------------------------------- fp32 GEMM helpers

@@ -35,8 +35,8 @@ def test_forward_against_oracle():
     assert float(X[:, :64].max()) == -3.0 and float(X[:, 100:].max()) == -3.0
 
 
-@pytest.mark.parametrize("group_stride", [0, 128, 1, 50])
-def test_backward_against_oracle(group_stride):
+@pytest.mark.parametrize("copies", [1, 7, 64])
+def test_backward_against_oracle(copies):
     idx, feats, counter = _case()
     m = idx.shape[0]
     fr = feats.clone().requires_grad_(True)
@@ -48,8 +48,8 @@ def test_backward_against_oracle(group_stride):
     gX = torch.randn(m, 132, device=d)                     # columns outside 64..98 must be ignored (99 = variance slot)
     gX[:, 64:99] = g.to(d)
     gf = ops.aggregate_backward(idx.to(torch.int32).to(d).contiguous(), counter.to(d), gX.data_ptr() + 4 * 64, 132, 6890,
-                                group_stride=group_stride)
+                                copies=copies)
     e = maxabs(gf[:, :35], fr.grad) / float(fr.grad.abs().max())
-    report(f"aggregate_bwd[gs={group_stride}]", rel=e)
+    report(f"aggregate_bwd[copies={copies}]", rel=e)
     assert e < 1e-5
     assert float(gf[:, 35].abs().max()) == 0.0
