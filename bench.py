@@ -286,6 +286,7 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=device)
     from occnerf_b200 import _lib
     _lib.load()

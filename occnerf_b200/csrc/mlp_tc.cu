@@ -135,11 +135,30 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// the same copy, delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask` of the cluster
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrives on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 // D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::f16 (bf16 operands, fp32 accumulate), issued by one thread
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -254,6 +273,7 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
     constexpr int KC = (NPASS == 1) ? 64 : 32;
     constexpr int NP = (NPASS == 1) ? 1 : 2;
     uint32_t it = 0;
+    const uint32_t rank = cluster_ctarank();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int l = 0; l < kLayers; ++l) {
             const int K = chain_K(args.chain, l), N = chain_N(args.chain, l);
@@ -262,13 +282,19 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
             const unsigned char *src = args.packed + args.w_off[l];
             for (int c = 0; c < nch; ++c, ++it) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                mbar_wait(sm.bar_w_empty + 8 * s, ph ^ 1);
+                mbar_wait(sm.bar_w_empty + 8 * s, ph ^ 1);          // BOTH CTAs of the pair have consumed the slot
                 const int kc = min(KC, K - c * KC);
                 const uint32_t bytes = (uint32_t)N * kc * 2;       // per part; the k8-outer image is contiguous
-                mbar_arrive_expect_tx(sm.bar_w_full + 8 * s, bytes * NP);
+                mbar_arrive_expect_tx(sm.bar_w_full + 8 * s, bytes * NP);   // what lands in MY slot (from both CTAs)
                 const uint32_t dst = smem_u32(sm.W + s * kStageBytes);
-                for (int p = 0; p < NP; ++p)
-                    bulk_g2s(dst + p * (kStageBytes / NP), src + ((long)c * NP + p) * pb, bytes, sm.bar_w_full + 8 * s);
+                // the two CTAs of a cluster walk the same weight stream: each fetches one half from L2 and multicasts
+                // it into both shared memories, halving the L2 -> SM weight traffic
+                if (NP == 2) {
+                    bulk_g2s_mc(dst + rank * (kStageBytes / 2), src + ((long)c * 2 + rank) * pb, bytes, sm.bar_w_full + 8 * s, 3);
+                } else {
+                    const uint32_t half = bytes / 2;
+                    bulk_g2s_mc(dst + rank * half, src + (long)c * pb + rank * half, half, sm.bar_w_full + 8 * s, 3);
+                }
             }
         }
     }
@@ -314,7 +340,7 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
                         tc_mma(d_tmem, da_lo, db_hi, idesc, 1u);
                     }
                 }
-                tc_commit(sm.bar_w_empty + 8 * s);       // frees the ring slot when these MMAs have read it
+                tc_commit_mc(sm.bar_w_empty + 8 * s, 3);  // frees the ring slot in both CTAs of the pair once these MMAs have read it
             }
             tc_commit(sm.bar_acc_full);                  // accumulator of GEMM l complete
         }
@@ -597,10 +623,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
     sm.bar_a_ready = smem_u32(bars + 2 * kStages);
     sm.bar_acc_full = smem_u32(bars + 2 * kStages + kGroups);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = (args.m + kTileM - 1) / kTileM;
+    // both CTAs of a cluster must walk weight streams of equal length: the tile count is padded to an even number and
+    // a padding tile simply has no valid rows
+    const int num_tiles = ((args.m + kTileM - 1) / kTileM + 1) & ~1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(sm.bar_w_full + 8 * s, 1); mbar_init(sm.bar_w_empty + 8 * s, 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(sm.bar_w_full + 8 * s, 1); mbar_init(sm.bar_w_empty + 8 * s, 2); }
         for (int g = 0; g < kGroups; ++g) mbar_init(sm.bar_a_ready + 8 * g, kTileM);
         mbar_init(sm.bar_acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -611,6 +639,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                       // the peer's barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -624,6 +653,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                       // nobody leaves while the peer may still signal into this CTA
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
@@ -639,10 +669,21 @@ int launch_chain(const ChainArgs &a, cudaStream_t st) {
     int dev = 0, sms = 148;
     OCC_CUDA(cudaGetDevice(&dev));
     OCC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int tiles = (a.m + kTileM - 1) / kTileM;
-    const int grid = tiles < sms ? tiles : sms;
-    mlp_chain_tc_kernel<NPASS, CHAIN><<<grid, kThreads, smem_bytes, st>>>(a);
-    OCC_LAUNCH_CHECK();
+    const int tiles = ((a.m + kTileM - 1) / kTileM + 1) & ~1;
+    const int grid = tiles < (sms & ~1) ? tiles : (sms & ~1);          // CTA pairs
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OCC_CUDA(cudaLaunchKernelEx(&cfg, mlp_chain_tc_kernel<NPASS, CHAIN>, a));
     return OCCNERF_OK;
 }
 
