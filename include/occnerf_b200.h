@@ -90,6 +90,17 @@ int occnerf_knn_hier(const float *queries, int m, int group_stride, const float 
                      const int32_t *cluster_ranges, int nf, int nc, const int32_t *fine_gid, const int32_t *center_gid,
                      int k, int32_t *out_fine, int32_t *out_center, int out_stride, occnerf_stream_t stream);
 
+/* All four OccNeRF levels in one launch through a three-level cluster tree (level 3 clusters levels 2 and 1, level 2
+ * clusters level 0); ids bit-identical to occnerf_knn.  Tables are built once per subject (occnerf_b200.ops.build_knn_tree):
+ * p0s [n0,4] level-0 points sorted by level-2 cluster in p2s order (.w = vertex id bits); p1s [n1,4] / p2s [n2,4] sorted by
+ * level-3 cluster (.w = row in the level); p3 [n3,4]; c2tab [n2,4] = (radius, begin0, count0, -) per p2s entry;
+ * c3tab [n3,4] = (r32, r31, R30, -); c3rng [n3,4] int32 = (begin2, count2, begin1, count1); gid1/2/3: level row -> vertex
+ * id; inv2 [n2]: level-2 row -> position in p2s.  out [m,4,k] int32. */
+int occnerf_knn_tree(const float *queries, int m, int group_stride, const float *p0s, const float *p1s, const float *p2s,
+                     const float *p3, const float *c2tab, const float *c3tab, const int32_t *c3rng, const int32_t *gid1,
+                     const int32_t *gid2, const int32_t *gid3, const int32_t *inv2, int n0, int n1, int n2, int n3, int k,
+                     int32_t *out, occnerf_stream_t stream);
+
 /* ---- per-sample surface geometry -> 4-D hash-grid input (occnerf_mlp.py:146-167) --------------------
  * knn_idx rows have `knn_stride` int32 entries, the first 10 being the level-0 neighbours.
  * enc_in [m,4] = (cos-weighted mean of the 3 nearest base vertices normalised to [0,1]^3, clamp((d+.2)/.5));
@@ -155,16 +166,17 @@ int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int c
  * act_dtype != 0.  raw [m, ldr]: columns 0..3 = (rgb_pre3, sigma_pre1) are written.
  * act_save: NULL (act_dtype 0, inference) or a buffer [slots][slot_stride][256] receiving the post-ReLU activations of
  * the 8 hidden layers (slots 0..3 = pts1..4, 4..7 = rgb1..4) for the backward pass: fp32 (act_dtype 1, 8 slots) or
- * bf16 (act_dtype 2, 10 slots: slot 8 = input of pts0 (80 columns), slot 9 = input of rgb0 (144 columns)). */
+ * bf16 (act_dtype 2, 10 slots: slot 8 = input of pts0 (80 columns), slot 9 = input of rgb0 (144 columns)).
+ * relu_mask: NULL or [8][slot_stride][8] uint32 receiving one bit per hidden unit (activation > 0) for the backward chain. */
 int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, float *raw, int ldr, void *act_save,
-                           int act_dtype, long slot_stride, occnerf_stream_t stream);
+                           int act_dtype, long slot_stride, void *relu_mask, occnerf_stream_t stream);
 
 /* Fused data-gradient chain (the transposed layers in reverse order, ReLU masks from the saved bf16 activations).
- * g_raw [m,5] (d rgb_pre3, d sigma_pre, unused); act_bf16 [10][slot_stride][256] as saved by occnerf_mlp_forward_tc.
+ * g_raw [m,5] (d rgb_pre3, d sigma_pre, unused); relu_mask [8][slot_stride][8] as saved by occnerf_mlp_forward_tc.
  * Writes gXB [m,132] columns 64..131 = d(agg35, var1, h32) summed over both trunks, and g_save [10][slot_stride][256]
  * bf16 = gradients w.r.t. the pre-activations: slots 0..3 = rgb3, rgb2, rgb1, rgb0; 4 = geo (columns 0..63 features,
  * 64 sigma); 5..8 = pts3, pts2, pts1, pts0; 9 = d raw[:, :3]. */
-int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, const void *act_bf16, float *gXB,
+int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, const void *relu_mask, float *gXB,
                             void *g_save, long slot_stride, occnerf_stream_t stream);
 
 /* Weight and bias gradients dW_l = G_l^T X_l, db_l = colsum(G_l) of all 10 layers from the two bf16 buffers above

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "occnerf_warp_backward": [_vp] * 8 + [_i] * 6 + [_vp, _vp],
     "occnerf_knn": [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "occnerf_knn_hier": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp],
+    "occnerf_knn_tree": [_vp, _i, _i] + [_vp] * 11 + [_i] * 5 + [_vp, _vp],
     "occnerf_sample_geometry": [_vp, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _vp],
     "occnerf_hashgrid_level_scales": [_f, _u, _u, _vp, _vp],
     "occnerf_hashgrid_forward": [_vp] * 5 + [_i, _i] + [_u] * 4 + [_vp] * 4,
@@ -38,7 +39,7 @@ _SIGNATURES = {
     "occnerf_sgemm": [_vp, _l, _l, _vp, _l, _l, _vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp],
     "occnerf_colsum": [_vp, _l, _vp, _l, _i, _i, _vp, _vp],
     "occnerf_mlp_pack_weights": [C.POINTER(MlpParams), _i, _i, _vp, _vp],
-    "occnerf_mlp_forward_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _l, _vp],
+    "occnerf_mlp_forward_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _l, _vp, _vp],
     "occnerf_mlp_backward_tc": [_vp, _i, _vp, _i, _vp, _vp, _vp, _l, _vp],
     "occnerf_mlp_wgrad_tc": [_vp, _vp, _i, _l, _vp, _vp, _vp],
     "occnerf_composite_forward": [_vp] * 5 + [_i, _i] + [_vp] * 7,

@@ -255,9 +255,10 @@ struct ChainArgs {
     void *act_save;                  // [8 or 10][slot_stride][256] post-ReLU activations (fp32 / bf16) or NULL;
                                      // bf16 mode adds slot 8 = pts0 input (80 cols) and slot 9 = rgb0 input (144 cols)
     int act_dtype;                   // 0 none, 1 fp32, 2 bf16
+    uint32_t *relu_mask;             // [8][slot_stride][8] one bit per hidden unit (> 0), written by the forward chain in
+                                     // bf16 mode and read by the backward chain: 32 B per row and layer instead of 512 B
     // backward
     const float *g_raw;              // [m,5]
-    const __nv_bfloat16 *act;        // [8][m][256] bf16 (saved by the forward kernel)
     float *gXB;                      // [m,132]: cols 64..131 written (d agg, d var, d h; both trunks summed)
     __nv_bfloat16 *g_save;           // [10][slot_stride][256] bf16: gradients w.r.t. the pre-activations (slot 9 = d raw[:, :3])
 };
@@ -417,17 +418,23 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                 const int slot = l < 4 ? l : l - 1;                  // 0..3 = pts1..4, 4..7 = rgb1..4
                 // software pipeline over the eight 32-column groups: the TMEM load and the bias of group g+1 are in
                 // flight while group g is processed (4 epilogue warps per SM cannot hide those latencies by themselves)
+                const bool want_mask = args.relu_mask != nullptr;
                 auto load_bias = [&](int cg, float4 (&b)[8]) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) b[i] = __ldg(reinterpret_cast<const float4 *>(bias + cg * 32) + i);
                 };
                 auto process = [&](int cg, const uint32_t (&r)[32], const float4 (&b)[8]) {
+                    uint32_t bits = 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float bj[8] = {b[2 * j].x, b[2 * j].y, b[2 * j].z, b[2 * j].w, b[2 * j + 1].x, b[2 * j + 1].y, b[2 * j + 1].z, b[2 * j + 1].w};
                         float v[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[j * 8 + i]) + bj[i], 0.f);
+                        if (want_mask) {                              // ReLU'(x) = [x > 0]; v >= 0 here, so > 0 <=> any bit set
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) bits += min(__float_as_uint(v[i]), 1u) << (j * 8 + i);
+                        }
                         store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
                         const long e = ((long)slot * args.slot_stride + grow) * 256 + cg * 32 + j * 8;
                         if (valid && args.act_dtype == 1) {
@@ -438,6 +445,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                             *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(args.act_save) + e) = pack_bf16x8(v);
                         }
                     }
+                    if (valid && want_mask) args.relu_mask[((long)slot * args.slot_stride + grow) * 8 + cg] = bits;
                     publish(sm, cg, cg + 1);
                 };
                 uint32_t ra[32], rb[32];
@@ -489,6 +497,13 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
             publish(sm, 0, 1);
         }
         for (int d = 0; d < kLayers; ++d, ++acc_cnt) {
+            uint4 m0 = make_uint4(0u, 0u, 0u, 0u), m1 = m0;          // the layer's 8 ReLU-mask words, fetched before the wait
+            if (valid && d != 9 && d != 4) {
+                const int slot = d < 4 ? 7 - d : 8 - d;              // d0..3 -> R4..R1 (slots 7..4); d5..8 -> H4..H1 (slots 3..0)
+                const uint4 *mp = reinterpret_cast<const uint4 *>(args.relu_mask + ((long)slot * args.slot_stride + grow) * 8);
+                m0 = __ldg(mp);
+                m1 = __ldg(mp + 1);
+            }
             mbar_wait(sm.bar_acc_full, acc_cnt & 1);
             tc_fence_after();
             const uint32_t t_acc = t_lane + (uint32_t)(d & 1) * 256;
@@ -564,45 +579,31 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
                 publish(sm, 2, 3);
             } else {
                 // through a ReLU: G = acc * (saved activation > 0) -> next A operand, and saved for the weight gradient
-                const int slot = d < 4 ? 7 - d : 8 - d;              // d0..3 -> R4..R1 (slots 7..4); d5..8 -> H4..H1 (slots 3..0)
                 const int gslot = d;                                 // g_save: 0..3 rgb3..rgb0, 4 geo, 5..8 pts3..pts0
-                const __nv_bfloat16 *arow = args.act + (slot * args.slot_stride + (valid ? grow : 0)) * 256;
-                auto load_mask = [&](int cg, uint4 (&mk)[4]) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) mk[j] = __ldg(reinterpret_cast<const uint4 *>(arow + cg * 32 + j * 8));
-                };
-                auto process = [&](int cg, const uint32_t (&r)[32], const uint4 (&mk)[4]) {
+                // the ReLU masks of this layer: 8 words per row, loaded before the accumulator is even waited for
+                auto process = [&](int cg, const uint32_t (&r)[32], uint32_t bits) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t w[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
                         float v[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            // bf16 > 0  <=>  sign bit clear and not zero (activations are post-ReLU, never negative)
-                            const uint32_t half = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
-                            v[i] = (valid && (half & 0x7FFFu) != 0u && (half & 0x8000u) == 0u) ? __uint_as_float(r[j * 8 + i]) : 0.f;
-                        }
+                        for (int i = 0; i < 8; ++i) v[i] = ((bits >> (j * 8 + i)) & 1u) ? __uint_as_float(r[j * 8 + i]) : 0.f;
                         store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
                         if (valid) *reinterpret_cast<uint4 *>(args.g_save + (gslot * args.slot_stride + grow) * 256 + cg * 32 + j * 8) = pack_bf16x8(v);
                     }
                     publish(sm, cg, cg + 1);
                 };
                 uint32_t ra[32], rb[32];
-                uint4 ma[4], mb[4];
                 tmem_ld32_issue(t_acc, ra);
-                load_mask(0, ma);
 #pragma unroll 1
                 for (int cg = 0; cg < 8; cg += 2) {
                     tmem_ld_wait();
                     tmem_ld32_issue(t_acc + (cg + 1) * 32, rb);
-                    load_mask(cg + 1, mb);
-                    process(cg, ra, ma);
+                    process(cg, ra, m0.x);
                     tmem_ld_wait();
-                    if (cg + 2 < 8) {
-                        tmem_ld32_issue(t_acc + (cg + 2) * 32, ra);
-                        load_mask(cg + 2, ma);
-                    }
-                    process(cg + 1, rb, mb);
+                    if (cg + 2 < 8) tmem_ld32_issue(t_acc + (cg + 2) * 32, ra);
+                    process(cg + 1, rb, m0.y);
+                    m0 = make_uint4(m0.z, m0.w, m1.x, m1.y);         // rotate the words (keeps them in registers)
+                    m1 = make_uint4(m1.z, m1.w, 0u, 0u);
                 }
             }
         }
@@ -719,7 +720,7 @@ extern "C" int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_
 }
 
 extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, float *raw, int ldr, void *act_save,
-                                      int act_dtype, long slot_stride, occnerf_stream_t stream) {
+                                      int act_dtype, long slot_stride, void *relu_mask, occnerf_stream_t stream) {
     if (m == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(XB && packed && raw, "mlp_forward_tc: null pointer");
     OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "mlp_forward_tc: n_pass=%d (supported: 1, 3)", n_pass);
@@ -732,20 +733,22 @@ extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int 
     fill_layout(a, n_pass, 0, packed);
     OCC_CHECK_ARG(act_dtype == 0 || slot_stride >= m, "mlp_forward_tc: slot_stride=%ld < m=%d", slot_stride, m);
     a.XB = XB; a.raw = raw; a.ldr = ldr; a.act_save = act_save; a.act_dtype = act_dtype; a.slot_stride = slot_stride;
+    a.relu_mask = (uint32_t *)relu_mask;
+    OCC_CHECK_ARG(((uintptr_t)relu_mask & 15) == 0, "mlp_forward_tc: relu_mask must be 16-byte aligned");
     return n_pass == 1 ? launch_chain<1, 0>(a, (cudaStream_t)stream) : launch_chain<3, 0>(a, (cudaStream_t)stream);
 }
 
-extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, const void *act_bf16,
+extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, const void *relu_mask,
                                        float *gXB, void *g_save, long slot_stride, occnerf_stream_t stream) {
     if (m == 0) return OCCNERF_OK;
-    OCC_CHECK_ARG(g_raw && packed_bwd && act_bf16 && gXB && g_save, "mlp_backward_tc: null pointer");
+    OCC_CHECK_ARG(g_raw && packed_bwd && relu_mask && gXB && g_save, "mlp_backward_tc: null pointer");
     OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "mlp_backward_tc: n_pass=%d (supported: 1, 3)", n_pass);
-    OCC_CHECK_ARG(((uintptr_t)gXB & 15) == 0 && ((uintptr_t)packed_bwd & 15) == 0 && ((uintptr_t)act_bf16 & 15) == 0 &&
+    OCC_CHECK_ARG(((uintptr_t)gXB & 15) == 0 && ((uintptr_t)packed_bwd & 15) == 0 && ((uintptr_t)relu_mask & 15) == 0 &&
                   ((uintptr_t)g_save & 15) == 0, "mlp_backward_tc: buffers must be 16-byte aligned");
     ChainArgs a = {};
     a.m = m;
     fill_layout(a, n_pass, 1, packed_bwd);
     OCC_CHECK_ARG(slot_stride >= m, "mlp_backward_tc: slot_stride=%ld < m=%d", slot_stride, m);
-    a.g_raw = g_raw; a.act = (const __nv_bfloat16 *)act_bf16; a.gXB = gXB; a.g_save = (__nv_bfloat16 *)g_save; a.slot_stride = slot_stride;
+    a.g_raw = g_raw; a.relu_mask = (uint32_t *)relu_mask; a.gXB = gXB; a.g_save = (__nv_bfloat16 *)g_save; a.slot_stride = slot_stride;
     return n_pass == 1 ? launch_chain<1, 1>(a, (cudaStream_t)stream) : launch_chain<3, 1>(a, (cudaStream_t)stream);
 }

@@ -40,14 +40,16 @@ class MlpTc:
         m, dev = XB.shape[0], XB.device
         packed = self.pack(W, dev, 0)
         stride = (m + 63) // 64 * 64
-        acts = None
+        acts, mask = None, None
         if save:
             acts = torch.empty(10, stride, 256, device=dev, dtype=bf16)
+            mask = torch.empty(8, stride, 8, device=dev, dtype=torch.int32)      # one bit per hidden unit: ReLU'(x)
             if stride > m:
                 acts[:, m:].zero_()
         call("occnerf_mlp_forward_tc", XB.data_ptr(), m, packed.data_ptr(), self.n_pass, raw.data_ptr(), raw.shape[1],
-             acts.data_ptr() if save else None, 2 if save else 0, stride, stream(), work=M.FLOP_FWD * m)
-        return {"acts": acts} if save else None
+             acts.data_ptr() if save else None, 2 if save else 0, stride, mask.data_ptr() if save else None, stream(),
+             work=M.FLOP_FWD * m)
+        return {"acts": acts, "mask": mask} if save else None
 
     def backward(self, XB, g_raw, W: M.MlpWeights, saved):
         m, dev = XB.shape[0], XB.device
@@ -58,7 +60,7 @@ class MlpTc:
         g_save = torch.empty(10, stride, 256, device=dev, dtype=bf16)
         if stride > m:
             g_save[:, m:].zero_()
-        call("occnerf_mlp_backward_tc", g_raw.data_ptr(), m, packed.data_ptr(), self.n_pass, acts.data_ptr(), gXB.data_ptr(),
+        call("occnerf_mlp_backward_tc", g_raw.data_ptr(), m, packed.data_ptr(), self.n_pass, saved["mask"].data_ptr(), gXB.data_ptr(),
              g_save.data_ptr(), stride, stream(), work=M.FLOP_FWD * m)
         if self.wgrad == "lib":
             with _lib.region("lib:wgrad(cuBLAS bf16)+bias sums"):

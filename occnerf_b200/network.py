@@ -165,7 +165,7 @@ class RenderConfig:
     ignore_non_rigid_motions: bool = False
     bgcolor: tuple = (0.0, 0.0, 0.0)
     mlp_engine: str = "fp32"        # "fp32" (exact SIMT) | "tc3" (tcgen05 split-bf16) | "tc1" (tcgen05 bf16)
-    knn_mode: str = "hier"          # "hier" (cluster-pruned exact search) | "brute" (tiled brute force); same ids
+    knn_mode: str = "tree"          # "tree" (one launch, 3-level cluster tree) | "hier" (two 2-level launches) | "brute"; same ids
 
 
 # ----------------------------------------------------------------------------- differentiable stages
@@ -229,6 +229,8 @@ class _QueryFn(torch.autograd.Function):
             xyz = M.nonrigid_offsets(xyz, nr_cond, nr_window, nw, nb, const_off=getattr(net, "_nr_const", None))
         if net.cfg.knn_mode == "brute":
             knn_idx = ops.knn(xyz, st["supports4"], st["level_begin"], 10, support_gid=st["support_gid"])
+        elif net.cfg.knn_mode == "tree":
+            knn_idx = ops.knn_tree(xyz, max(1, int(getattr(net, "_group_stride", 1))), st["tree"])
         else:
             knn_idx = torch.empty(m, 4, 10, device=dev, dtype=i32)
             gs = max(1, int(getattr(net, "_group_stride", 1)))
@@ -344,7 +346,7 @@ class Network(nn.Module):
                                # cluster hierarchies for the pruned exact search: level 0 around level 2, level 1 around level 3
                                hier0=ops.build_knn_hierarchy(base, base[fps[1]]), gid2=fps[1].to(i32).contiguous(),
                                hier1=ops.build_knn_hierarchy(base[fps[0]], base[fps[2]]), gid1=fps[0].to(i32).contiguous(),
-                               gid3=fps[2].to(i32).contiguous())
+                               gid3=fps[2].to(i32).contiguous(), tree=ops.build_knn_tree(base, fps))
         return self._cache
 
     def _engine(self):

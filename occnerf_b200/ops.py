@@ -104,6 +104,73 @@ def knn_hier(queries, group_stride, fine4, centers4, ranges, out, fine_level, ce
     return out
 
 
+def _nearest(fine, centers):
+    diff = fine[:, None, :].float() - centers[None, :, :].float()
+    return torch.sqrt((diff * diff).sum(-1)).min(1)                    # explicit differences (no matmul trick)
+
+
+def _inflate(r):
+    return r * 1.00001 + 1e-6
+
+
+def build_knn_tree(base: torch.Tensor, fps):
+    """Static three-level cluster tree for occnerf_knn_tree (see include/occnerf_b200.h for the table layout)."""
+    dev = base.device
+    P1, P2, P3 = base[fps[0]], base[fps[1]], base[fps[2]]
+    n0, n1, n2, n3 = base.shape[0], P1.shape[0], P2.shape[0], P3.shape[0]
+
+    def bits(t):
+        return t.to(i32).view(f32)
+
+    def amax(n, idx, val):
+        return torch.zeros(n, device=dev, dtype=f32).scatter_reduce(0, idx, val, reduce="amax", include_self=True)
+
+    d23, a23 = _nearest(P2, P3)
+    order2 = torch.argsort(a23, stable=True)
+    cnt32 = torch.bincount(a23, minlength=n3)
+    beg32 = torch.cumsum(cnt32, 0) - cnt32
+    inv2 = torch.empty(n2, device=dev, dtype=torch.int64)
+    inv2[order2] = torch.arange(n2, device=dev)
+    d13, a13 = _nearest(P1, P3)
+    order1 = torch.argsort(a13, stable=True)
+    cnt31 = torch.bincount(a13, minlength=n3)
+    beg31 = torch.cumsum(cnt31, 0) - cnt31
+    d02, a02 = _nearest(base, P2)
+    pos0 = inv2[a02]                                                   # cluster of every vertex, as a position in p2s
+    order0 = torch.argsort(pos0, stable=True)
+    cnt20 = torch.bincount(pos0, minlength=n2)
+    beg20 = torch.cumsum(cnt20, 0) - cnt20
+    r20 = _inflate(amax(n2, pos0, d02))
+    R30 = _inflate(amax(n3, a23[order2], d23[order2] + r20))
+
+    def f4(pts, order):
+        out = torch.empty(pts.shape[0], 4, device=dev, dtype=f32)
+        out[:, :3] = pts[order].float()
+        out[:, 3] = bits(order)
+        return out.contiguous()
+
+    zero2, zero3 = torch.zeros(n2, device=dev), torch.zeros(n3, device=dev)
+    return dict(
+        p0s=f4(base, order0), p1s=f4(P1, order1), p2s=f4(P2, order2), p3=to_float4(P3),
+        c2tab=torch.stack([r20, bits(beg20), bits(cnt20), zero2], 1).contiguous(),
+        c3tab=torch.stack([_inflate(amax(n3, a23, d23)), _inflate(amax(n3, a13, d13)), R30, zero3], 1).contiguous(),
+        c3rng=torch.stack([beg32, cnt32, beg31, cnt31], 1).to(i32).contiguous(),
+        gid1=fps[0].to(i32).contiguous(), gid2=fps[1].to(i32).contiguous(), gid3=fps[2].to(i32).contiguous(),
+        inv2=inv2.to(i32).contiguous(), n=(n0, n1, n2, n3))
+
+
+def knn_tree(queries, group_stride, tree, out=None):
+    """All 4 levels x k=10 in one launch -> (m,4,10) int32 vertex ids."""
+    m = queries.shape[0]
+    if out is None:
+        out = torch.empty(m, 4, 10, device=queries.device, dtype=i32)
+    t = tree
+    call("occnerf_knn_tree", ptr(queries, f32), m, int(group_stride), ptr(t["p0s"], f32), ptr(t["p1s"], f32), ptr(t["p2s"], f32),
+         ptr(t["p3"], f32), ptr(t["c2tab"], f32), ptr(t["c3tab"], f32), ptr(t["c3rng"], i32), ptr(t["gid1"], i32),
+         ptr(t["gid2"], i32), ptr(t["gid3"], i32), ptr(t["inv2"], i32), *t["n"], 10, ptr(out, i32), stream())
+    return out
+
+
 def sample_geometry(xyz, knn_idx, point_base, point_norms, bound, raw=None):
     """-> enc_in (m,4), dist.  With `raw` (m,5) given, dist is written into raw[:,4] in place and returned as a view."""
     m = xyz.shape[0]
