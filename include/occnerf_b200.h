@@ -95,8 +95,10 @@ int occnerf_knn_hier(const float *queries, int m, int group_stride, const float 
  * p0s [n0,4] level-0 points sorted by level-2 cluster in p2s order (.w = vertex id bits); p1s [n1,4] / p2s [n2,4] sorted by
  * level-3 cluster (.w = row in the level); p3 [n3,4]; c2tab [n2,4] = (radius, begin0, count0, -) per p2s entry;
  * c3tab [n3,4] = (r32, r31, R30, -); c3rng [n3,4] int32 = (begin2, count2, begin1, count1); gid1/2/3: level row -> vertex
- * id; inv2 [n2]: level-2 row -> position in p2s.  out [m,4,k] int32. */
-int occnerf_knn_tree(const float *queries, int m, int group_stride, const float *p0s, const float *p1s, const float *p2s,
+ * id; inv2 [n2]: level-2 row -> position in p2s.  out [m,4,k] int32.
+ * Queries are laid out [rays, group_stride]; a warp takes lane_rays consecutive rays x (32 / lane_rays) consecutive
+ * samples (lane_rays a power of two <= 32) -- a pure scheduling hint, the ids do not depend on it. */
+int occnerf_knn_tree(const float *queries, int m, int group_stride, int lane_rays, const float *p0s, const float *p1s, const float *p2s,
                      const float *p3, const float *c2tab, const float *c3tab, const int32_t *c3rng, const int32_t *gid1,
                      const int32_t *gid2, const int32_t *gid3, const int32_t *inv2, int n0, int n1, int n2, int n3, int k,
                      int32_t *out, occnerf_stream_t stream);
@@ -119,10 +121,13 @@ int occnerf_hashgrid_forward(const float *inputs, const float *embeddings, const
                              const float *level_scales, float *outputs, int layout, int ld, uint32_t B, uint32_t D,
                              uint32_t C, uint32_t L, float *dy_dx, uint32_t *cells, uint32_t *slots,
                              occnerf_stream_t stream);
-/* grad per `layout`; grad_embeddings accumulated in place (caller zeroes, as grid.py:78 does). */
+/* grad per `layout`; grad_embeddings accumulated in place (caller zeroes, as grid.py:78 does).
+ * run_length: 0 = one thread per (sample, level); 8 or 16 = one thread per (run of that many consecutive samples,
+ * level), which merges the reductions of consecutive samples that share a grid cell (inputs ordered along rays).
+ * Same sums either way. */
 int occnerf_hashgrid_backward(const float *grad, int layout, int ld, const float *inputs, const int32_t *offsets,
                               const float *level_scales, float *grad_embeddings, uint32_t B, uint32_t D, uint32_t C,
-                              uint32_t L, occnerf_stream_t stream);
+                              uint32_t L, int run_length, occnerf_stream_t stream);
 /* grad_inputs[b,d] = sum_{l,c} grad[b,l,c] * dy_dx[b,l,d,c]  (gridencoder.cu:343-369) */
 int occnerf_hashgrid_input_backward(const float *grad, int layout, int ld, const float *dy_dx, float *grad_inputs,
                                     uint32_t B, uint32_t D, uint32_t C, uint32_t L, occnerf_stream_t stream);

@@ -225,6 +225,80 @@ hashgrid_bwd_kernel(const float *__restrict__ grad, int layout, long ld, const f
     }
 }
 
+// Run-length variant of the scatter for inputs that are ordered along rays (what the render path produces): thread =
+// (segment of SEG consecutive samples, level), level fastest.  Neighbouring samples fall into the same grid cell at the
+// coarse levels (and ~1/3 of the time even at the finest), so the thread accumulates the 2^D corner gradients of the
+// current cell in registers and issues its reductions only when the cell changes: 1.5-4.5x fewer L2 atomics on the
+// addresses that are contended the most.  Mathematically the same sum as hashgrid_bwd_kernel (fp32 addition order differs,
+// as it does between any two runs of an atomic scatter).
+template <uint32_t D, uint32_t C, uint32_t SEG>
+__global__ void __launch_bounds__(kThreads)
+hashgrid_bwd_runs_kernel(const float *__restrict__ grad, int layout, long ld, const float *__restrict__ inputs,
+                         const int32_t *__restrict__ offsets, const float *__restrict__ scales, float *__restrict__ g_emb,
+                         uint32_t B, uint32_t L) {
+    const unsigned long long gid = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+    const uint32_t nseg = (B + SEG - 1) / SEG;
+    if (gid >= (unsigned long long)nseg * L) return;
+    const uint32_t seg = (uint32_t)(gid / L), level = (uint32_t)(gid - (unsigned long long)seg * L);
+    const uint32_t off = (uint32_t)__ldg(offsets + level);
+    const uint32_t hashmap_size = (uint32_t)__ldg(offsets + level + 1) - off;
+    const float scale = __ldg(scales + level);
+    const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+    float *gg = g_emb + (size_t)off * C;
+    constexpr uint32_t NC = 1u << D;
+    uint32_t cur[D];
+    float acc[NC][C];
+    bool have = false;
+    auto flush = [&]() {
+#pragma unroll
+        for (uint32_t k = 0; k < NC; ++k) {
+            uint32_t gl[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) gl[d] = cur[d] + ((k >> d) & 1u);
+            float *dst = gg + (size_t)cell_slot<D>(gl, hashmap_size, resolution) * C;
+            if constexpr (C == 2) {
+                red_add_v2(dst, acc[k][0], acc[k][1]);
+            } else {
+#pragma unroll
+                for (uint32_t c = 0; c < C; ++c) atomicAdd(dst + c, acc[k][c]);
+            }
+        }
+    };
+    const uint32_t b0 = seg * SEG, b1 = min(B, b0 + SEG);
+    for (uint32_t b = b0; b < b1; ++b) {
+        const Located<D> loc = locate<D>(inputs + (size_t)b * D, scale);
+        if (!loc.inside) continue;
+        const float *gp = layout == OCCNERF_LAYOUT_LBC ? grad + ((size_t)level * B + b) * C : grad + (size_t)b * ld + level * C;
+        float g[C];
+        bool any = false;
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) { g[c] = __ldg(gp + c); any |= g[c] != 0.0f; }
+        if (!any) continue;
+        bool same = have;
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) same = same && (loc.g[d] == cur[d]);
+        if (!same) {
+            if (have) flush();
+            have = true;
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) cur[d] = loc.g[d];
+#pragma unroll
+            for (uint32_t k = 0; k < NC; ++k)
+#pragma unroll
+                for (uint32_t c = 0; c < C; ++c) acc[k][c] = 0.0f;
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < NC; ++k) {
+            float w = 1.0f;
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) w *= (k & (1u << d)) ? loc.frac[d] : 1.0f - loc.frac[d];
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) acc[k][c] = __fmaf_rn(w, g[c], acc[k][c]);
+        }
+    }
+    if (have) flush();
+}
+
 __global__ void __launch_bounds__(kThreads)
 hashgrid_input_bwd_kernel(const float *__restrict__ grad, int layout, long ld, const float *__restrict__ dy_dx,
                           float *__restrict__ g_in, uint32_t B, uint32_t D, uint32_t C, uint32_t L) {
@@ -252,7 +326,16 @@ int launch_fwd(const float *inputs, const float *emb, const int32_t *offsets, co
 }
 template <uint32_t D, uint32_t C>
 int launch_bwd(const float *grad, int layout, long ld, const float *inputs, const int32_t *offsets,
-               const float *scales, float *g_emb, uint32_t B, uint32_t L, cudaStream_t st) {
+               const float *scales, float *g_emb, uint32_t B, uint32_t L, int run_length, cudaStream_t st) {
+    if (run_length == 8 || run_length == 16) {
+        const long nseg = ((long)B + run_length - 1) / run_length;
+        if (run_length == 8)
+            hashgrid_bwd_runs_kernel<D, C, 8><<<occ_div_up(nseg * L, kThreads), kThreads, 0, st>>>(grad, layout, ld, inputs, offsets, scales, g_emb, B, L);
+        else
+            hashgrid_bwd_runs_kernel<D, C, 16><<<occ_div_up(nseg * L, kThreads), kThreads, 0, st>>>(grad, layout, ld, inputs, offsets, scales, g_emb, B, L);
+        OCC_LAUNCH_CHECK();
+        return OCCNERF_OK;
+    }
     hashgrid_bwd_kernel<D, C><<<occ_div_up((long)B * L, kThreads), kThreads, 0, st>>>(grad, layout, ld, inputs, offsets,
                                                                                      scales, g_emb, B, L);
     OCC_LAUNCH_CHECK();
@@ -313,13 +396,15 @@ extern "C" int occnerf_hashgrid_forward(const float *inputs, const float *embedd
 
 extern "C" int occnerf_hashgrid_backward(const float *grad, int layout, int ld, const float *inputs,
                                          const int32_t *offsets, const float *level_scales, float *grad_embeddings,
-                                         uint32_t B, uint32_t D, uint32_t C, uint32_t L, occnerf_stream_t stream) {
+                                         uint32_t B, uint32_t D, uint32_t C, uint32_t L, int run_length,
+                                         occnerf_stream_t stream) {
     if (B == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(grad && inputs && offsets && level_scales && grad_embeddings, "hashgrid_backward: null pointer");
+    OCC_CHECK_ARG(run_length == 0 || run_length == 8 || run_length == 16, "hashgrid_backward: run_length=%d (0, 8 or 16)", run_length);
     if (int e = check_layout(layout, ld, L, C)) return e;
     if (B == 0) return OCCNERF_OK;
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(DD, CC) launch_bwd<DD, CC>(grad, layout, ld, inputs, offsets, level_scales, grad_embeddings, B, L, st)
+#define CALL(DD, CC) launch_bwd<DD, CC>(grad, layout, ld, inputs, offsets, level_scales, grad_embeddings, B, L, run_length, st)
     OCC_DISPATCH_DC(D, C, CALL)
 #undef CALL
 }

@@ -184,6 +184,15 @@ __device__ __forceinline__ float dist2_rn(float qx, float qy, float qz, const fl
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// A cluster (centre c, radius r >= every member's distance to c, inflated on the host) can be skipped when
+// |q-c| - r > sqrt(U), U = the current k-th squared distance.  `prune_reach` turns U into the reach sqrt(U) (+ margins far
+// above fp32 rounding) once per bound update; the per-cluster test is then sqrt-free: |q-c|^2 > (reach + r)^2.
+__device__ __forceinline__ float prune_reach(float worst_d2) { return sqrtf(worst_d2) * 1.00001f + 1e-6f; }
+__device__ __forceinline__ bool cannot_prune(float d2_centre, float radius, float reach) {
+    const float t = (reach + radius) * 1.000001f;
+    return !(d2_centre > t * t);
+}
+
 constexpr int kHierThreads = 1024;   // one CTA per SM (the fine level fills most of shared memory) -> 32 warps/SM
 
 template <int K>
@@ -243,11 +252,12 @@ knn_hier_kernel(const float *__restrict__ queries, int m, int group_stride, cons
         }
     }
     // ---- pass 2: every other cluster that can still contain one of the k nearest
+    float reach = prune_reach(dk[K - 1]);
 #pragma unroll 2
     for (int c = 0; c < nc; ++c) {
         const float4 cc = s_cent[c];
-        const float lb = sqrtf(dist2_rn(qx, qy, qz, cc)) - cc.w;
-        const bool need = active && c != seed && !(lb > sqrtf(dk[K - 1]) * 1.00001f + 1e-6f);
+        const float t = (reach + cc.w) * 1.000001f;
+        const bool need = active && c != seed && !(dist2_rn(qx, qy, qz, cc) > t * t);
         if (!__any_sync(OCC_FULL, need)) continue;
         const int2 rg = s_rng[c];
         for (int i = rg.x; i < rg.x + rg.y; ++i) {
@@ -256,6 +266,7 @@ knn_hier_kernel(const float *__restrict__ queries, int m, int group_stride, cons
             const int row = __float_as_int(p.w);
             if (need && (d < dk[K - 1] || (d == dk[K - 1] && row < ik[K - 1]))) topk_insert_lex<K>(dk, ik, d, row);
         }
+        reach = prune_reach(dk[K - 1]);
     }
     if (active) {
         int32_t *o = out_fine + q * out_stride;
@@ -303,13 +314,11 @@ __device__ __forceinline__ void write_topk(int32_t *__restrict__ o, const int (&
 #pragma unroll
     for (int t = 0; t < K; ++t) o[t] = (ik[t] == 0x7fffffff) ? -1 : (gid ? __ldg(gid + ik[t]) : ik[t]);
 }
-__device__ __forceinline__ bool cannot_prune(float d2_centre, float radius, float worst_d2) {
-    return !(sqrtf(d2_centre) - radius > sqrtf(worst_d2) * 1.00001f + 1e-6f);
-}
 
 template <int K>
 __global__ void __launch_bounds__(kHierThreads)
-knn_tree_kernel(const float *__restrict__ queries, int m, int group_stride, const TreeArgs T, int32_t *__restrict__ out) {
+knn_tree_kernel(const float *__restrict__ queries, int m, int group_stride, int lane_rays, const TreeArgs T,
+                int32_t *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char hier_smem[];
     float4 *s0 = reinterpret_cast<float4 *>(hier_smem);
     float4 *s1 = s0 + T.n0, *s2 = s1 + T.n1, *s3 = s2 + T.n2, *sc2 = s3 + T.n3, *sc3 = sc2 + T.n2;
@@ -319,11 +328,19 @@ knn_tree_kernel(const float *__restrict__ queries, int m, int group_stride, cons
     for (int i = threadIdx.x; i < T.n2; i += kHierThreads) { s2[i] = __ldg(T.p2s + i); sc2[i] = __ldg(T.c2tab + i); }
     for (int i = threadIdx.x; i < T.n3; i += kHierThreads) { s3[i] = __ldg(T.p3 + i); sc3[i] = __ldg(T.c3tab + i); sr3[i] = __ldg(T.c3rng + i); }
     __syncthreads();
-    const long warp_global = ((long)blockIdx.x * kHierThreads + threadIdx.x) >> 5;
+    // lane -> query: a warp covers `lane_rays` consecutive rays x (32 / lane_rays) consecutive samples, i.e. a compact patch
+    // of space (adjacent pixels are millimetres apart, adjacent samples ~1.5 cm), so its lanes need the same few clusters
     const int lane = threadIdx.x & 31;
-    const long j = warp_global % group_stride, r0 = (warp_global / group_stride) * 32;
-    const long q = (r0 + lane) * group_stride + j;
-    const bool active = q < m;
+    const int lane_samples = 32 / lane_rays;
+    const long jblocks = (group_stride + lane_samples - 1) / lane_samples;
+    // consecutive warps of a CTA take consecutive sample depths of the same rays: they run the same phases of the search at
+    // about the same time, which keeps the (large, unrolled) code of this kernel hot in the instruction cache.  Measured:
+    // a persistent grid-stride version that gives every warp a pseudo-random sequence of items is 1.4-1.7x SLOWER.
+    const long warp_global = ((long)blockIdx.x * kHierThreads + threadIdx.x) >> 5;
+    {
+    const long j = (warp_global % jblocks) * lane_samples + lane / lane_rays;
+    const long q = ((warp_global / jblocks) * lane_rays + lane % lane_rays) * group_stride + j;
+    const bool active = j < group_stride && q < m;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (active) { qx = __ldg(queries + q * 3); qy = __ldg(queries + q * 3 + 1); qz = __ldg(queries + q * 3 + 2); }
     int32_t *o = out + (active ? q : 0) * 4 * K;
@@ -354,12 +371,14 @@ knn_tree_kernel(const float *__restrict__ queries, int m, int group_stride, cons
             scan_members<K>(pts, lev == 2 ? rg.x : rg.z, lev == 2 ? rg.y : rg.w, need, qx, qy, qz, dk, ik);
             todo &= ~__ballot_sync(OCC_FULL, need);
         }
+        float reach = prune_reach(dk[K - 1]);
         for (int c = 0; c < T.n3; ++c) {
             const float4 tab = sc3[c];
-            const bool need = active && c != seed3 && cannot_prune(dist2_rn(qx, qy, qz, s3[c]), lev == 2 ? tab.x : tab.y, dk[K - 1]);
+            const bool need = active && c != seed3 && cannot_prune(dist2_rn(qx, qy, qz, s3[c]), lev == 2 ? tab.x : tab.y, reach);
             if (!__any_sync(OCC_FULL, need)) continue;
             const int4 rg = sr3[c];
             scan_members<K>(pts, lev == 2 ? rg.x : rg.z, lev == 2 ? rg.y : rg.w, need, qx, qy, qz, dk, ik);
+            reach = prune_reach(dk[K - 1]);
         }
         if (active) write_topk<K>(o + lev * K, ik, lev == 2 ? T.gid2 : T.gid1);
         if (lev == 2 && active && ik[0] != 0x7fffffff) seed2 = __ldg(T.inv2 + ik[0]);
@@ -377,18 +396,21 @@ knn_tree_kernel(const float *__restrict__ queries, int m, int group_stride, cons
             todo &= ~__ballot_sync(OCC_FULL, need);
         }
     }
+    float reach = prune_reach(dk[K - 1]);
     for (int c = 0; c < T.n3; ++c) {
-        const bool need3 = active && cannot_prune(dist2_rn(qx, qy, qz, s3[c]), sc3[c].z, dk[K - 1]);
+        const bool need3 = active && cannot_prune(dist2_rn(qx, qy, qz, s3[c]), sc3[c].z, reach);
         if (!__any_sync(OCC_FULL, need3)) continue;
         const int4 rg = sr3[c];
         for (int i2 = rg.x; i2 < rg.x + rg.y; ++i2) {
             const float4 ct = sc2[i2];
-            const bool need = need3 && i2 != seed2 && cannot_prune(dist2_rn(qx, qy, qz, s2[i2]), ct.x, dk[K - 1]);
+            const bool need = need3 && i2 != seed2 && cannot_prune(dist2_rn(qx, qy, qz, s2[i2]), ct.x, reach);
             if (!__any_sync(OCC_FULL, need)) continue;
             scan_members<K>(s0, __float_as_int(ct.y), __float_as_int(ct.z), need, qx, qy, qz, dk, ik);
+            reach = prune_reach(dk[K - 1]);
         }
     }
     if (active) write_topk<K>(o, ik, nullptr);
+    }
 }
 
 int launch_knn(const float *queries, int m, const float *supports4, const int32_t *gid, const int32_t *lb, int n_levels,
@@ -458,7 +480,7 @@ extern "C" int occnerf_knn_hier(const float *queries, int m, int group_stride, c
     return OCCNERF_OK;
 }
 
-extern "C" int occnerf_knn_tree(const float *queries, int m, int group_stride, const float *p0s, const float *p1s,
+extern "C" int occnerf_knn_tree(const float *queries, int m, int group_stride, int lane_rays, const float *p0s, const float *p1s,
                                 const float *p2s, const float *p3, const float *c2tab, const float *c3tab, const int32_t *c3rng,
                                 const int32_t *gid1, const int32_t *gid2, const int32_t *gid3, const int32_t *inv2, int n0,
                                 int n1, int n2, int n3, int k, int32_t *out, occnerf_stream_t stream) {
@@ -467,6 +489,8 @@ extern "C" int occnerf_knn_tree(const float *queries, int m, int group_stride, c
                   "knn_tree: null pointer");
     OCC_CHECK_ARG(k == 10, "knn_tree: k=%d (supported: 10)", k);
     OCC_CHECK_ARG(group_stride >= 1 && n0 >= 1 && n1 >= 1 && n2 >= 1 && n3 >= 1, "knn_tree: bad sizes");
+    OCC_CHECK_ARG(lane_rays == 1 || lane_rays == 2 || lane_rays == 4 || lane_rays == 8 || lane_rays == 16 || lane_rays == 32,
+                  "knn_tree: lane_rays=%d (a power of two <= 32)", lane_rays);
     OCC_CHECK_ARG((((uintptr_t)p0s | (uintptr_t)p1s | (uintptr_t)p2s | (uintptr_t)p3 | (uintptr_t)c2tab | (uintptr_t)c3tab |
                     (uintptr_t)c3rng) & 15) == 0, "knn_tree: tables must be 16-byte aligned");
     const size_t smem = (size_t)(n0 + n1 + 2 * n2 + 3 * n3) * 16;
@@ -482,9 +506,10 @@ extern "C" int occnerf_knn_tree(const float *queries, int m, int group_stride, c
     T.gid1 = gid1; T.gid2 = gid2; T.gid3 = gid3; T.inv2 = inv2;
     T.n0 = n0; T.n1 = n1; T.n2 = n2; T.n3 = n3;
     const long rays = (m + group_stride - 1) / group_stride;
-    const long warps = ((rays + 31) / 32) * group_stride;
+    const int lane_samples = 32 / lane_rays;
+    const long warps = ((rays + lane_rays - 1) / lane_rays) * ((group_stride + lane_samples - 1) / lane_samples);
     knn_tree_kernel<10><<<occ_div_up(warps * 32, kHierThreads), kHierThreads, smem, (cudaStream_t)stream>>>(queries, m, group_stride,
-                                                                                                      T, out);
+                                                                                                      lane_rays, T, out);
     OCC_LAUNCH_CHECK();
     return OCCNERF_OK;
 }

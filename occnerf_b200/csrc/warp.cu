@@ -150,50 +150,67 @@ warp_fwd_kernel(const float *__restrict__ rays, const float *__restrict__ t_lin,
 }
 
 // d(mask)/d(vol): every in-range corner of every bone receives g_mask * trilinear weight.
+//
+// Mapping: thread = (segment of kSeg consecutive samples of one ray, bone), bone fastest.  Consecutive samples (~1.5 cm
+// apart) stay in the same voxel (~7 cm) of a bone's volume for several steps, so the thread sums the 8 corner
+// contributions in registers and issues the 8 reductions only when the floor voxel changes: ~3x fewer L2 atomics than
+// one-thread-per-sample, and the lanes of a warp (different bones) never hit the same address at the same time.
+constexpr int kSeg = 16;
+
 __global__ void __launch_bounds__(kThreads)
 warp_bwd_kernel(const float *__restrict__ rays, const float *__restrict__ t_lin, const float *__restrict__ t_rand,
                 const float *__restrict__ Rs, const float *__restrict__ Ts, const float *__restrict__ bmin,
-                const float *__restrict__ bscale, const float *__restrict__ g_mask, long M, int S, int nb, int vd,
+                const float *__restrict__ bscale, const float *__restrict__ g_mask, long N, int S, int nb, int vd,
                 int vh, int vw, float *__restrict__ g_vol) {
     __shared__ BoneSmem sm;
     load_bones(sm, Rs, Ts, bmin, bscale, nb);
-    const long m = (long)blockIdx.x * kThreads + threadIdx.x;
-    if (m >= M) return;
-    const float gm = __ldg(g_mask + m);
-    if (gm == 0.f) return;
-    const long ray = m / S;
-    const int j = (int)(m - ray * S);
+    const int segs = (S + kSeg - 1) / kSeg;
+    const long gid = (long)blockIdx.x * kThreads + threadIdx.x;
+    if (gid >= N * segs * nb) return;
+    const int i = (int)(gid % nb);
+    const long rs = gid / nb;
+    const long ray = rs / segs;
+    const int j0 = (int)(rs - ray * segs) * kSeg, j1 = min(S, j0 + kSeg);
     const float4 r0 = __ldg(reinterpret_cast<const float4 *>(rays) + ray * 2);
     const float4 r1 = __ldg(reinterpret_cast<const float4 *>(rays) + ray * 2 + 1);
-    const float z = sample_z(r1.z, r1.w, t_lin, t_rand, ray, j, S);
-    const float px = __fadd_rn(r0.x, __fmul_rn(r0.w, z));
-    const float py = __fadd_rn(r0.y, __fmul_rn(r1.x, z));
-    const float pz = __fadd_rn(r0.z, __fmul_rn(r1.y, z));
     const long plane = (long)vh * vw, cube = (long)vd * plane;
-    for (int i = 0; i < nb; ++i) {
+    float *v = g_vol + (long)i * cube;
+    int cx = 0, cy = 0, cz = 0;
+    bool have = false;
+    float acc[8];
+    auto flush = [&]() {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int xi = cx + (k & 1), yi = cy + ((k >> 1) & 1), zi = cz + (k >> 2);
+            if (acc[k] != 0.f && xi >= 0 && xi < vw && yi >= 0 && yi < vh && zi >= 0 && zi < vd)
+                atomicAdd(v + zi * plane + (long)yi * vw + xi, acc[k]);
+        }
+    };
+    for (int j = j0; j < j1; ++j) {
+        const float gm = __ldg(g_mask + ray * S + j);
+        if (gm == 0.f) continue;
+        const float z = sample_z(r1.z, r1.w, t_lin, t_rand, ray, j, S);
+        const float px = __fadd_rn(r0.x, __fmul_rn(r0.w, z));
+        const float py = __fadd_rn(r0.y, __fmul_rn(r1.x, z));
+        const float pz = __fadd_rn(r0.z, __fmul_rn(r1.y, z));
         Cell c;
         locate(sm, i, px, py, pz, vd, vh, vw, c);
         const int x0 = c.c0[0], y0 = c.c0[1], z0 = c.c0[2];
-        if (x0 < -1 || x0 >= vw || y0 < -1 || y0 >= vh || z0 < -1 || z0 >= vd) continue;
-        float *v = g_vol + (long)i * cube;
+        if (x0 < -1 || x0 >= vw || y0 < -1 || y0 >= vh || z0 < -1 || z0 >= vd) continue;   // all 8 corners outside
+        if (!have || x0 != cx || y0 != cy || z0 != cz) {
+            if (have) flush();
+            cx = x0; cy = y0; cz = z0;
+            have = true;
 #pragma unroll
-        for (int dz = 0; dz < 2; ++dz) {
-            const int zi = z0 + dz;
-            const float wz = dz ? c.f1[2] : c.f0[2];
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        }
 #pragma unroll
-            for (int dy = 0; dy < 2; ++dy) {
-                const int yi = y0 + dy;
-                const float wy = dy ? c.f1[1] : c.f0[1];
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const int xi = x0 + dx;
-                    const float wx = dx ? c.f1[0] : c.f0[0];
-                    if (xi >= 0 && xi < vw && yi >= 0 && yi < vh && zi >= 0 && zi < vd)
-                        atomicAdd(v + zi * plane + (long)yi * vw + xi, gm * ((wx * wy) * wz));
-                }
-            }
+        for (int k = 0; k < 8; ++k) {
+            const float wx = (k & 1) ? c.f1[0] : c.f0[0], wy = (k & 2) ? c.f1[1] : c.f0[1], wz = (k & 4) ? c.f1[2] : c.f0[2];
+            acc[k] += gm * ((wx * wy) * wz);
         }
     }
+    if (have) flush();
 }
 
 int check_common(const void *rays, const void *t_lin, const void *Rs, const void *Ts, int N, int S, int nb, int vd,
@@ -232,8 +249,9 @@ extern "C" int occnerf_warp_backward(const float *rays, const float *t_lin, cons
     OCC_CHECK_ARG(bbox_min && bbox_scale && g_mask && g_vol, "warp_backward: null pointer");
     const long M = (long)N * S;
     if (M == 0) return OCCNERF_OK;
-    warp_bwd_kernel<<<occ_div_up(M, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        rays, t_lin, t_rand, Rs, Ts, bbox_min, bbox_scale, g_mask, M, S, nb, vd, vh, vw, g_vol);
+    const long threads = (long)N * ((S + kSeg - 1) / kSeg) * nb;
+    warp_bwd_kernel<<<occ_div_up(threads, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        rays, t_lin, t_rand, Rs, Ts, bbox_min, bbox_scale, g_mask, N, S, nb, vd, vh, vw, g_vol);
     OCC_LAUNCH_CHECK();
     return OCCNERF_OK;
 }

@@ -39,7 +39,7 @@ def grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, 
     _check(gridtype, align_corners, interp)
     scales = ops.level_scales(float(S), int(H), int(L), inputs.device)
     _lib.call("occnerf_hashgrid_backward", ptr(grad, f32), _lib.LAYOUT_LBC, int(L * C), ptr(inputs, f32), ptr(offsets, ops.i32),
-              ptr(scales, f32), ptr(grad_embeddings, f32), int(B), int(D), int(C), int(L), _lib.stream())
+              ptr(scales, f32), ptr(grad_embeddings, f32), int(B), int(D), int(C), int(L), 0, _lib.stream())
     if dy_dx is not None:
         _lib.call("occnerf_hashgrid_input_backward", ptr(grad, f32), _lib.LAYOUT_LBC, int(L * C), ptr(dy_dx, f32),
                   ptr(grad_inputs, f32), int(B), int(D), int(C), int(L), _lib.stream())

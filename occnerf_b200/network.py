@@ -215,27 +215,14 @@ class _CompositeFn(torch.autograd.Function):
 
 
 class _QueryFn(torch.autograd.Function):
-    """Canonical query of one chunk of points: non-rigid offset -> multi-scale KNN -> surface geometry ->
-    attention aggregation + hash encode -> MLP  (network.py:225-299 + occnerf_mlp.py:142-199).
+    """Canonical query of one chunk of (already offset) points with their multi-scale neighbour ids: surface geometry ->
+    attention aggregation + hash encode -> MLP  (network.py:256-299 + occnerf_mlp.py:142-199).
     Differentiable w.r.t. the per-vertex feature table, the hash table and the 20 MLP tensors."""
 
     @staticmethod
-    def forward(ctx, xyz, feats36, embeddings, net, nr_cond, nr_window, *mlp_params):
-        xyz = xyz.detach().contiguous().float()
+    def forward(ctx, xyz, knn_idx, feats36, embeddings, net, shared, *mlp_params):
         m, dev = xyz.shape[0], xyz.device
         st = net._static()
-        if nr_window is not None:
-            nw, nb = net.non_rigid_mlp.module.flat()
-            xyz = M.nonrigid_offsets(xyz, nr_cond, nr_window, nw, nb, const_off=getattr(net, "_nr_const", None))
-        if net.cfg.knn_mode == "brute":
-            knn_idx = ops.knn(xyz, st["supports4"], st["level_begin"], 10, support_gid=st["support_gid"])
-        elif net.cfg.knn_mode == "tree":
-            knn_idx = ops.knn_tree(xyz, max(1, int(getattr(net, "_group_stride", 1))), st["tree"])
-        else:
-            knn_idx = torch.empty(m, 4, 10, device=dev, dtype=i32)
-            gs = max(1, int(getattr(net, "_group_stride", 1)))
-            ops.knn_hier(xyz, gs, *st["hier0"], knn_idx, 0, 2, None, st["gid2"])
-            ops.knn_hier(xyz, gs, *st["hier1"], knn_idx, 1, 3, st["gid1"], st["gid3"])
         raw = torch.empty(m, 5, device=dev, dtype=f32)
         enc_in, _ = ops.sample_geometry(xyz, knn_idx, st["point_base"], st["point_norms"], net.bound, raw=raw)
         XB = torch.empty(m, M.XB_LD, device=dev, dtype=f32)
@@ -252,21 +239,32 @@ class _QueryFn(torch.autograd.Function):
         saved = engine.forward(XB, raw, W, save=need_grad)
         if need_grad:
             ctx.state = dict(knn_idx=knn_idx, enc_in=enc_in, XB=XB, W=W, saved=saved, engine=engine, counter=counter,
-                             offsets=enc.offsets, scales=scales, emb_shape=tuple(embeddings.shape), V=feats36.shape[0])
-        ctx.mark_non_differentiable(knn_idx)
-        return raw, knn_idx
+                             offsets=enc.offsets, scales=scales, emb_shape=tuple(embeddings.shape), V=feats36.shape[0],
+                             shared=shared)
+            shared["pending"] = shared.get("pending", 0) + 1
+        return raw
 
     @staticmethod
-    def backward(ctx, g_raw, _gk):
+    def backward(ctx, g_raw):
         s = ctx.state
         g_raw = g_raw.contiguous().float()
         gXB, g_params = s["engine"].backward(s["XB"], g_raw, s["W"], s["saved"])
-        g_emb = torch.zeros(s["emb_shape"], device=g_raw.device, dtype=f32)
-        ops.hashgrid_backward(gXB.data_ptr() + 4 * M.H_OFF, M.XB_LD, 0, s["enc_in"], s["offsets"], s["scales"], g_emb,
-                              s["emb_shape"][1])
-        g_feats = ops.aggregate_backward(s["knn_idx"], s["counter"], gXB.data_ptr() + 4 * M.X0_OFF, M.XB_LD, s["V"])
+        # the chunks of one _query_mlp call scatter into ONE table-gradient buffer (and one set of privatised vertex-gradient
+        # replicas); the chunk whose backward runs last hands it to autograd, the others contribute None (= zero).  That
+        # replaces a 59 MiB memset + a 59 MiB add per chunk by one memset per call.
+        sh = s["shared"]
+        if "g_emb" not in sh:
+            sh["g_emb"] = torch.zeros(s["emb_shape"], device=g_raw.device, dtype=f32)
+            sh["g_priv"] = torch.zeros(ops.AGG_BWD_COPIES, s["V"], 36, device=g_raw.device, dtype=f32)
+        ops.hashgrid_backward(gXB.data_ptr() + 4 * M.H_OFF, M.XB_LD, 0, s["enc_in"], s["offsets"], s["scales"], sh["g_emb"],
+                              s["emb_shape"][1], run_length=ops.HASH_BWD_RUN)           # samples are ordered along rays
+        ops.aggregate_backward(s["knn_idx"], s["counter"], gXB.data_ptr() + 4 * M.X0_OFF, M.XB_LD, s["V"], g_priv=sh["g_priv"])
         ctx.state = None
-        return (None, g_feats, g_emb, None, None, None, *g_params)
+        sh["pending"] -= 1
+        g_emb = g_feats = None
+        if sh["pending"] == 0:
+            g_emb, g_feats = sh.pop("g_emb"), sh.pop("g_priv").sum(0)
+        return (None, None, g_feats, g_emb, None, None, *g_params)
 
 
 # ----------------------------------------------------------------------------- the model
@@ -399,19 +397,44 @@ class Network(nn.Module):
         if window is not None and cond is None and all(v == 0.0 for v in window):
             nw, nb = self.non_rigid_mlp.module.flat()
             self._nr_const = M.nonrigid_offsets(pos_flat[:1].detach().contiguous().float(), None, window, nw, nb, return_const=True)
-        cm = self.cnl_mlp.module
+        # non-rigid offsets (network.py:225-232) and the multi-scale neighbour search (network.py:236-255) run under no_grad
+        # in the reference and do not depend on the chunking: one search over all points keeps the SMs full (per-chunk
+        # launches of ~2 waves lose a third of their time to the tail), the memory-heavy part below stays chunked
         chunk = self.cfg.netchunk_per_gpu
-        raws, knns = [], []
+        xyz_all = pos_flat.detach().contiguous().float()
+        if window is not None:
+            if self._nr_const is not None:
+                xyz_all = xyz_all + self._nr_const
+            else:
+                nw, nb = self.non_rigid_mlp.module.flat()
+                moved = torch.empty_like(xyz_all)
+                for i in range(0, xyz_all.shape[0], chunk):
+                    moved[i:i + chunk] = M.nonrigid_offsets(xyz_all[i:i + chunk], cond, window, nw, nb)
+                xyz_all = moved
+        knn_all = self._knn(xyz_all, self._group_stride)
+        cm = self.cnl_mlp.module
+        raws, shared = [], {}
         for i in range(0, pos_flat.shape[0], chunk):
-            raw, knn_idx = _QueryFn.apply(pos_flat[i:i + chunk], feats36, cm.encoder.embeddings, self, cond, window,
-                                          *cm.flat_params())
-            raws.append(raw)
-            knns.append(knn_idx)
+            raws.append(_QueryFn.apply(xyz_all[i:i + chunk], knn_all[i:i + chunk], feats36, cm.encoder.embeddings, self, shared,
+                                       *cm.flat_params()))
         raws_flat = raws[0] if len(raws) == 1 else torch.cat(raws, 0)
         out = {"raws": raws_flat.reshape(list(pos_xyz.shape[:-1]) + [5])}
         if _return_knn:
-            out["knn_idxs"] = knns[0] if len(knns) == 1 else torch.cat(knns, 0)
+            out["knn_idxs"] = knn_all
         return out
+
+    def _knn(self, xyz, group_stride):
+        """(m,3) -> (m,4,10) int32 vertex ids on the four levels (exact; the three modes return identical ids)."""
+        st = self._static()
+        gs = max(1, int(group_stride))
+        if self.cfg.knn_mode == "brute":
+            return ops.knn(xyz, st["supports4"], st["level_begin"], 10, support_gid=st["support_gid"])
+        if self.cfg.knn_mode == "tree":
+            return ops.knn_tree(xyz, gs, st["tree"])
+        knn_idx = torch.empty(xyz.shape[0], 4, 10, device=xyz.device, dtype=i32)
+        ops.knn_hier(xyz, gs, *st["hier0"], knn_idx, 0, 2, None, st["gid2"])
+        ops.knn_hier(xyz, gs, *st["hier1"], knn_idx, 1, 3, st["gid1"], st["gid3"])
+        return knn_idx
 
     def get_non_rigid_embedder(self, multires, is_identity, iter_val):
         return HannEmbedder(ops.hann_window(iter_val, self.cfg.non_rigid_kick_in_iter, self.cfg.non_rigid_full_band_iter,

@@ -159,13 +159,17 @@ def build_knn_tree(base: torch.Tensor, fps):
         inv2=inv2.to(i32).contiguous(), n=(n0, n1, n2, n3))
 
 
-def knn_tree(queries, group_stride, tree, out=None):
+KNN_LANE_RAYS = 32
+
+
+def knn_tree(queries, group_stride, tree, out=None, lane_rays=None):
     """All 4 levels x k=10 in one launch -> (m,4,10) int32 vertex ids."""
+    lane_rays = KNN_LANE_RAYS if lane_rays is None else lane_rays
     m = queries.shape[0]
     if out is None:
         out = torch.empty(m, 4, 10, device=queries.device, dtype=i32)
     t = tree
-    call("occnerf_knn_tree", ptr(queries, f32), m, int(group_stride), ptr(t["p0s"], f32), ptr(t["p1s"], f32), ptr(t["p2s"], f32),
+    call("occnerf_knn_tree", ptr(queries, f32), m, int(group_stride), int(lane_rays), ptr(t["p0s"], f32), ptr(t["p1s"], f32), ptr(t["p2s"], f32),
          ptr(t["p3"], f32), ptr(t["c2tab"], f32), ptr(t["c3tab"], f32), ptr(t["c3rng"], i32), ptr(t["gid1"], i32),
          ptr(t["gid2"], i32), ptr(t["gid3"], i32), ptr(t["inv2"], i32), *t["n"], 10, ptr(out, i32), stream())
     return out
@@ -221,11 +225,15 @@ def hashgrid_forward(inputs, embeddings, offsets, scales, *, out=None, out_ptr=N
     return out, dy_dx, cells, slots
 
 
-def hashgrid_backward(grad_ptr, ld, layout, inputs, offsets, scales, g_emb, Cc):
+HASH_BWD_RUN = 16
+
+
+def hashgrid_backward(grad_ptr, ld, layout, inputs, offsets, scales, g_emb, Cc, run_length=0):
+    """run_length 8/16: inputs are ordered along rays -> merge the reductions of consecutive samples in one cell."""
     B, D = inputs.shape
     L = offsets.shape[0] - 1
     call("occnerf_hashgrid_backward", grad_ptr, layout, ld, ptr(inputs, f32), ptr(offsets, i32), ptr(scales, f32),
-         ptr(g_emb, f32), B, D, Cc, L, stream())
+         ptr(g_emb, f32), B, D, Cc, L, int(run_length), stream())
     return g_emb
 
 
@@ -278,10 +286,15 @@ def aggregate_forward(knn_idx, point_counter, feats36, X_ptr, ldx):
 AGG_BWD_COPIES = 64
 
 
-def aggregate_backward(knn_idx, point_counter, gX_ptr, ldg, V, copies=None):
-    """g_feats (V,36): one vector reduction per (sample, neighbour, column chunk) into `copies` privatised replicas."""
+def aggregate_backward(knn_idx, point_counter, gX_ptr, ldg, V, copies=None, g_priv=None):
+    """g_feats (V,36): one vector reduction per (sample, neighbour, column chunk) into `copies` privatised replicas.
+    With `g_priv` (copies,V,36) given, accumulates into it and returns it (the caller sums the replicas)."""
     m = knn_idx.shape[0]
     nn = knn_idx.numel() // max(m, 1)
+    if g_priv is not None:
+        call("occnerf_aggregate_backward", ptr(knn_idx, i32), ptr(point_counter, f32), gX_ptr, ldg, m, nn, ptr(g_priv, f32), V,
+             g_priv.shape[0], stream())
+        return g_priv
     copies = AGG_BWD_COPIES if copies is None else copies
     g_priv = torch.zeros(copies, V, 36, device=knn_idx.device, dtype=f32)
     call("occnerf_aggregate_backward", ptr(knn_idx, i32), ptr(point_counter, f32), gX_ptr, ldg, m, nn, ptr(g_priv), V, copies,

@@ -68,6 +68,22 @@ def test_backward_and_input_backward():
     report("hashgrid_bwd", g_emb_rel_vs_f64=e, oracle_f32_rel_vs_f64=maxabs(ref32, ref64) / float(ref64.abs().max()))
     assert e < 1e-5
     assert torch.equal((g_emb != 0).cpu(), ref64 != 0) or float((g_emb.cpu() - ref64.float()).abs().max()) < 1e-6
+    # run-length variants (consecutive samples sharing a cell are merged before the reduction): same sums.
+    # Inputs that really share cells: short random walks, plus out-of-range rows and zero gradients in the middle of runs
+    gen = torch.Generator().manual_seed(11)
+    xw = (torch.rand(400, 1, 4, generator=gen) + torch.cumsum(torch.randn(400, 16, 4, generator=gen) * 2e-3, 1)).reshape(-1, 4)
+    xw[37] = 1.5
+    xw[1000:1003] = -0.1
+    gw = torch.randn(6400, 32, generator=gen)
+    gw[5::7] = 0.0
+    refw32, refw64 = hashgrid_c.backward(gw, xw.contiguous(), offs, emb.shape[0], 2, Sv, 16, level_scales=scales.cpu().contiguous(), want_f64=True)
+    gw_d, xw_d = gw.to(d), xw.to(d).contiguous()
+    for rl in (0, 8, 16):
+        ge = torch.zeros_like(emb).to(d)
+        ops.hashgrid_backward(gw_d.data_ptr(), 32, _lib.LAYOUT_BLC, xw_d, offs.to(d), scales, ge, 2, run_length=rl)
+        e = maxabs(ge, refw64) / float(refw64.abs().max())
+        report(f"hashgrid_bwd_runs{rl}", g_emb_rel_vs_f64=e)
+        assert e < 1e-5, (rl, e)
     # input gradient
     _o, dy_dx, _c, _s = ops.hashgrid_forward(x.to(d), emb.to(d), offs.to(d), scales, want_dy_dx=True)
     gi = ops.hashgrid_input_backward(g_d.data_ptr(), 32, _lib.LAYOUT_BLC, dy_dx, 6000, 4, 2, 16)
