@@ -166,27 +166,35 @@ typedef struct {
 } occnerf_mlp_params;
 /* chain 0 = forward images (W, plus the padded biases), chain 1 = data-gradient images (W^T). */
 long occnerf_mlp_packed_bytes(int n_pass, int chain);
+/* Debug only (tools/mlp_stalls.py): with OCCNERF_MLP_DEBUG=1 in the environment the chain kernels accumulate the cycles
+ * their role threads spend blocked on each mbarrier.  Synchronises the device, copies the 16 counters to host8 (may be
+ * NULL) and clears them when reset != 0.  [0] MMA<-weights [1] MMA<-A operand [2] epilogue<-accumulator
+ * [3] producer<-free slot [4] MMA thread total [5] epilogue thread total [6] CTAs [8] epilogue<-TMEM load
+ * [9] epilogue in fence+arrive; others unused. */
+int occnerf_mlp_debug_counters(unsigned long long *host8, int reset);
 int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, void *packed, occnerf_stream_t stream);
 /* XB [m,132]: columns 64..131 = (agg35, var1, h32) are read; columns 0..63 receive the 64 geometry features when
  * act_dtype != 0.  raw [m, ldr]: columns 0..3 = (rgb_pre3, sigma_pre1) are written.
- * act_save: NULL (act_dtype 0, inference) or a buffer [slots][slot_stride][256] receiving the post-ReLU activations of
- * the 8 hidden layers (slots 0..3 = pts1..4, 4..7 = rgb1..4) for the backward pass: fp32 (act_dtype 1, 8 slots) or
- * bf16 (act_dtype 2, 10 slots: slot 8 = input of pts0 (80 columns), slot 9 = input of rgb0 (144 columns)).
- * relu_mask: NULL or [8][slot_stride][8] uint32 receiving one bit per hidden unit (activation > 0) for the backward chain. */
+ * act_save: NULL (act_dtype 0, inference) or a buffer receiving the post-ReLU activations of the 8 hidden layers
+ * (slots 0..3 = pts1..4, 4..7 = rgb1..4) for the backward pass: fp32 row-major [8][slot_stride][256] (act_dtype 1) or
+ * bf16 CHUNK-MAJOR [10][32][slot_stride][8] (act_dtype 2; element (slot, row, col) at ((slot*32 + col/8)*slot_stride +
+ * row)*8 + col%8; slot 8 = input of pts0 (80 columns), slot 9 = input of rgb0 (144 columns)) -- the layout in which a
+ * warp's stores are contiguous and which the weight-gradient kernel's TMA consumes directly.
+ * relu_mask: NULL or [8][32][slot_stride] bytes: bit i of byte (slot, k8, row) = [hidden unit 8*k8+i > 0]. */
 int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, float *raw, int ldr, void *act_save,
                            int act_dtype, long slot_stride, void *relu_mask, occnerf_stream_t stream);
 
 /* Fused data-gradient chain (the transposed layers in reverse order, ReLU masks from the saved bf16 activations).
- * g_raw [m,5] (d rgb_pre3, d sigma_pre, unused); relu_mask [8][slot_stride][8] as saved by occnerf_mlp_forward_tc.
- * Writes gXB [m,132] columns 64..131 = d(agg35, var1, h32) summed over both trunks, and g_save [10][slot_stride][256]
- * bf16 = gradients w.r.t. the pre-activations: slots 0..3 = rgb3, rgb2, rgb1, rgb0; 4 = geo (columns 0..63 features,
- * 64 sigma); 5..8 = pts3, pts2, pts1, pts0; 9 = d raw[:, :3]. */
+ * g_raw [m,5] (d rgb_pre3, d sigma_pre, unused); relu_mask [8][32][slot_stride] as saved by occnerf_mlp_forward_tc.
+ * Writes gXB [m,132] columns 64..131 = d(agg35, var1, h32) summed over both trunks, and g_save, bf16 chunk-major
+ * [10][32][slot_stride][8] like act_save = gradients w.r.t. the pre-activations: slots 0..3 = rgb3, rgb2, rgb1, rgb0;
+ * 4 = geo (columns 0..63 features, 64 sigma); 5..8 = pts3, pts2, pts1, pts0; 9 = d raw[:, :3]. */
 int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, const void *relu_mask, float *gXB,
                             void *g_save, long slot_stride, occnerf_stream_t stream);
 
 /* Weight and bias gradients dW_l = G_l^T X_l, db_l = colsum(G_l) of all 10 layers from the two bf16 buffers above
- * (TMA + MN-major tcgen05, contraction over the sample axis).  slot_stride must be a multiple of 64 and the rows
- * m..slot_stride-1 of every slot zero.  dW [10][256][256], dB [10][256] fp32 are ACCUMULATED (caller zeroes), in the
+ * (chunk-major layout; TMA + MN-major tcgen05, contraction over the sample axis).  slot_stride must be a multiple of 64
+ * and the rows m..slot_stride-1 of every slot zero.  dW [10][256][256], dB [10][256] fp32 are ACCUMULATED (caller zeroes), in the
  * padded/permuted layer layout of the fused kernels (see occnerf_b200/mlp_tc.py for the mapping back to nn.Linear). */
 int occnerf_mlp_wgrad_tc(const void *g_save, const void *act_bf16, int m, long slot_stride, float *dW, float *dB,
                          occnerf_stream_t stream);

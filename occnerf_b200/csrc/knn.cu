@@ -84,6 +84,61 @@ knn_kernel(const float *__restrict__ queries, int m, const float4 *__restrict__ 
     }
 }
 
+// Warp-per-query variant of the brute-force search for SMALL query sets (the per-vertex block: 6890 queries, k = 3; the
+// visibility vote: <= one query per ray, k = 10).  One thread per query would leave most of the GPU idle there; here the 32
+// lanes of a warp scan interleaved slices of the support set (coalesced 512-byte reads), each keeps its own sorted top-k,
+// and k rounds of a lexicographic (distance, row) warp arg-min merge the 32 lists.  Same arithmetic and tie rule as
+// knn_kernel, so the ids are identical.
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+knn_warp_kernel(const float *__restrict__ queries, int m, const float4 *__restrict__ supports, const int32_t *__restrict__ gid,
+                int lv0, int lv1, int lv2, int lv3, int lv4, int n_levels, const uint8_t *__restrict__ query_sel,
+                int32_t *__restrict__ out) {
+    const int q = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= m) return;
+    if (query_sel && query_sel[q] == 0) return;
+    const float qx = __ldg(queries + (size_t)q * 3 + 0), qy = __ldg(queries + (size_t)q * 3 + 1), qz = __ldg(queries + (size_t)q * 3 + 2);
+    const int begins[5] = {lv0, lv1, lv2, lv3, lv4};
+#pragma unroll 1
+    for (int lev = 0; lev < n_levels; ++lev) {
+        const int s0 = begins[lev], s1 = begins[lev + 1];
+        float dk[K];
+        int ik[K];
+#pragma unroll
+        for (int t = 0; t < K; ++t) { dk[t] = INFINITY; ik[t] = 0x7fffffff; }
+#pragma unroll 2
+        for (int i = s0 + lane; i < s1; i += 32) {
+            const float4 s = __ldg(supports + i);
+            const float dx = __fsub_rn(qx, s.x), dy = __fsub_rn(qy, s.y), dz = __fsub_rn(qz, s.z);
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (d < dk[K - 1]) topk_insert<K>(dk, ik, d, i);        // rows ascend within a lane: strict < keeps the lower row on ties
+        }
+        int mine = -1;                                               // lane t ends up with the t-th neighbour
+#pragma unroll 1
+        for (int t = 0; t < K; ++t) {
+            float bd = dk[0];
+            int bi = ik[0];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(OCC_FULL, bd, o);
+                const int oi = __shfl_xor_sync(OCC_FULL, bi, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            if (bi == ik[0] && bi != 0x7fffffff) {                   // this lane's head won: pop it
+#pragma unroll
+                for (int u = 0; u + 1 < K; ++u) { dk[u] = dk[u + 1]; ik[u] = ik[u + 1]; }
+                dk[K - 1] = INFINITY; ik[K - 1] = 0x7fffffff;
+            }
+            if (lane == t) mine = bi;
+        }
+        if (lane < K) {
+            int v = mine;
+            v = (v == 0x7fffffff) ? -1 : (gid ? __ldg(gid + v) : v - s0);
+            out[((size_t)q * n_levels + lev) * K + lane] = v;
+        }
+    }
+}
+
 // occnerf_mlp.py:146-167
 __global__ void __launch_bounds__(kThreads)
 sample_geometry_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ knn_idx, int knn_stride,
@@ -417,6 +472,17 @@ int launch_knn(const float *queries, int m, const float *supports4, const int32_
                int k, const uint8_t *query_sel, int32_t *out, cudaStream_t st) {
     int b[5] = {0, 0, 0, 0, 0};
     for (int i = 0; i <= n_levels; ++i) b[i] = lb[i];
+    if (m <= 32768) {                                                // few queries: one warp each
+        const unsigned wgrid = occ_div_up((long)m * 32, kThreads);
+        if (k == 10)
+            knn_warp_kernel<10><<<wgrid, kThreads, 0, st>>>(queries, m, (const float4 *)supports4, gid, b[0], b[1], b[2], b[3], b[4],
+                                                             n_levels, query_sel, out);
+        else
+            knn_warp_kernel<3><<<wgrid, kThreads, 0, st>>>(queries, m, (const float4 *)supports4, gid, b[0], b[1], b[2], b[3], b[4],
+                                                            n_levels, query_sel, out);
+        OCC_LAUNCH_CHECK();
+        return OCCNERF_OK;
+    }
     const unsigned grid = occ_div_up(m, kThreads);
     if (k == 10)
         knn_kernel<10><<<grid, kThreads, 0, st>>>(queries, m, (const float4 *)supports4, gid, b[0], b[1], b[2], b[3], b[4],

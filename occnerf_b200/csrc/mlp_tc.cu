@@ -17,15 +17,21 @@
 // Precision: n_pass = 1 is bf16 x bf16 -> fp32.  n_pass = 3 is split-bf16, x = hi + lo (both bf16),
 //   x.w ~= hi.whi + hi.wlo + lo.whi (three MMAs per K-step on one fp32 accumulator, ~2^-16 relative error per product).
 //
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = 32 samples each), warp 4 lane 0 weight producer,
-// warp 5 lane 0 MMA issuer.  Every mbarrier wait has a spin limit that traps instead of hanging the GPU.
+// Warp roles (576 threads): warps 0-15 epilogue -- warp w owns TMEM lane quarter w & 3 (32 samples) and, as member of
+// epilogue set w >> 2, the 8-column chunks k8 = set (mod 4) of every layer (one chunk of each 32-column group), so each
+// SM sub-partition holds FOUR epilogue warps that hide each other's TMEM-load / conversion latencies and every A group
+// is completed by all four sets together, in consumption order; warp 16 lane 0 weight producer, warp 17 lane 0 MMA issuer.
+// Every mbarrier wait has a spin limit that traps instead of hanging the GPU.
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 576;
+constexpr int kEpiSets = 4;                 // epilogue warps per TMEM lane quarter
+constexpr int kEpiThreads = kEpiSets * 128;
 constexpr int kStages = 3;
 constexpr int kStageBytes = 32768;
 constexpr int kLayers = 10;
@@ -184,6 +190,11 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -195,8 +206,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 // bf16 split of 8 consecutive K values of one row -> one 16-byte store per part into the A operand image
+// (returns the packed bf16 "hi" part: exactly what the backward pass wants saved)
 template <int NPASS>
-__device__ __forceinline__ void store_a8(unsigned char *a_base, int row, int k8, const float (&v)[8]) {
+__device__ __forceinline__ uint4 store_a8(unsigned char *a_base, int row, int k8, const float (&v)[8]) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -211,6 +223,7 @@ __device__ __forceinline__ void store_a8(unsigned char *a_base, int row, int k8,
     const uint32_t off = (uint32_t)(k8 * 16 + (row >> 3)) * 128 + (row & 7) * 16;
     *reinterpret_cast<uint4 *>(a_base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     if (NPASS == 3) *reinterpret_cast<uint4 *>(a_base + kAPartBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    return make_uint4(hi[0], hi[1], hi[2], hi[3]);
 }
 __device__ __forceinline__ uint4 pack_bf16x8(const float (&v)[8]) {
     uint32_t pk[4];
@@ -222,23 +235,20 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&v)[8]) {
     return make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
-// the (agg35, var, h32) part of a sample's input row -> A columns [8*k8_0, 8*k8_0 + 80), zero padded beyond 68
+// chunk g (8 columns) of the (agg35, var, h32) part of a sample's input row -> A chunk k8_0 + g, zero padded beyond column 68
 template <int NPASS>
-__device__ __forceinline__ void stage_x0(unsigned char *a_base, int row, const float *__restrict__ xrow, bool valid, int k8_0,
-                                         __nv_bfloat16 *save_row = nullptr) {
+__device__ __forceinline__ void stage_x0_chunk(unsigned char *a_base, int row, const float *__restrict__ xrow, bool valid, int k8_0,
+                                               int g, __nv_bfloat16 *save_chunk) {
+    float v[8];
 #pragma unroll
-    for (int g = 0; g < 10; ++g) {
-        float v[8];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int c = g * 8 + h * 4;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid && c < 68) x = __ldg(reinterpret_cast<const float4 *>(xrow + c));
-            v[h * 4 + 0] = x.x; v[h * 4 + 1] = x.y; v[h * 4 + 2] = x.z; v[h * 4 + 3] = x.w;
-        }
-        store_a8<NPASS>(a_base, row, k8_0 + g, v);
-        if (save_row) *reinterpret_cast<uint4 *>(save_row + g * 8) = pack_bf16x8(v);
+    for (int h = 0; h < 2; ++h) {
+        const int c = g * 8 + h * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && c < 68) x = __ldg(reinterpret_cast<const float4 *>(xrow + c));
+        v[h * 4 + 0] = x.x; v[h * 4 + 1] = x.y; v[h * 4 + 2] = x.z; v[h * 4 + 3] = x.w;
     }
+    const uint4 hi = store_a8<NPASS>(a_base, row, k8_0 + g, v);
+    if (save_chunk) *reinterpret_cast<uint4 *>(save_chunk) = hi;       // (few per tile: not worth reordering after the publish)
 }
 
 struct ChainArgs {
@@ -252,16 +262,32 @@ struct ChainArgs {
     float *XB;                       // [m,132]: cols 64..131 in; cols 0..63 out (geo features) when act_dtype != 0
     float *raw;                      // [m, ldr]: cols 0..2 rgb_pre, col 3 sigma_pre
     int ldr;
-    void *act_save;                  // [8 or 10][slot_stride][256] post-ReLU activations (fp32 / bf16) or NULL;
-                                     // bf16 mode adds slot 8 = pts0 input (80 cols) and slot 9 = rgb0 input (144 cols)
+    void *act_save;                  // post-ReLU activations or NULL: fp32 [8][slot_stride][256], or bf16 chunk-major
+                                     // [10][32][slot_stride][8] (see saved_off) with slot 8 = pts0 input (80 cols) and
+                                     // slot 9 = rgb0 input (144 cols)
     int act_dtype;                   // 0 none, 1 fp32, 2 bf16
-    uint32_t *relu_mask;             // [8][slot_stride][8] one bit per hidden unit (> 0), written by the forward chain in
-                                     // bf16 mode and read by the backward chain: 32 B per row and layer instead of 512 B
+    uint8_t *relu_mask;              // [8][32][slot_stride] bytes: bit i of byte (slot, k8, row) = [unit 8*k8+i > 0]; written by
+                                     // the forward chain in bf16 mode and read by the backward chain (32 B per row and layer)
+    int debug;
     // backward
     const float *g_raw;              // [m,5]
     float *gXB;                      // [m,132]: cols 64..131 written (d agg, d var, d h; both trunks summed)
-    __nv_bfloat16 *g_save;           // [10][slot_stride][256] bf16: gradients w.r.t. the pre-activations (slot 9 = d raw[:, :3])
+    __nv_bfloat16 *g_save;           // bf16 chunk-major [10][32][slot_stride][8]: gradients w.r.t. the pre-activations
+                                     // (slot 9 = d raw[:, :3])
 };
+
+// Debug instrumentation (tools/mlp_stalls.py): with OCCNERF_MLP_DEBUG=1 in the environment the role threads accumulate the
+// cycles they spend blocked on each mbarrier; summed over all CTAs into g_dbg.  [0] MMA waits for weights, [1] MMA waits for
+// the A operand, [2] epilogue (row 0, set 0) waits for the accumulator, [3] producer waits for a free ring slot,
+// [4] MMA thread total, [5] epilogue thread total, [6] CTAs.
+__device__ unsigned long long g_dbg[16];
+__device__ __forceinline__ long long clk() { return clock64(); }
+
+// bf16 activations / gradients saved for the weight-gradient kernel use a CHUNK-MAJOR layout [slot][k8 = col/8][row][8]:
+// the 32 lanes of an epilogue warp (32 consecutive rows, one 8-column chunk) then write 512 contiguous bytes instead of
+// 32 separate 16-byte pieces 512 B apart (which cost one L1 tag cycle each: measured 8k cycles per layer and tile), and
+// the weight-gradient kernel's TMA boxes land in shared memory directly in the no-swizzle MN-major UMMA layout.
+__device__ __forceinline__ long saved_off(int slot, int k8, long stride, long row) { return (((long)slot * 32 + k8) * stride + row) * 8; }
 
 struct Smem {
     unsigned char *A, *W;
@@ -274,6 +300,7 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
     constexpr int KC = (NPASS == 1) ? 64 : 32;
     constexpr int NP = (NPASS == 1) ? 1 : 2;
     uint32_t it = 0;
+    long long dbg_wait = 0;
     const uint32_t rank = cluster_ctarank();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int l = 0; l < kLayers; ++l) {
@@ -283,7 +310,9 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
             const unsigned char *src = args.packed + args.w_off[l];
             for (int c = 0; c < nch; ++c, ++it) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                const long long t0 = args.debug ? clk() : 0;
                 mbar_wait(sm.bar_w_empty + 8 * s, ph ^ 1);          // BOTH CTAs of the pair have consumed the slot
+                if (args.debug) dbg_wait += clk() - t0;
                 const int kc = min(KC, K - c * KC);
                 const uint32_t bytes = (uint32_t)N * kc * 2;       // per part; the k8-outer image is contiguous
                 mbar_arrive_expect_tx(sm.bar_w_full + 8 * s, bytes * NP);   // what lands in MY slot (from both CTAs)
@@ -299,6 +328,7 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
             }
         }
     }
+    if (args.debug) atomicAdd(&g_dbg[3], (unsigned long long)dbg_wait);
 }
 
 // ---- MMA issuer: GEMM l accumulates into TMEM buffer (l & 1); it consumes the A operand group by group as the
@@ -307,6 +337,8 @@ template <int NPASS>
 __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base) {
     constexpr int KC = (NPASS == 1) ? 64 : 32;
     uint32_t it = 0, a_phase = 0;      // a_phase: one parity bit per A group
+    long long dbg_w = 0, dbg_a = 0;
+    const long long dbg_t0 = args.debug ? clk() : 0;
     const uint32_t a_base = smem_u32(sm.A);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int l = 0; l < kLayers; ++l) {
@@ -318,14 +350,20 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
             uint32_t first = 1;
             for (int c = 0; c < nch; ++c, ++it) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                mbar_wait(sm.bar_w_full + 8 * s, ph);
+                {
+                    const long long t0 = args.debug ? clk() : 0;
+                    mbar_wait(sm.bar_w_full + 8 * s, ph);
+                    if (args.debug) dbg_w += clk() - t0;
+                }
                 const int kc = min(KC, K - c * KC);
                 const uint32_t wbase = smem_u32(sm.W + s * kStageBytes);
                 for (int k16 = 0; k16 < kc / 16; ++k16) {
                     const int t = c * (KC / 16) + k16;             // global K-step of this GEMM
                     if ((t & 1) == 0) {                            // first step of a 32-column group: wait for the epilogue
                         const int g = t >> 1;
+                        const long long t0 = args.debug ? clk() : 0;
                         mbar_wait(sm.bar_a_ready + 8 * g, (a_phase >> g) & 1);
+                        if (args.debug) dbg_a += clk() - t0;
                         a_phase ^= 1u << g;
                     }
                     tc_fence_after();
@@ -346,268 +384,284 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
             tc_commit(sm.bar_acc_full);                  // accumulator of GEMM l complete
         }
     }
+    if (args.debug) {
+        atomicAdd(&g_dbg[0], (unsigned long long)dbg_w);
+        atomicAdd(&g_dbg[1], (unsigned long long)dbg_a);
+        atomicAdd(&g_dbg[4], (unsigned long long)(clk() - dbg_t0));
+        atomicAdd(&g_dbg[6], 1ull);
+    }
 }
 
-// publish A groups [g0, g1) to the MMA issuer
-__device__ __forceinline__ void publish(const Smem &sm, int g0, int g1) {
+// one arrival of this thread on A group g.  EVERY epilogue thread arrives exactly once per group and GEMM, after the chunk
+// it owns in that group -- if any -- is in shared memory and after all of its TMEM reads of older accumulators: a group
+// therefore completes only when all 512 threads are past the previous layer, which is what makes it safe for GEMM l+2 to
+// overwrite the TMEM buffer of GEMM l.
+__device__ __forceinline__ void publish(const Smem &sm, int g) {
     tc_fence_before();
     fence_proxy_async();
-    for (int g = g0; g < g1; ++g) mbar_arrive(sm.bar_a_ready + 8 * g);
+    mbar_arrive(sm.bar_a_ready + 8 * g);
 }
 
-// ---- forward epilogue
+// ---- forward epilogue.  Thread = (row, set): the 8-column chunks k8 = set, set+4, ... of every layer.
 template <int NPASS>
 __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base, int warp) {
-    const int row = threadIdx.x;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int quarter = warp & 3, set = warp >> 2;
+    const int row = quarter * 32 + (threadIdx.x & 31);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float *bias_all = reinterpret_cast<const float *>(args.packed + args.bias_off);
     uint32_t acc_cnt = 0;
+    const bool dbg_on = args.debug && threadIdx.x == 0;
+    long long dbg_acc = 0, dbg_ld = 0, dbg_pub = 0;
+    const long long dbg_t0 = dbg_on ? clk() : 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long grow = (long)tile * kTileM + row;
         const bool valid = grow < args.m;
         const float *xrow = args.XB + grow * 132 + 64;
         __nv_bfloat16 *sv = (valid && args.act_dtype == 2) ? reinterpret_cast<__nv_bfloat16 *>(args.act_save) : nullptr;
-        stage_x0<NPASS>(sm.A, row, xrow, valid, 0, sv ? sv + (8 * args.slot_stride + grow) * 256 : nullptr);   // GEMM 0 operand: A[:, 0:80)
-        publish(sm, 0, 3);
+        {   // GEMM 0 operand A[:, 0:80) = (agg35, var, h32, pad): chunks 0..9 -> A groups 0, 1, 2
+            auto sv8 = [&](int g) { return sv ? sv + saved_off(8, g, args.slot_stride, grow) : nullptr; };
+            stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 0, set, sv8(set));
+            publish(sm, 0);
+            stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 0, set + 4, sv8(set + 4));
+            publish(sm, 1);
+            if (set < 2) stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 0, set + 8, sv8(set + 8));
+            publish(sm, 2);
+        }
         for (int l = 0; l < kLayers; ++l, ++acc_cnt) {
-            mbar_wait(sm.bar_acc_full, acc_cnt & 1);
+            {
+                const long long t0 = dbg_on ? clk() : 0;
+                mbar_wait(sm.bar_acc_full, acc_cnt & 1);
+                if (dbg_on) dbg_acc += clk() - t0;
+            }
             tc_fence_after();
             const uint32_t t_acc = t_lane + (uint32_t)(l & 1) * 256;
             const float *bias = bias_all + l * 256;
             if (l == 9) {
-                uint32_t r[16];
-                tmem_ld16(t_acc, r);
-                if (valid) {
-                    float *o = args.raw + grow * args.ldr;
-                    o[0] = __uint_as_float(r[0]) + __ldg(bias + 0);
-                    o[1] = __uint_as_float(r[1]) + __ldg(bias + 1);
-                    o[2] = __uint_as_float(r[2]) + __ldg(bias + 2);
+                if (set == 0) {
+                    uint32_t r[8];
+                    tmem_ld8_issue(t_acc, r);
+                    tmem_ld_wait();
+                    if (valid) {
+                        float *o = args.raw + grow * args.ldr;
+                        o[0] = __uint_as_float(r[0]) + __ldg(bias + 0);
+                        o[1] = __uint_as_float(r[1]) + __ldg(bias + 1);
+                        o[2] = __uint_as_float(r[2]) + __ldg(bias + 2);
+                    }
                 }
                 tc_fence_before();
             } else if (l == 4) {
-                // geometry head: columns 0..63 = features (-> A[:, 0:64) of the colour trunk), column 64 = sigma
-#pragma unroll 1
-                for (int cg = 0; cg < 2; ++cg) {
-                    uint32_t r[32];
-                    tmem_ld32_issue(t_acc + cg * 32, r);
+                // geometry head: columns 0..63 = features (-> A[:, 0:64) of the colour trunk), column 64 = sigma.
+                // All TMEM reads of a thread come before its last publish (see the backward chain, d == 4).
+                if (set == 0) {
+                    uint32_t r[8];
+                    tmem_ld8_issue(t_acc + 64, r);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]) + __ldg(bias + cg * 32 + j * 8 + i);
-                        store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
-                        if (valid && args.act_dtype != 0) {
-                            float4 *dst = reinterpret_cast<float4 *>(args.XB + grow * 132 + cg * 32 + j * 8);
-                            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                            if (sv) *reinterpret_cast<uint4 *>(sv + (9 * args.slot_stride + grow) * 256 + cg * 32 + j * 8) = pack_bf16x8(v);
-                        }
-                    }
-                    publish(sm, cg, cg + 1);
-                }
-                {
-                    uint32_t r[16];
-                    tmem_ld16(t_acc + 64, r);
                     if (valid) args.raw[grow * args.ldr + 3] = __uint_as_float(r[0]) + __ldg(bias + 64);
                 }
-                stage_x0<NPASS>(sm.A, row, xrow, valid, 8, sv ? sv + (9 * args.slot_stride + grow) * 256 + 64 : nullptr);   // A[:, 64:144)
-                publish(sm, 2, 5);
+#pragma unroll 1
+                for (int cg = 0; cg < 2; ++cg) {
+                    const int k8 = cg * 4 + set;
+                    uint32_t r[8];
+                    tmem_ld8_issue(t_acc + k8 * 8, r);
+                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + k8 * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + k8 * 8 + 4));
+                    tmem_ld_wait();
+                    const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) + bj[i];
+                    const uint4 hi = store_a8<NPASS>(sm.A, row, k8, v);
+                    publish(sm, cg);
+                    if (valid && args.act_dtype != 0) {
+                        float4 *dst = reinterpret_cast<float4 *>(args.XB + grow * 132 + k8 * 8);
+                        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        if (sv) *reinterpret_cast<uint4 *>(sv + saved_off(9, k8, args.slot_stride, grow)) = hi;
+                    }
+                }
+                // A[:, 64:144) = (agg35, var, h32, pad): chunks 8..17 -> A groups 2, 3, 4
+                auto sv9 = [&](int g) { return sv ? sv + saved_off(9, 8 + g, args.slot_stride, grow) : nullptr; };
+                stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 8, set, sv9(set));
+                publish(sm, 2);
+                stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 8, set + 4, sv9(set + 4));
+                publish(sm, 3);
+                if (set < 2) stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 8, set + 8, sv9(set + 8));
+                publish(sm, 4);
             } else {
-                // hidden layer: +bias, ReLU -> next A operand (and the saved activation for the backward pass)
+                // hidden layer: +bias, ReLU -> next A operand (and the saved activation / ReLU mask for the backward pass)
                 const int slot = l < 4 ? l : l - 1;                  // 0..3 = pts1..4, 4..7 = rgb1..4
-                // software pipeline over the eight 32-column groups: the TMEM load and the bias of group g+1 are in
-                // flight while group g is processed (4 epilogue warps per SM cannot hide those latencies by themselves)
-                const bool want_mask = args.relu_mask != nullptr;
-                auto load_bias = [&](int cg, float4 (&b)[8]) {
+                uint8_t *mask_row = args.relu_mask ? args.relu_mask + ((long)slot * 32 * args.slot_stride + grow) : nullptr;   // + k8 * stride
+                uint32_t ra[8], rb[8];
+                auto process = [&](int cg, const uint32_t (&r)[8]) {
+                    const int k8 = cg * 4 + set;
+                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + k8 * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + k8 * 8 + 4));
+                    const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    float v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) b[i] = __ldg(reinterpret_cast<const float4 *>(bias + cg * 32) + i);
-                };
-                auto process = [&](int cg, const uint32_t (&r)[32], const float4 (&b)[8]) {
-                    uint32_t bits = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float bj[8] = {b[2 * j].x, b[2 * j].y, b[2 * j].z, b[2 * j].w, b[2 * j + 1].x, b[2 * j + 1].y, b[2 * j + 1].z, b[2 * j + 1].w};
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[j * 8 + i]) + bj[i], 0.f);
-                        if (want_mask) {                              // ReLU'(x) = [x > 0]; v >= 0 here, so > 0 <=> any bit set
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) bits += min(__float_as_uint(v[i]), 1u) << (j * 8 + i);
-                        }
-                        store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
-                        const long e = ((long)slot * args.slot_stride + grow) * 256 + cg * 32 + j * 8;
-                        if (valid && args.act_dtype == 1) {
+                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[i]) + bj[i], 0.f);
+                    const uint4 hi = store_a8<NPASS>(sm.A, row, k8, v);
+                    // publish FIRST: the arrive has release semantics and would otherwise wait for the global stores below
+                    // (measured: 21-25 % of the epilogue's time with them in front of it)
+                    const long long c0 = dbg_on ? clk() : 0;
+                    publish(sm, cg);
+                    if (dbg_on) dbg_pub += clk() - c0;
+                    if (valid) {
+                        if (args.act_dtype == 1) {
+                            const long e = ((long)slot * args.slot_stride + grow) * 256 + k8 * 8;
                             float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(args.act_save) + e);
                             dst[0] = make_float4(v[0], v[1], v[2], v[3]);
                             dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                        } else if (valid && args.act_dtype == 2) {
-                            *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(args.act_save) + e) = pack_bf16x8(v);
+                        } else if (args.act_dtype == 2) {
+                            *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(args.act_save) + saved_off(slot, k8, args.slot_stride, grow)) = hi;
+                        }
+                        if (mask_row) {                               // ReLU'(x) = [x > 0]; v >= 0 here, so > 0 <=> any bit set
+                            uint32_t bits = 0;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) bits += min(__float_as_uint(v[i]), 1u) << i;
+                            mask_row[(long)k8 * args.slot_stride] = (uint8_t)bits;
                         }
                     }
-                    if (valid && want_mask) args.relu_mask[((long)slot * args.slot_stride + grow) * 8 + cg] = bits;
-                    publish(sm, cg, cg + 1);
                 };
-                uint32_t ra[32], rb[32];
-                float4 ba[8], bb[8];
-                tmem_ld32_issue(t_acc, ra);
-                load_bias(0, ba);
+                tmem_ld8_issue(t_acc + set * 8, ra);
 #pragma unroll 1
                 for (int cg = 0; cg < 8; cg += 2) {
+                    long long c0 = dbg_on ? clk() : 0;
                     tmem_ld_wait();
-                    tmem_ld32_issue(t_acc + (cg + 1) * 32, rb);
-                    load_bias(cg + 1, bb);
-                    process(cg, ra, ba);
+                    if (dbg_on) dbg_ld += clk() - c0;
+                    tmem_ld8_issue(t_acc + ((cg + 1) * 4 + set) * 8, rb);
+                    process(cg, ra);
+                    c0 = dbg_on ? clk() : 0;
                     tmem_ld_wait();
-                    if (cg + 2 < 8) {
-                        tmem_ld32_issue(t_acc + (cg + 2) * 32, ra);
-                        load_bias(cg + 2, ba);
-                    }
-                    process(cg + 1, rb, bb);
+                    if (dbg_on) dbg_ld += clk() - c0;
+                    if (cg + 2 < 8) tmem_ld8_issue(t_acc + ((cg + 2) * 4 + set) * 8, ra);
+                    process(cg + 1, rb);
                 }
             }
         }
     }
+    if (dbg_on) { atomicAdd(&g_dbg[2], (unsigned long long)dbg_acc); atomicAdd(&g_dbg[5], (unsigned long long)(clk() - dbg_t0));
+                  atomicAdd(&g_dbg[8], (unsigned long long)dbg_ld); atomicAdd(&g_dbg[9], (unsigned long long)dbg_pub); }
 }
 
 // ---- backward (data-gradient) epilogue.  Chain position d: 0 out^T, 1..3 rgb3..1^T, 4 rgb0^T, 5 geo^T, 6..8 pts3..1^T, 9 pts0^T
 template <int NPASS>
 __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base, int warp) {
-    const int row = threadIdx.x;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int quarter = warp & 3, set = warp >> 2;
+    const int row = quarter * 32 + (threadIdx.x & 31);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t acc_cnt = 0;
+    const bool dbg_on = args.debug && threadIdx.x == 0;
+    long long dbg_acc = 0;
+    const long long dbg_t0 = dbg_on ? clk() : 0;
+    // 8 accumulator columns [col, col+8) -> gXB[:, 64 + c*8 ...) (chunk c of the 68 (agg,var,h) columns; chunk 8 has 4)
+    auto gxb_chunk = [&](uint32_t t_acc, int col, int c, long grow, bool valid, bool accumulate) {
+        uint32_t r[8];
+        tmem_ld8_issue(t_acc + col, r);
+        tmem_ld_wait();
+        if (!valid) return;
+        float4 *dst = reinterpret_cast<float4 *>(args.gXB + grow * 132 + 64 + c * 8);
+        const int n4 = c < 8 ? 2 : 1;
+        for (int i = 0; i < n4; ++i) {
+            float4 o = accumulate ? dst[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            o.x += __uint_as_float(r[4 * i + 0]); o.y += __uint_as_float(r[4 * i + 1]);
+            o.z += __uint_as_float(r[4 * i + 2]); o.w += __uint_as_float(r[4 * i + 3]);
+            dst[i] = o;
+        }
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long grow = (long)tile * kTileM + row;
         const bool valid = grow < args.m;
         float g_sigma = 0.f;
-        {   // GEMM 0 operand: d raw[:, 0:3] in A[:, 0:16)
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (valid) {
-                const float *gr = args.g_raw + grow * 5;
-                v[0] = __ldg(gr + 0); v[1] = __ldg(gr + 1); v[2] = __ldg(gr + 2);
-                g_sigma = __ldg(gr + 3);
+        {   // GEMM 0 operand: d raw[:, 0:3] in A[:, 0:16): chunk 0 by set 0, chunk 1 (zeros) by set 1
+            if (set < 2) {
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (valid && set == 0) {
+                    const float *gr = args.g_raw + grow * 5;
+                    v[0] = __ldg(gr + 0); v[1] = __ldg(gr + 1); v[2] = __ldg(gr + 2);
+                    g_sigma = __ldg(gr + 3);
+                }
+                store_a8<NPASS>(sm.A, row, set, v);
+                if (valid) *reinterpret_cast<uint4 *>(args.g_save + saved_off(9, set, args.slot_stride, grow)) = pack_bf16x8(v);
             }
-            store_a8<NPASS>(sm.A, row, 0, v);
-            store_a8<NPASS>(sm.A, row, 1, z);
-            if (valid) {
-                __nv_bfloat16 *gs = args.g_save + (9 * args.slot_stride + grow) * 256;
-                *reinterpret_cast<uint4 *>(gs) = pack_bf16x8(v);
-                *reinterpret_cast<uint4 *>(gs + 8) = pack_bf16x8(z);
-            }
-            publish(sm, 0, 1);
+            publish(sm, 0);
         }
         for (int d = 0; d < kLayers; ++d, ++acc_cnt) {
-            uint4 m0 = make_uint4(0u, 0u, 0u, 0u), m1 = m0;          // the layer's 8 ReLU-mask words, fetched before the wait
+            uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};        // this thread's 8 ReLU-mask bytes of the layer, fetched before the wait
             if (valid && d != 9 && d != 4) {
                 const int slot = d < 4 ? 7 - d : 8 - d;              // d0..3 -> R4..R1 (slots 7..4); d5..8 -> H4..H1 (slots 3..0)
-                const uint4 *mp = reinterpret_cast<const uint4 *>(args.relu_mask + ((long)slot * args.slot_stride + grow) * 8);
-                m0 = __ldg(mp);
-                m1 = __ldg(mp + 1);
+                const uint8_t *mp = args.relu_mask + ((long)slot * 32 + set) * args.slot_stride + grow;
+#pragma unroll
+                for (int cg = 0; cg < 8; ++cg) mw[cg] = __ldg(mp + (long)cg * 4 * args.slot_stride);
             }
-            mbar_wait(sm.bar_acc_full, acc_cnt & 1);
+            {
+                const long long t0 = dbg_on ? clk() : 0;
+                mbar_wait(sm.bar_acc_full, acc_cnt & 1);
+                if (dbg_on) dbg_acc += clk() - t0;
+            }
             tc_fence_after();
             const uint32_t t_acc = t_lane + (uint32_t)(d & 1) * 256;
             if (d == 9) {
                 // pts0^T: 68 (+12 pad) columns, accumulated onto the colour trunk's share of d(agg,var,h)
-#pragma unroll 1
-                for (int cg = 0; cg < 3; ++cg) {
-                    uint32_t r[32];
-                    if (cg < 2) { tmem_ld32_issue(t_acc + cg * 32, r); tmem_ld_wait(); }
-                    else {
-                        uint32_t q[16];
-                        tmem_ld16(t_acc + 64, q);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) r[i] = q[i];
-                    }
-                    if (valid) {
-                        float4 *dst = reinterpret_cast<float4 *>(args.gXB + grow * 132 + 64 + cg * 32);
-                        const int n4 = cg < 2 ? 8 : 1;               // 64 + 4 = 68 columns
-                        for (int i = 0; i < n4; ++i) {
-                            float4 o = dst[i];
-                            o.x += __uint_as_float(r[4 * i + 0]); o.y += __uint_as_float(r[4 * i + 1]);
-                            o.z += __uint_as_float(r[4 * i + 2]); o.w += __uint_as_float(r[4 * i + 3]);
-                            dst[i] = o;
-                        }
-                    }
-                }
+                gxb_chunk(t_acc, set * 8, set, grow, valid, true);
+                gxb_chunk(t_acc, (set + 4) * 8, set + 4, grow, valid, true);
+                if (set == 0) gxb_chunk(t_acc, 64, 8, grow, valid, true);
                 tc_fence_before();
             } else if (d == 4) {
-                // rgb0^T: columns 0..63 = d geo features (-> operand of geo^T together with d sigma), 64..131 = d(agg,var,h)
+                // rgb0^T: columns 0..63 = d geo features (-> operand of geo^T together with d sigma), 64..131 = d(agg,var,h).
+                // Every TMEM read of a thread comes BEFORE its last publish: GEMM d+2 overwrites this buffer as soon as some
+                // threads have published the first group of layer d+1, which they can only do after GEMM d+1 has consumed
+                // everything published here.
+                gxb_chunk(t_acc, 64 + set * 8, set, grow, valid, false);
+                gxb_chunk(t_acc, 64 + (set + 4) * 8, set + 4, grow, valid, false);
+                if (set == 0) gxb_chunk(t_acc, 128, 8, grow, valid, false);
 #pragma unroll 1
                 for (int cg = 0; cg < 2; ++cg) {
-                    uint32_t r[32];
-                    tmem_ld32_issue(t_acc + cg * 32, r);
+                    const int k8 = cg * 4 + set;
+                    uint32_t r[8];
+                    tmem_ld8_issue(t_acc + k8 * 8, r);
                     tmem_ld_wait();
+                    float v[8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
-                        store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
-                        if (valid) *reinterpret_cast<uint4 *>(args.g_save + (4 * args.slot_stride + grow) * 256 + cg * 32 + j * 8) = pack_bf16x8(v);
-                    }
-                    publish(sm, cg, cg + 1);
+                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+                    const uint4 hi = store_a8<NPASS>(sm.A, row, k8, v);
+                    publish(sm, cg);
+                    if (valid) *reinterpret_cast<uint4 *>(args.g_save + saved_off(4, k8, args.slot_stride, grow)) = hi;
                 }
-                {   // A[:, 64:80) = (d sigma, 0...)
-                    float v[8] = {g_sigma, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    store_a8<NPASS>(sm.A, row, 8, v);
-                    store_a8<NPASS>(sm.A, row, 9, z);
-                    if (valid) {
-                        __nv_bfloat16 *gs = args.g_save + (4 * args.slot_stride + grow) * 256 + 64;
-                        *reinterpret_cast<uint4 *>(gs) = pack_bf16x8(v);
-                        *reinterpret_cast<uint4 *>(gs + 8) = pack_bf16x8(z);
-                    }
+                if (set < 2) {   // A[:, 64:80) = (d sigma, 0...): chunk 8 by set 0, chunk 9 (zeros) by set 1
+                    float v[8] = {set == 0 ? g_sigma : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    store_a8<NPASS>(sm.A, row, 8 + set, v);
+                    if (valid) *reinterpret_cast<uint4 *>(args.g_save + saved_off(4, 8 + set, args.slot_stride, grow)) = pack_bf16x8(v);
                 }
-#pragma unroll 1
-                for (int cg = 2; cg < 5; ++cg) {                     // columns 64..143 of the accumulator -> gXB[:, 64:132)
-                    uint32_t r[32];
-                    if (cg < 4) { tmem_ld32_issue(t_acc + cg * 32, r); tmem_ld_wait(); }
-                    else {
-                        uint32_t q[16];
-                        tmem_ld16(t_acc + 128, q);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) r[i] = q[i];
-                    }
-                    if (valid) {
-                        float4 *dst = reinterpret_cast<float4 *>(args.gXB + grow * 132 + 64 + (cg - 2) * 32);
-                        const int n4 = cg < 4 ? 8 : 1;
-                        for (int i = 0; i < n4; ++i)
-                            dst[i] = make_float4(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1]),
-                                                 __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                    }
-                }
-                publish(sm, 2, 3);
+                publish(sm, 2);
             } else {
                 // through a ReLU: G = acc * (saved activation > 0) -> next A operand, and saved for the weight gradient
                 const int gslot = d;                                 // g_save: 0..3 rgb3..rgb0, 4 geo, 5..8 pts3..pts0
-                // the ReLU masks of this layer: 8 words per row, loaded before the accumulator is even waited for
-                auto process = [&](int cg, const uint32_t (&r)[32], uint32_t bits) {
+                uint32_t ra[8], rb[8];
+                auto process = [&](int cg, const uint32_t (&r)[8], uint32_t word) {
+                    const int k8 = cg * 4 + set;
+                    const uint32_t bits = word;
+                    float v[8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = ((bits >> (j * 8 + i)) & 1u) ? __uint_as_float(r[j * 8 + i]) : 0.f;
-                        store_a8<NPASS>(sm.A, row, cg * 4 + j, v);
-                        if (valid) *reinterpret_cast<uint4 *>(args.g_save + (gslot * args.slot_stride + grow) * 256 + cg * 32 + j * 8) = pack_bf16x8(v);
-                    }
-                    publish(sm, cg, cg + 1);
+                    for (int i = 0; i < 8; ++i) v[i] = ((bits >> i) & 1u) ? __uint_as_float(r[i]) : 0.f;
+                    const uint4 hi = store_a8<NPASS>(sm.A, row, k8, v);
+                    publish(sm, cg);                                 // before the global store (see the forward epilogue)
+                    if (valid) *reinterpret_cast<uint4 *>(args.g_save + saved_off(gslot, k8, args.slot_stride, grow)) = hi;
                 };
-                uint32_t ra[32], rb[32];
-                tmem_ld32_issue(t_acc, ra);
-#pragma unroll 1
+                tmem_ld8_issue(t_acc + set * 8, ra);
+#pragma unroll
                 for (int cg = 0; cg < 8; cg += 2) {
                     tmem_ld_wait();
-                    tmem_ld32_issue(t_acc + (cg + 1) * 32, rb);
-                    process(cg, ra, m0.x);
+                    tmem_ld8_issue(t_acc + ((cg + 1) * 4 + set) * 8, rb);
+                    process(cg, ra, mw[cg]);
                     tmem_ld_wait();
-                    if (cg + 2 < 8) tmem_ld32_issue(t_acc + (cg + 2) * 32, ra);
-                    process(cg + 1, rb, m0.y);
-                    m0 = make_uint4(m0.z, m0.w, m1.x, m1.y);         // rotate the words (keeps them in registers)
-                    m1 = make_uint4(m1.z, m1.w, 0u, 0u);
+                    if (cg + 2 < 8) tmem_ld8_issue(t_acc + ((cg + 2) * 4 + set) * 8, ra);
+                    process(cg + 1, rb, mw[cg + 1]);
                 }
             }
         }
     }
+    if (dbg_on) { atomicAdd(&g_dbg[2], (unsigned long long)dbg_acc); atomicAdd(&g_dbg[5], (unsigned long long)(clk() - dbg_t0)); }
 }
 
 template <int NPASS, int CHAIN>
@@ -630,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(sm.bar_w_full + 8 * s, 1); mbar_init(sm.bar_w_empty + 8 * s, 2); }
-        for (int g = 0; g < kGroups; ++g) mbar_init(sm.bar_a_ready + 8 * g, kTileM);
+        for (int g = 0; g < kGroups; ++g) mbar_init(sm.bar_a_ready + 8 * g, kEpiThreads);
         mbar_init(sm.bar_acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -644,9 +698,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 4 * kEpiSets) {
         if (lane == 0) producer_loop<NPASS>(args, sm, num_tiles);
-    } else if (warp == 5) {
+    } else if (warp == 4 * kEpiSets + 1) {
         if (lane == 0) mma_loop<NPASS>(args, sm, num_tiles, tmem_base);
     } else {
         if (CHAIN == 0) fwd_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
@@ -689,6 +743,8 @@ int launch_chain(const ChainArgs &a, cudaStream_t st) {
 }
 
 void fill_layout(ChainArgs &a, int n_pass, int chain, const void *packed) {
+    static const int debug = getenv("OCCNERF_MLP_DEBUG") ? atoi(getenv("OCCNERF_MLP_DEBUG")) : 0;
+    a.debug = debug;
     const PackedLayout pl = packed_layout(n_pass, chain);
     for (int l = 0; l < kLayers; ++l) a.w_off[l] = pl.w_off[l];
     a.bias_off = pl.bias_off;
@@ -697,6 +753,17 @@ void fill_layout(ChainArgs &a, int n_pass, int chain, const void *packed) {
 }
 
 }  // namespace
+
+// debug only: reads (and optionally clears) the stall counters described at g_dbg
+extern "C" int occnerf_mlp_debug_counters(unsigned long long *host8, int reset) {
+    OCC_CUDA(cudaDeviceSynchronize());
+    if (host8) OCC_CUDA(cudaMemcpyFromSymbol(host8, g_dbg, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        OCC_CUDA(cudaMemcpyToSymbol(g_dbg, z, sizeof(z)));
+    }
+    return OCCNERF_OK;
+}
 
 extern "C" long occnerf_mlp_packed_bytes(int n_pass, int chain) {
     if ((n_pass != 1 && n_pass != 3) || (chain != 0 && chain != 1)) return -1;
@@ -733,7 +800,7 @@ extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int 
     fill_layout(a, n_pass, 0, packed);
     OCC_CHECK_ARG(act_dtype == 0 || slot_stride >= m, "mlp_forward_tc: slot_stride=%ld < m=%d", slot_stride, m);
     a.XB = XB; a.raw = raw; a.ldr = ldr; a.act_save = act_save; a.act_dtype = act_dtype; a.slot_stride = slot_stride;
-    a.relu_mask = (uint32_t *)relu_mask;
+    a.relu_mask = (uint8_t *)relu_mask;
     OCC_CHECK_ARG(((uintptr_t)relu_mask & 15) == 0, "mlp_forward_tc: relu_mask must be 16-byte aligned");
     return n_pass == 1 ? launch_chain<1, 0>(a, (cudaStream_t)stream) : launch_chain<3, 0>(a, (cudaStream_t)stream);
 }
@@ -749,6 +816,6 @@ extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *pa
     a.m = m;
     fill_layout(a, n_pass, 1, packed_bwd);
     OCC_CHECK_ARG(slot_stride >= m, "mlp_backward_tc: slot_stride=%ld < m=%d", slot_stride, m);
-    a.g_raw = g_raw; a.relu_mask = (uint32_t *)relu_mask; a.gXB = gXB; a.g_save = (__nv_bfloat16 *)g_save; a.slot_stride = slot_stride;
+    a.g_raw = g_raw; a.relu_mask = (uint8_t *)relu_mask; a.gXB = gXB; a.g_save = (__nv_bfloat16 *)g_save; a.slot_stride = slot_stride;
     return n_pass == 1 ? launch_chain<1, 1>(a, (cudaStream_t)stream) : launch_chain<3, 1>(a, (cudaStream_t)stream);
 }

@@ -1,9 +1,11 @@
 // K3c: weight (and bias) gradients of the canonical MLP on tcgen05/TMEM:  dW_l[n,k] = sum_m G_l[m,n] * X_l[m,k].
 //
-// The contraction runs over the SAMPLE axis, so both operands are "MN-major" for the tensor core: the row-major
-// [sample][feature] bf16 tensors that the fused forward (X_l) and data-gradient (G_l) kernels leave in HBM are consumed
-// as they are -- TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, 64-feature x 64-sample boxes) drops them into shared memory
-// in the canonical MN-major SW128 UMMA layout, no transposes anywhere.
+// The contraction runs over the SAMPLE axis, so both operands are "MN-major" for the tensor core.  The fused forward (X_l)
+// and data-gradient (G_l) kernels leave their bf16 tensors in HBM chunk-major, [slot][feature/8][sample][8 features]
+// (the layout in which their epilogue stores coalesce); a TMA box of 8 features x 64 samples x 8 chunks
+// (cp.async.bulk.tensor.3d, no swizzle) lands in shared memory as [chunk][sample][16 B], which IS the canonical
+// no-swizzle MN-major UMMA layout: 8 consecutive samples x 16 B = one 128-byte core matrix, core matrices 128 B apart
+// along K (samples), 1024 B apart along MN (feature chunks).  No transposes anywhere.
 //
 // One persistent CTA per SM; for every layer a CTA owns a contiguous range of 64-sample tiles and accumulates its
 // partial dW (256 x 256 fp32 = 2 x 128 TMEM lanes x 256 columns = all 512 TMEM columns) over that range, then adds it
@@ -21,7 +23,7 @@ namespace {
 constexpr int kThreads = 192;
 constexpr int kStages = 3;
 constexpr int kTileS = 64;                          // samples per stage
-constexpr int kBlockBytes = kTileS * 128;           // one 64-feature x 64-sample SW128 block = 8 KB
+constexpr int kBlockBytes = kTileS * 128;           // one 64-feature x 64-sample block = 8 chunks x 64 samples x 16 B = 8 KB
 constexpr int kOperandBytes = 4 * kBlockBytes;      // up to 256 features
 constexpr int kStageBytes = 2 * kOperandBytes;      // G tile + X tile = 64 KB
 constexpr int kLayers = 10;
@@ -61,9 +63,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > kSpinLimit) __trap();
     }
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -74,10 +76,11 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
     asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// MN-major SWIZZLE_128B operand: 64-element (128 B) rows, 8-row groups 1024 B apart (SBO), 64-feature blocks kBlockBytes apart (LBO)
-__device__ __forceinline__ uint64_t smem_desc_mn128(uint32_t addr) {
-    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((kBlockBytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((1024 >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+// MN-major, no swizzle (INTERLEAVE): core matrix = 8 samples (K) x 8 features (16 B, MN-contiguous) = 128 B;
+// LBO = stride between core matrices along K (next 8 samples) = 128 B, SBO = stride along MN (next 8-feature chunk) = 1024 B
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((128 >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((kTileS * 16 >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
 // kind::f16: D=f32, A=B=bf16, both MN-major, M=128
 __device__ __forceinline__ uint32_t instr_desc_mn(int n) {
@@ -143,10 +146,9 @@ mlp_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_cons
                         mbar_wait(bar_empty + 8 * s, ph ^ 1);
                         mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(gb + xb) * kBlockBytes);
                         const uint32_t dst = smem_u32(smem + s * kStageBytes);
-                        const int row_g = (int)(L.g_slot * args.slot_stride + (long)t * kTileS);
-                        const int row_x = (int)(L.x_slot * args.slot_stride + (long)t * kTileS);
-                        for (int b = 0; b < gb; ++b) tma_load_2d(dst + b * kBlockBytes, &map_g, b * 64, row_g, bar_full + 8 * s);
-                        for (int b = 0; b < xb; ++b) tma_load_2d(dst + kOperandBytes + b * kBlockBytes, &map_x, b * 64, row_x, bar_full + 8 * s);
+                        const int row = t * (kTileS / 32);              // in units of 32 rows (see make_map)
+                        for (int b = 0; b < gb; ++b) tma_load_3d(dst + b * kBlockBytes, &map_g, 0, row, L.g_slot * 32 + b * 8, bar_full + 8 * s);
+                        for (int b = 0; b < xb; ++b) tma_load_3d(dst + kOperandBytes + b * kBlockBytes, &map_x, 0, row, L.x_slot * 32 + b * 8, bar_full + 8 * s);
                     }
                 }
             }
@@ -167,9 +169,9 @@ mlp_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_cons
                         const uint32_t g_base = smem_u32(smem + s * kStageBytes), x_base = g_base + kOperandBytes;
 #pragma unroll
                         for (int k16 = 0; k16 < kTileS / 16; ++k16) {
-                            const uint64_t db = smem_desc_mn128(x_base + k16 * 2048);
+                            const uint64_t db = smem_desc_mn(x_base + k16 * 256);          // 16 samples = 2 core matrices along K
                             for (int h = 0; h < halves; ++h) {
-                                const uint64_t da = smem_desc_mn128(g_base + h * 2 * kBlockBytes + k16 * 2048);
+                                const uint64_t da = smem_desc_mn(g_base + h * 2 * kBlockBytes + k16 * 256);
                                 tc_mma(tmem_base + h * 256, da, db, idesc, first ? 0u : 1u);
                             }
                             first = 0;
@@ -189,15 +191,16 @@ mlp_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_cons
                 const int halves = (L.n_pad <= 128) ? 1 : 2;
                 const bool bias_cols = 2 * tid < L.n_pad;
                 float s0 = 0.f, s1 = 0.f;
-                const int blk = (2 * tid) >> 6, chunk = ((2 * tid) & 63) >> 3, within = ((2 * tid) & 7) * 2;
+                const int chunk = (2 * tid) >> 3, within = ((2 * tid) & 7) * 2;   // feature chunk (1 KB slab) and byte offset in its 16 B
                 for (int t = t0; t < t1; ++t, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     mbar_wait(bar_full + 8 * s, ph);
                     if (bias_cols) {
-                        const unsigned char *g = smem + s * kStageBytes + blk * kBlockBytes;
+                        const unsigned char *g = smem + s * kStageBytes + chunk * (kTileS * 16) + within;
 #pragma unroll 8
                         for (int r = 0; r < kTileS; ++r) {
-                            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162 *>(g + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
+                            const int rr = (r + chunk) & (kTileS - 1);       // rotate per chunk: the 8 chunks of a warp hit different banks
+                            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162 *>(g + rr * 16);
                             const float2 f = __bfloat1622float2(v);
                             s0 += f.x; s1 += f.y;
                         }
@@ -240,7 +243,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(CUtensorMap *map, const void *base, long rows) {
+int make_map(CUtensorMap *map, const void *base, long rows, int slots) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         cudaDriverEntryPointQueryResult q;
@@ -249,12 +252,15 @@ int make_map(CUtensorMap *map, const void *base, long rows) {
         OCC_CHECK_ARG(fn && q == cudaDriverEntryPointSuccess, "mlp_wgrad: cuTensorMapEncodeTiled is not available from this driver");
         encode = (EncodeTiledFn)fn;
     }
-    const cuuint64_t dims[2] = {256, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {256 * sizeof(__nv_bfloat16)};
-    const cuuint32_t box[2] = {64, (cuuint32_t)kTileS};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    // chunk-major [slots*32][rows][8].  Rows of one chunk are contiguous (16 B each), so the map folds 32 of them into the
+    // innermost dimension (512-byte bursts instead of 16-byte ones): dim0 = 32 rows x 8 features, dim1 = row / 32,
+    // dim2 = slot*32 + chunk.  The box (256, 2, 8) lands in shared memory as [chunk][64 rows][16 B] all the same.
+    const cuuint64_t dims[3] = {256, (cuuint64_t)rows / 32, (cuuint64_t)slots * 32};
+    const cuuint64_t strides[2] = {256 * sizeof(__nv_bfloat16), (cuuint64_t)rows * 8 * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[3] = {256, (cuuint32_t)kTileS / 32, 8};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     OCC_CHECK_ARG(r == CUDA_SUCCESS, "mlp_wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return OCCNERF_OK;
@@ -268,11 +274,11 @@ extern "C" int occnerf_mlp_wgrad_tc(const void *g_save, const void *act_bf16, in
     OCC_CHECK_ARG(g_save && act_bf16 && dW && dB, "mlp_wgrad_tc: null pointer");
     OCC_CHECK_ARG(slot_stride >= m && slot_stride % kTileS == 0, "mlp_wgrad_tc: slot_stride=%ld must be a multiple of %d and >= m=%d",
                   slot_stride, kTileS, m);
-    OCC_CHECK_ARG(10 * slot_stride < (1l << 31), "mlp_wgrad_tc: too many rows for 32-bit TMA coordinates");
+    OCC_CHECK_ARG(slot_stride < (1l << 31), "mlp_wgrad_tc: too many rows for 32-bit TMA coordinates");
     OCC_CHECK_ARG((((uintptr_t)g_save | (uintptr_t)act_bf16 | (uintptr_t)dW) & 15) == 0, "mlp_wgrad_tc: buffers must be 16-byte aligned");
     CUtensorMap map_g, map_x;
-    if (int e = make_map(&map_g, g_save, 10 * slot_stride)) return e;
-    if (int e = make_map(&map_x, act_bf16, 10 * slot_stride)) return e;
+    if (int e = make_map(&map_g, g_save, slot_stride, 10)) return e;
+    if (int e = make_map(&map_x, act_bf16, slot_stride, 10)) return e;
     const int smem_bytes = kStages * kStageBytes + 256;
     static bool configured = false;
     if (!configured) {

@@ -42,10 +42,11 @@ class MlpTc:
         stride = (m + 63) // 64 * 64
         acts, mask = None, None
         if save:
-            acts = torch.empty(10, stride, 256, device=dev, dtype=bf16)
-            mask = torch.empty(8, stride, 8, device=dev, dtype=torch.int32)      # one bit per hidden unit: ReLU'(x)
+            # chunk-major [slot][col/8][row][8] (include/occnerf_b200.h): coalesced epilogue stores, TMA-ready for wgrad
+            acts = torch.empty(10, 32, stride, 8, device=dev, dtype=bf16)
+            mask = torch.empty(8, 32, stride, device=dev, dtype=torch.uint8)      # one bit per hidden unit: ReLU'(x)
             if stride > m:
-                acts[:, m:].zero_()
+                acts[:, :, m:].zero_()
         call("occnerf_mlp_forward_tc", XB.data_ptr(), m, packed.data_ptr(), self.n_pass, raw.data_ptr(), raw.shape[1],
              acts.data_ptr() if save else None, 2 if save else 0, stride, mask.data_ptr() if save else None, stream(),
              work=M.FLOP_FWD * m)
@@ -54,17 +55,19 @@ class MlpTc:
     def backward(self, XB, g_raw, W: M.MlpWeights, saved):
         m, dev = XB.shape[0], XB.device
         acts = saved["acts"]
-        stride = acts.shape[1]
+        stride = acts.shape[2]
         packed = self.pack(W, dev, 1)
         gXB = torch.empty(m, M.XB_LD, device=dev, dtype=f32)
-        g_save = torch.empty(10, stride, 256, device=dev, dtype=bf16)
+        g_save = torch.empty(10, 32, stride, 8, device=dev, dtype=bf16)
         if stride > m:
-            g_save[:, m:].zero_()
+            g_save[:, :, m:].zero_()
         call("occnerf_mlp_backward_tc", g_raw.data_ptr(), m, packed.data_ptr(), self.n_pass, saved["mask"].data_ptr(), gXB.data_ptr(),
              g_save.data_ptr(), stride, stream(), work=M.FLOP_FWD * m)
         if self.wgrad == "lib":
             with _lib.region("lib:wgrad(cuBLAS bf16)+bias sums"):
-                return gXB, self._wgrad_lib(XB, g_raw, acts[:, :m], g_save[:, :m])
+                def rows(t):     # chunk-major -> row-major [slot][row][256]
+                    return t.permute(0, 2, 1, 3).reshape(10, stride, 256)[:, :m]
+                return gXB, self._wgrad_lib(XB, g_raw, rows(acts), rows(g_save))
         dW = torch.zeros(10, 256, 256, device=dev, dtype=f32)
         dB = torch.zeros(10, 256, device=dev, dtype=f32)
         call("occnerf_mlp_wgrad_tc", g_save.data_ptr(), acts.data_ptr(), m, stride, dW.data_ptr(), dB.data_ptr(), stream(),

@@ -396,7 +396,12 @@ class Network(nn.Module):
         self._nr_const = None
         if window is not None and cond is None and all(v == 0.0 for v in window):
             nw, nb = self.non_rigid_mlp.module.flat()
-            self._nr_const = M.nonrigid_offsets(pos_flat[:1].detach().contiguous().float(), None, window, nw, nb, return_const=True)
+            # ... and only when the non-rigid MLP's tensors have changed (they get no gradient before kick_in_iter)
+            key = tuple((t.data_ptr(), t._version) for t in nw + nb)
+            if getattr(self, "_nr_const_key", None) != key:
+                self._nr_const_val = M.nonrigid_offsets(pos_flat[:1].detach().contiguous().float(), None, window, nw, nb, return_const=True)
+                self._nr_const_key = key
+            self._nr_const = self._nr_const_val
         # non-rigid offsets (network.py:225-232) and the multi-scale neighbour search (network.py:236-255) run under no_grad
         # in the reference and do not depend on the chunking: one search over all points keeps the SMs full (per-chunk
         # launches of ~2 waves lose a third of their time to the tail), the memory-heavy part below stays chunked

@@ -152,3 +152,28 @@ def test_full_size_step_runs_and_is_finite():
     before = net.point_counter.clone()
     net.apply_visibility(out["hits"])
     assert float((net.point_counter - before).sum()) == float(out["hits"].sum())
+
+
+def test_chunking_does_not_change_results():
+    """`chunk` (rays per _render_rays call) and `netchunk_per_gpu` (points per MLP call) only bound memory
+    (network.py:307-317, 202-220): outputs are identical and gradients equal up to fp32 summation order.  Exercises the
+    shared table-gradient buffer of the chunks of one _query_mlp call."""
+    sub, w, fr, vol, t_rand, rk, g = load_case("train_dense")
+    outs, grads = [], []
+    for chunk, netchunk in ((32768, 300000), (40, 1000)):
+        net = _net(sub, w, rk, "fp32")
+        net.cfg.chunk, net.cfg.netchunk_per_gpu = chunk, netchunk
+        vol_d = vol.to(dev()).requires_grad_(True)
+        out = _render(net, fr, vol_d, t_rand, rk["iter_val"])
+        make_golden.scalar_loss({k: out[k] for k in ("rgb", "alpha", "depth", "comp_loss")}).backward()
+        m = net.cnl_mlp.module
+        # (`hits` is excluded: the reference votes per _render_rays call -- network.py:502 -- so it depends on `chunk`)
+        outs.append({k: out[k].detach().cpu() for k in ("rgb", "alpha", "depth", "comp_loss")})
+        grads.append({"emb": m.encoder.embeddings.grad.cpu(), "vol": vol_d.grad.cpu(), "pd": net.point_dist.grad.cpu(),
+                      "w": m.pts_linears[2].weight.grad.cpu(), "b": m.rgb_linears[0].bias.grad.cpu()})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k].reshape(-1), outs[1][k].reshape(-1)), k
+    # (sums of float atomics: the order differs from run to run, and point_dist's gradient is a small difference of
+    # large per-sample contributions -- see the tolerances of test_render_matches_reference_golden)
+    for k in grads[0]:
+        assert normwise_close(grads[1][k].numpy(), grads[0][k].numpy(), 1e-3 if k == "pd" else 1e-4), k
