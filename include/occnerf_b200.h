@@ -103,6 +103,18 @@ int occnerf_knn_tree(const float *queries, int m, int group_stride, int lane_ray
                      const int32_t *gid2, const int32_t *gid3, const int32_t *inv2, int n0, int n1, int n2, int n3, int k,
                      int32_t *out, occnerf_stream_t stream);
 
+/* All four levels through precomputed per-cell candidate lists over a static uniform grid (the support sets never move);
+ * ids bit-identical to occnerf_knn.  p0..p3 [n,4]: the level points in their own row order; gid1/2/3: level row ->
+ * vertex id; cell_tab [cells,4,2] int32 = (offset into lists, count) per cell and level, cells x-fastest;
+ * lists: uint16 level-local rows, every cell's list being a superset of the k nearest of any query inside the cell
+ * (occnerf_b200.ops.build_knn_grid states the bound).  grid_min_invh_host = (min x, min y, min z, 1 / cell size) and
+ * grid_dims_host = (nx, ny, nz) are HOST arrays.  Queries outside the grid are searched exhaustively (still exact). */
+int occnerf_knn_grid(const float *queries, int m, int group_stride, int lane_rays, const float *p0, const float *p1,
+                     const float *p2, const float *p3, int n0, int n1, int n2, int n3, const int32_t *gid1,
+                     const int32_t *gid2, const int32_t *gid3, const int32_t *cell_tab, const uint16_t *lists,
+                     const float *grid_min_invh_host, const int32_t *grid_dims_host, int k, int32_t *out,
+                     occnerf_stream_t stream);
+
 /* ---- per-sample surface geometry -> 4-D hash-grid input (occnerf_mlp.py:146-167) --------------------
  * knn_idx rows have `knn_stride` int32 entries, the first 10 being the level-0 neighbours.
  * enc_in [m,4] = (cos-weighted mean of the 3 nearest base vertices normalised to [0,1]^3, clamp((d+.2)/.5));

@@ -28,6 +28,7 @@ _SIGNATURES = {
     "occnerf_knn": [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "occnerf_knn_hier": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp],
     "occnerf_knn_tree": [_vp, _i, _i, _i] + [_vp] * 11 + [_i] * 5 + [_vp, _vp],
+    "occnerf_knn_grid": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     "occnerf_sample_geometry": [_vp, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _vp],
     "occnerf_hashgrid_level_scales": [_f, _u, _u, _vp, _vp],
     "occnerf_hashgrid_forward": [_vp] * 5 + [_i, _i] + [_u] * 4 + [_vp] * 4,

@@ -468,6 +468,87 @@ knn_tree_kernel(const float *__restrict__ queries, int m, int group_stride, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Candidate-list search over a static uniform grid.  The support sets never move (point_base is not trained), so for
+// every cell of a grid over the canonical volume and every level the host side precomputes (once per subject,
+// occnerf_b200.ops.build_knn_grid) the list of all points that can be among the k nearest of ANY query inside the cell:
+//     L(cell) = { p : |p - centre| <= d_k(centre) + 2*rho + margin },   rho = half the cell diagonal
+// (for q in the cell, d_k(q) <= d_k(centre) + rho, and a k-nearest p of q has |p - centre| <= |p - q| + rho), sorted by
+// distance to the centre.  A query then scans only its cell's list -- a few hundred candidates for all levels together
+// instead of ~1-1.4 k cluster-pruned (or 9152 brute-force) ones, with no pruning tests at all, and because the list is
+// nearest-first the running top-k is final after a handful of insertions.  The ranking is the same (distance, row)
+// lexicographic order on the same fp32 distances, so the ids are bit-identical to occnerf_knn.  Queries outside the grid
+// fall back to an exact scan of the whole level inside the same kernel.
+struct GridArgs {
+    const float4 *p[4];      // level points in their own row order (.w unused)
+    int n[4];
+    const int32_t *gid[4];   // level row -> vertex id (gid[0] unused: rows ARE vertex ids)
+    const int2 *cell_tab;    // [cells][4] (offset into lists, count) per level
+    const uint16_t *lists;   // level-local rows
+    float gmin[3], inv_h;
+    int dims[3];
+};
+
+template <int K>
+__global__ void __launch_bounds__(kHierThreads)
+knn_grid_kernel(const float *__restrict__ queries, int m, int group_stride, int lane_rays, const GridArgs G,
+                int32_t *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char hier_smem[];
+    float4 *s0 = reinterpret_cast<float4 *>(hier_smem);
+    float4 *s1 = s0 + G.n[0], *s2 = s1 + G.n[1], *s3 = s2 + G.n[2];
+    for (int i = threadIdx.x; i < G.n[0]; i += kHierThreads) s0[i] = __ldg(G.p[0] + i);
+    for (int i = threadIdx.x; i < G.n[1]; i += kHierThreads) s1[i] = __ldg(G.p[1] + i);
+    for (int i = threadIdx.x; i < G.n[2]; i += kHierThreads) s2[i] = __ldg(G.p[2] + i);
+    for (int i = threadIdx.x; i < G.n[3]; i += kHierThreads) s3[i] = __ldg(G.p[3] + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int lane_samples = 32 / lane_rays;
+    const long jblocks = (group_stride + lane_samples - 1) / lane_samples;
+    const long warp_global = ((long)blockIdx.x * kHierThreads + threadIdx.x) >> 5;
+    const long j = (warp_global % jblocks) * lane_samples + lane / lane_rays;
+    const long q = ((warp_global / jblocks) * lane_rays + lane % lane_rays) * group_stride + j;
+    const bool active = j < group_stride && q < m;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) { qx = __ldg(queries + q * 3); qy = __ldg(queries + q * 3 + 1); qz = __ldg(queries + q * 3 + 2); }
+    int32_t *o = out + (active ? q : 0) * 4 * K;
+    float dk[K];
+    int ik[K];
+
+    // ---- the query's cell
+    const float fx = (qx - G.gmin[0]) * G.inv_h, fy = (qy - G.gmin[1]) * G.inv_h, fz = (qz - G.gmin[2]) * G.inv_h;
+    const bool in_grid = active && fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)G.dims[0] && fy < (float)G.dims[1] &&
+                         fz < (float)G.dims[2];
+    const long cell = in_grid ? ((long)(int)fz * G.dims[1] + (int)fy) * G.dims[0] + (int)fx : 0;
+    const bool stray = active && !in_grid;
+
+#pragma unroll 1
+    for (int lev = 3; lev >= 0; --lev) {
+        const float4 *pts = lev == 0 ? s0 : (lev == 1 ? s1 : (lev == 2 ? s2 : s3));
+        const int n_lev = lev == 0 ? G.n[0] : (lev == 1 ? G.n[1] : (lev == 2 ? G.n[2] : G.n[3]));
+        reset_topk<K>(dk, ik);
+        int2 oc = make_int2(0, 0);
+        if (in_grid) oc = __ldg(G.cell_tab + cell * 4 + lev);
+        const uint16_t *lst = G.lists + oc.x;
+        const int cnt = oc.y;
+        const int cmax = __reduce_max_sync(OCC_FULL, cnt);
+#pragma unroll 2
+        for (int i = 0; i < cmax; ++i) {
+            if (i < cnt) {
+                const int row = (int)__ldg(lst + i);
+                const float d = dist2_rn(qx, qy, qz, pts[row]);
+                if (d < dk[K - 1] || (d == dk[K - 1] && row < ik[K - 1])) topk_insert_lex<K>(dk, ik, d, row);
+            }
+        }
+        if (__any_sync(OCC_FULL, stray)) {                  // outside the grid: exact scan of the whole level
+            for (int c = 0; c < n_lev; ++c) {
+                const float d = dist2_rn(qx, qy, qz, pts[c]);
+                if (stray && d < dk[K - 1]) topk_insert<K>(dk, ik, d, c);
+            }
+        }
+        if (active) write_topk<K>(o + lev * K, ik, lev == 0 ? nullptr : (lev == 1 ? G.gid[1] : (lev == 2 ? G.gid[2] : G.gid[3])));
+    }
+}
+
 int launch_knn(const float *queries, int m, const float *supports4, const int32_t *gid, const int32_t *lb, int n_levels,
                int k, const uint8_t *query_sel, int32_t *out, cudaStream_t st) {
     int b[5] = {0, 0, 0, 0, 0};
@@ -598,6 +679,46 @@ extern "C" int occnerf_visibility_hits(const float *depth, const int64_t *term, 
     const int32_t lb[2] = {0, V};
     if (int e = launch_knn(qpts, N, cloud4, nullptr, lb, 1, k, sel, idx, st)) return e;
     vis_mark_kernel<<<occ_div_up(N, 256), 256, 0, st>>>(count, sel, idx, N, k, hits);
+    OCC_LAUNCH_CHECK();
+    return OCCNERF_OK;
+}
+
+extern "C" int occnerf_knn_grid(const float *queries, int m, int group_stride, int lane_rays, const float *p0, const float *p1,
+                                const float *p2, const float *p3, int n0, int n1, int n2, int n3, const int32_t *gid1,
+                                const int32_t *gid2, const int32_t *gid3, const int32_t *cell_tab, const uint16_t *lists,
+                                const float *grid_min_invh_host, const int32_t *grid_dims_host, int k, int32_t *out,
+                                occnerf_stream_t stream) {
+    if (m <= 0) return OCCNERF_OK;
+    OCC_CHECK_ARG(queries && p0 && p1 && p2 && p3 && gid1 && gid2 && gid3 && cell_tab && lists && grid_min_invh_host &&
+                  grid_dims_host && out, "knn_grid: null pointer");
+    OCC_CHECK_ARG(k == 10, "knn_grid: k=%d (supported: 10)", k);
+    OCC_CHECK_ARG(group_stride >= 1 && n0 >= 1 && n1 >= 1 && n2 >= 1 && n3 >= 1 && n0 <= 65535, "knn_grid: bad sizes");
+    OCC_CHECK_ARG(lane_rays == 1 || lane_rays == 2 || lane_rays == 4 || lane_rays == 8 || lane_rays == 16 || lane_rays == 32,
+                  "knn_grid: lane_rays=%d (a power of two <= 32)", lane_rays);
+    OCC_CHECK_ARG((((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)p3) & 15) == 0 && ((uintptr_t)cell_tab & 7) == 0,
+                  "knn_grid: point arrays must be 16-byte and cell_tab 8-byte aligned");
+    OCC_CHECK_ARG(grid_dims_host[0] >= 1 && grid_dims_host[1] >= 1 && grid_dims_host[2] >= 1 && grid_min_invh_host[3] > 0.f,
+                  "knn_grid: bad grid");
+    const size_t smem = (size_t)(n0 + n1 + n2 + n3) * 16;
+    OCC_CHECK_ARG(smem <= 227 * 1024, "knn_grid: %d support points do not fit in shared memory", n0 + n1 + n2 + n3);
+    static size_t configured = 0;
+    if (configured < smem) {
+        OCC_CUDA(cudaFuncSetAttribute(knn_grid_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    GridArgs G;
+    G.p[0] = (const float4 *)p0; G.p[1] = (const float4 *)p1; G.p[2] = (const float4 *)p2; G.p[3] = (const float4 *)p3;
+    G.n[0] = n0; G.n[1] = n1; G.n[2] = n2; G.n[3] = n3;
+    G.gid[0] = nullptr; G.gid[1] = gid1; G.gid[2] = gid2; G.gid[3] = gid3;
+    G.cell_tab = (const int2 *)cell_tab;
+    G.lists = lists;
+    for (int a = 0; a < 3; ++a) { G.gmin[a] = grid_min_invh_host[a]; G.dims[a] = grid_dims_host[a]; }
+    G.inv_h = grid_min_invh_host[3];
+    const long rays = (m + group_stride - 1) / group_stride;
+    const int lane_samples = 32 / lane_rays;
+    const long warps = ((rays + lane_rays - 1) / lane_rays) * ((group_stride + lane_samples - 1) / lane_samples);
+    knn_grid_kernel<10><<<occ_div_up(warps * 32, kHierThreads), kHierThreads, smem, (cudaStream_t)stream>>>(queries, m, group_stride,
+                                                                                                      lane_rays, G, out);
     OCC_LAUNCH_CHECK();
     return OCCNERF_OK;
 }

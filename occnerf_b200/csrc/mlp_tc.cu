@@ -32,7 +32,7 @@ constexpr int kTileM = 128;
 constexpr int kThreads = 576;
 constexpr int kEpiSets = 4;                 // epilogue warps per TMEM lane quarter
 constexpr int kEpiThreads = kEpiSets * 128;
-constexpr int kStages = 3;
+constexpr int kStages = 3;                  // (6 x 16 KB with half-size chunks was measured 15 % slower: more, smaller bulk copies)
 constexpr int kStageBytes = 32768;
 constexpr int kLayers = 10;
 constexpr int kAPartBytes = 65536;          // 128 rows x 256 K x bf16

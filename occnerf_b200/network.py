@@ -165,7 +165,7 @@ class RenderConfig:
     ignore_non_rigid_motions: bool = False
     bgcolor: tuple = (0.0, 0.0, 0.0)
     mlp_engine: str = "fp32"        # "fp32" (exact SIMT) | "tc3" (tcgen05 split-bf16) | "tc1" (tcgen05 bf16)
-    knn_mode: str = "tree"          # "tree" (one launch, 3-level cluster tree) | "hier" (two 2-level launches) | "brute"; same ids
+    knn_mode: str = "grid"          # "grid" (per-cell candidate lists) | "tree" (3-level cluster tree) | "hier" | "brute"; same ids
 
 
 # ----------------------------------------------------------------------------- differentiable stages
@@ -434,6 +434,10 @@ class Network(nn.Module):
         gs = max(1, int(group_stride))
         if self.cfg.knn_mode == "brute":
             return ops.knn(xyz, st["supports4"], st["level_begin"], 10, support_gid=st["support_gid"])
+        if self.cfg.knn_mode == "grid":
+            if "grid" not in st:
+                st["grid"] = ops.build_knn_grid(st["point_base"], [f.to(xyz.device) for f in self.fps_index])
+            return ops.knn_grid(xyz, gs, st["grid"])
         if self.cfg.knn_mode == "tree":
             return ops.knn_tree(xyz, gs, st["tree"])
         knn_idx = torch.empty(xyz.shape[0], 4, 10, device=xyz.device, dtype=i32)

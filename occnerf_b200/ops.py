@@ -175,6 +175,79 @@ def knn_tree(queries, group_stride, tree, out=None, lane_rays=None):
     return out
 
 
+_GRID_CACHE = {}
+
+
+def build_knn_grid(base: torch.Tensor, fps, cell: float = 0.025, pad: float = 0.35, k: int = 10):
+    """Static candidate lists for occnerf_knn_grid (include/occnerf_b200.h).  A uniform grid of `cell`-sized cells covers the
+    vertex bounding box +- `pad`; for every cell (centre o, half diagonal rho) and level the list holds every point p with
+        |p - o| <= d_k(o) + 2*rho + margin,     d_k(o) = distance from o to its k-th nearest point of the level.
+    Superset proof: a query q in the cell has |q - o| <= rho, hence d_k(q) <= d_k(o) + rho (the k points within d_k(o) of
+    o are within d_k(o) + rho of q), and every k-nearest p of q satisfies |p - o| <= |p - q| + rho <= d_k(o) + 2*rho.  The
+    margin (1e-4 + 1e-5*d) is far above fp32 rounding.  Lists are sorted by |p - o| and padded to nothing; built once per
+    subject on the device (a few seconds, ~0.3 GB at the defaults)."""
+    dev = base.device
+    key = (str(dev), tuple(base.shape), float(base.double().sum()), float(base.double().abs().sum()), cell, pad, k,
+           tuple(int(f.shape[0]) for f in fps), tuple(int(f.long().sum()) for f in fps))
+    if key in _GRID_CACHE:
+        return _GRID_CACHE[key]
+    base = base.float()
+    levels = [base, base[fps[0]], base[fps[1]], base[fps[2]]]
+    gmin = base.min(0)[0] - pad
+    dims = torch.ceil((base.max(0)[0] + pad - gmin) / cell).long().tolist()
+    ncell = dims[0] * dims[1] * dims[2]
+    rho = cell * math.sqrt(3.0) / 2.0
+    idx = torch.arange(ncell, device=dev)
+    ix, iy, iz = idx % dims[0], (idx // dims[0]) % dims[1], idx // (dims[0] * dims[1])
+    centres = torch.stack([ix, iy, iz], 1).float().add_(0.5).mul_(cell).add_(gmin)
+    cell_tab = torch.zeros(ncell, 4, 2, device=dev, dtype=i32)
+    lists, total = [], 0
+    for lev in range(4):
+        P = levels[lev]
+        n = P.shape[0]
+        chunk = max(256, (64 << 20) // n)                      # ~256 MB of fp32 distances per chunk
+        for c0 in range(0, ncell, chunk):
+            c = centres[c0:c0 + chunk]
+            d = torch.zeros(c.shape[0], n, device=dev)
+            for a in range(3):
+                d += (c[:, a:a + 1] - P[None, :, a]) ** 2
+            d.sqrt_()
+            ds, order = torch.sort(d, dim=1)
+            thr = ds[:, min(k, n) - 1]
+            thr = thr + 2.0 * rho + 1e-4 + 1e-5 * thr
+            cnt = (ds <= thr[:, None]).sum(1)
+            width = int(cnt.max())
+            keep = torch.arange(width, device=dev)[None, :] < cnt[:, None]
+            lists.append(order[:, :width][keep].to(torch.int16))
+            off = torch.cumsum(cnt, 0) - cnt + total
+            cell_tab[c0:c0 + chunk, lev, 0] = off.to(i32)
+            cell_tab[c0:c0 + chunk, lev, 1] = cnt.to(i32)
+            total += int(cnt.sum())
+            del d, ds, order, keep
+    assert total < 2 ** 31
+    grid = dict(
+        p=[to_float4(P).contiguous() for P in levels], n=tuple(int(P.shape[0]) for P in levels),
+        gid=[f.to(i32).contiguous() for f in fps], cell_tab=cell_tab.contiguous(), lists=torch.cat(lists).contiguous(),
+        params=(C.c_float * 4)(float(gmin[0]), float(gmin[1]), float(gmin[2]), float(np.float32(1.0) / np.float32(cell))),
+        dims=(C.c_int32 * 3)(*dims), entries=total, cells=ncell)
+    _GRID_CACHE[key] = grid
+    return grid
+
+
+def knn_grid(queries, group_stride, grid, out=None, lane_rays=None):
+    """All 4 levels x k=10 through the per-cell candidate lists -> (m,4,10) int32 vertex ids (bit-identical to knn)."""
+    m = queries.shape[0]
+    lane_rays = KNN_LANE_RAYS if lane_rays is None else lane_rays
+    if out is None:
+        out = torch.empty(m, 4, 10, device=queries.device, dtype=i32)
+    g = grid
+    call("occnerf_knn_grid", ptr(queries, f32), m, int(group_stride), int(lane_rays), ptr(g["p"][0], f32), ptr(g["p"][1], f32),
+         ptr(g["p"][2], f32), ptr(g["p"][3], f32), *g["n"], ptr(g["gid"][0], i32), ptr(g["gid"][1], i32), ptr(g["gid"][2], i32),
+         ptr(g["cell_tab"], i32), ptr(g["lists"], torch.int16), C.cast(g["params"], C.c_void_p), C.cast(g["dims"], C.c_void_p), 10,
+         ptr(out, i32), stream())
+    return out
+
+
 def sample_geometry(xyz, knn_idx, point_base, point_norms, bound, raw=None):
     """-> enc_in (m,4), dist.  With `raw` (m,5) given, dist is written into raw[:,4] in place and returned as a view."""
     m = xyz.shape[0]

@@ -116,5 +116,9 @@ def test_hierarchical_search_is_bit_identical_to_brute_force():
             out_t = ops.knn_tree(q, S_, tree, lane_rays=lane_rays)
             bad = (out_t != ref).any(-1)
             assert not bool(bad.any()), ("tree", S_, lane_rays, int(bad.sum()), bad.nonzero()[:5].tolist())
+        grid = ops.build_knn_grid(base, fps)
+        out_g = ops.knn_grid(q, S_, grid)            # `far` and part of `near` lie outside the grid: exhaustive fallback
+        bad = (out_g != ref).any(-1)
+        assert not bool(bad.any()), ("grid", S_, int(bad.sum()), bad.nonzero()[:5].tolist())
     ref_cpu = O.multiscale_knn(near[:4000], sub.point_base, sub.fps_index, 10)
     assert torch.equal(out[:4000].cpu().long(), ref_cpu)

@@ -26,6 +26,22 @@ ref = idx.clone()
 for lr in (32, 16, 8, 4, 2, 1):
     res[f"knn_tree_lr{lr}_ms"] = t(lambda: ops.knn_tree(xyz, 128, st["tree"], lane_rays=lr))
     res[f"knn_tree_lr{lr}_equal"] = bool(torch.equal(ops.knn_tree(xyz, 128, st["tree"], lane_rays=lr), ref))
+import time
+torch.cuda.synchronize(); t0 = time.time()
+grid = ops.build_knn_grid(st["point_base"], [f.to(d) for f in net.fps_index])
+torch.cuda.synchronize(); res["grid_build_s"] = round(time.time() - t0, 2)
+for cs in (0.02, 0.015):
+    g2 = ops.build_knn_grid(st["point_base"], [f.to(d) for f in net.fps_index], cell=cs)
+    res[f"knn_grid_cell{cs}_ms"] = t(lambda: ops.knn_grid(xyz, 128, g2, lane_rays=32))
+    res[f"knn_grid_cell{cs}_MB"] = round((g2["entries"] * 2 + g2["cells"] * 32) / 2 ** 20, 1)
+    res[f"knn_grid_cell{cs}_equal"] = bool(torch.equal(ops.knn_grid(xyz, 128, g2, lane_rays=32), ref))
+    del g2
+res["grid_cells"], res["grid_entries"], res["grid_MB"] = grid["cells"], grid["entries"], round((grid["entries"] * 2 + grid["cells"] * 24) / 2 ** 20, 1)
+for lr in (32, 8):
+    res[f"knn_grid_lr{lr}_ms"] = t(lambda: ops.knn_grid(xyz, 128, grid, lane_rays=lr))
+    res[f"knn_grid_lr{lr}_equal"] = bool(torch.equal(ops.knn_grid(xyz, 128, grid, lane_rays=lr), ref))
+ct = grid["cell_tab"][:, :, 1].float()
+res["grid_mean_list_len"] = [round(float(ct[:, l].mean()), 1) for l in range(4)]
 def chunked():
     for i in range(0, m, 300000):
         ops.knn_tree(xyz[i:i + 300000], 128, st["tree"], lane_rays=32)
