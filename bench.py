@@ -184,6 +184,18 @@ class Workload:
             self.vol.grad = None
             net.apply_visibility(hits)
 
+    def make_graphed(self):
+        """The e2e step as one CUDA graph (occnerf_b200/train_step.py); single-GPU only."""
+        from occnerf_b200.train_step import GraphedTrainStep
+        params = [p for p in self.net.parameters() if p.requires_grad]
+        opt = torch.optim.Adam(params, lr=5e-4, fused=True, capturable=True)
+        self.graphed = GraphedTrainStep(self.net, opt, lambda out, d: self.loss({"rgb": out["rgb"], "comp_loss": out["comp_loss"]}, d["target"]),
+                                        self.host, self.iter_val, params=params)
+        return self.graphed
+
+    def step_e2e_graphed(self, world):
+        self.graphed.step(self.host)
+
     def step_e2e(self, world):
         """One step through the public API with host buffers: H2D of the frame, Network.forward, loss, backward,
         all-reduce, optimizer, D2H of the loss."""
@@ -272,6 +284,7 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("OCCNERF_ENGINE", "tc3"), choices=["fp32", "tc3", "tc1"])
     ap.add_argument("--ref-rays", type=int, default=96, help="rays per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the e2e step eagerly instead of as one CUDA graph")
     ap.add_argument("--profile-mode", action="store_true", help="device-resident steps only (no e2e, no CPU baseline): for ncu runs")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -312,7 +325,17 @@ def main():
         if rank == 0:
             print(json.dumps({"profile_mode": True, "ms_per_step": ms, "kernels": [(r["call"], round(r["ms_per_step"], 4)) for r in table]}))
         return
-    ms_e2e = timed_loop(lambda: wl.step_e2e(world), args.steps, args.warmup, world, flush)
+    e2e_mode, e2e_launches = "eager", None
+    if world == 1 and not args.no_graph:
+        try:
+            g = wl.make_graphed()
+            e2e_mode, e2e_launches = "cuda_graph", g.launches
+        except Exception as exc:                                   # capture is an optimisation, never a requirement
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            print(f"bench.py: CUDA-graph capture of the e2e step failed ({type(exc).__name__}: {exc}); timing the eager step", file=sys.stderr)
+    step = wl.step_e2e_graphed if e2e_mode == "cuda_graph" else wl.step_e2e
+    ms_e2e = timed_loop(lambda: step(world), args.steps, args.warmup, world, flush)
 
     if rank == 0:
         peaks = load_peaks()
@@ -326,7 +349,8 @@ def main():
                        "optimizer": "grad-clip + fused Adam (library) inside the step", "parallelism": f"dp{world}"},
             "clocks": clocks,
             "e2e": {"value": world * RAYS_PER_STEP / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": wl.h2d_bytes,
-                    "d2h_bytes_per_step": 4, "api": "Network.forward (prologue + ray path) + loss + backward + optimizer"},
+                    "d2h_bytes_per_step": 4, "api": "Network.forward (prologue + ray path) + loss + backward + optimizer",
+                    "launch": e2e_mode, "our_launches_per_step": e2e_launches},
             "gpu_launches": launches,
             "roofline": roof_all[0] if roof_all else None,
             "kernels": [{"call": r["call"], "ms_per_step": round(r["ms_per_step"], 4), "launches_per_step": r["launches_per_step"]} for r in table],

@@ -292,17 +292,18 @@ class Network(nn.Module):
         for m in (self.mweight_vol_decoder, self.pose_decoder):
             m.to(dev)
 
-        def run(dst_Rs, dst_Ts, cnl_gtfms, priors, dst_posevec, iter_val):
-            dst_Rs = dst_Rs[None]
-            if iter_val >= pose_kick_in_iter:
-                refined = self.pose_decoder(dst_posevec[None])["Rs"]
-                no_root = torch.matmul(dst_Rs[:, 1:].reshape(-1, 3, 3), refined.reshape(-1, 3, 3)).reshape(-1, 23, 3, 3)
-                dst_Rs = torch.cat([dst_Rs[:, 0:1], no_root], dim=1)
-            Rs, Ts = self.motion_basis_computer(dst_Rs, dst_Ts[None], cnl_gtfms[None])
-            return Rs, Ts, self.mweight_vol_decoder(motion_weights_priors=priors[None])[0]
-
-        self.prologue = run
+        self._pose_kick_in_iter = pose_kick_in_iter
+        self.prologue = "modules"          # (not a closure: the modules are looked up on `self`, so copies of the network work)
         return self
+
+    def _run_prologue(self, dst_Rs, dst_Ts, cnl_gtfms, priors, dst_posevec, iter_val):
+        dst_Rs = dst_Rs[None]
+        if iter_val >= self._pose_kick_in_iter:
+            refined = self.pose_decoder(dst_posevec[None])["Rs"]
+            no_root = torch.matmul(dst_Rs[:, 1:].reshape(-1, 3, 3), refined.reshape(-1, 3, 3)).reshape(-1, 23, 3, 3)
+            dst_Rs = torch.cat([dst_Rs[:, 0:1], no_root], dim=1)
+        Rs, Ts = self.motion_basis_computer(dst_Rs, dst_Ts[None], cnl_gtfms[None])
+        return Rs, Ts, self.mweight_vol_decoder(motion_weights_priors=priors[None])[0]
 
     # -- per-subject state (network.py:90-146)
     def generate_neural_points(self, vertices, normals, fps_index, bbox_min=None, bbox_max=None, point_dist=None,
@@ -511,7 +512,8 @@ class Network(nn.Module):
             raise RuntimeError("Network.prologue is not set: the per-frame prologue (pose refinement, motion basis, "
                                "weight-volume decoder) is outside the ray path; install occnerf_b200.prologue.Prologue "
                                "or pass precomputed tensors to _batchify_rays()")
-        motion_scale_Rs, motion_Ts, vol = self.prologue(dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec, iter_val)
+        run = self.prologue if callable(self.prologue) else self._run_prologue
+        motion_scale_Rs, motion_Ts, vol = run(dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec, iter_val)
         emb_fn, _ = self.get_non_rigid_embedder(cfg.non_rigid_multires, 0, iter_val)
         if iter_val < cfg.non_rigid_kick_in_iter:
             nr_in = None

@@ -33,6 +33,7 @@ def _tree_levels():
 
 
 _LEVELS = _tree_levels()
+_LEVEL_IDX = {}
 
 
 def _init_seq(seq):
@@ -47,6 +48,21 @@ def _init_seq(seq):
             nn.init.zeros_(m.bias)
 
 
+def _affine_inverse(T):
+    """Inverse of a batch of affine 4x4 matrices [A t; 0 1] by cofactors (network_util.py:190 calls torch.inverse, whose
+    LU path synchronises with the host and cannot be captured in a CUDA graph; same result to fp32 rounding)."""
+    A, t = T[:, :3, :3], T[:, :3, 3]
+    a, b, c = A[:, :, 0], A[:, :, 1], A[:, :, 2]
+    bc, ca, ab = torch.cross(b, c, dim=1), torch.cross(c, a, dim=1), torch.cross(a, b, dim=1)
+    det = (a * bc).sum(1, keepdim=True)
+    Ainv = torch.stack([bc, ca, ab], 1) / det[:, :, None]
+    out = torch.zeros_like(T)
+    out[:, :3, :3] = Ainv
+    out[:, :3, 3] = -torch.matmul(Ainv, t[:, :, None])[:, :, 0]
+    out[:, 3, 3] = 1.0
+    return out
+
+
 class MotionBasisComputer(nn.Module):
     def forward(self, dst_Rs, dst_Ts, cnl_gtfms):
         B = dst_Rs.shape[0]
@@ -56,12 +72,15 @@ class MotionBasisComputer(nn.Module):
         G[:, :, 3, 3] = 1.0
         glob = [None] * 24
         glob[0] = G[:, 0]
-        for idx, par in _LEVELS:
-            prod = torch.matmul(torch.stack([glob[p] for p in par], 1), G[:, idx])
+        key = str(G.device)
+        if key not in _LEVEL_IDX:       # device-resident index tensors (a Python list index would be an H2D copy per call)
+            _LEVEL_IDX[key] = [torch.tensor(idx, device=G.device) for idx, _ in _LEVELS]
+        for (idx, par), idx_t in zip(_LEVELS, _LEVEL_IDX[key]):
+            prod = torch.matmul(torch.stack([glob[p] for p in par], 1), G.index_select(1, idx_t))
             for j, i in enumerate(idx):
                 glob[i] = prod[:, j]
         dst = torch.stack(glob, 1).view(-1, 4, 4)
-        f = torch.matmul(cnl_gtfms.view(-1, 4, 4), torch.inverse(dst)).view(B, 24, 4, 4)
+        f = torch.matmul(cnl_gtfms.view(-1, 4, 4), _affine_inverse(dst)).view(B, 24, 4, 4)
         return f[:, :, :3, :3], f[:, :, :3, 3]
 
 

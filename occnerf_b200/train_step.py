@@ -1,0 +1,75 @@
+"""One training iteration of the reference's trainer (core/train/trainers/occnerf/trainer.py:223-253: Network.forward,
+loss, backward, grad-norm clip, Adam, point_counter update) captured ONCE as a CUDA graph and replayed per step.
+
+The step launches ~300 kernels (60 of ours + the library prologue + optimizer); issued from Python it is host-bound by
+~2 ms on a B200 (measured: 13.6 ms of device work per 15.8 ms step).  All shapes on the path are static for a fixed ray
+budget, so the whole iteration replays from one cudaGraphLaunch: inputs are copied into static device buffers from pinned
+host memory, the loss comes back through a pinned scalar.
+
+Constraints (checked or documented): fixed number of rays and samples; `iter_val`-dependent host decisions (Hann window,
+non-rigid kick-in, pose-refinement kick-in) are baked in, so re-capture when the iteration crosses one of those
+thresholds (`needs_recapture`); the optimizer must be capturable (Adam(fused=True, capturable=True)).
+"""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, net, optimizer, loss_fn, host_batch: dict, iter_val: int, params=None, max_norm: float = 1.0, warmup: int = 3):
+        """host_batch: dict of pinned host tensors with the keys of `Network.forward`'s per-frame inputs
+        (rays_o, rays_d, near, far, dst_Rs, dst_Ts, cnl_gtfms, priors, posevec, bmin, bscale, bg) + whatever `loss_fn`
+        needs (e.g. target).  loss_fn(out_dict, static_batch) -> scalar tensor."""
+        self.net, self.opt, self.loss_fn, self.iter_val, self.max_norm = net, optimizer, loss_fn, iter_val, max_norm
+        self.params = params if params is not None else [p for p in net.parameters() if p.requires_grad]
+        dev = next(net.parameters()).device
+        self.static = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host_batch.items()}
+        self.loss_dev = torch.zeros(1, device=dev)
+        self.loss_host = torch.zeros(1).pin_memory()
+        self.launches = 0
+        self._load(host_batch)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # warm-up off the capture: builds caches, cuDNN plans, func attributes
+            for _ in range(warmup):
+                self._iteration()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.opt.zero_grad(set_to_none=True)
+        from occnerf_b200 import _lib
+        c0 = _lib.COUNTERS["launches"]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._iteration()
+        self.launches = _lib.COUNTERS["launches"] - c0
+
+    def _load(self, host_batch):
+        for k, v in host_batch.items():
+            self.static[k].copy_(v, non_blocking=True)
+
+    def _iteration(self):
+        d, net = self.static, self.net
+        out = net.forward((d["rays_o"], d["rays_d"]), d["dst_Rs"], d["dst_Ts"], d["cnl_gtfms"], d["priors"], dst_posevec=d["posevec"],
+                          near=d["near"], far=d["far"], iter_val=self.iter_val, cnl_bbox_min_xyz=d["bmin"], cnl_bbox_scale_xyz=d["bscale"],
+                          bgcolor=d["bg"])
+        loss = self.loss_fn(out, d)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.params, self.max_norm)
+        self.opt.step()
+        self.opt.zero_grad(set_to_none=True)
+        if "hits" in out:
+            net.apply_visibility(out["hits"])
+        self.loss_dev.copy_(loss.detach().reshape(1))
+
+    def needs_recapture(self, iter_val: int) -> bool:
+        cfg = self.net.cfg
+        marks = (cfg.non_rigid_kick_in_iter, cfg.non_rigid_full_band_iter)
+        return any((self.iter_val < m) != (iter_val < m) for m in marks) or \
+            (cfg.non_rigid_kick_in_iter <= iter_val < cfg.non_rigid_full_band_iter and iter_val != self.iter_val)
+
+    def step(self, host_batch: dict) -> torch.Tensor:
+        """H2D of the frame -> one graph launch -> D2H of the loss (returned as a pinned host tensor; valid after a sync)."""
+        self._load(host_batch)
+        self.graph.replay()
+        self.loss_host.copy_(self.loss_dev, non_blocking=True)
+        return self.loss_host

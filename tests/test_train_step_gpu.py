@@ -1,0 +1,70 @@
+"""GPU: the CUDA-graph training step (occnerf_b200/train_step.py) replays exactly what the eager step does."""
+import copy
+
+import pytest
+import torch
+
+from occnerf_b200 import synthetic as S
+from occnerf_b200.network import RenderConfig
+from occnerf_b200.train_step import GraphedTrainStep
+from tests.helpers import dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(seed=0):
+    d = dev()
+    sub = S.make_subject(seed=0)
+    w = S.make_weights(sub.bound, seed=0)
+    net = S.network_from_synthetic(sub, w, RenderConfig(perturb=0.0, mlp_engine="fp32"), device=d)   # no jitter: deterministic
+    net.train(True)
+    net.install_prologue()
+    fr = S.make_frame(sub, mode="patch", n_patches=2, patch=16, seed=5)
+    target = torch.rand(fr.rays_o.shape[0], 3, generator=torch.Generator().manual_seed(1))
+    host = {k: v.pin_memory() for k, v in dict(rays_o=fr.rays_o, rays_d=fr.rays_d, near=fr.near, far=fr.far, dst_Rs=fr.dst_Rs,
+            dst_Ts=fr.dst_Ts, cnl_gtfms=fr.cnl_gtfms, priors=sub.priors, posevec=fr.dst_posevec, bmin=fr.cnl_bbox_min_xyz,
+            bscale=fr.cnl_bbox_scale_xyz, bg=fr.bgcolor, target=target).items()}
+    return net, host
+
+
+def _loss(out, d):
+    return 0.2 * torch.mean((out["rgb"] - d["target"]) ** 2) + out["comp_loss"].mean()
+
+
+def test_graph_replay_matches_eager_steps():
+    d = dev()
+    net_e, host = _setup()
+    net_g = copy.deepcopy(net_e)
+    net_g._cache = None
+    assert net_g.mweight_vol_decoder is not net_e.mweight_vol_decoder
+    steps = 3
+    # eager reference: the same iteration body, run step by step
+    params_e = [p for p in net_e.parameters() if p.requires_grad]
+    opt_e = torch.optim.Adam(params_e, lr=5e-4, fused=True, capturable=True)
+    eager = GraphedTrainStep.__new__(GraphedTrainStep)
+    eager.net, eager.opt, eager.loss_fn, eager.iter_val, eager.max_norm, eager.params = net_e, opt_e, _loss, 500, 1.0, params_e
+    eager.static = {k: v.to(d) for k, v in host.items()}
+    eager.loss_dev = torch.zeros(1, device=d)
+    # the graphed step warms up with 3 real iterations before capture: give the eager model the same head start
+    losses_e = []
+    for i in range(3 + steps):
+        eager._iteration()
+        losses_e.append(float(eager.loss_dev))
+    params_g = [p for p in net_g.parameters() if p.requires_grad]
+    opt_g = torch.optim.Adam(params_g, lr=5e-4, fused=True, capturable=True)
+    gs = GraphedTrainStep(net_g, opt_g, _loss, host, 500, params=params_g, warmup=3)
+    assert gs.launches > 20, "the capture must contain the library's kernels"
+    losses_g = []
+    for i in range(steps):
+        lh = gs.step(host)
+        torch.cuda.synchronize()
+        losses_g.append(float(lh))
+    # float atomics make two runs of the same step differ in the last bits and Adam amplifies that from step to step:
+    # the first replay must agree to 1e-5, later ones to 2e-3
+    assert abs(losses_e[3] - losses_g[0]) <= 1e-5 * abs(losses_e[3]), (losses_e, losses_g)
+    for a, b in zip(losses_e[3:], losses_g):
+        assert abs(a - b) <= 2e-3 * max(abs(a), 1e-6), (losses_e, losses_g)
+    assert losses_g[-1] != losses_g[0], "replays must advance the optimisation"
+    for (n, pe), pg in zip(net_e.named_parameters(), net_g.parameters()):
+        assert torch.allclose(pe, pg, rtol=1e-2, atol=2 * 5e-4 * (3 + steps)), n     # within a couple of Adam steps (lr = 5e-4)
+    assert not gs.needs_recapture(501) and gs.needs_recapture(net_g.cfg.non_rigid_kick_in_iter)
