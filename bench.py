@@ -315,7 +315,11 @@ def main():
     for _ in range(args.warmup):
         wl.step_device(world)
     _lib.PROFILE, c0 = {}, dict(_lib.COUNTERS)
+    if args.profile_mode:
+        torch.cuda.profiler.start()              # `ncu --profile-from-start off` then sees the steady-state steps only
     ms = timed_loop(lambda: wl.step_device(world), args.steps, 0, world, flush)
+    if args.profile_mode:
+        torch.cuda.profiler.stop()
     launches = (_lib.COUNTERS["launches"] - c0["launches"]) / args.steps
     profile, _lib.PROFILE = _lib.PROFILE, None
     clocks = sampler.stop()

@@ -128,10 +128,12 @@ int occnerf_sample_geometry(const float *xyz, const int32_t *knn_idx, int knn_st
 int occnerf_hashgrid_level_scales(float S, uint32_t H, uint32_t L, float *level_scales, occnerf_stream_t stream);
 /* inputs [B,D] in [0,1]; embeddings [offsets[L], C]; offsets [L+1] int32 (device); outputs per `layout`
  * (ld = row stride in floats for BLC); dy_dx [B, L*D*C] or NULL; cells [B,L,D] / slots [B,L,2^D] uint32 or
- * NULL (integer cell coordinates and table slots, 0xFFFFFFFF where the sample is outside [0,1]^D). */
+ * NULL (integer cell coordinates and table slots, 0xFFFFFFFF where the sample is outside [0,1]^D).
+ * run_length 16 (only without dy_dx/cells/slots): inputs are ordered along rays -> one thread walks 16 consecutive
+ * samples of a level and re-fetches the 2^D corner vectors only when the cell changes; bitwise the same outputs. */
 int occnerf_hashgrid_forward(const float *inputs, const float *embeddings, const int32_t *offsets,
                              const float *level_scales, float *outputs, int layout, int ld, uint32_t B, uint32_t D,
-                             uint32_t C, uint32_t L, float *dy_dx, uint32_t *cells, uint32_t *slots,
+                             uint32_t C, uint32_t L, float *dy_dx, uint32_t *cells, uint32_t *slots, int run_length,
                              occnerf_stream_t stream);
 /* grad per `layout`; grad_embeddings accumulated in place (caller zeroes, as grid.py:78 does).
  * run_length: 0 = one thread per (sample, level); 8 or 16 = one thread per (run of that many consecutive samples,

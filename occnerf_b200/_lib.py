@@ -31,7 +31,7 @@ _SIGNATURES = {
     "occnerf_knn_grid": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     "occnerf_sample_geometry": [_vp, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _vp],
     "occnerf_hashgrid_level_scales": [_f, _u, _u, _vp, _vp],
-    "occnerf_hashgrid_forward": [_vp] * 5 + [_i, _i] + [_u] * 4 + [_vp] * 4,
+    "occnerf_hashgrid_forward": [_vp] * 5 + [_i, _i] + [_u] * 4 + [_vp] * 3 + [_i, _vp],
     "occnerf_hashgrid_backward": [_vp, _i, _i, _vp, _vp, _vp, _vp] + [_u] * 4 + [_i, _vp],
     "occnerf_hashgrid_input_backward": [_vp, _i, _i, _vp, _vp] + [_u] * 4 + [_vp],
     "occnerf_aggregate_forward": [_vp, _vp, _vp, _i, _i, _vp, _i, _vp],

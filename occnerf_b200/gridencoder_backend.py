@@ -29,7 +29,7 @@ def grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, 
     _check(gridtype, align_corners, interp)
     scales = ops.level_scales(float(S), int(H), int(L), inputs.device)
     _lib.call("occnerf_hashgrid_forward", ptr(inputs, f32), ptr(embeddings, f32), ptr(offsets, ops.i32), ptr(scales, f32),
-              ptr(outputs, f32), _lib.LAYOUT_LBC, int(L * C), int(B), int(D), int(C), int(L), ptr(dy_dx, f32), None, None,
+              ptr(outputs, f32), _lib.LAYOUT_LBC, int(L * C), int(B), int(D), int(C), int(L), ptr(dy_dx, f32), None, None, 0,
               _lib.stream())
 
 

@@ -232,7 +232,8 @@ class _QueryFn(torch.autograd.Function):
         ops.aggregate_forward(knn_idx, counter, feats_c, XB.data_ptr() + 4 * M.X0_OFF, M.XB_LD)
         enc = net.cnl_mlp.module.encoder
         scales = ops.level_scales(float(np.log2(enc.per_level_scale)), enc.base_resolution, enc.num_levels, dev)
-        ops.hashgrid_forward(enc_in, emb_c, enc.offsets, scales, out_ptr=XB.data_ptr() + 4 * M.H_OFF, ld=M.XB_LD)
+        ops.hashgrid_forward(enc_in, emb_c, enc.offsets, scales, out_ptr=XB.data_ptr() + 4 * M.H_OFF, ld=M.XB_LD,
+                             run_length=ops.HASH_BWD_RUN)                                    # samples are ordered along rays
         W = M.MlpWeights(mlp_params)
         need_grad = any(ctx.needs_input_grad)
         engine = net._engine()

@@ -280,7 +280,7 @@ def level_scales(S: float, H: int, L: int, device) -> torch.Tensor:
 
 
 def hashgrid_forward(inputs, embeddings, offsets, scales, *, out=None, out_ptr=None, ld=None, layout=_lib.LAYOUT_BLC,
-                     want_dy_dx=False, want_cells=False):
+                     want_dy_dx=False, want_cells=False, run_length=0):
     B, D = inputs.shape
     Cc, L = embeddings.shape[1], offsets.shape[0] - 1
     dev = inputs.device
@@ -294,7 +294,7 @@ def hashgrid_forward(inputs, embeddings, offsets, scales, *, out=None, out_ptr=N
     cells = torch.empty(B, L, D, device=dev, dtype=i32) if want_cells else None
     slots = torch.empty(B, L, 1 << D, device=dev, dtype=i32) if want_cells else None
     call("occnerf_hashgrid_forward", ptr(inputs, f32), ptr(embeddings, f32), ptr(offsets, i32), ptr(scales, f32), out_ptr,
-         layout, ld, B, D, Cc, L, ptr(dy_dx), ptr(cells), ptr(slots), stream())
+         layout, ld, B, D, Cc, L, ptr(dy_dx), ptr(cells), ptr(slots), int(run_length), stream())
     return out, dy_dx, cells, slots
 
 

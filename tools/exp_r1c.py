@@ -66,6 +66,7 @@ xr = torch.rand(m, 4, device=d)
 for rl in (0, 8):
     res2[f"hash_bwd_uniform_inputs_run{rl}_ms"] = t(lambda: ops.hashgrid_backward(gXB.data_ptr() + 4 * M.H_OFF, 132, 0, xr, enc.offsets, scales, g_emb, 2, run_length=rl))
 res2["hash_fwd_all_ms"] = t(lambda: ops.hashgrid_forward(enc_in, enc.embeddings.detach(), enc.offsets, scales))
+res2["hash_fwd_all_run16_ms"] = t(lambda: ops.hashgrid_forward(enc_in, enc.embeddings.detach(), enc.offsets, scales, run_length=16))
 res2["hash_fwd_uniform_inputs_ms"] = t(lambda: ops.hashgrid_forward(xr, enc.embeddings.detach(), enc.offsets, scales))
 g_mask = torch.randn(rays.shape[0], 128, device=d)
 res2["warp_bwd_ms"] = t(lambda: ops.warp_backward(rays, t_rand, fr.motion_scale_Rs.contiguous(), fr.motion_Ts.contiguous(), fr.cnl_bbox_min_xyz, fr.cnl_bbox_scale_xyz, g_mask, 128, tuple(vol.shape)))
