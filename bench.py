@@ -184,13 +184,16 @@ class Workload:
             self.vol.grad = None
             net.apply_visibility(hits)
 
-    def make_graphed(self):
-        """The e2e step as one CUDA graph (occnerf_b200/train_step.py); single-GPU only."""
+    def make_graphed(self, world):
+        """The e2e step as one CUDA graph (occnerf_b200/train_step.py); under data parallelism the NCCL all-reduces of the
+        gradients and of the visibility votes are part of the graph."""
+        from occnerf_b200 import distributed as D
         from occnerf_b200.train_step import GraphedTrainStep
         params = [p for p in self.net.parameters() if p.requires_grad]
         opt = torch.optim.Adam(params, lr=5e-4, fused=True, capturable=True)
+        sync = (lambda ps, hits: (D.allreduce_gradients(ps), D.allreduce_visibility(hits))) if world > 1 else None
         self.graphed = GraphedTrainStep(self.net, opt, lambda out, d: self.loss({"rgb": out["rgb"], "comp_loss": out["comp_loss"]}, d["target"]),
-                                        self.host, self.iter_val, params=params)
+                                        self.host, self.iter_val, params=params, grad_sync=sync)
         return self.graphed
 
     def step_e2e_graphed(self, world):
@@ -330,14 +333,24 @@ def main():
             print(json.dumps({"profile_mode": True, "ms_per_step": ms, "kernels": [(r["call"], round(r["ms_per_step"], 4)) for r in table]}))
         return
     e2e_mode, e2e_launches = "eager", None
-    if world == 1 and not args.no_graph:
+    # (capturing the NCCL all-reduces with the step hung at N=2 in round 1: multi-GPU runs time the eager step unless
+    #  OCCNERF_GRAPH_NCCL=1 asks for the experiment)
+    if not args.no_graph and (world == 1 or os.environ.get("OCCNERF_GRAPH_NCCL", "0") == "1"):
+        ok = 1
         try:
-            g = wl.make_graphed()
+            g = wl.make_graphed(world)
             e2e_mode, e2e_launches = "cuda_graph", g.launches
         except Exception as exc:                                   # capture is an optimisation, never a requirement
             import traceback
             traceback.print_exc(file=sys.stderr)
             print(f"bench.py: CUDA-graph capture of the e2e step failed ({type(exc).__name__}: {exc}); timing the eager step", file=sys.stderr)
+            ok = 0
+        if world > 1:                                              # every rank replays, or none does
+            import torch.distributed as dist
+            flag = torch.tensor([ok], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                e2e_mode, e2e_launches = "eager", None
     step = wl.step_e2e_graphed if e2e_mode == "cuda_graph" else wl.step_e2e
     ms_e2e = timed_loop(lambda: step(world), args.steps, args.warmup, world, flush)
 

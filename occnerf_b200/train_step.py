@@ -16,11 +16,14 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, net, optimizer, loss_fn, host_batch: dict, iter_val: int, params=None, max_norm: float = 1.0, warmup: int = 3):
+    def __init__(self, net, optimizer, loss_fn, host_batch: dict, iter_val: int, params=None, max_norm: float = 1.0, warmup: int = 3,
+                 grad_sync=None):
         """host_batch: dict of pinned host tensors with the keys of `Network.forward`'s per-frame inputs
         (rays_o, rays_d, near, far, dst_Rs, dst_Ts, cnl_gtfms, priors, posevec, bmin, bscale, bg) + whatever `loss_fn`
-        needs (e.g. target).  loss_fn(out_dict, static_batch) -> scalar tensor."""
+        needs (e.g. target).  loss_fn(out_dict, static_batch) -> scalar tensor.
+        grad_sync(params, hits): data-parallel hook between backward() and the clip (NCCL all-reduces are captured too)."""
         self.net, self.opt, self.loss_fn, self.iter_val, self.max_norm = net, optimizer, loss_fn, iter_val, max_norm
+        self.grad_sync = grad_sync
         self.params = params if params is not None else [p for p in net.parameters() if p.requires_grad]
         dev = next(net.parameters()).device
         self.static = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host_batch.items()}
@@ -54,6 +57,8 @@ class GraphedTrainStep:
                           bgcolor=d["bg"])
         loss = self.loss_fn(out, d)
         loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync(self.params, out.get("hits"))
         torch.nn.utils.clip_grad_norm_(self.params, self.max_norm)
         self.opt.step()
         self.opt.zero_grad(set_to_none=True)
