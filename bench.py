@@ -259,23 +259,38 @@ def kernel_table(profile, steps):
     return rows
 
 
-def roofline_for(row, peaks, M):
+# DRAM bytes per sample (dram__bytes_read.sum + dram__bytes_write.sum of one launch / samples of that launch) from the
+# `ncu --set full` capture summarised in profiles/r01c_kernels_full.md (300 000-sample launches of the same command)
+NCU_TRAFFIC_PER_SAMPLE = {"occnerf_mlp_forward_tc": (0.151179e9 + 1.470747e9) / 300000, "occnerf_mlp_backward_tc": (0.128911e9 + 1.335716e9) / 300000,
+                          "occnerf_mlp_wgrad_tc": (2.805448e9 + 0.006918e9) / 300000, "occnerf_aggregate_backward": (0.129910e9 + 0.009074e9) / 300000,
+                          "occnerf_aggregate_forward": (0.054303e9 + 0.017872e9) / 300000, "occnerf_hashgrid_backward": (0.113297e9 + 0.003756e9) / 300000}
+MMA_ISSUE_FACTOR = {"tc3": 3.0, "tc1": 1.0}      # split-bf16 issues three bf16 MMAs per algorithmic product
+
+
+def roofline_for(row, peaks, M, engine="tc3"):
     """Algorithmic work of one C call (SURVEY.md 8d / DESIGN.md) divided by its measured device time."""
     name, ms = row["call"], row["ms_per_step"] / max(row["launches_per_step"], 1e-9)
-    per_launch_samples = M
+    per_launch_samples = M / max(row["launches_per_step"], 1.0) if name.startswith(("occnerf_mlp", "occnerf_aggregate", "occnerf_hashgrid", "occnerf_sample")) else M
+    traffic = NCU_TRAFFIC_PER_SAMPLE.get(name)
+    traffic = traffic * per_launch_samples if traffic is not None else None
     hbm = {"occnerf_warp_forward": 20.25, "occnerf_warp_backward": 4.0, "occnerf_composite_forward": 28.0 + 28.0 / S_SAMPLES,
            "occnerf_composite_backward": 52.0, "occnerf_hashgrid_forward": 144.0, "occnerf_hashgrid_backward": 128.0,
            "occnerf_aggregate_forward": 160.0 + 144.0, "occnerf_aggregate_backward": 160.0 + 144.0, "occnerf_knn": 12.0 + 160.0,
-           "occnerf_sample_geometry": 12.0 + 40.0 + 20.0}
+           "occnerf_knn_grid": 12.0 + 160.0, "occnerf_knn_tree": 12.0 + 160.0, "occnerf_sample_geometry": 12.0 + 40.0 + 20.0}
     if name in ("occnerf_sgemm", "occnerf_mlp_forward_tc", "occnerf_mlp_backward_tc", "occnerf_mlp_wgrad_tc"):
         flops = row["work_per_step"] / max(row["launches_per_step"], 1e-9)
         ach = flops / (ms * 1e-3) / 1e12
-        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " bf16 dense (sustained)"}
+        out = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+               "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "peak_source": peaks["source"] + " bf16 dense (sustained)"}
+        if name in ("occnerf_mlp_forward_tc", "occnerf_mlp_backward_tc") and engine in MMA_ISSUE_FACTOR:
+            # what the tensor pipe actually executes: every fp32-grade product is 3 bf16 MMAs in the split-bf16 engine
+            out["issued_mma_tflops"] = ach * MMA_ISSUE_FACTOR[engine]
+            out["issued_mma_frac"] = out["issued_mma_tflops"] / peaks["bf16_tflops_sustained"]
+        return out
     bytes_ = hbm.get(name, 0.0) * per_launch_samples
     ach = bytes_ / (ms * 1e-3) / 1e9
     return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-            "traffic": None, "peak_source": peaks["source"] + " copy bandwidth"}
+            "traffic": traffic, "peak_source": peaks["source"] + " copy bandwidth"}
 
 
 def main():
@@ -356,7 +371,7 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
-        roof_all = [roofline_for(r, peaks, M) for r in table[:8]]
+        roof_all = [roofline_for(r, peaks, M, args.engine) for r in table[:10]]
         line = {
             "metric": "rays_per_sec_fwd_bwd_128spr", "value": world * RAYS_PER_STEP / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

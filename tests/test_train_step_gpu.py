@@ -44,7 +44,7 @@ def test_graph_replay_matches_eager_steps():
     eager = GraphedTrainStep.__new__(GraphedTrainStep)
     eager.net, eager.opt, eager.loss_fn, eager.iter_val, eager.max_norm, eager.params = net_e, opt_e, _loss, 500, 1.0, params_e
     eager.static = {k: v.to(d) for k, v in host.items()}
-    eager.loss_dev = torch.zeros(1, device=d)
+    eager.loss_dev, eager.grad_sync = torch.zeros(1, device=d), None
     # the graphed step warms up with 3 real iterations before capture: give the eager model the same head start
     losses_e = []
     for i in range(3 + steps):

@@ -14,6 +14,7 @@ sub = S.make_subject(0)
 net = S.network_from_synthetic(sub, S.make_weights(sub.bound), RenderConfig(), device=d)
 vol = S.make_motion_weights_vol(sub.priors, 0).to(d)
 fr0 = S.frame_to(S.make_frame(sub, mode="patch", n_patches=6, patch=32, seed=100), d)
+st = net._static()
 enc = net.cnl_mlp.module.encoder
 scales = ops.level_scales(float(np.log2(enc.per_level_scale)), enc.base_resolution, enc.num_levels, d)
 flush = torch.empty(64 * 1024 * 1024, device=d)
@@ -30,7 +31,7 @@ def t(fn, n=5):
 
 rows = []
 max_samples = int(os.environ.get("MAX_SAMPLES", 2 ** 27))
-for logn in (16, 18, 20):
+for logn in (16, 18):
     for Sn in (64, 128, 256):
         N = 2 ** logn
         M = N * Sn
@@ -52,13 +53,19 @@ for logn in (16, 18, 20):
         res["composite_fwd"] = (t(lambda: ops.composite_forward(raw, mask, z, rays, bg, want_comp=True)), 28.0 + 4.0 + 28.0 / Sn)
         g_rgb, g_acc, g_depth, g_comp = torch.randn(N, 3, device=d), torch.randn(N, device=d), torch.randn(N, device=d), torch.randn(N, Sn, device=d)
         res["composite_bwd"] = (t(lambda: ops.composite_backward(raw, mask, z, rays, bg, g_rgb, g_acc, g_depth, g_comp)), 52.0)
-        enc_in = torch.rand(M, 4, device=d)
-        # positions along rays -> realistic cell sharing: use warped positions normalised into the grid
-        enc_in[:, :3] = ((x.reshape(-1, 3) + net.bound) / (2 * net.bound)).clamp(0, 1)
+        # the real encoder input of these samples: multi-scale KNN -> surface projection + signed distance (smooth along a ray)
+        xyz = x.reshape(-1, 3).contiguous()
+        grid = ops.build_knn_grid(st["point_base"], [f.to(d) for f in net.fps_index])
+        res["knn_grid(4 levels x k=10)"] = (t(lambda: ops.knn_grid(xyz, Sn, grid), n=2), 12.0 + 160.0)
+        knn_idx = ops.knn_grid(xyz, Sn, grid)
+        res["sample_geometry"] = (t(lambda: ops.sample_geometry(xyz, knn_idx, st["point_base"], st["point_norms"], net.bound), n=2), 12.0 + 40.0 + 20.0)
+        enc_in, _ = ops.sample_geometry(xyz, knn_idx, st["point_base"], st["point_norms"], net.bound)
+        del knn_idx
         out = torch.empty(M, 32, device=d)
         res["hashgrid_fwd"] = (t(lambda: ops.hashgrid_forward(enc_in, enc.embeddings.detach(), enc.offsets, scales, out=out)), 144.0)
         g = torch.randn(M, 32, device=d)
         g_emb = torch.zeros_like(enc.embeddings)
+        res["hashgrid_fwd_run16"] = (t(lambda: ops.hashgrid_forward(enc_in, enc.embeddings.detach(), enc.offsets, scales, out=out, run_length=16)), 144.0)
         res["hashgrid_bwd_run16"] = (t(lambda: ops.hashgrid_backward(g.data_ptr(), 32, 0, enc_in, enc.offsets, scales, g_emb, 2, run_length=16)), 144.0)
         for k, (ms, bps) in res.items():
             gbs = bps * M / (ms * 1e-3) / 1e9
