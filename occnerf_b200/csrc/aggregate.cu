@@ -14,6 +14,10 @@
 // 3.2x.  Two shared-memory pre-reductions were tried and were slower: hash probing per CTA (latency-bound at 6 warps/SM),
 // and a per-CTA 431 x 36 table for the vertices of the two coarsest levels, which receive half of all contributions
 // (2.5 ms vs 1.0 ms: fp32 atomicAdd on shared memory is a compare-and-swap loop, slower than L2's native RED.ADD.F32)).
+// Run-length merging along rays (the vertex in a given neighbour slot stays the same from one sample of a ray to the next
+// 69-86 % of the time, tools/exp_knn_persist.py) was tried in three shapes -- a warp walking 16 samples with the slots
+// spread over its lanes, the same with a separate attention pass, and one thread per (run, slot, column chunk) -- and
+// all were 1.3-2.5x slower than this per-sample kernel on the B200; not understood yet, left for round 2 with ncu.
 #include "common.cuh"
 
 namespace {
