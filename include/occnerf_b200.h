@@ -148,13 +148,17 @@ int occnerf_hashgrid_input_backward(const float *grad, int layout, int ld, const
 
 /* ---- visibility-weighted neighbour aggregation (occnerf_mlp.py:110-126,175-178) ----------------------
  * knn_idx [m,nn] int32 vertex ids (nn <= 64); point_counter [V]; feats [V,36] (35 features + 1 pad);
- * writes X[i*ldx + 0..34] = sum_n softmax(att)_n * feats[idx_n], X[i*ldx + 35] = unbiased var(att). */
+ * writes X[i*ldx + 0..34] = sum_n softmax(att)_n * feats[idx_n], X[i*ldx + 35] = unbiased var(att).
+ * att_w [m,nn] or NULL: the forward pass also stores the attention weights there; the backward pass, given them (and
+ * nn % 4 == 0), takes the path for samples ordered along rays -- one thread per (run of 16 consecutive samples, 4 neighbour
+ * slots, 4 columns) sums its contributions in registers and issues one reduction per run of equal vertices (the vertex in
+ * a given slot stays the same from one sample of a ray to the next 69-86 % of the time).  Same sums. */
 int occnerf_aggregate_forward(const int32_t *knn_idx, const float *point_counter, const float *feats, int m, int nn,
-                              float *X, int ldx, occnerf_stream_t stream);
+                              float *X, int ldx, float *att_w, occnerf_stream_t stream);
 /* g_feats [copies][V,36] += att_n * gX[i*ldg + 0..34]  (att is detached in the reference, occnerf_mlp.py:123).
  * `copies` >= 1 privatised replicas spread the L2 reductions (CTA b adds into replica b % copies); the caller sums them. */
 int occnerf_aggregate_backward(const int32_t *knn_idx, const float *point_counter, const float *gX, int ldg, int m,
-                               int nn, float *g_feats, int V, int copies, occnerf_stream_t stream);
+                               int nn, float *g_feats, int V, int copies, const float *att_w, occnerf_stream_t stream);
 
 
 /* ---- Hann-windowed positional encoding (hannw_fourier.py:27-45), window weights from the host ------- */

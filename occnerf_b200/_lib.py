@@ -34,8 +34,8 @@ _SIGNATURES = {
     "occnerf_hashgrid_forward": [_vp] * 5 + [_i, _i] + [_u] * 4 + [_vp] * 3 + [_i, _vp],
     "occnerf_hashgrid_backward": [_vp, _i, _i, _vp, _vp, _vp, _vp] + [_u] * 4 + [_i, _vp],
     "occnerf_hashgrid_input_backward": [_vp, _i, _i, _vp, _vp] + [_u] * 4 + [_vp],
-    "occnerf_aggregate_forward": [_vp, _vp, _vp, _i, _i, _vp, _i, _vp],
-    "occnerf_aggregate_backward": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp],
+    "occnerf_aggregate_forward": [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp],
+    "occnerf_aggregate_backward": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp],
     "occnerf_hann_pe": [_vp, _i, _vp, _i, _vp, _i, _vp],
     "occnerf_sgemm": [_vp, _l, _l, _vp, _l, _l, _vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp],
     "occnerf_colsum": [_vp, _l, _vp, _l, _i, _i, _vp, _vp],

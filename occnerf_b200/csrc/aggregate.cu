@@ -14,10 +14,7 @@
 // 3.2x.  Two shared-memory pre-reductions were tried and were slower: hash probing per CTA (latency-bound at 6 warps/SM),
 // and a per-CTA 431 x 36 table for the vertices of the two coarsest levels, which receive half of all contributions
 // (2.5 ms vs 1.0 ms: fp32 atomicAdd on shared memory is a compare-and-swap loop, slower than L2's native RED.ADD.F32)).
-// Run-length merging along rays (the vertex in a given neighbour slot stays the same from one sample of a ray to the next
-// 69-86 % of the time, tools/exp_knn_persist.py) was tried in three shapes -- a warp walking 16 samples with the slots
-// spread over its lanes, the same with a separate attention pass, and one thread per (run, slot, column chunk) -- and
-// all were 1.3-2.5x slower than this per-sample kernel on the B200; not understood yet, left for round 2 with ncu.
+// What did work is merging runs of equal vertices along a ray in registers: aggregate_bwd_slot_kernel below.
 #include "common.cuh"
 
 namespace {
@@ -53,13 +50,15 @@ __device__ __forceinline__ float attention(const int32_t *__restrict__ idx_row, 
 
 __global__ void __launch_bounds__(kWarps * 32)
 aggregate_fwd_kernel(const int32_t *__restrict__ knn_idx, const float *__restrict__ counter,
-                     const float4 *__restrict__ feats, int m, int nn, float *__restrict__ X, long ldx) {
+                     const float4 *__restrict__ feats, int m, int nn, float *__restrict__ X, long ldx, float *__restrict__ att_w) {
     __shared__ int s_idx[kWarps][kMaxNN];
     __shared__ float s_w[kWarps][kMaxNN];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long q = (long)blockIdx.x * kWarps + wib;
     if (q >= m) return;
     const float var = attention(knn_idx + q * nn, counter, nn, lane, s_idx[wib], s_w[wib]);
+    if (att_w)                                                        // kept for the run-length backward
+        for (int n = lane; n < nn; n += 32) att_w[q * nn + n] = s_w[wib][n];
     const int grp = lane / kRowF4, col = lane - grp * kRowF4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (grp < 3) {
@@ -106,31 +105,90 @@ aggregate_bwd_kernel(const int32_t *__restrict__ knn_idx, const float *__restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Run-length backward for samples ordered along rays.  Measured on the bench workload (tools/exp_knn_persist.py): the
+// neighbour in a given slot (level, rank) of sample q+1 is the SAME vertex as in sample q in 69 % (level 0) to 86 %
+// (level 3) of the cases.  Thread = (run of kRun consecutive samples, 4 neighbour slots, 4-column chunk): it walks the run
+// with three vector loads per sample (4 ids, 4 attention weights from the forward pass, its gradient chunk), adds w * g
+// per slot in registers and issues one vector reduction per RUN OF EQUAL VERTICES instead of one per sample: 2.6x fewer
+// L2 reductions (ncu).  Same sums.
+constexpr int kRun = 16;
+
+__global__ void __launch_bounds__(256, 4)
+aggregate_bwd_slot_kernel(const int32_t *__restrict__ knn_idx, const float *__restrict__ att_w, const float *__restrict__ gX,
+                          long ldg, int m, int nn, float *__restrict__ g_feats, int copies, long copy_stride) {
+    const long gid = (long)blockIdx.x * 256 + threadIdx.x;
+    const int per_run = (nn / 4) * kRowF4;
+    const long run = gid / per_run;
+    const long q0 = run * kRun;
+    if (q0 >= m) return;
+    const int r = (int)(gid - run * per_run);
+    const int n4 = r / kRowF4, col = r - n4 * kRowF4;
+    g_feats += (long)(blockIdx.x % copies) * copy_stride;
+    const long q1 = q0 + kRun < m ? q0 + kRun : m;
+    int cur[4] = {-1, -1, -1, -1};
+    float4 sum[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sum[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto flush = [&](int k) {
+        if (cur[k] >= 0 && (sum[k].x != 0.f || sum[k].y != 0.f || sum[k].z != 0.f || sum[k].w != 0.f))
+            red_add_v4(g_feats + ((size_t)cur[k] * kRowF4 + col) * 4, sum[k].x, sum[k].y, sum[k].z, sum[k].w);
+    };
+#pragma unroll 2
+    for (long q = q0; q < q1; ++q) {
+        float4 g = __ldg(reinterpret_cast<const float4 *>(gX + q * ldg) + col);
+        if (col == kRowF4 - 1) g.w = 0.f;   // column 35 is the variance slot, not a feature
+        const int4 vi = __ldg(reinterpret_cast<const int4 *>(knn_idx + q * nn) + n4);
+        const float4 wf = __ldg(reinterpret_cast<const float4 *>(att_w + q * nn) + n4);
+        const int v[4] = {vi.x, vi.y, vi.z, vi.w};
+        const float w[4] = {wf.x, wf.y, wf.z, wf.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (v[k] != cur[k]) {
+                flush(k);
+                cur[k] = v[k];
+                sum[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            sum[k].x = fmaf(w[k], g.x, sum[k].x); sum[k].y = fmaf(w[k], g.y, sum[k].y);
+            sum[k].z = fmaf(w[k], g.z, sum[k].z); sum[k].w = fmaf(w[k], g.w, sum[k].w);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) flush(k);
+}
+
 }  // namespace
 
 extern "C" int occnerf_aggregate_forward(const int32_t *knn_idx, const float *point_counter, const float *feats, int m,
-                                         int nn, float *X, int ldx, occnerf_stream_t stream) {
+                                         int nn, float *X, int ldx, float *att_w, occnerf_stream_t stream) {
     OCC_CHECK_ARG(knn_idx && point_counter && feats && X, "aggregate_forward: null pointer");
     OCC_CHECK_ARG(nn >= 2 && nn <= kMaxNN, "aggregate_forward: nn=%d outside [2,%d]", nn, kMaxNN);
     OCC_CHECK_ARG(ldx >= 36 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)feats & 15) == 0,
                   "aggregate_forward: X/feats must be 16-byte aligned with ldx %% 4 == 0 (ldx=%d)", ldx);
     if (m <= 0) return OCCNERF_OK;
     aggregate_fwd_kernel<<<occ_div_up(m, kWarps), kWarps * 32, 0, (cudaStream_t)stream>>>(
-        knn_idx, point_counter, (const float4 *)feats, m, nn, X, ldx);
+        knn_idx, point_counter, (const float4 *)feats, m, nn, X, ldx, att_w);
     OCC_LAUNCH_CHECK();
     return OCCNERF_OK;
 }
 
 extern "C" int occnerf_aggregate_backward(const int32_t *knn_idx, const float *point_counter, const float *gX, int ldg,
-                                          int m, int nn, float *g_feats, int V, int copies, occnerf_stream_t stream) {
+                                          int m, int nn, float *g_feats, int V, int copies, const float *att_w,
+                                          occnerf_stream_t stream) {
     OCC_CHECK_ARG(knn_idx && point_counter && gX && g_feats, "aggregate_backward: null pointer");
     OCC_CHECK_ARG(nn >= 2 && nn <= kMaxNN, "aggregate_backward: nn=%d outside [2,%d]", nn, kMaxNN);
     OCC_CHECK_ARG(ldg >= 36 && ldg % 4 == 0 && ((uintptr_t)gX & 15) == 0 && ((uintptr_t)g_feats & 15) == 0,
                   "aggregate_backward: gX/g_feats must be 16-byte aligned with ldg %% 4 == 0 (ldg=%d)", ldg);
     if (m <= 0) return OCCNERF_OK;
     OCC_CHECK_ARG(copies >= 1 && V >= 1, "aggregate_backward: copies=%d V=%d", copies, V);
-    aggregate_bwd_kernel<<<occ_div_up(m, kWarps), kWarps * 32, 0, (cudaStream_t)stream>>>(knn_idx, point_counter, gX,
-                                                                                         ldg, m, nn, g_feats, copies, (long)V * 36);
+    if (att_w && nn % 4 == 0 && ((uintptr_t)knn_idx & 15) == 0 && ((uintptr_t)att_w & 15) == 0) {
+        const long threads = occ_div_up(m, kRun) * (long)(nn / 4) * kRowF4;
+        aggregate_bwd_slot_kernel<<<occ_div_up(threads, 256), 256, 0, (cudaStream_t)stream>>>(knn_idx, att_w, gX, ldg, m, nn, g_feats,
+                                                                                            copies, (long)V * 36);
+    } else {
+        aggregate_bwd_kernel<<<occ_div_up(m, kWarps), kWarps * 32, 0, (cudaStream_t)stream>>>(knn_idx, point_counter, gX,
+                                                                                             ldg, m, nn, g_feats, copies, (long)V * 36);
+    }
     OCC_LAUNCH_CHECK();
     return OCCNERF_OK;
 }

@@ -229,7 +229,8 @@ class _QueryFn(torch.autograd.Function):
         feats_c = feats36.detach().contiguous()
         emb_c = embeddings.detach().contiguous()
         counter = net.point_counter.detach().contiguous().float()
-        ops.aggregate_forward(knn_idx, counter, feats_c, XB.data_ptr() + 4 * M.X0_OFF, M.XB_LD)
+        att_w = ops.aggregate_forward(knn_idx, counter, feats_c, XB.data_ptr() + 4 * M.X0_OFF, M.XB_LD,
+                                      want_att=any(ctx.needs_input_grad))
         enc = net.cnl_mlp.module.encoder
         scales = ops.level_scales(float(np.log2(enc.per_level_scale)), enc.base_resolution, enc.num_levels, dev)
         ops.hashgrid_forward(enc_in, emb_c, enc.offsets, scales, out_ptr=XB.data_ptr() + 4 * M.H_OFF, ld=M.XB_LD,
@@ -241,7 +242,7 @@ class _QueryFn(torch.autograd.Function):
         if need_grad:
             ctx.state = dict(knn_idx=knn_idx, enc_in=enc_in, XB=XB, W=W, saved=saved, engine=engine, counter=counter,
                              offsets=enc.offsets, scales=scales, emb_shape=tuple(embeddings.shape), V=feats36.shape[0],
-                             shared=shared)
+                             shared=shared, att_w=att_w)
             shared["pending"] = shared.get("pending", 0) + 1
         return raw
 
@@ -259,7 +260,8 @@ class _QueryFn(torch.autograd.Function):
             sh["g_priv"] = torch.zeros(ops.AGG_BWD_COPIES, s["V"], 36, device=g_raw.device, dtype=f32)
         ops.hashgrid_backward(gXB.data_ptr() + 4 * M.H_OFF, M.XB_LD, 0, s["enc_in"], s["offsets"], s["scales"], sh["g_emb"],
                               s["emb_shape"][1], run_length=ops.HASH_BWD_RUN)           # samples are ordered along rays
-        ops.aggregate_backward(s["knn_idx"], s["counter"], gXB.data_ptr() + 4 * M.X0_OFF, M.XB_LD, s["V"], g_priv=sh["g_priv"])
+        ops.aggregate_backward(s["knn_idx"], s["counter"], gXB.data_ptr() + 4 * M.X0_OFF, M.XB_LD, s["V"], g_priv=sh["g_priv"],
+                               att_w=s["att_w"])                                         # samples are ordered along rays
         ctx.state = None
         sh["pending"] -= 1
         g_emb = g_feats = None

@@ -349,29 +349,33 @@ grid_encode = _GridEncode.apply
 
 
 # ----------------------------------------------------------------------------- aggregation
-def aggregate_forward(knn_idx, point_counter, feats36, X_ptr, ldx):
+def aggregate_forward(knn_idx, point_counter, feats36, X_ptr, ldx, want_att=False):
+    """want_att=True also returns the attention weights (m,nn), which select the run-length backward (samples ordered
+    along rays)."""
     m = knn_idx.shape[0]
     nn = knn_idx.numel() // max(m, 1)
+    att_w = torch.empty(m, nn, device=knn_idx.device, dtype=f32) if want_att else None
     call("occnerf_aggregate_forward", ptr(knn_idx, i32), ptr(point_counter, f32), ptr(feats36, f32), m, nn, X_ptr, ldx,
-         stream())
+         ptr(att_w), stream())
+    return att_w
 
 
 AGG_BWD_COPIES = 64
 
 
-def aggregate_backward(knn_idx, point_counter, gX_ptr, ldg, V, copies=None, g_priv=None):
+def aggregate_backward(knn_idx, point_counter, gX_ptr, ldg, V, copies=None, g_priv=None, att_w=None):
     """g_feats (V,36): one vector reduction per (sample, neighbour, column chunk) into `copies` privatised replicas.
     With `g_priv` (copies,V,36) given, accumulates into it and returns it (the caller sums the replicas)."""
     m = knn_idx.shape[0]
     nn = knn_idx.numel() // max(m, 1)
     if g_priv is not None:
         call("occnerf_aggregate_backward", ptr(knn_idx, i32), ptr(point_counter, f32), gX_ptr, ldg, m, nn, ptr(g_priv, f32), V,
-             g_priv.shape[0], stream())
+             g_priv.shape[0], ptr(att_w), stream())
         return g_priv
     copies = AGG_BWD_COPIES if copies is None else copies
     g_priv = torch.zeros(copies, V, 36, device=knn_idx.device, dtype=f32)
     call("occnerf_aggregate_backward", ptr(knn_idx, i32), ptr(point_counter, f32), gX_ptr, ldg, m, nn, ptr(g_priv), V, copies,
-         stream())
+         ptr(att_w), stream())
     return g_priv.sum(0) if copies > 1 else g_priv[0]
 
 

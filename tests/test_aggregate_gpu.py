@@ -53,3 +53,31 @@ def test_backward_against_oracle(copies):
     report(f"aggregate_bwd[copies={copies}]", rel=e)
     assert e < 1e-5
     assert float(gf[:, 35].abs().max()) == 0.0
+
+
+def test_run_length_backward_matches_per_sample_kernel():
+    """Run-length backward (one reduction per run of equal vertices in a neighbour slot, attention weights handed over by
+    the forward pass) against the per-sample kernel.  Ragged tail (m not a multiple of 16) included; the forward output
+    does not depend on whether the weights are exported."""
+    idx, feats, counter = _case()
+    m = idx.shape[0] - 5
+    idx = idx[:m]
+    d = dev()
+    f36 = torch.zeros(6890, 36, device=d)
+    f36[:, :35] = feats.to(d)
+    idx_d, cnt_d = idx.to(torch.int32).to(d).contiguous(), counter.to(d)
+    Xa = torch.full((m, 132), -3.0, device=d)
+    Xb = torch.full((m, 132), -3.0, device=d)
+    ops.aggregate_forward(idx_d, cnt_d, f36, Xa.data_ptr() + 4 * 64, 132)
+    att_w = ops.aggregate_forward(idx_d, cnt_d, f36, Xb.data_ptr() + 4 * 64, 132, want_att=True)
+    assert torch.equal(Xa, Xb)
+    assert float((att_w.sum(1) - 1).abs().max()) < 1e-5
+    same_slot = float((idx[1:] == idx[:-1]).float().mean())
+    assert same_slot > 0.3, "the case must actually contain runs"
+    gX = torch.randn(m, 132, device=d)
+    gX[::5, 64:100] = 0.0
+    ref = ops.aggregate_backward(idx_d, cnt_d, gX.data_ptr() + 4 * 64, 132, 6890, copies=4)
+    got = ops.aggregate_backward(idx_d, cnt_d, gX.data_ptr() + 4 * 64, 132, 6890, copies=4, att_w=att_w)
+    e = maxabs(got, ref) / float(ref.abs().max())
+    report("aggregate_runs", bwd_rel=e, same_slot=same_slot)
+    assert e < 1e-5 and float(got[:, 35].abs().max()) == 0.0
