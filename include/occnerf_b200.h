@@ -190,6 +190,9 @@ long occnerf_mlp_packed_bytes(int n_pass, int chain);
  * [3] producer<-free slot [4] MMA thread total [5] epilogue thread total [6] CTAs [8] epilogue<-TMEM load
  * [9] epilogue in fence+arrive; others unused. */
 int occnerf_mlp_debug_counters(unsigned long long *host8, int reset);
+/* Debug only: `iters` back-to-back tcgen05.mma (M=128, N=n, K=16, bf16, shared-memory operands) on `ctas` CTAs (one per
+ * SM) at once; out_dev[cta] = cycles from the first issue to the completion of the last (tools/mma_rate.py). */
+int occnerf_mlp_debug_mma_rate(int iters, int n, unsigned long long *out_dev, int ctas, occnerf_stream_t stream);
 int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, void *packed, occnerf_stream_t stream);
 /* XB [m,132]: columns 64..131 = (agg35, var1, h32) are read; columns 0..63 receive the 64 geometry features when
  * act_dtype != 0.  raw [m, ldr]: columns 0..3 = (rgb_pre3, sigma_pre1) are written.

@@ -742,6 +742,42 @@ int launch_chain(const ChainArgs &a, cudaStream_t st) {
     return OCCNERF_OK;
 }
 
+// Debug micro-benchmark: `iters` back-to-back tcgen05.mma (M=128, N=n, K=16, bf16, SS operands at fixed shared-memory
+// addresses, one accumulator) per CTA, timed with clock64 between the first issue and the arrival of the final commit.
+// Gives the issue-to-completion rate of the tensor pipe for exactly the instruction shape the chain kernels use.
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int n, unsigned long long *out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 65536 + 32768);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 2);
+    for (int i = threadIdx.x; i < (65536 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0u;
+    if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 65536);
+        const uint32_t idesc = instr_desc(n), b_lbo = (uint32_t)(n / 8) * 128;
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint64_t da = smem_desc(a_base + (uint32_t)(i & 15) * 4096, 2048, 128);
+            const uint64_t db = smem_desc(b_base + (uint32_t)(i & 1) * 2 * b_lbo, b_lbo, 128);
+            tc_mma(tmem_base + (uint32_t)(i & 1) * 256, da, db, idesc, i > 1 ? 1u : 0u);
+        }
+        tc_commit(smem_u32(bar));
+        mbar_wait(smem_u32(bar), 0);
+        out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
 void fill_layout(ChainArgs &a, int n_pass, int chain, const void *packed) {
     static const int debug = getenv("OCCNERF_MLP_DEBUG") ? atoi(getenv("OCCNERF_MLP_DEBUG")) : 0;
     a.debug = debug;
@@ -753,6 +789,16 @@ void fill_layout(ChainArgs &a, int n_pass, int chain, const void *packed) {
 }
 
 }  // namespace
+
+// debug only: cycles per tcgen05.mma (M=128, N=n, K=16) measured on every SM at once; out_dev [148+] device u64
+extern "C" int occnerf_mlp_debug_mma_rate(int iters, int n, unsigned long long *out_dev, int ctas, occnerf_stream_t stream) {
+    OCC_CHECK_ARG(out_dev && iters >= 2 && n >= 16 && n <= 256 && n % 16 == 0 && ctas >= 1, "mlp_debug_mma_rate: bad arguments");
+    const int smem_bytes = 65536 + 32768 + 64;
+    OCC_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    mma_rate_kernel<<<ctas, 128, smem_bytes, (cudaStream_t)stream>>>(iters, n, out_dev);
+    OCC_LAUNCH_CHECK();
+    return OCCNERF_OK;
+}
 
 // debug only: reads (and optionally clears) the stall counters described at g_dbg
 extern "C" int occnerf_mlp_debug_counters(unsigned long long *host8, int reset) {
