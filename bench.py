@@ -262,8 +262,8 @@ def kernel_table(profile, steps):
 # DRAM bytes per sample (dram__bytes_read.sum + dram__bytes_write.sum of one launch / samples of that launch) from the
 # `ncu --set full` capture summarised in profiles/r01c_kernels_full.md (300 000-sample launches of the same command)
 NCU_TRAFFIC_PER_SAMPLE = {"occnerf_mlp_forward_tc": (0.151179e9 + 1.470747e9) / 300000, "occnerf_mlp_backward_tc": (0.128911e9 + 1.335716e9) / 300000,
-                          "occnerf_mlp_wgrad_tc": (2.805448e9 + 0.006918e9) / 300000, "occnerf_aggregate_backward": (0.129910e9 + 0.009074e9) / 300000,
-                          "occnerf_aggregate_forward": (0.054303e9 + 0.017872e9) / 300000, "occnerf_hashgrid_backward": (0.113297e9 + 0.003756e9) / 300000}
+                          "occnerf_mlp_wgrad_tc": (2.805448e9 + 0.006918e9) / 300000, "occnerf_aggregate_backward": (0.194468e9 + 0.015459e9) / 300000,
+                          "occnerf_aggregate_forward": (0.054993e9 + 0.052413e9) / 300000, "occnerf_hashgrid_backward": (0.113153e9 + 0.007391e9) / 300000}
 MMA_ISSUE_FACTOR = {"tc3": 3.0, "tc1": 1.0}      # split-bf16 issues three bf16 MMAs per algorithmic product
 
 
