@@ -123,6 +123,19 @@ int occnerf_sample_geometry(const float *xyz, const int32_t *knn_idx, int knn_st
                             const float *point_norms, float bound, int m, float *enc_in, float *dist, int dist_stride,
                             occnerf_stream_t stream);
 
+/* ---- per-vertex block (network.py:263-284 + occnerf_mlp.py:171-175) ---------------------------------------
+ * pc = point_base + point_dist (point_dist [V], one scalar per vertex, added to all three coordinates); kidx3 [V,3] = the 3
+ * nearest base vertices of pc (occnerf_knn, k = 3).  Forward writes v_in [V,4] = ((|cos|-weighted mean of the 3 base
+ * vertices + bound) / (2 bound), clamp((signed mean distance + 0.2) / 0.8, 0, 1)) -- the vertex's hash-grid input -- and
+ * feats_tail[v*ld + 0..3] = (pc, 0) (columns 32..35 of the per-vertex feature table when ld = 36).
+ * Backward: g_point_dist [V] from g_v_in [V,4] (the hash grid's input gradient) and g_feats_tail (direct gradient of pc). */
+int occnerf_vertex_block_forward(const float *point_base, const float *point_dist, const float *point_norms,
+                                 const int32_t *kidx3, float bound, int V, float *v_in, float *feats_tail, int ld,
+                                 occnerf_stream_t stream);
+int occnerf_vertex_block_backward(const float *point_base, const float *point_dist, const float *point_norms,
+                                  const int32_t *kidx3, float bound, int V, const float *g_v_in, const float *g_feats_tail,
+                                  int ld, float *g_point_dist, occnerf_stream_t stream);
+
 /* ---- multi-resolution hash grid (gridencoder.h:12-15; gridencoder.cu:50-369) -------------------------
  * level_scales [L] = exp2f(l*S)*H-1 evaluated ON THE DEVICE exactly as gridencoder.cu:138 does. */
 int occnerf_hashgrid_level_scales(float S, uint32_t H, uint32_t L, float *level_scales, occnerf_stream_t stream);
@@ -193,6 +206,8 @@ int occnerf_mlp_debug_counters(unsigned long long *host8, int reset);
 /* Debug only: `iters` back-to-back tcgen05.mma (M=128, N=n, K=16, bf16, shared-memory operands) on `ctas` CTAs (one per
  * SM) at once; out_dev[cta] = cycles from the first issue to the completion of the last (tools/mma_rate.py). */
 int occnerf_mlp_debug_mma_rate(int iters, int n, unsigned long long *out_dev, int ctas, occnerf_stream_t stream);
+/* Debug only: cudaOccupancyMaxActiveClusters of the tc3 forward chain kernel for clusters of `cluster_size` CTAs (< 0: error). */
+int occnerf_mlp_debug_max_clusters(int cluster_size);
 int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, void *packed, occnerf_stream_t stream);
 /* XB [m,132]: columns 64..131 = (agg35, var1, h32) are read; columns 0..63 receive the 64 geometry features when
  * act_dtype != 0.  raw [m, ldr]: columns 0..3 = (rgb_pre3, sigma_pre1) are written.

@@ -30,6 +30,8 @@ _SIGNATURES = {
     "occnerf_knn_tree": [_vp, _i, _i, _i] + [_vp] * 11 + [_i] * 5 + [_vp, _vp],
     "occnerf_knn_grid": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     "occnerf_sample_geometry": [_vp, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _vp],
+    "occnerf_vertex_block_forward": [_vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _i, _vp],
+    "occnerf_vertex_block_backward": [_vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _i, _vp, _vp],
     "occnerf_hashgrid_level_scales": [_f, _u, _u, _vp, _vp],
     "occnerf_hashgrid_forward": [_vp] * 5 + [_i, _i] + [_u] * 4 + [_vp] * 3 + [_i, _vp],
     "occnerf_hashgrid_backward": [_vp, _i, _i, _vp, _vp, _vp, _vp] + [_u] * 4 + [_i, _vp],
@@ -44,6 +46,7 @@ _SIGNATURES = {
     "occnerf_mlp_backward_tc": [_vp, _i, _vp, _i, _vp, _vp, _vp, _l, _vp],
     "occnerf_mlp_debug_counters": [_vp, _i],
     "occnerf_mlp_debug_mma_rate": [_i, _i, _vp, _i, _vp],
+    "occnerf_mlp_debug_max_clusters": [_i],
     "occnerf_mlp_wgrad_tc": [_vp, _vp, _i, _l, _vp, _vp, _vp],
     "occnerf_composite_forward": [_vp] * 5 + [_i, _i] + [_vp] * 7,
     "occnerf_composite_backward": [_vp] * 9 + [_i, _i] + [_vp] * 3,

@@ -790,6 +790,24 @@ void fill_layout(ChainArgs &a, int n_pass, int chain, const void *packed) {
 
 }  // namespace
 
+// debug only: how many clusters of `cluster_size` CTAs of the tc3 forward chain kernel the device can hold at once
+extern "C" int occnerf_mlp_debug_max_clusters(int cluster_size) {
+    constexpr int smem_bytes = 2 * kAPartBytes + kStages * kStageBytes + 256;
+    if (cudaFuncSetAttribute(mlp_chain_tc_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return -1;
+    if (cluster_size > 8 && cudaFuncSetAttribute(mlp_chain_tc_kernel<3, 0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(148 / cluster_size * cluster_size);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, mlp_chain_tc_kernel<3, 0>, &cfg) != cudaSuccess) { cudaGetLastError(); return -3; }
+    return n;
+}
+
 // debug only: cycles per tcgen05.mma (M=128, N=n, K=16) measured on every SM at once; out_dev [148+] device u64
 extern "C" int occnerf_mlp_debug_mma_rate(int iters, int n, unsigned long long *out_dev, int ctas, occnerf_stream_t stream) {
     OCC_CHECK_ARG(out_dev && iters >= 2 && n >= 16 && n <= 256 && n % 16 == 0 && ctas >= 1, "mlp_debug_mma_rate: bad arguments");

@@ -270,6 +270,47 @@ class _QueryFn(torch.autograd.Function):
         return (None, None, g_feats, g_emb, None, None, *g_params)
 
 
+class _VertexFn(torch.autograd.Function):
+    """Per-vertex block (network.py:263-284 + occnerf_mlp.py:171-175): (point_dist, embeddings) -> feats36 (V,36) =
+    (hash-grid features of the vertex's surface projection (32), point_cloud (3), 0).  One kernel each way for the
+    geometry (csrc/vertex.cu) around the hash-grid kernels."""
+
+    @staticmethod
+    def forward(ctx, point_dist, embeddings, net):
+        st = net._static()
+        base, norms = st["point_base"], st["point_norms"]
+        V, dev = base.shape[0], base.device
+        pd = point_dist.detach().reshape(-1).contiguous().float()
+        pc = base + pd[:, None]
+        kidx = ops.knn(pc.contiguous(), st["base4"], [0, V], 3)[:, 0].contiguous()
+        v_in = torch.empty(V, 4, device=dev, dtype=f32)
+        feats36 = torch.empty(V, 36, device=dev, dtype=f32)
+        ops.vertex_block_forward(base, pd, norms, kidx, net.bound, v_in, feats36.data_ptr() + 4 * 32, 36)
+        enc = net.cnl_mlp.module.encoder
+        scales = ops.level_scales(float(np.log2(enc.per_level_scale)), enc.base_resolution, enc.num_levels, dev)
+        emb_c = embeddings.detach().contiguous()
+        _, dy_dx, _, _ = ops.hashgrid_forward(v_in, emb_c, enc.offsets, scales, out_ptr=feats36.data_ptr(), ld=36, want_dy_dx=True)
+        ctx.state = dict(pd=pd, kidx=kidx, v_in=v_in, dy_dx=dy_dx, scales=scales, offsets=enc.offsets, net=net,
+                         emb_shape=tuple(embeddings.shape))
+        ctx.mark_non_differentiable(pc)
+        return feats36, pc
+
+    @staticmethod
+    def backward(ctx, g_feats, _g_pc):
+        s = ctx.state
+        st = s["net"]._static()
+        g = g_feats.contiguous().float()
+        V = g.shape[0]
+        L, Cc = s["offsets"].shape[0] - 1, s["emb_shape"][1]
+        g_emb = torch.zeros(s["emb_shape"], device=g.device, dtype=f32)
+        ops.hashgrid_backward(g.data_ptr(), 36, 0, s["v_in"], s["offsets"], s["scales"], g_emb, Cc)
+        g_v_in = ops.hashgrid_input_backward(g.data_ptr(), 36, 0, s["dy_dx"], V, 4, Cc, L)
+        g_pd = ops.vertex_block_backward(st["point_base"], s["pd"], st["point_norms"], s["kidx"], s["net"].bound, g_v_in,
+                                         g.data_ptr() + 4 * 32, 36)
+        ctx.state = None
+        return g_pd[:, None], g_emb, None
+
+
 # ----------------------------------------------------------------------------- the model
 class Network(nn.Module):
     def __init__(self, cfg: RenderConfig | None = None):
@@ -360,27 +401,8 @@ class Network(nn.Module):
 
     # -- per-vertex block (network.py:263-284 + occnerf_mlp.py:171-175), once per call instead of once per chunk
     def vertex_features(self):
-        from occnerf_b200 import _lib
-        with _lib.region("lib:vertex block glue (torch, V=6890)"):
-            return self._vertex_features()
-
-    def _vertex_features(self):
-        st = self._static()
-        V = self.point_base.shape[0]
-        pc = self.point_base + self.point_dist
-        kidx = ops.knn(pc.detach().contiguous(), st["base4"], [0, V], 3)[:, 0].long()
-        b = self.point_base[kidx]
-        direction = pc[:, None, :] - b
-        n = self.point_norms[kidx]
-        a = torch.abs(torch.nn.functional.cosine_similarity(direction, n, dim=-1))[..., None]
-        knn_base = (a * b).sum(1) / a.sum(1)
-        inside = ((direction * n).sum(-1) < 0).sum(1) > 1.5
-        dist = direction.norm(dim=-1).mean(1, keepdim=True)
-        dist = torch.where(inside[:, None], -dist, dist)
-        v_in = torch.cat([(knn_base + self.bound) / (2 * self.bound), torch.clamp((dist + 0.2) / 0.8, 0.0, 1.0)], -1)
-        hv = self.cnl_mlp.module.encoder(v_in)
-        feats36 = torch.cat([hv, pc, torch.zeros(V, 1, device=pc.device, dtype=pc.dtype)], -1)
-        return feats36, pc
+        """-> (feats36 (V,36), point_cloud (V,3)); differentiable w.r.t. point_dist and the hash table."""
+        return _VertexFn.apply(self.point_dist, self.cnl_mlp.module.encoder.embeddings, self)
 
     # -- reference API: network.py:164-192
     def _query_mlp(self, pos_xyz, rays_d, pos_embed_fn, non_rigid_pos_embed_fn, non_rigid_mlp_input, _feats36=None,

@@ -265,6 +265,20 @@ def sample_geometry(xyz, knn_idx, point_base, point_norms, bound, raw=None):
     return enc_in, dist
 
 
+def vertex_block_forward(point_base, point_dist, point_norms, kidx3, bound, v_in, tail_ptr, ld):
+    V = point_base.shape[0]
+    call("occnerf_vertex_block_forward", ptr(point_base, f32), ptr(point_dist, f32), ptr(point_norms, f32), ptr(kidx3, i32),
+         float(bound), V, ptr(v_in, f32), tail_ptr, ld, stream())
+
+
+def vertex_block_backward(point_base, point_dist, point_norms, kidx3, bound, g_v_in, g_tail_ptr, ld):
+    V = point_base.shape[0]
+    g_pd = torch.empty(V, device=point_base.device, dtype=f32)
+    call("occnerf_vertex_block_backward", ptr(point_base, f32), ptr(point_dist, f32), ptr(point_norms, f32), ptr(kidx3, i32),
+         float(bound), V, ptr(g_v_in, f32), g_tail_ptr, ld, ptr(g_pd), stream())
+    return g_pd
+
+
 # ----------------------------------------------------------------------------- hash grid
 _SCALES = {}
 

@@ -65,5 +65,8 @@ def test_graph_replay_matches_eager_steps():
         assert abs(a - b) <= 5e-3 * max(abs(a), 1e-6), (losses_e, losses_g)
     assert losses_g[-1] != losses_g[0], "replays must advance the optimisation"
     for (n, pe), pg in zip(net_e.named_parameters(), net_g.parameters()):
+        if n == "point_counter":       # integer votes: a ray whose depth sits at the 0.5 threshold may vote in one run only
+            assert float((pe != pg).float().mean()) < 0.01, n
+            continue
         assert torch.allclose(pe, pg, rtol=1e-2, atol=2 * 5e-4 * (3 + steps)), n     # within a couple of Adam steps (lr = 5e-4)
     assert not gs.needs_recapture(501) and gs.needs_recapture(net_g.cfg.non_rigid_kick_in_iter)
