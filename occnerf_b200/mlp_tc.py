@@ -19,9 +19,12 @@ f32, bf16 = torch.float32, torch.bfloat16
 
 
 class MlpTc:
-    def __init__(self, n_pass: int = 3, wgrad: str = "tc"):
-        assert n_pass in (1, 3) and wgrad in ("tc", "lib")
+    def __init__(self, n_pass: int = 3, wgrad: str = "tc", bwd_pass: int | None = None):
+        assert n_pass in (1, 3) and wgrad in ("tc", "lib") and bwd_pass in (None, 1, 3)
         self.n_pass = n_pass
+        # precision of the data-gradient chain: by default that of the forward chain; 1 = bf16 operands (what the
+        # weight-gradient kernel uses anyway), independent of a split-bf16 forward
+        self.bwd_pass = n_pass if bwd_pass is None else bwd_pass
         self.wgrad = wgrad      # "tc": hand-written tcgen05 kernel; "lib": cuBLAS (test cross-check only)
         self.name = f"tc{n_pass}"
 
@@ -56,12 +59,14 @@ class MlpTc:
         m, dev = XB.shape[0], XB.device
         acts = saved["acts"]
         stride = acts.shape[2]
+        fwd_pass, self.n_pass = self.n_pass, self.bwd_pass
         packed = self.pack(W, dev, 1)
+        self.n_pass = fwd_pass
         gXB = torch.empty(m, M.XB_LD, device=dev, dtype=f32)
         g_save = torch.empty(10, 32, stride, 8, device=dev, dtype=bf16)
         if stride > m:
             g_save[:, :, m:].zero_()
-        call("occnerf_mlp_backward_tc", g_raw.data_ptr(), m, packed.data_ptr(), self.n_pass, saved["mask"].data_ptr(), gXB.data_ptr(),
+        call("occnerf_mlp_backward_tc", g_raw.data_ptr(), m, packed.data_ptr(), self.bwd_pass, saved["mask"].data_ptr(), gXB.data_ptr(),
              g_save.data_ptr(), stride, stream(), work=M.FLOP_FWD * m)
         if self.wgrad == "lib":
             with _lib.region("lib:wgrad(cuBLAS bf16)+bias sums"):

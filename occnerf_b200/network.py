@@ -164,7 +164,7 @@ class RenderConfig:
     non_rigid_multires: int = 6
     ignore_non_rigid_motions: bool = False
     bgcolor: tuple = (0.0, 0.0, 0.0)
-    mlp_engine: str = "fp32"        # "fp32" (exact SIMT) | "tc3" (tcgen05 split-bf16) | "tc1" (tcgen05 bf16)
+    mlp_engine: str = "fp32"        # "fp32" (exact SIMT) | "tc3" (tcgen05 split-bf16) | "tc3b1" (tc3 forward, bf16 dgrad) | "tc1" (tcgen05 bf16)
     knn_mode: str = "grid"          # "grid" (per-cell candidate lists) | "tree" (3-level cluster tree) | "hier" | "brute"; same ids
 
 
@@ -397,6 +397,8 @@ class Network(nn.Module):
         if e == "fp32":
             return M.MlpSimt()
         from occnerf_b200 import mlp_tc
+        if e == "tc3b1":         # split-bf16 forward (fp32-grade outputs), bf16-operand data gradients
+            return mlp_tc.MlpTc(n_pass=3, bwd_pass=1)
         return mlp_tc.MlpTc(n_pass=3 if e == "tc3" else 1)
 
     # -- per-vertex block (network.py:263-284 + occnerf_mlp.py:171-175), once per call instead of once per chunk
