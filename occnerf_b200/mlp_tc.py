@@ -39,9 +39,21 @@ class MlpTc:
         call("occnerf_mlp_pack_weights", ctypes.byref(P), self.n_pass, chain, packed.data_ptr(), stream())
         return packed
 
-    def forward(self, XB, raw, W: M.MlpWeights, save: bool):
+    def _packed(self, W, dev, chain, n_pass, shared):
+        """Packed operand images of the current weights; built once per _query_mlp call (`shared`) instead of once per chunk."""
+        key = ("packed", chain, n_pass)
+        if shared is not None and key in shared:
+            return shared[key]
+        keep, self.n_pass = self.n_pass, n_pass
+        packed = self.pack(W, dev, chain)
+        self.n_pass = keep
+        if shared is not None:
+            shared[key] = packed
+        return packed
+
+    def forward(self, XB, raw, W: M.MlpWeights, save: bool, shared=None):
         m, dev = XB.shape[0], XB.device
-        packed = self.pack(W, dev, 0)
+        packed = self._packed(W, dev, 0, self.n_pass, shared)
         stride = (m + 63) // 64 * 64
         acts, mask = None, None
         if save:
@@ -55,13 +67,14 @@ class MlpTc:
              work=M.FLOP_FWD * m)
         return {"acts": acts, "mask": mask} if save else None
 
-    def backward(self, XB, g_raw, W: M.MlpWeights, saved):
+    def backward(self, XB, g_raw, W: M.MlpWeights, saved, shared=None, last=True):
+        """-> (gXB, list of the 20 parameter gradients | None).  With `shared` (a dict living as long as one _query_mlp
+        call) the weight gradients of all its chunks accumulate in ONE dW/dB buffer -- the kernel adds into it anyway --
+        and only the chunk with last=True maps it back to the nn.Linear layout; the others return None (= zero)."""
         m, dev = XB.shape[0], XB.device
         acts = saved["acts"]
         stride = acts.shape[2]
-        fwd_pass, self.n_pass = self.n_pass, self.bwd_pass
-        packed = self.pack(W, dev, 1)
-        self.n_pass = fwd_pass
+        packed = self._packed(W, dev, 1, self.bwd_pass, shared)
         gXB = torch.empty(m, M.XB_LD, device=dev, dtype=f32)
         g_save = torch.empty(10, 32, stride, 8, device=dev, dtype=bf16)
         if stride > m:
@@ -73,10 +86,19 @@ class MlpTc:
                 def rows(t):     # chunk-major -> row-major [slot][row][256]
                     return t.permute(0, 2, 1, 3).reshape(10, stride, 256)[:, :m]
                 return gXB, self._wgrad_lib(XB, g_raw, rows(acts), rows(g_save))
-        dW = torch.zeros(10, 256, 256, device=dev, dtype=f32)
-        dB = torch.zeros(10, 256, device=dev, dtype=f32)
+        if shared is not None and "dW" in shared:
+            dW, dB = shared["dW"], shared["dB"]
+        else:
+            dW = torch.zeros(10, 256, 256, device=dev, dtype=f32)
+            dB = torch.zeros(10, 256, device=dev, dtype=f32)
+            if shared is not None:
+                shared["dW"], shared["dB"] = dW, dB
         call("occnerf_mlp_wgrad_tc", g_save.data_ptr(), acts.data_ptr(), m, stride, dW.data_ptr(), dB.data_ptr(), stream(),
              work=M.FLOP_FWD * m)
+        if shared is not None and not last:
+            return gXB, None
+        if shared is not None:
+            shared.pop("dW"), shared.pop("dB")
         g = {}
         g["pts_w0"], g["pts_b0"] = dW[0][:, :68].contiguous(), dB[0]
         for l in (1, 2, 3):

@@ -238,7 +238,8 @@ class _QueryFn(torch.autograd.Function):
         W = M.MlpWeights(mlp_params)
         need_grad = any(ctx.needs_input_grad)
         engine = net._engine()
-        saved = engine.forward(XB, raw, W, save=need_grad)
+        saved = engine.forward(XB, raw, W, save=need_grad, shared=shared) if hasattr(engine, "bwd_pass") else \
+            engine.forward(XB, raw, W, save=need_grad)
         if need_grad:
             ctx.state = dict(knn_idx=knn_idx, enc_in=enc_in, XB=XB, W=W, saved=saved, engine=engine, counter=counter,
                              offsets=enc.offsets, scales=scales, emb_shape=tuple(embeddings.shape), V=feats36.shape[0],
@@ -250,11 +251,17 @@ class _QueryFn(torch.autograd.Function):
     def backward(ctx, g_raw):
         s = ctx.state
         g_raw = g_raw.contiguous().float()
-        gXB, g_params = s["engine"].backward(s["XB"], g_raw, s["W"], s["saved"])
+        sh = s["shared"]
+        last = sh["pending"] == 1
+        if hasattr(s["engine"], "bwd_pass"):      # tensor-core engine: one weight-gradient buffer for all chunks of the call
+            gXB, g_params = s["engine"].backward(s["XB"], g_raw, s["W"], s["saved"], shared=sh, last=last)
+            if g_params is None:
+                g_params = [None] * 20
+        else:
+            gXB, g_params = s["engine"].backward(s["XB"], g_raw, s["W"], s["saved"])
         # the chunks of one _query_mlp call scatter into ONE table-gradient buffer (and one set of privatised vertex-gradient
         # replicas); the chunk whose backward runs last hands it to autograd, the others contribute None (= zero).  That
         # replaces a 59 MiB memset + a 59 MiB add per chunk by one memset per call.
-        sh = s["shared"]
         if "g_emb" not in sh:
             sh["g_emb"] = torch.zeros(s["emb_shape"], device=g_raw.device, dtype=f32)
             sh["g_priv"] = torch.zeros(ops.AGG_BWD_COPIES, s["V"], 36, device=g_raw.device, dtype=f32)
