@@ -223,6 +223,50 @@ class Workload:
         self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
 
 
+def forward_frame(wl, flush, repeats=3):
+    """BASELINE configs[0] shape on the GPU: forward render of every bbox-hitting pixel of one 512x512 view (eval mode, no
+    jitter, no gradients), through `Network._batchify_rays` in chunks of 32 768 rays.  Reported beside the training metric."""
+    S = wl.S
+    fr = S.frame_to(S.make_frame(wl.sub, mode="full", img=512, seed=3), wl.device)
+    packed = torch.cat([fr.rays_o, fr.rays_d, fr.near, fr.far], -1).contiguous()
+    net = wl.net
+    was_training, perturb = net.training, net.cfg.perturb
+    net.train(False)
+    net.cfg.perturb = 0.0
+    emb_fn, _ = net.get_non_rigid_embedder(6, 0, 10 ** 7)
+    vol = wl.vol.detach()
+
+    def render():
+        with torch.no_grad():
+            return net._batchify_rays(packed, pos_embed_fn=None, non_rigid_pos_embed_fn=emb_fn, non_rigid_mlp_input=fr.dst_posevec[None],
+                                      motion_scale_Rs=fr.motion_scale_Rs[None], motion_Ts=fr.motion_Ts[None], motion_weights_vol=vol,
+                                      cnl_bbox_min_xyz=fr.cnl_bbox_min_xyz, cnl_bbox_scale_xyz=fr.cnl_bbox_scale_xyz, bgcolor=fr.bgcolor)
+    render()
+    torch.cuda.synchronize()
+    from occnerf_b200 import _lib
+    _lib.PROFILE = {}
+    render()
+    torch.cuda.synchronize()
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    top = sorted(((sum(a.elapsed_time(b) for a, b, _w in evs), name) for name, evs in prof.items()), reverse=True)[:6]
+    tot = 0.0
+    for _ in range(repeats):
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = render()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    net.train(was_training)
+    net.cfg.perturb = perturb
+    ms = tot / repeats
+    n = packed.shape[0]
+    return {"workload": "forward render of one 512x512 view, all bbox-hitting pixels, 128 samples/ray, non-rigid MLP active (iter 1e7)",
+            "rays": n, "ms_per_frame": ms, "rays_per_sec": n / (ms * 1e-3), "finite": bool(torch.isfinite(out["rgb"]).all()),
+            "top_calls_ms": [[name, round(t, 2)] for t, name in top]}
+
+
 def timed_loop(fn, steps, warmup, world, flush):
     import torch.distributed as dist
     for _ in range(warmup):
@@ -388,6 +432,8 @@ def main():
             "kernels": [{"call": r["call"], "ms_per_step": round(r["ms_per_step"], 4), "launches_per_step": r["launches_per_step"]} for r in table],
             "roofline_all": roof_all,
         }
+        if world == 1:
+            line["forward_only"] = forward_frame(wl, flush)
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference(args.ref_rays, 2, 1)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "rays/s", "cores": cb["cores"], "kind": "port", "sample": cb["sample"]}

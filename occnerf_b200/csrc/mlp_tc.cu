@@ -44,8 +44,14 @@ constexpr uint32_t kSpinLimit = 1u << 27;
 // backward chain: out^T, rgb3..1^T, rgb0^T, geo^T, pts3..1^T, pts0^T   (position d uses forward layer 9-d)
 __host__ __device__ inline int fwd_K(int l) { return l == 0 ? 80 : (l == 5 ? 144 : 256); }
 __host__ __device__ inline int fwd_N(int l) { return l == 4 ? 80 : (l == 9 ? 16 : 256); }
-__host__ __device__ inline int chain_K(int chain, int l) { return chain == 0 ? fwd_K(l) : fwd_N(9 - l); }
-__host__ __device__ inline int chain_N(int chain, int l) { return chain == 0 ? fwd_N(l) : fwd_K(9 - l); }
+// chain 2 = the non-rigid motion MLP (non_rigid_motion_mlps/mlp_offset.py:7-62), forward only, 7 GEMMs:
+//   pe36 (+12 pad) -> 128 -> 128 -> 128 -> 128 -> [h128, pe36] (176) -> 128 -> 128 -> 3 (16)
+// (the 69-value pose condition is the same for every sample of a frame and is folded into the bias of layer 0)
+__host__ __device__ inline int nr_K(int l) { return l == 0 ? 48 : (l == 4 ? 176 : 128); }
+__host__ __device__ inline int nr_N(int l) { return l == 6 ? 16 : 128; }
+__host__ __device__ inline int n_layers(int chain) { return chain == 2 ? 7 : 10; }
+__host__ __device__ inline int chain_K(int chain, int l) { return chain == 0 ? fwd_K(l) : (chain == 1 ? fwd_N(9 - l) : nr_K(l)); }
+__host__ __device__ inline int chain_N(int chain, int l) { return chain == 0 ? fwd_N(l) : (chain == 1 ? fwd_K(9 - l) : nr_N(l)); }
 __host__ __device__ inline int chunk_K(int n_pass) { return n_pass == 1 ? 64 : 32; }
 __host__ __device__ inline int parts(int n_pass) { return n_pass == 1 ? 1 : 2; }
 
@@ -59,7 +65,8 @@ inline PackedLayout packed_layout(int n_pass, int chain) {
     PackedLayout p;
     long off = 0;
     const int KC = chunk_K(n_pass);
-    for (int l = 0; l < kLayers; ++l) {
+    for (int l = 0; l < kLayers; ++l) p.w_off[l] = 0;
+    for (int l = 0; l < n_layers(chain); ++l) {
         p.w_off[l] = off;
         const int K = chain_K(chain, l), N = chain_N(chain, l);
         off += (long)((K + KC - 1) / KC) * parts(n_pass) * N * KC * 2;
@@ -114,6 +121,40 @@ __global__ void pack_weights_kernel(occnerf_mlp_params P, DevLayout L, int n_pas
     if (chain == 0 && blockIdx.x == 0 && threadIdx.x < 256) {
         float *b = reinterpret_cast<float *>(out + L.bias_off) + l * 256;
         b[threadIdx.x] = threadIdx.x < N ? fwd_bias(P, l, threadIdx.x) : 0.f;
+    }
+}
+
+struct NrParams { const float *w[7]; const float *b[7]; const float *cond; };   // cond: 69 floats on the device or NULL
+
+__global__ void pack_nr_kernel(NrParams P, DevLayout L, int n_pass, unsigned char *out) {
+    const int l = blockIdx.y;
+    const int K = nr_K(l), N = nr_N(l), KC = chunk_K(n_pass), np = parts(n_pass);
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < (long)N * K) {
+        const int n = (int)(idx / K), k = (int)(idx % K);
+        float w = 0.f;
+        if (l == 0) w = k < 36 ? P.w[0][n * 105 + 69 + k] : 0.f;                 // the PE columns of [cond69, pe36]
+        else if (l == 4) w = k < 164 ? P.w[4][n * 164 + k] : 0.f;                // [h128, pe36]
+        else if (l == 6) w = n < 3 ? P.w[6][n * 128 + k] : 0.f;
+        else w = P.w[l][n * 128 + k];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        const int chunk = k / KC, kk = k % KC;
+        const long pb = (long)N * KC * 2;
+        const long base = L.w_off[l] + (long)chunk * np * pb;
+        const long inner = ((long)(kk / 8) * (N / 8) + n / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(out + base + inner) = hi;
+        if (np == 2) *reinterpret_cast<__nv_bfloat16 *>(out + base + pb + inner) = lo;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 256) {
+        const int n = threadIdx.x;
+        float b = 0.f;
+        if (n < N && (l != 6 || n < 3)) {
+            b = P.b[l][n];
+            if (l == 0 && P.cond)                                                 // fold the per-frame condition code
+                for (int k = 0; k < 69; ++k) b = fmaf(P.w[0][n * 105 + k], P.cond[k], b);
+        }
+        reinterpret_cast<float *>(out + L.bias_off)[l * 256 + n] = b;
     }
 }
 
@@ -269,6 +310,10 @@ struct ChainArgs {
     uint8_t *relu_mask;              // [8][32][slot_stride] bytes: bit i of byte (slot, k8, row) = [unit 8*k8+i > 0]; written by
                                      // the forward chain in bf16 mode and read by the backward chain (32 B per row and layer)
     int debug;
+    // non-rigid chain (chain 2)
+    const float *nr_xyz;             // [m,3]
+    const float *nr_pe;              // [m,36] Hann-windowed positional encoding (occnerf_hann_pe)
+    float *nr_out;                   // [m,3] = xyz + MLP(pe; cond)
     // backward
     const float *g_raw;              // [m,5]
     float *gXB;                      // [m,132]: cols 64..131 written (d agg, d var, d h; both trunks summed)
@@ -303,7 +348,7 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
     long long dbg_wait = 0;
     const uint32_t rank = cluster_ctarank();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int l = 0; l < kLayers; ++l) {
+        for (int l = 0; l < n_layers(args.chain); ++l) {
             const int K = chain_K(args.chain, l), N = chain_N(args.chain, l);
             const int nch = (K + KC - 1) / KC;
             const uint32_t pb = (uint32_t)N * KC * 2;
@@ -341,7 +386,7 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
     const long long dbg_t0 = args.debug ? clk() : 0;
     const uint32_t a_base = smem_u32(sm.A);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int l = 0; l < kLayers; ++l) {
+        for (int l = 0; l < n_layers(args.chain); ++l) {
             const int K = chain_K(args.chain, l), N = chain_N(args.chain, l);
             const int nch = (K + KC - 1) / KC;
             const uint32_t idesc = instr_desc(N);
@@ -664,6 +709,87 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
     if (dbg_on) { atomicAdd(&g_dbg[2], (unsigned long long)dbg_acc); atomicAdd(&g_dbg[5], (unsigned long long)(clk() - dbg_t0)); }
 }
 
+// ---- non-rigid chain epilogue (forward only, nothing saved)
+template <int NPASS>
+__device__ __forceinline__ void stage_pe_chunk(unsigned char *a_base, int row, const float *__restrict__ perow, bool valid, int k8_0, int g) {
+    float v[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = g * 8 + h * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && c < 36) x = __ldg(reinterpret_cast<const float4 *>(perow + c));
+        v[h * 4 + 0] = x.x; v[h * 4 + 1] = x.y; v[h * 4 + 2] = x.z; v[h * 4 + 3] = x.w;
+    }
+    store_a8<NPASS>(a_base, row, k8_0 + g, v);
+}
+
+template <int NPASS>
+__device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base, int warp) {
+    const int quarter = warp & 3, set = warp >> 2;
+    const int row = quarter * 32 + (threadIdx.x & 31);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float *bias_all = reinterpret_cast<const float *>(args.packed + args.bias_off);
+    uint32_t acc_cnt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long grow = (long)tile * kTileM + row;
+        const bool valid = grow < args.m;
+        const float *perow = args.nr_pe + grow * 36;
+        // GEMM 0 operand A[:, 0:48) = (pe36, pad): chunks 0..5 -> A groups 0, 1
+        stage_pe_chunk<NPASS>(sm.A, row, perow, valid, 0, set);
+        publish(sm, 0);
+        if (set < 2) stage_pe_chunk<NPASS>(sm.A, row, perow, valid, 0, set + 4);
+        publish(sm, 1);
+        for (int l = 0; l < 7; ++l, ++acc_cnt) {
+            mbar_wait(sm.bar_acc_full, acc_cnt & 1);
+            tc_fence_after();
+            const uint32_t t_acc = t_lane + (uint32_t)(l & 1) * 256;
+            const float *bias = bias_all + l * 256;
+            if (l == 6) {
+                if (set == 0) {
+                    uint32_t r[8];
+                    tmem_ld8_issue(t_acc, r);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            args.nr_out[grow * 3 + c] = __ldg(args.nr_xyz + grow * 3 + c) + (__uint_as_float(r[c]) + __ldg(bias + c));
+                    }
+                }
+                tc_fence_before();
+            } else {
+                uint32_t ra[8], rb[8];
+                auto process = [&](int cg, const uint32_t (&r)[8]) {
+                    const int k8 = cg * 4 + set;
+                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + k8 * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + k8 * 8 + 4));
+                    const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[i]) + bj[i], 0.f);
+                    store_a8<NPASS>(sm.A, row, k8, v);
+                    publish(sm, cg);
+                };
+                tmem_ld8_issue(t_acc + set * 8, ra);
+#pragma unroll 1
+                for (int cg = 0; cg < 4; cg += 2) {
+                    tmem_ld_wait();
+                    tmem_ld8_issue(t_acc + ((cg + 1) * 4 + set) * 8, rb);
+                    process(cg, ra);
+                    tmem_ld_wait();
+                    if (cg + 2 < 4) tmem_ld8_issue(t_acc + ((cg + 2) * 4 + set) * 8, ra);
+                    process(cg + 1, rb);
+                }
+                if (l == 3) {   // skip connection: A[:, 128:176) = (pe36, pad): chunks 16..21 -> A groups 4, 5
+                    stage_pe_chunk<NPASS>(sm.A, row, perow, valid, 16, set);
+                    publish(sm, 4);
+                    if (set < 2) stage_pe_chunk<NPASS>(sm.A, row, perow, valid, 16, set + 4);
+                    publish(sm, 5);
+                }
+            }
+        }
+    }
+}
+
 template <int NPASS, int CHAIN>
 __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_constant__ ChainArgs args) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -704,7 +830,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
         if (lane == 0) mma_loop<NPASS>(args, sm, num_tiles, tmem_base);
     } else {
         if (CHAIN == 0) fwd_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
-        else bwd_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
+        else if (CHAIN == 1) bwd_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
+        else nr_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
     }
     tc_fence_before();
     __syncthreads();
@@ -830,7 +957,7 @@ extern "C" int occnerf_mlp_debug_counters(unsigned long long *host8, int reset) 
 }
 
 extern "C" long occnerf_mlp_packed_bytes(int n_pass, int chain) {
-    if ((n_pass != 1 && n_pass != 3) || (chain != 0 && chain != 1)) return -1;
+    if ((n_pass != 1 && n_pass != 3) || chain < 0 || chain > 2) return -1;
     return packed_layout(n_pass, chain).total;
 }
 
@@ -882,4 +1009,39 @@ extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *pa
     OCC_CHECK_ARG(slot_stride >= m, "mlp_backward_tc: slot_stride=%ld < m=%d", slot_stride, m);
     a.g_raw = g_raw; a.relu_mask = (uint8_t *)relu_mask; a.gXB = gXB; a.g_save = (__nv_bfloat16 *)g_save; a.slot_stride = slot_stride;
     return n_pass == 1 ? launch_chain<1, 1>(a, (cudaStream_t)stream) : launch_chain<3, 1>(a, (cudaStream_t)stream);
+}
+
+// ---- non-rigid motion MLP on the same chain machinery (chain 2)
+extern "C" int occnerf_nonrigid_pack_weights(const void *const *w7_host, const void *const *b7_host, const float *cond_dev, int n_pass,
+                                             void *packed, occnerf_stream_t stream) {
+    OCC_CHECK_ARG(w7_host && b7_host && packed, "nonrigid_pack_weights: null pointer");
+    OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "nonrigid_pack_weights: n_pass=%d (supported: 1, 3)", n_pass);
+    NrParams P;
+    for (int l = 0; l < 7; ++l) {
+        OCC_CHECK_ARG(w7_host[l] && b7_host[l], "nonrigid_pack_weights: layer %d has a null pointer", l);
+        P.w[l] = (const float *)w7_host[l];
+        P.b[l] = (const float *)b7_host[l];
+    }
+    P.cond = cond_dev;
+    const PackedLayout pl = packed_layout(n_pass, 2);
+    DevLayout L;
+    for (int l = 0; l < kLayers; ++l) L.w_off[l] = pl.w_off[l];
+    L.bias_off = pl.bias_off;
+    dim3 grid(occ_div_up(176 * 128, 256), 7);
+    pack_nr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, L, n_pass, (unsigned char *)packed);
+    OCC_LAUNCH_CHECK();
+    return OCCNERF_OK;
+}
+
+extern "C" int occnerf_nonrigid_forward_tc(const float *xyz, const float *pe36, int m, const void *packed, int n_pass, float *out,
+                                           occnerf_stream_t stream) {
+    if (m == 0) return OCCNERF_OK;
+    OCC_CHECK_ARG(xyz && pe36 && packed && out && m > 0, "nonrigid_forward_tc: null pointer / m=%d", m);
+    OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "nonrigid_forward_tc: n_pass=%d (supported: 1, 3)", n_pass);
+    OCC_CHECK_ARG(((uintptr_t)pe36 & 15) == 0 && ((uintptr_t)packed & 15) == 0, "nonrigid_forward_tc: pe36/packed must be 16-byte aligned");
+    ChainArgs a = {};
+    a.m = m;
+    fill_layout(a, n_pass, 2, packed);
+    a.nr_xyz = xyz; a.nr_pe = pe36; a.nr_out = out;
+    return n_pass == 1 ? launch_chain<1, 2>(a, (cudaStream_t)stream) : launch_chain<3, 2>(a, (cudaStream_t)stream);
 }

@@ -448,8 +448,14 @@ class Network(nn.Module):
             else:
                 nw, nb = self.non_rigid_mlp.module.flat()
                 moved = torch.empty_like(xyz_all)
-                for i in range(0, xyz_all.shape[0], chunk):
-                    moved[i:i + chunk] = M.nonrigid_offsets(xyz_all[i:i + chunk], cond, window, nw, nb)
+                n_pass = {"tc3": 3, "tc3b1": 3, "tc1": 1}.get(self.cfg.mlp_engine)
+                if n_pass is not None:           # tensor-core engines: the fused tcgen05 chain (exact fp32 mode: SIMT GEMMs)
+                    packed = ops.nonrigid_pack(nw, nb, cond, n_pass)
+                    for i in range(0, xyz_all.shape[0], chunk):
+                        ops.nonrigid_forward_tc(xyz_all[i:i + chunk], window, packed, n_pass, out=moved[i:i + chunk])
+                else:
+                    for i in range(0, xyz_all.shape[0], chunk):
+                        moved[i:i + chunk] = M.nonrigid_offsets(xyz_all[i:i + chunk], cond, window, nw, nb)
                 xyz_all = moved
         knn_all = self._knn(xyz_all, self._group_stride)
         cm = self.cnl_mlp.module

@@ -423,6 +423,31 @@ def hann_pe(xyz, window, out=None):
     return out
 
 
+# ----------------------------------------------------------------------------- non-rigid MLP on tensor cores
+def nonrigid_pack(nr_w, nr_b, cond, n_pass):
+    """Packed UMMA operand images of the 7 non-rigid layers (cond (1,69) or None is folded into the first bias)."""
+    dev = nr_w[0].device
+    nbytes = _lib.load().occnerf_mlp_packed_bytes(n_pass, 2)
+    packed = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    ws = [t.detach().contiguous().float() for t in nr_w]
+    bs = [t.detach().contiguous().float() for t in nr_b]
+    wp = (C.c_void_p * 7)(*[t.data_ptr() for t in ws])
+    bp = (C.c_void_p * 7)(*[t.data_ptr() for t in bs])
+    cond_c = cond.detach().reshape(-1).contiguous().float() if cond is not None else None
+    call("occnerf_nonrigid_pack_weights", C.cast(wp, C.c_void_p), C.cast(bp, C.c_void_p), ptr(cond_c, f32), n_pass, ptr(packed), stream())
+    return packed
+
+
+def nonrigid_forward_tc(xyz, window, packed, n_pass, out=None):
+    """xyz (m,3) -> xyz + non-rigid offsets, through the fused tcgen05 chain (csrc/mlp_tc.cu, chain 2)."""
+    m = xyz.shape[0]
+    pe = hann_pe(xyz, window)
+    if out is None:
+        out = torch.empty(m, 3, device=xyz.device, dtype=f32)
+    call("occnerf_nonrigid_forward_tc", ptr(xyz, f32), ptr(pe, f32), m, ptr(packed), n_pass, ptr(out, f32), stream())
+    return out
+
+
 # ----------------------------------------------------------------------------- K4 compositing
 def composite_forward(raw, mask, z, rays, bg, want_weights=False, want_comp=False):
     N, S = z.shape

@@ -136,6 +136,35 @@ def test_nonrigid_full_band_against_oracle():
         assert e < 2e-6
 
 
+@pytest.mark.parametrize("n_pass,tol", [(3, 3e-5), (1, 2e-2)])
+def test_nonrigid_tensor_core_chain_against_oracle(n_pass, tol):
+    """The non-rigid MLP as a fused tcgen05 chain (csrc/mlp_tc.cu, chain 2): split-bf16 is fp32-grade, bf16 is not.
+    Offsets are scaled to ~1 so that the error is visible; m is not a multiple of the 128-sample tile."""
+    from occnerf_b200 import ops
+    sub = S.make_subject(seed=0)
+    w = S.make_weights(sub.bound, seed=3, nonzero_bias=True)
+    w.nr_w[6] = w.nr_w[6] * 1e4
+    gen = torch.Generator().manual_seed(2)
+    xyz = torch.rand(5001, 3, generator=gen) * 2 - 1
+    cond = torch.randn(1, 69, generator=gen) * 0.2
+    d = dev()
+    nw, nb = [t.to(d) for t in w.nr_w], [t.to(d) for t in w.nr_b]
+    for it in (10000000, 150000):
+        window = ops.hann_window(it, 100000, 200000)
+        packed = ops.nonrigid_pack(nw, nb, cond.to(d), n_pass)
+        got = ops.nonrigid_forward_tc(xyz.to(d).contiguous(), window, packed, n_pass)
+        pe = O.hann_pe(xyz, it, 100000, 200000)
+        want = xyz + O.non_rigid_offsets(xyz, cond, pe, w.nr_w, w.nr_b)
+        e, scale = maxabs(got, want), float((want - xyz).abs().max())
+        report(f"nonrigid_tc{n_pass}[{it}]", xyz=e, offset_scale=scale)
+        assert e < tol * max(scale, 1.0), (e, scale)
+    # no condition code (NULL pointer) = zeros
+    packed0 = ops.nonrigid_pack(nw, nb, None, n_pass)
+    got0 = ops.nonrigid_forward_tc(xyz.to(d).contiguous(), window, packed0, n_pass)
+    want0 = xyz + O.non_rigid_offsets(xyz, torch.zeros(1, 69), pe, w.nr_w, w.nr_b)
+    assert maxabs(got0, want0) < tol * max(float((want0 - xyz).abs().max()), 1.0)
+
+
 def test_full_size_step_runs_and_is_finite():
     """BASELINE config 2: 6 x 32 x 32 rays, 128 samples, forward + backward through the public interface."""
     sub = S.make_subject(seed=0)
