@@ -237,13 +237,14 @@ int occnerf_mlp_wgrad_tc(const void *g_save, const void *act_bf16, int m, long s
 
 /* ---- non-rigid motion MLP on tcgen05 (non_rigid_motion_mlps/mlp_offset.py:7-62; forward only, as in the reference its
  * output feeds no_grad code only).  out [m,3] = xyz + MLP([cond69, pe36]) with the 6 x 128 ReLU layers and the skip
- * connection of the reference; pe36 [m,36] = occnerf_hann_pe(xyz).  w7_host / b7_host: HOST arrays of 7 device pointers
+ * connection of the reference; the Hann-windowed positional encoding (6 bands, hannw_fourier.py:27-45, window weights
+ * window6_host = 6 HOST floats) is evaluated inside the kernel.  w7_host / b7_host: HOST arrays of 7 device pointers
  * (nn.Linear weights [128,105], [128,128] x3, [128,164], [128,128], [3,128] and their biases); cond_dev: the 69-value pose
  * condition on the device (folded into the first bias) or NULL (= zeros).  Buffer size: occnerf_mlp_packed_bytes(n_pass, 2). */
 int occnerf_nonrigid_pack_weights(const void *const *w7_host, const void *const *b7_host, const float *cond_dev, int n_pass,
                                   void *packed, occnerf_stream_t stream);
-int occnerf_nonrigid_forward_tc(const float *xyz, const float *pe36, int m, const void *packed, int n_pass, float *out,
-                                occnerf_stream_t stream);
+int occnerf_nonrigid_forward_tc(const float *xyz, const float *window6_host, int m, const void *packed, int n_pass,
+                                float *out, occnerf_stream_t stream);
 
 /* ---- alpha compositing (network.py:320-348) + completeness term (network.py:486-499) ----------------
  * raw [N,S,5] = (rgb_pre3, sigma_pre, dist); mask, z [N,S]; rays [N,8]; bg [3] (0..255).

@@ -312,7 +312,7 @@ struct ChainArgs {
     int debug;
     // non-rigid chain (chain 2)
     const float *nr_xyz;             // [m,3]
-    const float *nr_pe;              // [m,36] Hann-windowed positional encoding (occnerf_hann_pe)
+    float nr_window[6];              // Hann window weights of the 6 frequency bands (ops.hann_window)
     float *nr_out;                   // [m,3] = xyz + MLP(pe; cond)
     // backward
     const float *g_raw;              // [m,5]
@@ -710,17 +710,20 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
 }
 
 // ---- non-rigid chain epilogue (forward only, nothing saved)
-template <int NPASS>
-__device__ __forceinline__ void stage_pe_chunk(unsigned char *a_base, int row, const float *__restrict__ perow, bool valid, int k8_0, int g) {
-    float v[8];
+// chunk g (8 values) of the Hann-windowed positional encoding of one point (hannw_fourier.py:27-45; the arithmetic of
+// hann_pe_kernel in mlp_simt.cu: w_j * sinf / cosf(x_c * 2^j), layout [j][sin xyz, cos xyz]); zero beyond index 36
+__device__ __forceinline__ void pe_chunk(const float (&x)[3], const float (&win)[6], int g, float (&v)[8]) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int c = g * 8 + h * 4;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && c < 36) x = __ldg(reinterpret_cast<const float4 *>(perow + c));
-        v[h * 4 + 0] = x.x; v[h * 4 + 1] = x.y; v[h * 4 + 2] = x.z; v[h * 4 + 3] = x.w;
+    for (int i = 0; i < 8; ++i) {
+        const int idx = g * 8 + i;
+        float val = 0.f;
+        if (idx < 36) {
+            const int j = idx / 6, r = idx - j * 6, c = r >= 3 ? r - 3 : r;
+            const float a = x[c] * (float)(1 << j);
+            val = win[j] * (r >= 3 ? cosf(a) : sinf(a));
+        }
+        v[i] = val;
     }
-    store_a8<NPASS>(a_base, row, k8_0 + g, v);
 }
 
 template <int NPASS>
@@ -729,15 +732,24 @@ __device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Sm
     const int row = quarter * 32 + (threadIdx.x & 31);
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float *bias_all = reinterpret_cast<const float *>(args.packed + args.bias_off);
+    float win[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) win[j] = args.nr_window[j];
     uint32_t acc_cnt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long grow = (long)tile * kTileM + row;
         const bool valid = grow < args.m;
-        const float *perow = args.nr_pe + grow * 36;
+        float x[3] = {0.f, 0.f, 0.f};
+        if (valid) { x[0] = __ldg(args.nr_xyz + grow * 3); x[1] = __ldg(args.nr_xyz + grow * 3 + 1); x[2] = __ldg(args.nr_xyz + grow * 3 + 2); }
+        // this thread's chunks of the positional encoding (chunk `set`, and chunk set+4 for sets 0 and 1), kept in registers
+        // for the skip connection
+        float pe0[8], pe1[8];
+        pe_chunk(x, win, set, pe0);
+        pe_chunk(x, win, set + 4, pe1);                  // (all zeros for sets 2, 3: indices >= 48)
         // GEMM 0 operand A[:, 0:48) = (pe36, pad): chunks 0..5 -> A groups 0, 1
-        stage_pe_chunk<NPASS>(sm.A, row, perow, valid, 0, set);
+        store_a8<NPASS>(sm.A, row, set, pe0);
         publish(sm, 0);
-        if (set < 2) stage_pe_chunk<NPASS>(sm.A, row, perow, valid, 0, set + 4);
+        if (set < 2) store_a8<NPASS>(sm.A, row, set + 4, pe1);
         publish(sm, 1);
         for (int l = 0; l < 7; ++l, ++acc_cnt) {
             mbar_wait(sm.bar_acc_full, acc_cnt & 1);
@@ -751,8 +763,7 @@ __device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Sm
                     tmem_ld_wait();
                     if (valid) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            args.nr_out[grow * 3 + c] = __ldg(args.nr_xyz + grow * 3 + c) + (__uint_as_float(r[c]) + __ldg(bias + c));
+                        for (int c = 0; c < 3; ++c) args.nr_out[grow * 3 + c] = x[c] + (__uint_as_float(r[c]) + __ldg(bias + c));
                     }
                 }
                 tc_fence_before();
@@ -780,9 +791,9 @@ __device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Sm
                     process(cg + 1, rb);
                 }
                 if (l == 3) {   // skip connection: A[:, 128:176) = (pe36, pad): chunks 16..21 -> A groups 4, 5
-                    stage_pe_chunk<NPASS>(sm.A, row, perow, valid, 16, set);
+                    store_a8<NPASS>(sm.A, row, 16 + set, pe0);
                     publish(sm, 4);
-                    if (set < 2) stage_pe_chunk<NPASS>(sm.A, row, perow, valid, 16, set + 4);
+                    if (set < 2) store_a8<NPASS>(sm.A, row, 20 + set, pe1);
                     publish(sm, 5);
                 }
             }
@@ -1033,15 +1044,16 @@ extern "C" int occnerf_nonrigid_pack_weights(const void *const *w7_host, const v
     return OCCNERF_OK;
 }
 
-extern "C" int occnerf_nonrigid_forward_tc(const float *xyz, const float *pe36, int m, const void *packed, int n_pass, float *out,
-                                           occnerf_stream_t stream) {
+extern "C" int occnerf_nonrigid_forward_tc(const float *xyz, const float *window6_host, int m, const void *packed, int n_pass,
+                                           float *out, occnerf_stream_t stream) {
     if (m == 0) return OCCNERF_OK;
-    OCC_CHECK_ARG(xyz && pe36 && packed && out && m > 0, "nonrigid_forward_tc: null pointer / m=%d", m);
+    OCC_CHECK_ARG(xyz && window6_host && packed && out && m > 0, "nonrigid_forward_tc: null pointer / m=%d", m);
     OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "nonrigid_forward_tc: n_pass=%d (supported: 1, 3)", n_pass);
-    OCC_CHECK_ARG(((uintptr_t)pe36 & 15) == 0 && ((uintptr_t)packed & 15) == 0, "nonrigid_forward_tc: pe36/packed must be 16-byte aligned");
+    OCC_CHECK_ARG(((uintptr_t)packed & 15) == 0, "nonrigid_forward_tc: packed must be 16-byte aligned");
     ChainArgs a = {};
     a.m = m;
     fill_layout(a, n_pass, 2, packed);
-    a.nr_xyz = xyz; a.nr_pe = pe36; a.nr_out = out;
+    a.nr_xyz = xyz; a.nr_out = out;
+    for (int j = 0; j < 6; ++j) a.nr_window[j] = window6_host[j];
     return n_pass == 1 ? launch_chain<1, 2>(a, (cudaStream_t)stream) : launch_chain<3, 2>(a, (cudaStream_t)stream);
 }

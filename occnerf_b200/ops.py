@@ -441,10 +441,11 @@ def nonrigid_pack(nr_w, nr_b, cond, n_pass):
 def nonrigid_forward_tc(xyz, window, packed, n_pass, out=None):
     """xyz (m,3) -> xyz + non-rigid offsets, through the fused tcgen05 chain (csrc/mlp_tc.cu, chain 2)."""
     m = xyz.shape[0]
-    pe = hann_pe(xyz, window)
+    assert len(window) == 6, "the fused non-rigid chain is built for 6 frequency bands (cfg.non_rigid_motion_mlp.multires)"
     if out is None:
         out = torch.empty(m, 3, device=xyz.device, dtype=f32)
-    call("occnerf_nonrigid_forward_tc", ptr(xyz, f32), ptr(pe, f32), m, ptr(packed), n_pass, ptr(out, f32), stream())
+    w = (C.c_float * 6)(*window)
+    call("occnerf_nonrigid_forward_tc", ptr(xyz, f32), C.cast(w, C.c_void_p), m, ptr(packed), n_pass, ptr(out, f32), stream())
     return out
 
 
