@@ -39,6 +39,9 @@ constexpr int kAPartBytes = 65536;          // 128 rows x 256 K x bf16
 constexpr int kGroups = 8;                  // 32-column groups of the A operand
 constexpr uint32_t kSpinLimit = 1u << 27;
 
+// (Tried and reverted: evaluating the 256 -> 3 output layer -- 16 K-steps of at least 67 cycles each for 3 useful columns --
+//  with fp32 FMAs inside the rgb3 epilogue, and its transpose at the head of the backward chain.  Inference forward -2 %,
+//  but forward-with-saving +5 % and dgrad +7 %: the extra W_out loads and registers sit on the epilogue's critical path.)
 // padded GEMM shapes (K = contraction, N = output width; both multiples of 16)
 // forward chain : pts0, pts1-3, geo, rgb0, rgb1-3, out
 // backward chain: out^T, rgb3..1^T, rgb0^T, geo^T, pts3..1^T, pts0^T   (position d uses forward layer 9-d)
@@ -437,14 +440,15 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
     }
 }
 
-// one arrival of this thread on A group g.  EVERY epilogue thread arrives exactly once per group and GEMM, after the chunk
+// one arrival of this thread's WARP on A group g.  EVERY epilogue warp arrives exactly once per group and GEMM, after the chunk
 // it owns in that group -- if any -- is in shared memory and after all of its TMEM reads of older accumulators: a group
 // therefore completes only when all 512 threads are past the previous layer, which is what makes it safe for GEMM l+2 to
 // overwrite the TMEM buffer of GEMM l.
 __device__ __forceinline__ void publish(const Smem &sm, int g) {
     tc_fence_before();
     fence_proxy_async();
-    mbar_arrive(sm.bar_a_ready + 8 * g);
+    __syncwarp();                                    // the warp's 32 fenced writes are ordered before lane 0's release-arrive:
+    if ((threadIdx.x & 31) == 0) mbar_arrive(sm.bar_a_ready + 8 * g);   // 16 arrivals per group instead of 512
 }
 
 // ---- forward epilogue.  Thread = (row, set): the 8-column chunks k8 = set, set+4, ... of every layer.
@@ -821,7 +825,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(sm.bar_w_full + 8 * s, 1); mbar_init(sm.bar_w_empty + 8 * s, 2); }
-        for (int g = 0; g < kGroups; ++g) mbar_init(sm.bar_a_ready + 8 * g, kEpiThreads);
+        for (int g = 0; g < kGroups; ++g) mbar_init(sm.bar_a_ready + 8 * g, kEpiThreads / 32);
         mbar_init(sm.bar_acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
