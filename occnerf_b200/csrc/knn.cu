@@ -531,8 +531,37 @@ knn_grid_kernel(const float *__restrict__ queries, int m, int group_stride, int 
         const uint16_t *lst = G.lists + oc.x;
         const int cnt = oc.y;
         const int cmax = __reduce_max_sync(OCC_FULL, cnt);
+        // the first K candidates always enter the (empty) top-k: take them as they come and sort them once with a 29-comparator
+        // network (232 instructions) instead of K sorted insertions (~800)
+        int first = 0;
+        if (K == 10 && __all_sync(OCC_FULL, cnt == 0 || cnt >= K)) {
+#pragma unroll
+            for (int t = 0; t < K; ++t) {
+                if (cnt > 0) {
+                    const int row = (int)__ldg(lst + t);
+                    dk[t] = dist2_rn(qx, qy, qz, pts[row]);
+                    ik[t] = row;
+                }
+            }
+            auto cex = [&](int a, int b) {       // compare-exchange on (distance, row)
+                const bool swap = dk[b] < dk[a] || (dk[b] == dk[a] && ik[b] < ik[a]);
+                const float da = dk[a], db = dk[b];
+                const int ia = ik[a], ib = ik[b];
+                dk[a] = swap ? db : da; dk[b] = swap ? da : db;
+                ik[a] = swap ? ib : ia; ik[b] = swap ? ia : ib;
+            };
+            cex(0, 8); cex(1, 9); cex(2, 7); cex(3, 5); cex(4, 6);
+            cex(0, 2); cex(1, 4); cex(5, 8); cex(7, 9);
+            cex(0, 3); cex(2, 4); cex(5, 7); cex(6, 9);
+            cex(0, 1); cex(3, 6); cex(8, 9);
+            cex(1, 5); cex(2, 3); cex(4, 8); cex(6, 7);
+            cex(1, 2); cex(3, 5); cex(4, 6); cex(7, 8);
+            cex(2, 3); cex(4, 5); cex(6, 7);
+            cex(3, 4); cex(5, 6);
+            first = K;
+        }
 #pragma unroll 2
-        for (int i = 0; i < cmax; ++i) {
+        for (int i = first; i < cmax; ++i) {
             if (i < cnt) {
                 const int row = (int)__ldg(lst + i);
                 const float d = dist2_rn(qx, qy, qz, pts[row]);

@@ -159,7 +159,8 @@ def build_knn_tree(base: torch.Tensor, fps):
         inv2=inv2.to(i32).contiguous(), n=(n0, n1, n2, n3))
 
 
-KNN_LANE_RAYS = 32
+KNN_LANE_RAYS = 32        # cluster-tree kernels: 32 rays at one depth per warp
+KNN_GRID_LANE_RAYS = 8    # grid kernel: 8 rays x 4 depths (a compact patch -> similar candidate lists per lane)
 
 
 def knn_tree(queries, group_stride, tree, out=None, lane_rays=None):
@@ -237,7 +238,7 @@ def build_knn_grid(base: torch.Tensor, fps, cell: float = 0.025, pad: float = 0.
 def knn_grid(queries, group_stride, grid, out=None, lane_rays=None):
     """All 4 levels x k=10 through the per-cell candidate lists -> (m,4,10) int32 vertex ids (bit-identical to knn)."""
     m = queries.shape[0]
-    lane_rays = KNN_LANE_RAYS if lane_rays is None else lane_rays
+    lane_rays = KNN_GRID_LANE_RAYS if lane_rays is None else lane_rays
     if out is None:
         out = torch.empty(m, 4, 10, device=queries.device, dtype=i32)
     g = grid
