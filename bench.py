@@ -172,10 +172,10 @@ class Workload:
         self.loss(out, self.target).backward()
         hits = out["hits"]
         if world > 1:
-            import torch.distributed as dist
-            for g in self.grads_to_reduce():
-                dist.all_reduce(g, op=dist.ReduceOp.AVG)
-            dist.all_reduce(hits, op=dist.ReduceOp.MAX)
+            # one bucket for the 22 small tensors (MLP, point_dist, weight volume), the 59 MiB table gradient on its own
+            from occnerf_b200 import distributed as D
+            D.allreduce_gradients(self.path_params, extra=[self.vol.grad])
+            D.allreduce_visibility(hits)
         from occnerf_b200 import _lib
         with _lib.region("lib:clip+adam+zero_grad"):
             torch.nn.utils.clip_grad_norm_(self.path_params, 1.0)
@@ -211,11 +211,9 @@ class Workload:
         loss.backward()
         params = [p for p in net.parameters() if p.requires_grad]
         if world > 1:
-            import torch.distributed as dist
-            for p in params:
-                if p.grad is not None:
-                    dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
-            dist.all_reduce(out["hits"], op=dist.ReduceOp.MAX)
+            from occnerf_b200 import distributed as D
+            D.allreduce_gradients(params)
+            D.allreduce_visibility(out["hits"])
         torch.nn.utils.clip_grad_norm_(params, 1.0)
         self.opt_all.step()
         self.opt_all.zero_grad(set_to_none=True)
