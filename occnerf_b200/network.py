@@ -382,15 +382,17 @@ class Network(nn.Module):
         return self.point_base + self.point_dist
 
     def _static(self):
-        """Device-resident support arrays for the KNN (rebuilt when the module moves)."""
+        """Device-resident support arrays for the KNN: rebuilt when the module moves or when `point_base` / `point_norms`
+        are overwritten (e.g. `load_state_dict` of a reference checkpoint copies into them in place)."""
         dev = self.point_base.device
-        if self._cache is None or self._cache["device"] != dev:
+        key = (dev, self.point_base.data_ptr(), self.point_base._version, self.point_norms.data_ptr(), self.point_norms._version)
+        if self._cache is None or self._cache["key"] != key:
             base = self.point_base.detach()
             fps = [f.to(dev) for f in self.fps_index]
             sup = torch.cat([base] + [base[f] for f in fps], 0)
             gid = torch.cat([torch.arange(base.shape[0], device=dev)] + fps).to(i32)
             lb = np.cumsum([0, base.shape[0]] + [int(f.shape[0]) for f in fps]).tolist()
-            self._cache = dict(device=dev, supports4=ops.to_float4(sup), support_gid=gid.contiguous(), level_begin=lb,
+            self._cache = dict(device=dev, key=key, supports4=ops.to_float4(sup), support_gid=gid.contiguous(), level_begin=lb,
                                base4=ops.to_float4(base), point_base=base.contiguous().float(),
                                point_norms=self.point_norms.contiguous().float(),
                                # cluster hierarchies for the pruned exact search: level 0 around level 2, level 1 around level 3

@@ -207,3 +207,17 @@ def test_chunking_does_not_change_results():
     # large per-sample contributions -- see the tolerances of test_render_matches_reference_golden)
     for k in grads[0]:
         assert normwise_close(grads[1][k].numpy(), grads[0][k].numpy(), 1e-3 if k == "pd" else 1e-4), k
+
+
+def test_static_knn_state_follows_point_base():
+    """Loading a checkpoint copies into `point_base` in place (trainer.py:408-430): the cached KNN supports must be rebuilt."""
+    sub = S.make_subject(seed=0)
+    net = S.network_from_synthetic(sub, S.make_weights(sub.bound, seed=0), RenderConfig(), device=dev())
+    st0 = net._static()
+    assert net._static() is st0                       # cached while nothing changes
+    with torch.no_grad():
+        net.point_base.add_(0.01)
+    st1 = net._static()
+    assert st1 is not st0
+    assert torch.equal(st1["point_base"], net.point_base.detach())
+    assert float((st1["base4"][:, :3] - st0["base4"][:, :3] - 0.01).abs().max()) < 1e-6
