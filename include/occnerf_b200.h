@@ -17,6 +17,8 @@
  *   core/nets/occnerf/embedders/hannw_fourier.py:27-45                        -> occnerf_hann_pe
  *   core/nets/occnerf/network.py:320-348,486-499 (_raw2outputs, comp_loss)    -> occnerf_composite_*
  *   core/nets/occnerf/network.py:502-517 (visibility counter)                 -> occnerf_visibility_hits
+ *   core/utils/camera_util.py:133-160,163-212 (get_rays_from_KRT, rays_intersect_3d_bbox) + the masking at
+ *       core/data/occnerf/freeview.py:208-219, train.py:440-461                 -> occnerf_generate_rays
  */
 #ifndef OCCNERF_B200_H
 #define OCCNERF_B200_H
@@ -265,6 +267,22 @@ int occnerf_composite_backward(const float *raw, const float *mask, const float 
  * scratch: >= (N*(k+4) + 4) * 4 bytes. */
 int occnerf_visibility_hits(const float *depth, const int64_t *term, const float *x_skel, int N, int S, float thresh,
                             const float *cloud4, int V, int k, float *hits, void *scratch, occnerf_stream_t stream);
+
+/* ---- rays in front of the path: camera_util.py:133-160 + :163-212 + freeview.py:208-219 ----------------------
+ * All camera / box arguments are HOST pointers to float64 (they ride in the kernel arguments; there is no H2D copy):
+ * kinv_host [9] = inv(K) row major as numpy computed it in K's own dtype; k_is_f32 != 0 when K was float32 (the ZJU
+ * pickles), in which case `pixel_camera` is evaluated in float32 like numpy does; R_host [9], T_host [3] extrinsics;
+ * bbox_min/max_host [3] (the 1 cm margin of camera_util.py:180 is added inside).
+ * Outputs (device): mask [H*W] uint8 = `ray_mask`; count [1] = number of valid rays; rays [capacity, 8] =
+ * (o3, d3, near, far) float32 of the valid rays in pixel order (what `rays_o[ray_mask]` etc. produce; d carries the
+ * in-place 1e-5 clamp of camera_util.py:183); pixel_index [capacity] int32 = flat pixel of each ray, or NULL.
+ * Rays beyond `capacity` are dropped (compare count with capacity); capacity = 0 only fills mask and count.
+ * scratch: occnerf_rays_scratch_bytes(H, W) bytes. */
+long occnerf_rays_scratch_bytes(int H, int W);
+int occnerf_generate_rays(const double *kinv_host, int k_is_f32, const double *R_host, const double *T_host,
+                          const double *bbox_min_host, const double *bbox_max_host, int H, int W, int capacity,
+                          float *rays, uint8_t *mask, int *pixel_index, int *count, void *scratch,
+                          occnerf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -53,8 +53,10 @@ _SIGNATURES = {
     "occnerf_composite_forward": [_vp] * 5 + [_i, _i] + [_vp] * 7,
     "occnerf_composite_backward": [_vp] * 9 + [_i, _i] + [_vp] * 3,
     "occnerf_visibility_hits": [_vp, _vp, _vp, _i, _i, _f, _vp, _i, _i, _vp, _vp, _vp],
+    "occnerf_generate_rays": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
 }
-EXPORTED = sorted(list(_SIGNATURES) + ["occnerf_last_error", "occnerf_abi_version", "occnerf_mlp_packed_bytes"])
+EXPORTED = sorted(list(_SIGNATURES) + ["occnerf_last_error", "occnerf_abi_version", "occnerf_mlp_packed_bytes",
+                                           "occnerf_rays_scratch_bytes"])
 
 GEMM_BIAS, GEMM_RELU, GEMM_ACCUM, GEMM_RELUMASK = 1, 2, 4, 8
 LAYOUT_BLC, LAYOUT_LBC = 0, 1
@@ -77,6 +79,7 @@ def load(build_if_missing: bool = True):
     lib.occnerf_last_error.restype = C.c_char_p
     lib.occnerf_abi_version.restype = _i
     lib.occnerf_mlp_packed_bytes.argtypes, lib.occnerf_mlp_packed_bytes.restype = [_i, _i], _l
+    lib.occnerf_rays_scratch_bytes.argtypes, lib.occnerf_rays_scratch_bytes.restype = [_i, _i], _l
     _lib = lib
     return lib
 
@@ -104,7 +107,7 @@ def ptr(t, dtype=None):
 
 
 # kernels launched per C call (for the bench's `gpu_launches` claim); entries not listed launch exactly one
-KERNELS_PER_CALL = {"occnerf_visibility_hits": 3}
+KERNELS_PER_CALL = {"occnerf_visibility_hits": 3, "occnerf_generate_rays": 3}
 COUNTERS = {"calls": 0, "launches": 0}
 PROFILE = None   # set to {} to record (start_event, end_event, work) per C call on the current stream
 

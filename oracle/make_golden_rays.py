@@ -1,0 +1,66 @@
+"""ORACLE tooling: write tests/golden/rays_*.npz with the UNMODIFIED reference functions get_rays_from_KRT and
+rays_intersect_3d_bbox (core/utils/camera_util.py), imported from /root/reference in the build container.
+
+    python -m oracle.make_golden_rays
+
+cv2 and trimesh (imported at the top of camera_util.py, used by other functions only) are absent here and are
+replaced by empty modules.  Two cameras: `zju` = float32 K with float64 extrinsics (what train.py:425-448 ends up
+with after apply_global_tfm_to_camera) and `f64` = everything float64; both 64 x 48 pixels so that a row/column
+mix-up cannot pass.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("OCCNERF_REFERENCE_ROOT", "/root/reference")
+
+
+def _camera_util():
+    for name in ("cv2", "trimesh"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    spec = importlib.util.spec_from_file_location("_ref_camera_util", os.path.join(REF, "core", "utils", "camera_util.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cameras():
+    rng = np.random.default_rng(42)
+    out = {}
+    for name, kdt in (("zju", np.float32), ("f64", np.float64)):
+        H, W = 48, 64
+        K = np.array([[156.25 * 1.03, 0.0, W / 2 + 0.37], [0.0, 156.25 * 0.98, H / 2 - 0.21], [0.0, 0.0, 1.0]], kdt)
+        ax = rng.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        ang = 0.35
+        Kx = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        R = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+        campos = np.array([0.4, -0.25, 6.0]) + rng.normal(size=3) * 0.1
+        T = -R @ campos
+        bmin = np.array([-0.75, -1.1, -0.35], np.float32)
+        bmax = np.array([0.80, 0.55, 0.30], np.float32)
+        out[name] = dict(H=H, W=W, K=K, R=R, T=T, bbox_min=bmin, bbox_max=bmax)
+    return out
+
+
+def main():
+    cu = _camera_util()
+    for name, c in cameras().items():
+        o, d = cu.get_rays_from_KRT(c["H"], c["W"], c["K"], c["R"], c["T"])
+        o, d = o.reshape(-1, 3), d.reshape(-1, 3)
+        near, far, mask = cu.rays_intersect_3d_bbox({"min_xyz": c["bbox_min"], "max_xyz": c["bbox_max"]}, o, d)
+        path = os.path.join(ROOT, "tests", "golden", f"rays_{name}.npz")
+        np.savez_compressed(path, **c, rays_o=o[mask].astype(np.float32), rays_d=d[mask].astype(np.float32),
+                            near=near.astype(np.float32), far=far.astype(np.float32), ray_mask=mask,
+                            rays_d_f64=d[mask], near_f64=near, far_f64=far)
+        print(path, "valid rays", int(mask.sum()), "of", mask.size)
+
+
+if __name__ == "__main__":
+    main()

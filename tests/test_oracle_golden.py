@@ -65,3 +65,24 @@ def test_voxel_bins_bit_exact(name):
     _, _, bins = O.lbs_warp(pts, fr.motion_scale_Rs, fr.motion_Ts, vol, fr.cnl_bbox_min_xyz, fr.cnl_bbox_scale_xyz,
                             exact=True, return_bins=True)
     assert np.array_equal(bins.numpy().astype(np.int16), g["bins"])
+
+
+@pytest.mark.parametrize("name", ["zju", "f64"])
+def test_rays_oracle_matches_reference(name):
+    """oracle/rays_oracle.py against get_rays_from_KRT + rays_intersect_3d_bbox of the reference (camera_util.py:133-212),
+    fixtures by oracle/make_golden_rays.py.  float64 intermediates are compared exactly: same numpy calls, same dtypes."""
+    import os
+    from oracle import rays_oracle as RO
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"rays_{name}.npz"))
+    H, W = int(g["H"]), int(g["W"])
+    o, d = RO.pixel_rays(H, W, g["K"], g["R"], g["T"])
+    o, d = np.ascontiguousarray(o.reshape(-1, 3)), np.ascontiguousarray(d.reshape(-1, 3))
+    near, far, mask = RO.box_near_far(g["bbox_min"], g["bbox_max"], o, d)
+    assert np.array_equal(mask, g["ray_mask"])                                   # integer decision: bit-exact
+    assert 0 < mask.sum() < mask.size
+    assert np.abs(d[mask] - g["rays_d_f64"]).max() <= 1e-15
+    assert np.abs(near - g["near_f64"]).max() <= 1e-14 and np.abs(far - g["far_f64"]).max() <= 1e-14
+    packed, mask2, pix = RO.frame_rays(H, W, g["K"], g["R"], g["T"], g["bbox_min"], g["bbox_max"])
+    assert packed.dtype == np.float32 and np.array_equal(mask2, mask) and np.array_equal(pix, np.nonzero(mask)[0])
+    assert np.array_equal(packed[:, 0:3], g["rays_o"]) and np.array_equal(packed[:, 3:6], g["rays_d"])
+    assert np.array_equal(packed[:, 6], g["near"]) and np.array_equal(packed[:, 7], g["far"])
