@@ -1,0 +1,82 @@
+"""CPU: the per-pixel arithmetic of csrc/rays.cu (struct RayCam .. ray_for_pixel), compiled for the HOST with g++ -- the
+round-to-nearest intrinsics mapped to un-contracted IEEE operations and fma() -- must reproduce the reference's fixtures
+(tests/golden/rays_*.npz, written by camera_util.py itself): ray_mask bit-exact and o, d, near, far bitwise identical.
+This checks the kernel's rounding sequence without a GPU; it is a test harness around the device function's text, not
+a CPU path of the product (nothing in occnerf_b200/ can reach it).
+"""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "oracle", "_build")
+
+PRELUDE = r"""
+#include <math.h>
+#include <stdint.h>
+#define __device__
+#define __forceinline__ inline
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+"""
+
+DRIVER = r"""
+extern "C" void emulate(const double *kinv, int k_f32, const double *R, const double *T, const double *lo, const double *hi,
+                        int H, int W, float *rays, uint8_t *mask) {
+    RayCam c;
+    for (int a = 0; a < 9; ++a) { c.kinv[a] = kinv[a]; c.R[a] = R[a]; }
+    for (int a = 0; a < 3; ++a) {
+        c.T[a] = T[a]; c.lo[a] = lo[a] + -0.01; c.hi[a] = hi[a] + 0.01;
+        double acc = R[a] * T[0]; acc = fma(R[3 + a], T[1], acc); acc = fma(R[6 + a], T[2], acc);
+        c.o[a] = -acc;
+    }
+    c.H = H; c.W = W; c.k_f32 = k_f32;
+    for (int p = 0; p < H * W; ++p) {
+        RayOut r = ray_for_pixel(c, p);
+        mask[p] = r.hit;
+        float *q = rays + 8 * (long)p;
+        for (int a = 0; a < 3; ++a) { q[a] = (float)c.o[a]; q[3 + a] = (float)r.d[a]; }
+        q[6] = r.near; q[7] = r.far;
+    }
+}
+"""
+
+
+def _build():
+    src = open(os.path.join(ROOT, "occnerf_b200", "csrc", "rays.cu")).read()
+    m = re.search(r"(struct RayCam \{.*?)\n// hits of this thread's pixel", src, flags=re.S)
+    assert m, "rays.cu no longer has the RayCam .. ray_for_pixel section this harness extracts"
+    body = m.group(1).replace("#pragma unroll", "")
+    os.makedirs(BUILD, exist_ok=True)
+    cpp, so = os.path.join(BUILD, "rays_host_emulation.cpp"), os.path.join(BUILD, "rays_host_emulation.so")
+    with open(cpp, "w") as f:
+        f.write(PRELUDE + body + DRIVER)
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", cpp, "-o", so], check=True)
+    return ctypes.CDLL(so)
+
+
+@pytest.mark.parametrize("name", ["zju", "f64"])
+def test_device_arithmetic_reproduces_the_reference(name):
+    lib = _build()
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"rays_{name}.npz"))
+    H, W, K = int(g["H"]), int(g["W"]), g["K"]
+    kinv = np.ascontiguousarray(np.linalg.inv(K).astype(np.float64))
+    R, T = np.ascontiguousarray(g["R"], np.float64), np.ascontiguousarray(g["T"], np.float64)
+    lo, hi = g["bbox_min"].astype(np.float64), g["bbox_max"].astype(np.float64)
+    rays = np.zeros((H * W, 8), np.float32)
+    mask = np.zeros(H * W, np.uint8)
+    dp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.emulate(dp(kinv), int(K.dtype == np.float32), dp(R), dp(T), dp(lo), dp(hi), H, W, dp(rays), dp(mask))
+    hit = mask.astype(bool)
+    assert np.array_equal(hit, g["ray_mask"])
+    assert np.array_equal(rays[hit, 0:3], g["rays_o"]) and np.array_equal(rays[hit, 3:6], g["rays_d"])
+    assert np.array_equal(rays[hit, 6], g["near"]) and np.array_equal(rays[hit, 7], g["far"])
