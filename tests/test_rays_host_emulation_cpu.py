@@ -80,3 +80,25 @@ def test_device_arithmetic_reproduces_the_reference(name):
     assert np.array_equal(hit, g["ray_mask"])
     assert np.array_equal(rays[hit, 0:3], g["rays_o"]) and np.array_equal(rays[hit, 3:6], g["rays_d"])
     assert np.array_equal(rays[hit, 6], g["near"]) and np.array_equal(rays[hit, 7], g["far"])
+
+
+@pytest.mark.parametrize("H,W,yaw,k_dtype", [(200, 300, 0.0, np.float32), (256, 256, 0.7, np.float64), (97, 131, 2.1, np.float32)])
+def test_device_arithmetic_against_oracle(H, W, yaw, k_dtype):
+    """Same harness against oracle/rays_oracle.py on the synthetic look-at camera (rotated views, non-square frames)."""
+    from occnerf_b200 import synthetic as S
+    from oracle import rays_oracle as RO
+    lib = _build()
+    K, R, T = S.lookat_camera(max(H, W), yaw=yaw)
+    K = K.astype(k_dtype)
+    K[0, 2], K[1, 2] = W / 2.0, H / 2.0
+    R, T = np.ascontiguousarray(R, np.float64), np.ascontiguousarray(T, np.float64)
+    bmin, bmax = np.array([-0.95, -1.35, -0.45], np.float32), np.array([0.95, 0.65, 0.45], np.float32)
+    want, wmask, _ = RO.frame_rays(H, W, K, R, T, bmin, bmax)
+    kinv = np.ascontiguousarray(np.linalg.inv(K).astype(np.float64))
+    lo, hi = bmin.astype(np.float64), bmax.astype(np.float64)
+    rays, mask = np.zeros((H * W, 8), np.float32), np.zeros(H * W, np.uint8)
+    dp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.emulate(dp(kinv), int(K.dtype == np.float32), dp(R), dp(T), dp(lo), dp(hi), H, W, dp(rays), dp(mask))
+    hit = mask.astype(bool)
+    assert 0.05 * H * W < hit.sum() < H * W
+    assert np.array_equal(hit, wmask) and np.array_equal(rays[hit], want)
