@@ -497,6 +497,7 @@ def generate_rays(H, W, K, R, T, bbox_min, bbox_max, device="cuda", capacity=Non
     Returns (rays [n,8] float32 = (o, d, near, far) of the valid rays in pixel order -- the `ray_batch` layout of
     Network._render_rays --, ray_mask [H*W] bool, count, pixel_index [n] int32 or None).  With sync=False nothing is read
     back: rays has `capacity` rows (default H*W), of which the first count[0] (a device tensor) are valid.
+    capacity=0 only fills ray_mask and the count; a capacity > 0 that is too small raises.
     """
     K = np.asarray(K)
     if K.dtype not in (np.float32, np.float64):
@@ -523,6 +524,8 @@ def generate_rays(H, W, K, R, T, bbox_min, bbox_max, device="cuda", capacity=Non
     if not sync:
         return rays, mask.view(torch.bool), count, pix
     n = int(count.item())
+    if cap == 0:                                   # mask / count query: nothing was asked to fit
+        return rays, mask.view(torch.bool), n, pix
     if n > cap:
         raise RuntimeError(f"generate_rays: {n} valid rays do not fit the capacity of {cap}")
     return rays[:n], mask.view(torch.bool), n, (pix[:n] if pix is not None else None)
