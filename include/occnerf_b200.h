@@ -19,6 +19,7 @@
  *   core/nets/occnerf/network.py:502-517 (visibility counter)                 -> occnerf_visibility_hits
  *   core/utils/camera_util.py:133-160,163-212 (get_rays_from_KRT, rays_intersect_3d_bbox) + the masking at
  *       core/data/occnerf/freeview.py:208-219, train.py:440-461                 -> occnerf_generate_rays
+ *   run.py:39-66 (unpack_alpha_map, unpack_to_image) + core/utils/image_util.py:19-20 (to_8b_image) -> occnerf_unpack_image
  */
 #ifndef OCCNERF_B200_H
 #define OCCNERF_B200_H
@@ -283,6 +284,17 @@ int occnerf_generate_rays(const double *kinv_host, int k_is_f32, const double *R
                           const double *bbox_min_host, const double *bbox_max_host, int H, int W, int capacity,
                           float *rays, uint8_t *mask, int *pixel_index, int *count, void *scratch,
                           occnerf_stream_t stream);
+
+/* ---- image assembly behind the path: run.py:39-66 + image_util.py:19-20 ---------------------------------------
+ * rgb [n,3], alpha [n] or NULL: outputs of the n rays whose flat pixels are pixel_index [n] (int32, from
+ * occnerf_generate_rays; a rank of a sharded render passes its own range).  bgcolor_host [3]: HOST floats in [0,1]
+ * (run.py:118 passes cfg.bgcolor / 255).  fill != 0 first paints the whole frame with the background (alpha 0), as
+ * np.full / np.zeros do in the reference; fill = 0 only scatters (further shards into the same frame).
+ * Outputs: rgb8 [H*W,3] uint8 = to_8b_image of the assembled frame, alpha8 [H*W] uint8 or NULL (one channel; the
+ * reference stacks it three times for display).  bad [1] int32 (caller-zeroed) counts pixel indices outside the frame. */
+int occnerf_unpack_image(const float *rgb, const float *alpha, const int *pixel_index, int n, int H, int W,
+                         const float *bgcolor_host, int fill, uint8_t *rgb8, uint8_t *alpha8, int *bad,
+                         occnerf_stream_t stream);
 
 #ifdef __cplusplus
 }

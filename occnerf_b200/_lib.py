@@ -54,6 +54,7 @@ _SIGNATURES = {
     "occnerf_composite_backward": [_vp] * 9 + [_i, _i] + [_vp] * 3,
     "occnerf_visibility_hits": [_vp, _vp, _vp, _i, _i, _f, _vp, _i, _i, _vp, _vp, _vp],
     "occnerf_generate_rays": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "occnerf_unpack_image": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
 }
 EXPORTED = sorted(list(_SIGNATURES) + ["occnerf_last_error", "occnerf_abi_version", "occnerf_mlp_packed_bytes",
                                            "occnerf_rays_scratch_bytes"])
@@ -107,7 +108,7 @@ def ptr(t, dtype=None):
 
 
 # kernels launched per C call (for the bench's `gpu_launches` claim); entries not listed launch exactly one
-KERNELS_PER_CALL = {"occnerf_visibility_hits": 3, "occnerf_generate_rays": 3}
+KERNELS_PER_CALL = {"occnerf_visibility_hits": 3, "occnerf_generate_rays": 3, "occnerf_unpack_image": 2}
 COUNTERS = {"calls": 0, "launches": 0}
 PROFILE = None   # set to {} to record (start_event, end_event, work) per C call on the current stream
 

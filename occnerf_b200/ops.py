@@ -529,3 +529,30 @@ def generate_rays(H, W, K, R, T, bbox_min, bbox_max, device="cuda", capacity=Non
     if n > cap:
         raise RuntimeError(f"generate_rays: {n} valid rays do not fit the capacity of {cap}")
     return rays[:n], mask.view(torch.bool), n, (pix[:n] if pix is not None else None)
+
+
+# ----------------------------------------------------------------------------- image assembly behind the path
+def unpack_image(rgb, alpha, pixel_index, H, W, bgcolor, out=None, fill=True):
+    """run.py:39-66 (unpack_to_image / unpack_alpha_map) + image_util.py:19-20 (to_8b_image) on the device.
+
+    rgb [n,3], alpha [n] or None, pixel_index [n] int32 (from generate_rays); bgcolor: three HOST numbers in [0,1]
+    (run.py:118 passes cfg.bgcolor / 255).  Returns (rgb8 [H,W,3] uint8, alpha8 [H,W] uint8).  `out=(rgb8, alpha8)` with
+    fill=False scatters a further shard of rays into an already painted frame."""
+    n = int(rgb.shape[0])
+    dev = rgb.device
+    if out is None:
+        if not fill:
+            raise RuntimeError("unpack_image: fill=False needs the frame to scatter into (out=...)")
+        rgb8 = torch.empty(H, W, 3, device=dev, dtype=u8)
+        alpha8 = torch.empty(H, W, device=dev, dtype=u8)
+    else:
+        rgb8, alpha8 = out
+        if tuple(rgb8.shape) != (H, W, 3) or (alpha8 is not None and tuple(alpha8.shape) != (H, W)):
+            raise RuntimeError(f"unpack_image: out has shapes {tuple(rgb8.shape)} / {None if alpha8 is None else tuple(alpha8.shape)}, "
+                               f"expected ({H}, {W}, 3) / ({H}, {W})")
+    bg = np.ascontiguousarray(np.asarray(bgcolor, dtype=np.float64).reshape(3).astype(np.float32))   # np.full(..., dtype='float32')
+    bad = torch.zeros(1, device=dev, dtype=i32)
+    call("occnerf_unpack_image", ptr(rgb, f32) if n else None, ptr(alpha, f32) if (n and alpha is not None) else None,
+         ptr(pixel_index, i32) if n else None, n, int(H), int(W), bg.ctypes.data_as(C.c_void_p), 1 if fill else 0,
+         ptr(rgb8, u8), ptr(alpha8, u8), ptr(bad, i32), stream())
+    return rgb8, alpha8, bad

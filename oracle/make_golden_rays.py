@@ -49,7 +49,39 @@ def cameras():
     return out
 
 
+def _unpack_to_image():
+    """run.py cannot be imported (it pulls the config system and the whole model); its two image functions are taken as
+    they are written -- the function source text is exec'd unmodified -- over the real core/utils/image_util.py."""
+    import ast
+    sys.modules.setdefault("termcolor", types.SimpleNamespace(colored=lambda s, *a, **k: s))
+    spec = importlib.util.spec_from_file_location("_ref_image_util", os.path.join(REF, "core", "utils", "image_util.py"))
+    iu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(iu)
+    src = open(os.path.join(REF, "run.py")).read()
+    ns = {"np": np, "to_8b_image": iu.to_8b_image, "to_8b3ch_image": iu.to_8b3ch_image}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("unpack_alpha_map", "unpack_to_image"):
+            exec(compile(ast.Module([node], []), "run.py", "exec"), ns)
+    return ns["unpack_to_image"]
+
+
+def image_case():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "rays_zju.npz"))
+    rng = np.random.default_rng(7)
+    mask = g["ray_mask"]
+    n = int(mask.sum())
+    rgb = rng.uniform(-0.2, 1.2, (n, 3)).astype(np.float32)
+    rgb[:16] = np.linspace(0.0, 1.0, 48, dtype=np.float32).reshape(16, 3)          # exact grid values incl. 0 and 1
+    alpha = rng.uniform(-0.1, 1.1, n).astype(np.float32)
+    return dict(H=int(g["H"]), W=int(g["W"]), ray_mask=mask, rgb=rgb, alpha=alpha, bgcolor=np.array([255.0, 128.0, 7.0]))
+
+
 def main():
+    c = image_case()
+    rgb_img, alpha_img, _ = _unpack_to_image()(c["W"], c["H"], c["ray_mask"], c["bgcolor"] / 255., c["rgb"], c["alpha"])
+    path = os.path.join(ROOT, "tests", "golden", "image_unpack.npz")
+    np.savez_compressed(path, **c, rgb_image=rgb_img, alpha_image=alpha_img)
+    print(path, rgb_img.shape, rgb_img.dtype, alpha_img.shape)
     cu = _camera_util()
     for name, c in cameras().items():
         o, d = cu.get_rays_from_KRT(c["H"], c["W"], c["K"], c["R"], c["T"])

@@ -86,3 +86,15 @@ def test_rays_oracle_matches_reference(name):
     assert packed.dtype == np.float32 and np.array_equal(mask2, mask) and np.array_equal(pix, np.nonzero(mask)[0])
     assert np.array_equal(packed[:, 0:3], g["rays_o"]) and np.array_equal(packed[:, 3:6], g["rays_d"])
     assert np.array_equal(packed[:, 6], g["near"]) and np.array_equal(packed[:, 7], g["far"])
+
+
+def test_image_oracle_matches_reference():
+    """oracle/image_oracle.py against run.py:39-66 unpack_to_image (+ image_util.to_8b_image), fixture by
+    oracle/make_golden_rays.py: 8-bit frames are integer work -> bit-exact."""
+    import os
+    from oracle import image_oracle as IO
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "image_unpack.npz"))
+    rgb8, alpha8 = IO.unpack(int(g["W"]), int(g["H"]), g["ray_mask"], g["bgcolor"] / 255., g["rgb"], g["alpha"])
+    assert np.array_equal(rgb8, g["rgb_image"])
+    assert np.array_equal(alpha8, g["alpha_image"][..., 0]) and np.array_equal(alpha8, g["alpha_image"][..., 2])
+    assert 0 in rgb8 and 255 in rgb8
