@@ -38,7 +38,8 @@ def warp_forward(rays, t_rand, Rs, Ts, vol, bbox_min, bbox_scale, S, want_bins=F
     mask = torch.empty(N, S, device=dev, dtype=f32)
     bins = torch.empty(N, S, nb, 3, device=dev, dtype=i32) if want_bins else None
     vd, vh, vw = vol.shape[-3:]
-    assert vol.shape[0] >= nb
+    if vol.shape[0] < nb:
+        raise RuntimeError(f"warp_forward: the weight volume has {vol.shape[0]} channels for {nb} bones")
     call("occnerf_warp_forward", ptr(rays, f32), ptr(t_lin(S, dev), f32), ptr(t_rand, f32), ptr(Rs, f32), ptr(Ts, f32),
          ptr(vol, f32), ptr(bbox_min, f32), ptr(bbox_scale, f32), N, S, nb, vd, vh, vw, ptr(z), ptr(x_skel), ptr(mask),
          ptr(bins), stream())
@@ -225,7 +226,8 @@ def build_knn_grid(base: torch.Tensor, fps, cell: float = 0.025, pad: float = 0.
             cell_tab[c0:c0 + chunk, lev, 1] = cnt.to(i32)
             total += int(cnt.sum())
             del d, ds, order, keep
-    assert total < 2 ** 31
+    if total >= 2 ** 31:
+        raise RuntimeError(f"build_knn_grid: {total} candidate entries overflow the int32 offsets; use a coarser cell")
     grid = dict(
         p=[to_float4(P).contiguous() for P in levels], n=tuple(int(P.shape[0]) for P in levels),
         gid=[f.to(i32).contiguous() for f in fps], cell_tab=cell_tab.contiguous(), lists=torch.cat(lists).contiguous(),
@@ -258,7 +260,8 @@ def sample_geometry(xyz, knn_idx, point_base, point_norms, bound, raw=None):
         dist = torch.empty(m, device=xyz.device, dtype=f32)
         dptr, dstride = ptr(dist), 1
     else:
-        assert raw.shape == (m, 5) and raw.is_contiguous()
+        if tuple(raw.shape) != (m, 5) or not raw.is_contiguous():
+            raise RuntimeError(f"sample_geometry: raw must be a contiguous ({m}, 5) tensor, got {tuple(raw.shape)}")
         dist = raw[:, 4]
         dptr, dstride = raw.data_ptr() + 16, 5
     call("occnerf_sample_geometry", ptr(xyz, f32), ptr(knn_idx, i32), stride_knn, ptr(point_base, f32),
@@ -442,7 +445,8 @@ def nonrigid_pack(nr_w, nr_b, cond, n_pass):
 def nonrigid_forward_tc(xyz, window, packed, n_pass, out=None):
     """xyz (m,3) -> xyz + non-rigid offsets, through the fused tcgen05 chain (csrc/mlp_tc.cu, chain 2)."""
     m = xyz.shape[0]
-    assert len(window) == 6, "the fused non-rigid chain is built for 6 frequency bands (cfg.non_rigid_motion_mlp.multires)"
+    if len(window) != 6:
+        raise RuntimeError("the fused non-rigid chain is built for 6 frequency bands (cfg.non_rigid_motion_mlp.multires)")
     if out is None:
         out = torch.empty(m, 3, device=xyz.device, dtype=f32)
     w = (C.c_float * 6)(*window)
