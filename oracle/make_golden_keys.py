@@ -1,0 +1,33 @@
+"""ORACLE tooling: write tests/golden/state_dict_keys.json = name -> [shape, dtype] of the UNMODIFIED reference
+Network's state_dict (core/nets/occnerf/network.py:29-88 + the per-subject parameters of generate_neural_points,
+network.py:90-146), built on CPU through oracle/ref_shim.py.  This is what a reference checkpoint
+(trainer.py:398-415, `{'network': state_dict}`) contains, so it pins the drop-in claim "reference checkpoints load".
+
+    python -m oracle.make_golden_keys
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import warnings
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from occnerf_b200 import synthetic as S  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "state_dict_keys.json")
+
+
+def main():
+    warnings.filterwarnings("ignore", category=FutureWarning)
+    sub = S.make_subject(seed=0)
+    net = ref_shim.build_reference_network(sub, S.make_weights(sub.bound, seed=0))
+    keys = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in net.state_dict().items()}
+    with open(PATH, "w") as f:
+        json.dump(keys, f, indent=1, sort_keys=True)
+    print(PATH, len(keys), "entries,", sum(int(__import__("math").prod(s)) for s, _ in keys.values()), "elements")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,43 @@
+"""CPU: the drop-in claim "reference checkpoints load" (trainer.py:398-415 saves {'network': state_dict}).
+tests/golden/state_dict_keys.json lists name -> shape, dtype of the UNMODIFIED reference Network's state_dict
+(oracle/make_golden_keys.py); occnerf_b200.network.Network must expose exactly that set, and a strict load of a
+checkpoint with those entries must succeed and land in the tensors the kernels read."""
+import json
+import os
+
+import torch
+
+from occnerf_b200 import synthetic as S
+from occnerf_b200.network import RenderConfig
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "state_dict_keys.json")
+
+
+def _net():
+    sub = S.make_subject(seed=0)
+    net = S.network_from_synthetic(sub, S.make_weights(sub.bound, seed=0), RenderConfig(), device="cpu")
+    net.install_prologue()
+    return net
+
+
+def test_state_dict_matches_the_reference_checkpoint_layout():
+    want = json.load(open(GOLDEN))
+    got = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in _net().state_dict().items()}
+    assert sorted(got) == sorted(want), (sorted(set(want) - set(got)), sorted(set(got) - set(want)))
+    assert got == want
+    assert any(k.startswith("cnl_mlp.module.") for k in want)          # the nn.DataParallel level of the reference's keys
+
+
+def test_strict_load_of_a_reference_shaped_checkpoint():
+    want = json.load(open(GOLDEN))
+    gen = torch.Generator().manual_seed(0)
+    ckpt = {}
+    for k, (shape, dtype) in want.items():
+        dt = getattr(torch, dtype)
+        ckpt[k] = torch.rand(shape, generator=gen).to(dt) if dt.is_floating_point else torch.zeros(shape, dtype=dt)
+    net = _net()
+    res = net.load_state_dict(ckpt, strict=True)                        # run.py:34
+    assert not res.missing_keys and not res.unexpected_keys
+    m = net.cnl_mlp.module
+    assert torch.equal(m.encoder.embeddings, ckpt["cnl_mlp.module.encoder.embeddings"])
+    assert torch.equal(net.point_dist, ckpt["point_dist"]) and torch.equal(net.point_base, ckpt["point_base"])
