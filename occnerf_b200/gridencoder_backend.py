@@ -45,6 +45,6 @@ def grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, 
                   ptr(grad_inputs, f32), int(B), int(D), int(C), int(L), _lib.stream())
 
 
-def grad_total_variation(*_args, **_kwargs):
+def grad_total_variation(inputs, embeddings, grad, offsets, weight, B, D, C, L, S, H, gridtype, align_corners):
     raise RuntimeError("grad_total_variation is never called on OccNeRF's path (GridEncoder.grad_total_variation has no "
                        "caller, SURVEY.md section 2.2) and is not built")

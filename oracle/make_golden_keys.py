@@ -19,8 +19,28 @@ from oracle import ref_shim  # noqa: E402
 PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "state_dict_keys.json")
 
 
+SIG_PATH = os.path.join(os.path.dirname(PATH), "gridencoder_signatures.json")
+
+
+def operator_signatures():
+    """Parameter names, in order, of the three functions the reference's pybind module exports
+    (gridencoder/src/gridencoder.h:12-15, bound by name in src/bindings.cpp:5-9), parsed from the header itself."""
+    import re
+    hdr = open(os.path.join(ref_shim.REF_ROOT, "core", "nets", "occnerf", "gridencoder", "src", "gridencoder.h")).read()
+    bind = open(os.path.join(ref_shim.REF_ROOT, "core", "nets", "occnerf", "gridencoder", "src", "bindings.cpp")).read()
+    out = {}
+    for name, args in re.findall(r"void\s+(\w+)\s*\(([^;]*)\)\s*;", hdr):
+        assert f'"{name}"' in bind, f"{name} is declared but not bound"
+        out[name] = [a.strip().split()[-1] for a in args.split(",")]
+    return out
+
+
 def main():
     warnings.filterwarnings("ignore", category=FutureWarning)
+    sigs = operator_signatures()
+    with open(SIG_PATH, "w") as f:
+        json.dump(sigs, f, indent=1, sort_keys=True)
+    print(SIG_PATH, {k: len(v) for k, v in sigs.items()})
     sub = S.make_subject(seed=0)
     net = ref_shim.build_reference_network(sub, S.make_weights(sub.bound, seed=0))
     keys = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in net.state_dict().items()}
