@@ -377,6 +377,12 @@ class Network(nn.Module):
         self._cache = None
         return self
 
+    def deploy_mlps_to_secondary_gpus(self):
+        """network.py:149-154: the reference moves the two MLPs to `cfg.secondary_gpus[0]` for nn.DataParallel.  Here every
+        process owns one GPU and the whole model lives on it, so there is nothing to move; the method stays because every
+        reference caller chains it (`model.cuda().deploy_mlps_to_secondary_gpus()`: run.py:37, eval.py:52, trainer.py:52)."""
+        return self
+
     @property
     def point_cloud(self):
         return self.point_base + self.point_dist

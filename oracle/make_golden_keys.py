@@ -35,8 +35,30 @@ def operator_signatures():
     return out
 
 
+API_PATH = os.path.join(os.path.dirname(PATH), "network_signatures.json")
+API_METHODS = ("forward", "_render_rays", "_query_mlp", "_batchify_rays", "deploy_mlps_to_secondary_gpus")
+
+
+def network_api():
+    """Positional parameter names (and the **kwargs name) of the Network methods that stay as the API surface
+    (network.py:542-549, 435-447, 164-170, 307, 149), read from the reference source with ast."""
+    import ast
+    src = open(os.path.join(ref_shim.REF_ROOT, "core", "nets", "occnerf", "network.py")).read()
+    out = {}
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.ClassDef) and node.name == "Network":
+            for f in node.body:
+                if isinstance(f, ast.FunctionDef) and f.name in API_METHODS:
+                    out[f.name] = {"args": [a.arg for a in f.args.args], "kwargs": f.args.kwarg.arg if f.args.kwarg else None}
+    assert sorted(out) == sorted(API_METHODS)
+    return out
+
+
 def main():
     warnings.filterwarnings("ignore", category=FutureWarning)
+    with open(API_PATH, "w") as f:
+        json.dump(network_api(), f, indent=1, sort_keys=True)
+    print(API_PATH)
     sigs = operator_signatures()
     with open(SIG_PATH, "w") as f:
         json.dump(sigs, f, indent=1, sort_keys=True)

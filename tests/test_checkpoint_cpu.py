@@ -41,3 +41,21 @@ def test_strict_load_of_a_reference_shaped_checkpoint():
     m = net.cnl_mlp.module
     assert torch.equal(m.encoder.embeddings, ckpt["cnl_mlp.module.encoder.embeddings"])
     assert torch.equal(net.point_dist, ckpt["point_dist"]) and torch.equal(net.point_base, ckpt["point_base"])
+
+
+def test_network_api_surface_matches_the_reference():
+    """Network.forward / _render_rays / _query_mlp / _batchify_rays take the reference's parameters, same names,
+    same order (tests/golden/network_signatures.json, read from the reference's network.py by oracle/make_golden_keys.py);
+    anything added after them is optional, and a reference method that swallows **kwargs still does."""
+    import inspect
+    from occnerf_b200.network import Network
+    want = json.load(open(os.path.join(os.path.dirname(GOLDEN), "network_signatures.json")))
+    for name, ref in want.items():
+        params = list(inspect.signature(getattr(Network, name)).parameters.values())
+        names = [p.name for p in params if p.kind == p.POSITIONAL_OR_KEYWORD]
+        assert names[:len(ref["args"])] == ref["args"], (name, names, ref["args"])
+        extras = [p for p in params if p.kind == p.POSITIONAL_OR_KEYWORD][len(ref["args"]):]
+        assert all(p.default is not inspect.Parameter.empty for p in extras), (name, [p.name for p in extras])
+        assert (ref["kwargs"] is not None) == any(p.kind == p.VAR_KEYWORD for p in params), name
+    net = _net()
+    assert net.deploy_mlps_to_secondary_gpus() is net                    # run.py:37 chains it
