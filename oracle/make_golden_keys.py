@@ -66,6 +66,12 @@ def main():
     sub = S.make_subject(seed=0)
     net = ref_shim.build_reference_network(sub, S.make_weights(sub.bound, seed=0))
     keys = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in net.state_dict().items()}
+    enc = net.cnl_mlp.module.encoder                      # GridEncoder.__init__, grid.py:97-141: the level table
+    grid = {"offsets": [int(o) for o in enc.offsets.tolist()], "per_level_scale": float(enc.per_level_scale),
+            "base_resolution": int(enc.base_resolution), "num_levels": int(enc.num_levels), "level_dim": int(enc.level_dim),
+            "input_dim": int(enc.input_dim), "n_params": int(enc.n_params), "bound": float(sub.bound)}
+    with open(os.path.join(os.path.dirname(PATH), "hashgrid_levels.json"), "w") as f:
+        json.dump(grid, f, indent=1, sort_keys=True)
     with open(PATH, "w") as f:
         json.dump(keys, f, indent=1, sort_keys=True)
     print(PATH, len(keys), "entries,", sum(int(__import__("math").prod(s)) for s, _ in keys.values()), "elements")

@@ -59,3 +59,18 @@ def test_network_api_surface_matches_the_reference():
         assert (ref["kwargs"] is not None) == any(p.kind == p.VAR_KEYWORD for p in params), name
     net = _net()
     assert net.deploy_mlps_to_secondary_gpus() is net                    # run.py:37 chains it
+
+
+def test_hashgrid_level_table_matches_the_reference():
+    """The level table of the reference's GridEncoder (grid.py:102-135; values in tests/golden/hashgrid_levels.json, read from
+    the reference module itself): offsets are integer work -> identical, and so is per_level_scale (it enters exp2f)."""
+    want = json.load(open(os.path.join(os.path.dirname(GOLDEN), "hashgrid_levels.json")))
+    sub = S.make_subject(seed=0)
+    assert abs(sub.bound - want["bound"]) < 1e-7
+    offs, pls = S.hashgrid_offsets(desired_resolution=2048 * sub.bound)
+    assert offs.tolist() == want["offsets"] and pls == want["per_level_scale"]
+    enc = _net().cnl_mlp.module.encoder
+    assert enc.offsets.tolist() == want["offsets"] and enc.offsets.dtype == torch.int32
+    assert tuple(enc.embeddings.shape) == (want["offsets"][-1], want["level_dim"])
+    assert 2 * want["offsets"][-1] == want["n_params"]
+    assert float(enc.per_level_scale) == want["per_level_scale"]
