@@ -271,14 +271,17 @@ int occnerf_visibility_hits(const float *depth, const int64_t *term, const float
 
 /* ---- rays in front of the path: camera_util.py:133-160 + :163-212 + freeview.py:208-219 ----------------------
  * All camera / box arguments are HOST pointers to float64 (they ride in the kernel arguments; there is no H2D copy):
- * kinv_host [9] = inv(K) row major as numpy computed it in K's own dtype; k_is_f32 != 0 when K was float32 (the ZJU
- * pickles), in which case `pixel_camera` is evaluated in float32 like numpy does; R_host [9], T_host [3] extrinsics;
+ * kinv_host [9] = inv(K) row major as numpy computed it in K's own dtype; k_is_f32 = OCCNERF_RAYS_K_F32 when K was
+ * float32 (the ZJU pickles), in which case `pixel_camera` is evaluated in float32 like numpy does, OCCNERF_RAYS_ALL_F32
+ * when K, R and T all were float32 (tpose.py:66-84: origin, directions and |d| stay float32), else OCCNERF_RAYS_F64;
+ * R_host [9], T_host [3] extrinsics;
  * bbox_min/max_host [3] (the 1 cm margin of camera_util.py:180 is added inside).
  * Outputs (device): mask [H*W] uint8 = `ray_mask`; count [1] = number of valid rays; rays [capacity, 8] =
  * (o3, d3, near, far) float32 of the valid rays in pixel order (what `rays_o[ray_mask]` etc. produce; d carries the
  * in-place 1e-5 clamp of camera_util.py:183); pixel_index [capacity] int32 = flat pixel of each ray, or NULL.
  * Rays beyond `capacity` are dropped (compare count with capacity); capacity = 0 only fills mask and count.
  * scratch: occnerf_rays_scratch_bytes(H, W) bytes. */
+enum { OCCNERF_RAYS_F64 = 0, OCCNERF_RAYS_K_F32 = 1, OCCNERF_RAYS_ALL_F32 = 2 };
 long occnerf_rays_scratch_bytes(int H, int W);
 int occnerf_generate_rays(const double *kinv_host, int k_is_f32, const double *R_host, const double *T_host,
                           const double *bbox_min_host, const double *bbox_max_host, int H, int W, int capacity,

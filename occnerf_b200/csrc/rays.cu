@@ -4,7 +4,8 @@
 // Follows core/utils/camera_util.py:133-160 (get_rays_from_KRT) and :163-212 (rays_intersect_3d_bbox) and the
 // masking that every dataset applies right after them (freeview.py:208-219, train.py:440-461):
 //   pixel_camera = [i, j, 1] . inv(K)^T           (float32 when K is float32 -- ZJU pickles -- else float64)
-//   rays_d       = (pixel_camera - T) . R - rays_o,   rays_o = -R^T T                    (float64)
+//   rays_d       = (pixel_camera - T) . R - rays_o,   rays_o = -R^T T     (float64; float32 when K, R and T all are --
+//                                                       tpose.py:66-84 --, then |d| is a float32 norm too)
 //   rays_d[|rays_d| < 1e-5] = 1e-5                    (in place: the rays handed to the network carry it)
 //   six plane hits of the box grown by 1 cm, kept when inside the box (+-1e-6); a ray is valid when exactly two are
 //   near/far = min/max of |p - o| / |d|,   cast to float32 together with o, d
@@ -23,7 +24,7 @@ struct RayCam {
     double T[3];
     double o[3];      // -R^T T
     double lo[3], hi[3];   // box grown by 1 cm
-    int H, W, k_f32;
+    int H, W, k_f32, all_f32;
 };
 
 struct RayOut {
@@ -58,13 +59,28 @@ __device__ __forceinline__ RayOut ray_for_pixel(const RayCam &c, int pix) {
         for (int a = 0; a < 3; ++a)
             cam[a] = dot3_chain((double)i, (double)j, 1.0, c.kinv[3 * a], c.kinv[3 * a + 1], c.kinv[3 * a + 2]);
     }
-    const double q0 = __dsub_rn(cam[0], c.T[0]), q1 = __dsub_rn(cam[1], c.T[1]), q2 = __dsub_rn(cam[2], c.T[2]);
+    if (c.all_f32) {
+        // every operand is float32 (numpy keeps float32 throughout get_rays_from_KRT); the clamp compares and assigns float32(1e-5)
+        const float q0 = __fsub_rn((float)cam[0], (float)c.T[0]), q1 = __fsub_rn((float)cam[1], (float)c.T[1]),
+                    q2 = __fsub_rn((float)cam[2], (float)c.T[2]);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        double w = dot3_chain(q0, q1, q2, c.R[a], c.R[3 + a], c.R[6 + a]);
-        double d = __dsub_rn(w, c.o[a]);
-        if (fabs(d) < 1e-5) d = 1e-5;
-        r.d[a] = d;
+        for (int a = 0; a < 3; ++a) {
+            // numpy hands this [H*W,3] x [3,3] product to sgemm; OpenBLAS' kernel (the build behind the fixtures) unrolls k by
+            // two -- fma(q0 r0, q1 r1) -- and adds the odd k = 2 product afterwards.  Any other BLAS differs by <= 1 float32 ulp.
+            float w = __fadd_rn(__fmaf_rn(q0, (float)c.R[a], __fmul_rn(q1, (float)c.R[3 + a])), __fmul_rn(q2, (float)c.R[6 + a]));
+            float d = __fsub_rn(w, (float)c.o[a]);
+            if (fabsf(d) < 1e-5f) d = 1e-5f;
+            r.d[a] = (double)d;
+        }
+    } else {
+        const double q0 = __dsub_rn(cam[0], c.T[0]), q1 = __dsub_rn(cam[1], c.T[1]), q2 = __dsub_rn(cam[2], c.T[2]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double w = dot3_chain(q0, q1, q2, c.R[a], c.R[3 + a], c.R[6 + a]);
+            double d = __dsub_rn(w, c.o[a]);
+            if (fabs(d) < 1e-5) d = 1e-5;
+            r.d[a] = d;
+        }
     }
     // six plane hits in the reference's order: (min x, min y, min z, max x, max y, max z)
     const double eps = 1e-6;
@@ -91,7 +107,13 @@ __device__ __forceinline__ RayOut ray_for_pixel(const RayCam &c, int pix) {
         }
     }
     r.hit = n_in == 2;
-    const double nd = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(r.d[0], r.d[0]), __dmul_rn(r.d[1], r.d[1])), __dmul_rn(r.d[2], r.d[2])));
+    double nd;
+    if (c.all_f32) {                                   // np.linalg.norm of a float32 array stays float32
+        const float x = (float)r.d[0], y = (float)r.d[1], z = (float)r.d[2];
+        nd = (double)__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    } else {
+        nd = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(r.d[0], r.d[0]), __dmul_rn(r.d[1], r.d[1])), __dmul_rn(r.d[2], r.d[2])));
+    }
     const double d0 = __ddiv_rn(dist[0], nd), d1 = __ddiv_rn(dist[1], nd);
     r.near = (float)fmin(d0, d1);
     r.far = (float)fmax(d0, d1);
@@ -196,6 +218,7 @@ extern "C" int occnerf_generate_rays(const double *kinv_host, int k_is_f32, cons
                                      float *rays, uint8_t *mask, int *pixel_index, int *count, void *scratch,
                                      occnerf_stream_t stream) {
     OCC_CHECK_ARG(kinv_host && R_host && T_host && bbox_min_host && bbox_max_host, "occnerf_generate_rays: NULL camera / box");
+    OCC_CHECK_ARG(k_is_f32 >= 0 && k_is_f32 <= OCCNERF_RAYS_ALL_F32, "occnerf_generate_rays: camera dtype mode %d", k_is_f32);
     OCC_CHECK_ARG(H > 0 && W > 0 && (long)H * W < (1L << 31), "occnerf_generate_rays: H=%d W=%d out of range", H, W);
     OCC_CHECK_ARG(capacity >= 0 && (capacity == 0 || rays), "occnerf_generate_rays: rays is NULL with capacity %d", capacity);
     OCC_CHECK_ARG(mask && count && scratch, "occnerf_generate_rays: NULL mask / count / scratch");
@@ -212,15 +235,24 @@ extern "C" int occnerf_generate_rays(const double *kinv_host, int k_is_f32, cons
         c.hi[a] = bbox_max_host[a] + 0.01;
     }
     // rays_o = -np.dot(R.T, T): o[a] = -sum_k R[k][a] T[k]  (same k = 0,1,2 chain as on the device)
+    const bool all_f32 = k_is_f32 == OCCNERF_RAYS_ALL_F32;
     for (int a = 0; a < 3; ++a) {
-        double acc = R_host[a] * T_host[0];
-        acc = __builtin_fma(R_host[3 + a], T_host[1], acc);
-        acc = __builtin_fma(R_host[6 + a], T_host[2], acc);
-        c.o[a] = -acc;
+        if (all_f32) {
+            float acc = (float)R_host[a] * (float)T_host[0];
+            acc = __builtin_fmaf((float)R_host[3 + a], (float)T_host[1], acc);
+            acc = __builtin_fmaf((float)R_host[6 + a], (float)T_host[2], acc);
+            c.o[a] = (double)-acc;
+        } else {
+            double acc = R_host[a] * T_host[0];
+            acc = __builtin_fma(R_host[3 + a], T_host[1], acc);
+            acc = __builtin_fma(R_host[6 + a], T_host[2], acc);
+            c.o[a] = -acc;
+        }
     }
     c.H = H;
     c.W = W;
     c.k_f32 = k_is_f32 ? 1 : 0;
+    c.all_f32 = all_f32 ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned nb = occ_div_up((long)H * W, RAYS_BLOCK);
     int *block_count = (int *)scratch;

@@ -496,8 +496,8 @@ def generate_rays(H, W, K, R, T, bbox_min, bbox_max, device="cuda", capacity=Non
     """camera_util.py:133-160 + :163-212 + the dataset masking (freeview.py:208-219) on the device.
 
     K [3,3], R [3,3], T [3], bbox_min/max [3] are HOST arrays (numpy or CPU tensors) in the dtypes the reference's
-    dataset holds them in; a float32 K makes `pixel_camera` float32 exactly as numpy would (the ZJU pickles), everything
-    else is evaluated in float64.  Only these ~30 numbers cross to the device -- as kernel arguments.
+    dataset holds them in; a float32 K makes `pixel_camera` float32 exactly as numpy would (the ZJU pickles), all-float32
+    K, R, T (tpose.py:66-84) keep origin, directions and |d| in float32 as numpy does, everything else is float64.  Only these ~30 numbers cross to the device -- as kernel arguments.
     Returns (rays [n,8] float32 = (o, d, near, far) of the valid rays in pixel order -- the `ray_batch` layout of
     Network._render_rays --, ray_mask [H*W] bool, count, pixel_index [n] int32 or None).  With sync=False nothing is read
     back: rays has `capacity` rows (default H*W), of which the first count[0] (a device tensor) are valid.
@@ -507,6 +507,8 @@ def generate_rays(H, W, K, R, T, bbox_min, bbox_max, device="cuda", capacity=Non
     if K.dtype not in (np.float32, np.float64):
         raise RuntimeError(f"generate_rays: K must be float32 or float64 like the reference's cameras, got {K.dtype}")
     kinv = np.ascontiguousarray(np.linalg.inv(K).astype(np.float64))       # inverse in K's own dtype (camera_util.py:154)
+    all_f32 = K.dtype == np.float32 and np.asarray(R).dtype == np.float32 and np.asarray(T).dtype == np.float32
+    mode = 2 if all_f32 else (1 if K.dtype == np.float32 else 0)           # OCCNERF_RAYS_ALL_F32 / _K_F32 / _F64
     Rm = np.ascontiguousarray(np.asarray(R, dtype=np.float64).reshape(3, 3))
     Tv = np.ascontiguousarray(np.asarray(T, dtype=np.float64).reshape(3))
     lo = np.ascontiguousarray(np.asarray(bbox_min, dtype=np.float64).reshape(3))
@@ -523,7 +525,7 @@ def generate_rays(H, W, K, R, T, bbox_min, bbox_max, device="cuda", capacity=Non
         count = torch.empty(1, device=dev, dtype=i32)
         scratch = torch.empty(max(1, _lib.load().occnerf_rays_scratch_bytes(H, W) // 4), device=dev, dtype=i32)
         dp = lambda a: a.ctypes.data_as(C.c_void_p)
-        call("occnerf_generate_rays", dp(kinv), 1 if K.dtype == np.float32 else 0, dp(Rm), dp(Tv), dp(lo), dp(hi), H, W, cap,
+        call("occnerf_generate_rays", dp(kinv), mode, dp(Rm), dp(Tv), dp(lo), dp(hi), H, W, cap,
              ptr(rays, f32), ptr(mask, u8), ptr(pix, i32), ptr(count, i32), ptr(scratch, i32), stream())
     if not sync:
         return rays, mask.view(torch.bool), count, pix

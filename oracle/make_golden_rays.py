@@ -6,7 +6,7 @@ rays_intersect_3d_bbox (core/utils/camera_util.py), imported from /root/referenc
 cv2 and trimesh (imported at the top of camera_util.py, used by other functions only) are absent here and are
 replaced by empty modules.  Two cameras: `zju` = float32 K with float64 extrinsics (what train.py:425-448 ends up
 with after apply_global_tfm_to_camera) and `f64` = everything float64; both 64 x 48 pixels so that a row/column
-mix-up cannot pass.
+mix-up cannot pass; `f32` = everything float32 (tpose.py:66-84).
 """
 from __future__ import annotations
 
@@ -33,18 +33,20 @@ def _camera_util():
 def cameras():
     rng = np.random.default_rng(42)
     out = {}
-    for name, kdt in (("zju", np.float32), ("f64", np.float64)):
+    for name, kdt in (("zju", np.float32), ("f64", np.float64), ("f32", np.float32)):
         H, W = 48, 64
         K = np.array([[156.25 * 1.03, 0.0, W / 2 + 0.37], [0.0, 156.25 * 0.98, H / 2 - 0.21], [0.0, 0.0, 1.0]], kdt)
         ax = rng.normal(size=3)
         ax /= np.linalg.norm(ax)
-        ang = 0.35
+        ang = 0.12 if name == "f32" else 0.35      # (the third random axis at 0.35 rad turns the box out of the frame)
         Kx = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
         R = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
         campos = np.array([0.4, -0.25, 6.0]) + rng.normal(size=3) * 0.1
         T = -R @ campos
         bmin = np.array([-0.75, -1.1, -0.35], np.float32)
         bmax = np.array([0.80, 0.55, 0.30], np.float32)
+        if name == "f32":                      # tpose.py:66-84 builds K and E in float32 -> numpy keeps float32 throughout
+            R, T = R.astype(np.float32), T.astype(np.float32)
         out[name] = dict(H=H, W=W, K=K, R=R, T=T, bbox_min=bmin, bbox_max=bmax)
     return out
 

@@ -67,7 +67,7 @@ def test_voxel_bins_bit_exact(name):
     assert np.array_equal(bins.numpy().astype(np.int16), g["bins"])
 
 
-@pytest.mark.parametrize("name", ["zju", "f64"])
+@pytest.mark.parametrize("name", ["zju", "f64", "f32"])
 def test_rays_oracle_matches_reference(name):
     """oracle/rays_oracle.py against get_rays_from_KRT + rays_intersect_3d_bbox of the reference (camera_util.py:133-212),
     fixtures by oracle/make_golden_rays.py.  float64 intermediates are compared exactly: same numpy calls, same dtypes."""

@@ -26,6 +26,9 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 """
 
@@ -36,10 +39,15 @@ extern "C" void emulate(const double *kinv, int k_f32, const double *R, const do
     for (int a = 0; a < 9; ++a) { c.kinv[a] = kinv[a]; c.R[a] = R[a]; }
     for (int a = 0; a < 3; ++a) {
         c.T[a] = T[a]; c.lo[a] = lo[a] + -0.01; c.hi[a] = hi[a] + 0.01;
-        double acc = R[a] * T[0]; acc = fma(R[3 + a], T[1], acc); acc = fma(R[6 + a], T[2], acc);
-        c.o[a] = -acc;
+        if (k_f32 == 2) {
+            float acc = (float)R[a] * (float)T[0]; acc = fmaf((float)R[3 + a], (float)T[1], acc); acc = fmaf((float)R[6 + a], (float)T[2], acc);
+            c.o[a] = (double)-acc;
+        } else {
+            double acc = R[a] * T[0]; acc = fma(R[3 + a], T[1], acc); acc = fma(R[6 + a], T[2], acc);
+            c.o[a] = -acc;
+        }
     }
-    c.H = H; c.W = W; c.k_f32 = k_f32;
+    c.H = H; c.W = W; c.k_f32 = k_f32 ? 1 : 0; c.all_f32 = k_f32 == 2;
     for (int p = 0; p < H * W; ++p) {
         RayOut r = ray_for_pixel(c, p);
         mask[p] = r.hit;
@@ -64,7 +72,7 @@ def _build():
     return ctypes.CDLL(so)
 
 
-@pytest.mark.parametrize("name", ["zju", "f64"])
+@pytest.mark.parametrize("name", ["zju", "f64", "f32"])
 def test_device_arithmetic_reproduces_the_reference(name):
     lib = _build()
     g = np.load(os.path.join(ROOT, "tests", "golden", f"rays_{name}.npz"))
@@ -75,7 +83,8 @@ def test_device_arithmetic_reproduces_the_reference(name):
     rays = np.zeros((H * W, 8), np.float32)
     mask = np.zeros(H * W, np.uint8)
     dp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    lib.emulate(dp(kinv), int(K.dtype == np.float32), dp(R), dp(T), dp(lo), dp(hi), H, W, dp(rays), dp(mask))
+    mode = 2 if (K.dtype == np.float32 and g["R"].dtype == np.float32 and g["T"].dtype == np.float32) else int(K.dtype == np.float32)
+    lib.emulate(dp(kinv), mode, dp(R), dp(T), dp(lo), dp(hi), H, W, dp(rays), dp(mask))
     hit = mask.astype(bool)
     assert np.array_equal(hit, g["ray_mask"])
     assert np.array_equal(rays[hit, 0:3], g["rays_o"]) and np.array_equal(rays[hit, 3:6], g["rays_d"])

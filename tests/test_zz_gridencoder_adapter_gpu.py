@@ -65,3 +65,20 @@ def test_adapter_against_compiled_reference_module():
     assert float((ours[1] - theirs[1]).abs().max()) <= 1e-6 * float(theirs[1].abs().max())
     assert normwise_close(ours[2].cpu().numpy(), theirs[2].cpu().numpy(), 1e-5) and torch.equal(ours[2] != 0, theirs[2] != 0)
     assert normwise_close(ours[3].cpu().numpy(), theirs[3].cpu().numpy(), 1e-5)
+
+
+def test_rays_all_float32_camera_fixture():
+    """occnerf_generate_rays in OCCNERF_RAYS_ALL_F32 mode (tpose.py:66-84 cameras) against the fixture the reference's
+    functions wrote for a float32 K, R, T.  Lives in this run-last file for the same reason as the tests above: the mode was
+    added after the GPU budget ended; its arithmetic is checked bitwise on the host by tests/test_rays_host_emulation_cpu.py.
+    Bar: ray_mask identical, o exact, d / near / far within 1e-6 relative."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rays_f32.npz"))
+    assert g["K"].dtype == g["R"].dtype == g["T"].dtype == np.float32
+    rays, mask, n, _ = ops.generate_rays(int(g["H"]), int(g["W"]), g["K"], g["R"], g["T"], g["bbox_min"], g["bbox_max"])
+    rays, mask = rays.cpu().numpy(), mask.cpu().numpy()
+    assert np.array_equal(mask, g["ray_mask"]) and n == int(g["ray_mask"].sum()) > 0
+    assert np.array_equal(rays[:, 0:3], g["rays_o"])
+    for got, want in ((rays[:, 3:6], g["rays_d"]), (rays[:, 6], g["near"]), (rays[:, 7], g["far"])):
+        assert np.all(np.abs(got - want) <= 1e-6 * np.maximum(1.0, np.abs(want)))
