@@ -65,8 +65,9 @@ __device__ __forceinline__ RayOut ray_for_pixel(const RayCam &c, int pix) {
                     q2 = __fsub_rn((float)cam[2], (float)c.T[2]);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            // numpy hands this [H*W,3] x [3,3] product to sgemm; OpenBLAS' kernel (the build behind the fixtures) unrolls k by
-            // two -- fma(q0 r0, q1 r1) -- and adds the odd k = 2 product afterwards.  Any other BLAS differs by <= 1 float32 ulp.
+            // numpy evaluates this (H,W,3) x (3,3) np.dot one element at a time through the BLAS sdot; OpenBLAS' kernel (the build
+            // behind the fixtures) pairs k = 0,1 -- fma(q0 r0, q1 r1) -- and adds the odd k = 2 product afterwards.  Any other BLAS
+            // differs by <= 1 float32 ulp.
             float w = __fadd_rn(__fmaf_rn(q0, (float)c.R[a], __fmul_rn(q1, (float)c.R[3 + a])), __fmul_rn(q2, (float)c.R[6 + a]));
             float d = __fsub_rn(w, (float)c.o[a]);
             if (fabsf(d) < 1e-5f) d = 1e-5f;

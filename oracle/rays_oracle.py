@@ -19,8 +19,10 @@ def pixel_rays(H: int, W: int, K: np.ndarray, R: np.ndarray, T: np.ndarray):
     cols = np.arange(W, dtype=np.float32)[None, :].repeat(H, 0)                 # :150-152  i = column, j = row
     rows = np.arange(H, dtype=np.float32)[:, None].repeat(W, 1)
     homog = np.concatenate([cols[..., None], rows[..., None], np.ones((H, W, 1), np.float32)], -1)
-    cam = homog @ np.linalg.inv(K).T                                            # :154
-    world = (cam - T.reshape(3)) @ R                                            # :155
+    # np.dot on the 3-D operand, as the reference calls it: numpy evaluates an N-D x 2-D dot one output element at a time
+    # through the BLAS dot routine, whose float32 rounding differs from what `@` / a 2-D gemm give (1 ulp in rays_d)
+    cam = np.dot(homog, np.linalg.inv(K).T)                                     # :154
+    world = np.dot(cam - T.reshape(3), R)                                       # :155
     dirs = world - origin                                                       # :157
     return np.broadcast_to(origin, dirs.shape), dirs
 
