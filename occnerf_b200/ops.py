@@ -542,7 +542,8 @@ def unpack_image(rgb, alpha, pixel_index, H, W, bgcolor, out=None, fill=True):
     """run.py:39-66 (unpack_to_image / unpack_alpha_map) + image_util.py:19-20 (to_8b_image) on the device.
 
     rgb [n,3], alpha [n] or None, pixel_index [n] int32 (from generate_rays); bgcolor: three HOST numbers in [0,1]
-    (run.py:118 passes cfg.bgcolor / 255).  Returns (rgb8 [H,W,3] uint8, alpha8 [H,W] uint8).  `out=(rgb8, alpha8)` with
+    (run.py:118 passes cfg.bgcolor / 255).  Returns (rgb8 [H,W,3] uint8, alpha8 [H,W] uint8, bad [1] int32 = number of
+    pixel indices outside the frame, a device tensor so that nothing is read back here).  `out=(rgb8, alpha8)` with
     fill=False scatters a further shard of rays into an already painted frame."""
     n = int(rgb.shape[0])
     dev = rgb.device
