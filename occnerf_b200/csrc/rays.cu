@@ -46,6 +46,13 @@ __device__ __forceinline__ float dot3_chain_f(float a0, float a1, float a2, floa
     return __fmaf_rn(a2, b2, acc);
 }
 
+// float32 length-3 dot as numpy's N-D np.dot evaluates it through OpenBLAS' sdot (the build behind the fixtures): k = 0,1 paired
+// -- fma(a0 b0, a1 b1) -- then the odd k = 2 product added.  Equal to the chain whenever a1 b1 = 0 (a K without skew); any other
+// BLAS differs by <= 1 float32 ulp.
+__device__ __forceinline__ float dot3_sdot_f(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return __fadd_rn(__fmaf_rn(a0, b0, __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
+}
+
 __device__ __forceinline__ RayOut ray_for_pixel(const RayCam &c, int pix) {
     RayOut r;
     const int j = pix / c.W, i = pix - j * c.W;
@@ -53,6 +60,8 @@ __device__ __forceinline__ RayOut ray_for_pixel(const RayCam &c, int pix) {
     if (c.k_f32) {
 #pragma unroll
         for (int a = 0; a < 3; ++a)
+            // (every K of the reference has zero skew: the middle product is 0 and any summation order rounds alike; with a skewed
+            //  float32 K numpy's strided BLAS dot was seen to round differently in the last ulp -- not reproduced)
             cam[a] = (double)dot3_chain_f((float)i, (float)j, 1.0f, (float)c.kinv[3 * a], (float)c.kinv[3 * a + 1], (float)c.kinv[3 * a + 2]);
     } else {
 #pragma unroll
@@ -65,10 +74,7 @@ __device__ __forceinline__ RayOut ray_for_pixel(const RayCam &c, int pix) {
                     q2 = __fsub_rn((float)cam[2], (float)c.T[2]);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            // numpy evaluates this (H,W,3) x (3,3) np.dot one element at a time through the BLAS sdot; OpenBLAS' kernel (the build
-            // behind the fixtures) pairs k = 0,1 -- fma(q0 r0, q1 r1) -- and adds the odd k = 2 product afterwards.  Any other BLAS
-            // differs by <= 1 float32 ulp.
-            float w = __fadd_rn(__fmaf_rn(q0, (float)c.R[a], __fmul_rn(q1, (float)c.R[3 + a])), __fmul_rn(q2, (float)c.R[6 + a]));
+            float w = dot3_sdot_f(q0, q1, q2, (float)c.R[a], (float)c.R[3 + a], (float)c.R[6 + a]);
             float d = __fsub_rn(w, (float)c.o[a]);
             if (fabsf(d) < 1e-5f) d = 1e-5f;
             r.d[a] = (double)d;
