@@ -306,7 +306,7 @@ def kernel_table(profile, steps):
 NCU_TRAFFIC_PER_SAMPLE = {"occnerf_mlp_forward_tc": (0.151179e9 + 1.470747e9) / 300000, "occnerf_mlp_backward_tc": (0.128911e9 + 1.335716e9) / 300000,
                           "occnerf_mlp_wgrad_tc": (2.805448e9 + 0.006918e9) / 300000, "occnerf_aggregate_backward": (0.194468e9 + 0.015459e9) / 300000,
                           "occnerf_aggregate_forward": (0.054993e9 + 0.052413e9) / 300000, "occnerf_hashgrid_backward": (0.113153e9 + 0.007391e9) / 300000}
-MMA_ISSUE_FACTOR = {"tc3": 3.0, "tc3b1": 3.0, "tc1": 1.0}      # split-bf16 issues three bf16 MMAs per algorithmic product
+MMA_ISSUE_FACTOR = {"tc3": 3.0, "tc3b1": 3.0, "tc1": 1.0, "tf32": 2.0}   # bf16-equivalent tensor-pipe work per algorithmic product (split-bf16: 3 MMAs; tf32: half rate)
 
 
 def roofline_for(row, peaks, M, engine="tc3"):
@@ -341,7 +341,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("OCCNERF_ENGINE", "tc3"), choices=["fp32", "tc3", "tc3b1", "tc1"])
+    ap.add_argument("--engine", default=os.environ.get("OCCNERF_ENGINE", "tc3"), choices=["fp32", "tf32", "tc3", "tc3b1", "tc1"])
     ap.add_argument("--ref-rays", type=int, default=96, help="rays per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the e2e step eagerly instead of as one CUDA graph")
@@ -417,7 +417,7 @@ def main():
         line = {
             "metric": "rays_per_sec_fwd_bwd_128spr", "value": world * RAYS_PER_STEP / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "tc3": "bf16x3(split)->f32", "tc3b1": "bf16x3(split)->f32 fwd, bf16->f32 dgrad", "tc1": "bf16->f32"}[args.engine], "data": "synthetic",
+            "dtype": {"fp32": "f32", "tf32": "tf32->f32", "tc3": "bf16x3(split)->f32", "tc3b1": "bf16x3(split)->f32 fwd, bf16->f32 dgrad", "tc1": "bf16->f32"}[args.engine], "data": "synthetic",
             "config": {"workload": "zju387_train_step_6x32x32_rays_128spr_fwd_bwd", "rays_per_step_per_gpu": RAYS_PER_STEP, "samples_per_ray": S_SAMPLES,
                        "mlp_engine": args.engine, "l2": "256 MiB flush write between timed steps", "timing": "cuda events per step, max over ranks",
                        "optimizer": "grad-clip + fused Adam (library) inside the step", "parallelism": f"dp{world}"},

@@ -16,6 +16,9 @@
 //
 // Precision: n_pass = 1 is bf16 x bf16 -> fp32.  n_pass = 3 is split-bf16, x = hi + lo (both bf16),
 //   x.w ~= hi.whi + hi.wlo + lo.whi (three MMAs per K-step on one fp32 accumulator, ~2^-16 relative error per product).
+//   n_pass = 2 is kind::tf32: fp32 operands in shared memory, rounded to nearest-tf32 (10-bit mantissa, fp32 exponent
+//   range) by the epilogue / the weight packer; one tf32 MMA covers K = 8 at the cycle cost of a K = 16 bf16 MMA, i.e. two
+//   bf16-units per product instead of the three of the split (the A operand is 128 KB either way).
 //
 // Warp roles (576 threads): warps 0-15 epilogue -- warp w owns TMEM lane quarter w & 3 (32 samples) and, as member of
 // epilogue set w >> 2, the 8-column chunks k8 = set (mod 4) of every layer (one chunk of each 32-column group), so each
@@ -56,7 +59,9 @@ __host__ __device__ inline int n_layers(int chain) { return chain == 2 ? 7 : 10;
 __host__ __device__ inline int chain_K(int chain, int l) { return chain == 0 ? fwd_K(l) : (chain == 1 ? fwd_N(9 - l) : nr_K(l)); }
 __host__ __device__ inline int chain_N(int chain, int l) { return chain == 0 ? fwd_N(l) : (chain == 1 ? fwd_K(9 - l) : nr_N(l)); }
 __host__ __device__ inline int chunk_K(int n_pass) { return n_pass == 1 ? 64 : 32; }
-__host__ __device__ inline int parts(int n_pass) { return n_pass == 1 ? 1 : 2; }
+__host__ __device__ inline int parts(int n_pass) { return n_pass == 3 ? 2 : 1; }
+__host__ __device__ inline int elem_bytes(int n_pass) { return n_pass == 2 ? 4 : 2; }
+__host__ __device__ inline bool valid_pass(int n_pass) { return n_pass >= 1 && n_pass <= 3; }
 
 struct PackedLayout {
     long w_off[kLayers];
@@ -72,7 +77,7 @@ inline PackedLayout packed_layout(int n_pass, int chain) {
     for (int l = 0; l < n_layers(chain); ++l) {
         p.w_off[l] = off;
         const int K = chain_K(chain, l), N = chain_N(chain, l);
-        off += (long)((K + KC - 1) / KC) * parts(n_pass) * N * KC * 2;
+        off += (long)((K + KC - 1) / KC) * parts(n_pass) * N * KC * elem_bytes(n_pass);
     }
     p.bias_off = off;
     off += kLayers * 256 * 4;
@@ -105,21 +110,41 @@ __device__ __forceinline__ float fwd_bias(const occnerf_mlp_params &P, int l, in
 
 struct DevLayout { long w_off[kLayers]; long bias_off; };
 
+__device__ __forceinline__ uint32_t to_tf32(float x) {       // round to nearest (ties away), low 13 mantissa bits cleared
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return u;
+}
+
+// element (n, k) of a padded N x K weight matrix -> its place in the packed operand image of layer `base`:
+// per K-chunk of KC columns [part][k-slab][n/8][n%8][16 B] (K-major, no swizzle: 8 rows x 16 B core matrices, a k-slab =
+// 8 bf16 / 4 tf32 columns of all N rows)
+__device__ __forceinline__ void pack_store(unsigned char *out, long base, int n_pass, int N, int n, int k, float w) {
+    const int KC = chunk_K(n_pass), np = parts(n_pass);
+    const int chunk = k / KC, kk = k % KC;
+    if (n_pass == 2) {
+        const long cb = base + (long)chunk * N * KC * 4;
+        const long inner = ((long)(kk / 4) * (N / 8) + n / 8) * 128 + (n % 8) * 16 + (kk % 4) * 4;
+        *reinterpret_cast<uint32_t *>(out + cb + inner) = to_tf32(w);
+        return;
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    const long pb = (long)N * KC * 2;
+    const long cb = base + (long)chunk * np * pb;
+    const long inner = ((long)(kk / 8) * (N / 8) + n / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2;
+    *reinterpret_cast<__nv_bfloat16 *>(out + cb + inner) = hi;
+    if (np == 2) *reinterpret_cast<__nv_bfloat16 *>(out + cb + pb + inner) = lo;
+}
+
 __global__ void pack_weights_kernel(occnerf_mlp_params P, DevLayout L, int n_pass, int chain, unsigned char *out) {
     const int l = blockIdx.y;
-    const int K = chain_K(chain, l), N = chain_N(chain, l), KC = chunk_K(n_pass), np = parts(n_pass);
+    const int K = chain_K(chain, l), N = chain_N(chain, l);
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < (long)N * K) {
         const int n = (int)(idx / K), k = (int)(idx % K);
         const float w = chain == 0 ? fwd_weight(P, l, n, k) : fwd_weight(P, 9 - l, k, n);     // backward chain: W^T
-        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-        const int chunk = k / KC, kk = k % KC;
-        const long pb = (long)N * KC * 2;
-        const long base = L.w_off[l] + (long)chunk * np * pb;
-        const long inner = ((long)(kk / 8) * (N / 8) + n / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2;
-        *reinterpret_cast<__nv_bfloat16 *>(out + base + inner) = hi;
-        if (np == 2) *reinterpret_cast<__nv_bfloat16 *>(out + base + pb + inner) = lo;
+        pack_store(out, L.w_off[l], n_pass, N, n, k, w);
     }
     if (chain == 0 && blockIdx.x == 0 && threadIdx.x < 256) {
         float *b = reinterpret_cast<float *>(out + L.bias_off) + l * 256;
@@ -131,7 +156,7 @@ struct NrParams { const float *w[7]; const float *b[7]; const float *cond; };   
 
 __global__ void pack_nr_kernel(NrParams P, DevLayout L, int n_pass, unsigned char *out) {
     const int l = blockIdx.y;
-    const int K = nr_K(l), N = nr_N(l), KC = chunk_K(n_pass), np = parts(n_pass);
+    const int K = nr_K(l), N = nr_N(l);
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < (long)N * K) {
         const int n = (int)(idx / K), k = (int)(idx % K);
@@ -140,14 +165,7 @@ __global__ void pack_nr_kernel(NrParams P, DevLayout L, int n_pass, unsigned cha
         else if (l == 4) w = k < 164 ? P.w[4][n * 164 + k] : 0.f;                // [h128, pe36]
         else if (l == 6) w = n < 3 ? P.w[6][n * 128 + k] : 0.f;
         else w = P.w[l][n * 128 + k];
-        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-        const int chunk = k / KC, kk = k % KC;
-        const long pb = (long)N * KC * 2;
-        const long base = L.w_off[l] + (long)chunk * np * pb;
-        const long inner = ((long)(kk / 8) * (N / 8) + n / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2;
-        *reinterpret_cast<__nv_bfloat16 *>(out + base + inner) = hi;
-        if (np == 2) *reinterpret_cast<__nv_bfloat16 *>(out + base + pb + inner) = lo;
+        pack_store(out, L.w_off[l], n_pass, N, n, k, w);
     }
     if (blockIdx.x == 0 && threadIdx.x < 256) {
         const int n = threadIdx.x;
@@ -215,6 +233,11 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
     asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// the same with kind::tf32 (fp32 containers in shared memory, K = 8 per instruction)
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // K-major, no-swizzle shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout, version 1 = Blackwell)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
@@ -223,6 +246,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
 __device__ __forceinline__ uint32_t instr_desc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32 (format 2), both K-major, M=128
+__device__ __forceinline__ uint32_t instr_desc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -249,11 +276,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ uint4 pack_bf16x8(const float (&v)[8]) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        pk[i] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    return make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
 // bf16 split of 8 consecutive K values of one row -> one 16-byte store per part into the A operand image
 // (returns the packed bf16 "hi" part: exactly what the backward pass wants saved)
 template <int NPASS>
 __device__ __forceinline__ uint4 store_a8(unsigned char *a_base, int row, int k8, const float (&v)[8]) {
     uint32_t hi[4], lo[4];
+    if (NPASS == 2) {
+        // tf32 engine: the operand is fp32-sized, 4 columns per 16-byte core-matrix row -> k-slabs 2*k8 and 2*k8+1
+        const uint32_t off = (uint32_t)(k8 * 32 + (row >> 3)) * 128 + (row & 7) * 16;
+        *reinterpret_cast<uint4 *>(a_base + off) = make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+        *reinterpret_cast<uint4 *>(a_base + off + 2048) = make_uint4(to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7]));
+        return pack_bf16x8(v);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
@@ -268,15 +312,6 @@ __device__ __forceinline__ uint4 store_a8(unsigned char *a_base, int row, int k8
     *reinterpret_cast<uint4 *>(a_base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     if (NPASS == 3) *reinterpret_cast<uint4 *>(a_base + kAPartBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     return make_uint4(hi[0], hi[1], hi[2], hi[3]);
-}
-__device__ __forceinline__ uint4 pack_bf16x8(const float (&v)[8]) {
-    uint32_t pk[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        pk[i] = *reinterpret_cast<const uint32_t *>(&h);
-    }
-    return make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
 // chunk g (8 columns) of the (agg35, var, h32) part of a sample's input row -> A chunk k8_0 + g, zero padded beyond column 68
@@ -346,7 +381,8 @@ struct Smem {
 template <int NPASS>
 __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem &sm, int num_tiles) {
     constexpr int KC = (NPASS == 1) ? 64 : 32;
-    constexpr int NP = (NPASS == 1) ? 1 : 2;
+    constexpr int NP = (NPASS == 3) ? 2 : 1;
+    constexpr int EB = (NPASS == 2) ? 4 : 2;
     uint32_t it = 0;
     long long dbg_wait = 0;
     const uint32_t rank = cluster_ctarank();
@@ -354,7 +390,7 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
         for (int l = 0; l < n_layers(args.chain); ++l) {
             const int K = chain_K(args.chain, l), N = chain_N(args.chain, l);
             const int nch = (K + KC - 1) / KC;
-            const uint32_t pb = (uint32_t)N * KC * 2;
+            const uint32_t pb = (uint32_t)N * KC * EB;
             const unsigned char *src = args.packed + args.w_off[l];
             for (int c = 0; c < nch; ++c, ++it) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
@@ -362,7 +398,7 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
                 mbar_wait(sm.bar_w_empty + 8 * s, ph ^ 1);          // BOTH CTAs of the pair have consumed the slot
                 if (args.debug) dbg_wait += clk() - t0;
                 const int kc = min(KC, K - c * KC);
-                const uint32_t bytes = (uint32_t)N * kc * 2;       // per part; the k8-outer image is contiguous
+                const uint32_t bytes = (uint32_t)N * kc * EB;      // per part; the k-slab-outer image is contiguous
                 mbar_arrive_expect_tx(sm.bar_w_full + 8 * s, bytes * NP);   // what lands in MY slot (from both CTAs)
                 const uint32_t dst = smem_u32(sm.W + s * kStageBytes);
                 // the two CTAs of a cluster walk the same weight stream: each fetches one half from L2 and multicasts
@@ -384,6 +420,8 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
 template <int NPASS>
 __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base) {
     constexpr int KC = (NPASS == 1) ? 64 : 32;
+    constexpr int KS = (NPASS == 2) ? 8 : 16;          // K per MMA instruction (32 bytes of operand row)
+    constexpr int SPG = 32 / KS;                       // MMA steps per 32-column A group
     uint32_t it = 0, a_phase = 0;      // a_phase: one parity bit per A group
     long long dbg_w = 0, dbg_a = 0;
     const long long dbg_t0 = args.debug ? clk() : 0;
@@ -392,7 +430,7 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
         for (int l = 0; l < n_layers(args.chain); ++l) {
             const int K = chain_K(args.chain, l), N = chain_N(args.chain, l);
             const int nch = (K + KC - 1) / KC;
-            const uint32_t idesc = instr_desc(N);
+            const uint32_t idesc = NPASS == 2 ? instr_desc_tf32(N) : instr_desc(N);
             const uint32_t b_lbo = (uint32_t)(N / 8) * 128;
             const uint32_t d_tmem = tmem_base + (uint32_t)(l & 1) * 256;
             uint32_t first = 1;
@@ -405,10 +443,10 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
                 }
                 const int kc = min(KC, K - c * KC);
                 const uint32_t wbase = smem_u32(sm.W + s * kStageBytes);
-                for (int k16 = 0; k16 < kc / 16; ++k16) {
-                    const int t = c * (KC / 16) + k16;             // global K-step of this GEMM
-                    if ((t & 1) == 0) {                            // first step of a 32-column group: wait for the epilogue
-                        const int g = t >> 1;
+                for (int k16 = 0; k16 < kc / KS; ++k16) {
+                    const int t = c * (KC / KS) + k16;             // global K-step of this GEMM
+                    if ((t % SPG) == 0) {                          // first step of a 32-column group: wait for the epilogue
+                        const int g = t / SPG;
                         const long long t0 = args.debug ? clk() : 0;
                         mbar_wait(sm.bar_a_ready + 8 * g, (a_phase >> g) & 1);
                         if (args.debug) dbg_a += clk() - t0;
@@ -418,7 +456,8 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
                     const uint32_t a_hi = a_base + (uint32_t)t * 4096;
                     const uint32_t b_hi = wbase + (uint32_t)k16 * 2 * b_lbo;
                     const uint64_t da_hi = smem_desc(a_hi, 2048, 128), db_hi = smem_desc(b_hi, b_lbo, 128);
-                    tc_mma(d_tmem, da_hi, db_hi, idesc, first ? 0u : 1u);
+                    if (NPASS == 2) tc_mma_tf32(d_tmem, da_hi, db_hi, idesc, first ? 0u : 1u);
+                    else tc_mma(d_tmem, da_hi, db_hi, idesc, first ? 0u : 1u);
                     first = 0;
                     if (NPASS == 3) {
                         const uint64_t da_lo = smem_desc(a_hi + kAPartBytes, 2048, 128);
@@ -808,7 +847,7 @@ __device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Sm
 template <int NPASS, int CHAIN>
 __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_constant__ ChainArgs args) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);
+    constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);     // bf16: 64 KB; hi+lo or tf32: 128 KB
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kABytes + kStages * kStageBytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
     Smem sm;
@@ -972,14 +1011,14 @@ extern "C" int occnerf_mlp_debug_counters(unsigned long long *host8, int reset) 
 }
 
 extern "C" long occnerf_mlp_packed_bytes(int n_pass, int chain) {
-    if ((n_pass != 1 && n_pass != 3) || chain < 0 || chain > 2) return -1;
+    if (!valid_pass(n_pass) || chain < 0 || chain > 2) return -1;
     return packed_layout(n_pass, chain).total;
 }
 
 extern "C" int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, void *packed,
                                         occnerf_stream_t stream) {
     OCC_CHECK_ARG(p_host && packed, "mlp_pack_weights: null pointer");
-    OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "mlp_pack_weights: n_pass=%d (supported: 1, 3)", n_pass);
+    OCC_CHECK_ARG(valid_pass(n_pass), "mlp_pack_weights: n_pass=%d (supported: 1 bf16, 2 tf32, 3 split-bf16)", n_pass);
     OCC_CHECK_ARG(chain == 0 || chain == 1, "mlp_pack_weights: chain=%d (0 forward, 1 backward)", chain);
     for (int l = 0; l < kLayers; ++l) OCC_CHECK_ARG(p_host->w[l] && p_host->b[l], "mlp_pack_weights: layer %d has a null pointer", l);
     const PackedLayout pl = packed_layout(n_pass, chain);
@@ -996,7 +1035,7 @@ extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int 
                                       int act_dtype, long slot_stride, void *relu_mask, occnerf_stream_t stream) {
     if (m == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(XB && packed && raw, "mlp_forward_tc: null pointer");
-    OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "mlp_forward_tc: n_pass=%d (supported: 1, 3)", n_pass);
+    OCC_CHECK_ARG(valid_pass(n_pass), "mlp_forward_tc: n_pass=%d (supported: 1 bf16, 2 tf32, 3 split-bf16)", n_pass);
     OCC_CHECK_ARG(m > 0 && ldr >= 4, "mlp_forward_tc: m=%d ldr=%d", m, ldr);
     OCC_CHECK_ARG(act_dtype >= 0 && act_dtype <= 2 && (act_dtype == 0 || act_save), "mlp_forward_tc: act_dtype=%d / act_save mismatch", act_dtype);
     OCC_CHECK_ARG(((uintptr_t)XB & 15) == 0 && ((uintptr_t)packed & 15) == 0 && ((uintptr_t)act_save & 15) == 0,
@@ -1008,14 +1047,14 @@ extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int 
     a.XB = XB; a.raw = raw; a.ldr = ldr; a.act_save = act_save; a.act_dtype = act_dtype; a.slot_stride = slot_stride;
     a.relu_mask = (uint8_t *)relu_mask;
     OCC_CHECK_ARG(((uintptr_t)relu_mask & 15) == 0, "mlp_forward_tc: relu_mask must be 16-byte aligned");
-    return n_pass == 1 ? launch_chain<1, 0>(a, (cudaStream_t)stream) : launch_chain<3, 0>(a, (cudaStream_t)stream);
+    return n_pass == 1 ? launch_chain<1, 0>(a, (cudaStream_t)stream) : n_pass == 2 ? launch_chain<2, 0>(a, (cudaStream_t)stream) : launch_chain<3, 0>(a, (cudaStream_t)stream);
 }
 
 extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, const void *relu_mask,
                                        float *gXB, void *g_save, long slot_stride, occnerf_stream_t stream) {
     if (m == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(g_raw && packed_bwd && relu_mask && gXB && g_save, "mlp_backward_tc: null pointer");
-    OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "mlp_backward_tc: n_pass=%d (supported: 1, 3)", n_pass);
+    OCC_CHECK_ARG(valid_pass(n_pass), "mlp_backward_tc: n_pass=%d (supported: 1 bf16, 2 tf32, 3 split-bf16)", n_pass);
     OCC_CHECK_ARG(((uintptr_t)gXB & 15) == 0 && ((uintptr_t)packed_bwd & 15) == 0 && ((uintptr_t)relu_mask & 15) == 0 &&
                   ((uintptr_t)g_save & 15) == 0, "mlp_backward_tc: buffers must be 16-byte aligned");
     ChainArgs a = {};
@@ -1023,14 +1062,14 @@ extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *pa
     fill_layout(a, n_pass, 1, packed_bwd);
     OCC_CHECK_ARG(slot_stride >= m, "mlp_backward_tc: slot_stride=%ld < m=%d", slot_stride, m);
     a.g_raw = g_raw; a.relu_mask = (uint8_t *)relu_mask; a.gXB = gXB; a.g_save = (__nv_bfloat16 *)g_save; a.slot_stride = slot_stride;
-    return n_pass == 1 ? launch_chain<1, 1>(a, (cudaStream_t)stream) : launch_chain<3, 1>(a, (cudaStream_t)stream);
+    return n_pass == 1 ? launch_chain<1, 1>(a, (cudaStream_t)stream) : n_pass == 2 ? launch_chain<2, 1>(a, (cudaStream_t)stream) : launch_chain<3, 1>(a, (cudaStream_t)stream);
 }
 
 // ---- non-rigid motion MLP on the same chain machinery (chain 2)
 extern "C" int occnerf_nonrigid_pack_weights(const void *const *w7_host, const void *const *b7_host, const float *cond_dev, int n_pass,
                                              void *packed, occnerf_stream_t stream) {
     OCC_CHECK_ARG(w7_host && b7_host && packed, "nonrigid_pack_weights: null pointer");
-    OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "nonrigid_pack_weights: n_pass=%d (supported: 1, 3)", n_pass);
+    OCC_CHECK_ARG(valid_pass(n_pass), "nonrigid_pack_weights: n_pass=%d (supported: 1 bf16, 2 tf32, 3 split-bf16)", n_pass);
     NrParams P;
     for (int l = 0; l < 7; ++l) {
         OCC_CHECK_ARG(w7_host[l] && b7_host[l], "nonrigid_pack_weights: layer %d has a null pointer", l);
@@ -1052,12 +1091,12 @@ extern "C" int occnerf_nonrigid_forward_tc(const float *xyz, const float *window
                                            float *out, occnerf_stream_t stream) {
     if (m == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(xyz && window6_host && packed && out && m > 0, "nonrigid_forward_tc: null pointer / m=%d", m);
-    OCC_CHECK_ARG(n_pass == 1 || n_pass == 3, "nonrigid_forward_tc: n_pass=%d (supported: 1, 3)", n_pass);
+    OCC_CHECK_ARG(valid_pass(n_pass), "nonrigid_forward_tc: n_pass=%d (supported: 1 bf16, 2 tf32, 3 split-bf16)", n_pass);
     OCC_CHECK_ARG(((uintptr_t)packed & 15) == 0, "nonrigid_forward_tc: packed must be 16-byte aligned");
     ChainArgs a = {};
     a.m = m;
     fill_layout(a, n_pass, 2, packed);
     a.nr_xyz = xyz; a.nr_out = out;
     for (int j = 0; j < 6; ++j) a.nr_window[j] = window6_host[j];
-    return n_pass == 1 ? launch_chain<1, 2>(a, (cudaStream_t)stream) : launch_chain<3, 2>(a, (cudaStream_t)stream);
+    return n_pass == 1 ? launch_chain<1, 2>(a, (cudaStream_t)stream) : n_pass == 2 ? launch_chain<2, 2>(a, (cudaStream_t)stream) : launch_chain<3, 2>(a, (cudaStream_t)stream);
 }

@@ -20,13 +20,13 @@ f32, bf16 = torch.float32, torch.bfloat16
 
 class MlpTc:
     def __init__(self, n_pass: int = 3, wgrad: str = "tc", bwd_pass: int | None = None):
-        assert n_pass in (1, 3) and wgrad in ("tc", "lib") and bwd_pass in (None, 1, 3)
+        assert n_pass in (1, 2, 3) and wgrad in ("tc", "lib") and bwd_pass in (None, 1, 2, 3)
         self.n_pass = n_pass
         # precision of the data-gradient chain: by default that of the forward chain; 1 = bf16 operands (what the
         # weight-gradient kernel uses anyway), independent of a split-bf16 forward
         self.bwd_pass = n_pass if bwd_pass is None else bwd_pass
         self.wgrad = wgrad      # "tc": hand-written tcgen05 kernel; "lib": cuBLAS (test cross-check only)
-        self.name = f"tc{n_pass}"
+        self.name = "tf32" if n_pass == 2 else f"tc{n_pass}"      # 1 bf16 | 2 tf32 (kind::tf32) | 3 split-bf16
 
     def pack(self, W: M.MlpWeights, device, chain: int):
         nbytes = _lib.load().occnerf_mlp_packed_bytes(self.n_pass, chain)

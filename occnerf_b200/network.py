@@ -24,6 +24,7 @@ from occnerf_b200 import mlp as M
 from occnerf_b200 import ops
 
 f32, i32 = torch.float32, torch.int32
+TC_PASSES = {"tc1": 1, "tf32": 2, "tc3": 3, "tc3b1": 3}     # tcgen05 engines -> n_pass of csrc/mlp_tc.cu
 
 
 # ----------------------------------------------------------------------------- parameter containers
@@ -164,7 +165,7 @@ class RenderConfig:
     non_rigid_multires: int = 6
     ignore_non_rigid_motions: bool = False
     bgcolor: tuple = (0.0, 0.0, 0.0)
-    mlp_engine: str = "fp32"        # "fp32" (exact SIMT) | "tc3" (tcgen05 split-bf16) | "tc3b1" (tc3 forward, bf16 dgrad) | "tc1" (tcgen05 bf16)
+    mlp_engine: str = "fp32"        # "fp32" (exact SIMT) | "tf32" (tcgen05 kind::tf32) | "tc3" (tcgen05 split-bf16) | "tc3b1" (tc3 forward, bf16 dgrad) | "tc1" (tcgen05 bf16)
     knn_mode: str = "grid"          # "grid" (per-cell candidate lists) | "tree" (3-level cluster tree) | "hier" | "brute"; same ids
 
 
@@ -414,7 +415,9 @@ class Network(nn.Module):
         from occnerf_b200 import mlp_tc
         if e == "tc3b1":         # split-bf16 forward (fp32-grade outputs), bf16-operand data gradients
             return mlp_tc.MlpTc(n_pass=3, bwd_pass=1)
-        return mlp_tc.MlpTc(n_pass=3 if e == "tc3" else 1)
+        if e not in TC_PASSES:
+            raise ValueError(f"unknown mlp_engine {e!r}")
+        return mlp_tc.MlpTc(n_pass=TC_PASSES[e])
 
     # -- per-vertex block (network.py:263-284 + occnerf_mlp.py:171-175), once per call instead of once per chunk
     def vertex_features(self):
@@ -456,7 +459,7 @@ class Network(nn.Module):
             else:
                 nw, nb = self.non_rigid_mlp.module.flat()
                 moved = torch.empty_like(xyz_all)
-                n_pass = {"tc3": 3, "tc3b1": 3, "tc1": 1}.get(self.cfg.mlp_engine)
+                n_pass = TC_PASSES.get(self.cfg.mlp_engine)
                 if n_pass is not None:           # tensor-core engines: the fused tcgen05 chain (exact fp32 mode: SIMT GEMMs)
                     packed = ops.nonrigid_pack(nw, nb, cond, n_pass)
                     for i in range(0, xyz_all.shape[0], chunk):

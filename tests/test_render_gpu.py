@@ -16,7 +16,7 @@ from tests.helpers import dev, load_case, maxabs, normwise_close, report
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = ["fp32", "tc3", "tc3b1", "tc1"]
+ENGINES = ["fp32", "tf32", "tc3", "tc3b1", "tc1"]
 
 
 def _net(sub, w, rk, engine="fp32"):
@@ -45,14 +45,14 @@ def test_render_matches_reference_golden(name, engine):
     net = _net(sub, w, rk, engine)
     vol_d = vol.to(dev()).requires_grad_(True)
     out = _render(net, fr, vol_d, t_rand, rk["iter_val"])
-    tol = {"fp32": 2e-5, "tc3": 1e-4, "tc3b1": 1e-4, "tc1": 1e-3}[engine]
+    tol = {"fp32": 2e-5, "tf32": 3e-4, "tc3": 1e-4, "tc3b1": 1e-4, "tc1": 1e-3}[engine]
     errs = {k: maxabs(out[k], g[k]) for k in ("rgb", "alpha", "depth")}
     report(f"render_golden[{name},{engine}]", **errs)
     for k, e in errs.items():
         assert e < tol, (k, e)
     if not rk["training"]:
         return
-    assert maxabs(out["comp_loss"], g["comp_loss"]) < {"fp32": 1e-5, "tc3": 1e-4, "tc3b1": 1e-4, "tc1": 2e-2}[engine]
+    assert maxabs(out["comp_loss"], g["comp_loss"]) < {"fp32": 1e-5, "tf32": 3e-3, "tc3": 1e-4, "tc3b1": 1e-4, "tc1": 2e-2}[engine]
     assert np.array_equal(out["hits"].cpu().numpy(), g["counter_delta"]), "visibility votes differ"
     make_golden.scalar_loss({k: out[k] for k in ("rgb", "alpha", "depth", "comp_loss")}).backward()
     m = net.cnl_mlp.module
@@ -61,8 +61,8 @@ def test_render_matches_reference_golden(name, engine):
     # points that any re-ordered fp32 GEMM (non-rigid MLP) produces move interpolation weights by ~0.4 %.
     # They get 2e-2; everything else, and the per-level L2 norms of the table gradient, are held to 1e-3 (fp32).
     # (tc3b1 = split-bf16 forward, bf16-operand data gradients: outputs as tc3, gradients at bf16 precision)
-    rel = {"fp32": 1e-3, "tc3": 5e-3, "tc3b1": 1.5e-2, "tc1": 5e-2}[engine]
-    loose = {"fp32": 2e-2, "tc3": 2e-2, "tc3b1": 2e-2, "tc1": 1e-1}[engine]
+    rel = {"fp32": 1e-3, "tf32": 1e-2, "tc3": 5e-3, "tc3b1": 1.5e-2, "tc1": 5e-2}[engine]
+    loose = {"fp32": 2e-2, "tf32": 2e-2, "tc3": 2e-2, "tc3b1": 2e-2, "tc1": 1e-1}[engine]
 
     def nw(a, b):
         a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
@@ -111,7 +111,7 @@ def test_query_stages_against_oracle(engine):
     assert torch.equal(out["knn_idxs"].cpu().long(), aux["knn_idxs"])
     e = maxabs(out["raws"].reshape(-1, 5), raw_o)
     report(f"query_vs_oracle[{engine}]", raw=e)
-    assert e < {"fp32": 5e-5, "tc3": 2e-4, "tc3b1": 2e-4, "tc1": 5e-2}[engine]
+    assert e < {"fp32": 5e-5, "tf32": 5e-3, "tc3": 2e-4, "tc3b1": 2e-4, "tc1": 5e-2}[engine]
     assert maxabs(out["raws"].reshape(-1, 5)[:, 4], raw_o[:, 4]) < 1e-6      # signed distance channel is engine independent
 
 
@@ -136,7 +136,7 @@ def test_nonrigid_full_band_against_oracle():
         assert e < 2e-6
 
 
-@pytest.mark.parametrize("n_pass,tol", [(3, 3e-5), (1, 2e-2)])
+@pytest.mark.parametrize("n_pass,tol", [(3, 3e-5), (2, 3e-3), (1, 2e-2)])
 def test_nonrigid_tensor_core_chain_against_oracle(n_pass, tol):
     """The non-rigid MLP as a fused tcgen05 chain (csrc/mlp_tc.cu, chain 2): split-bf16 is fp32-grade, bf16 is not.
     Offsets are scaled to ~1 so that the error is visible; m is not a multiple of the 128-sample tile."""

@@ -22,7 +22,7 @@ def read(reset=1):
             "epi_publish_pct": round(100 * v[9] / max(v[5], 1), 1), "producer_wait_slot_cycles_per_cta": v[3] // ctas,
             "mma_thread_cycles_per_cta": v[4] // ctas, "epi_thread_cycles_per_cta": v[5] // ctas, "ctas": v[6]}
 res = {}
-for name, eng in [("tc1", mlp_tc.MlpTc(1)), ("tc3", mlp_tc.MlpTc(3))]:
+for name, eng in [("tc1", mlp_tc.MlpTc(1)), ("tf32", mlp_tc.MlpTc(2)), ("tc3", mlp_tc.MlpTc(3))]:
     for save in (False, True):
         s = eng.forward(XB, raw, W, save=save)
         read()
