@@ -147,24 +147,21 @@ class MlpSimt:
 
 def nonrigid_offsets(xyz, cond, window, nr_w, nr_b, const_off=None, return_const=False):
     """xyz (m,3) -> xyz + MLP([cond69, hann_pe36])  (mlp_offset.py:45-62), fp32, forward only (its output feeds
-    no_grad code only).  When the Hann window is fully closed and the condition code is
-    zero (every training iteration before kick_in_iter, network.py:579-583) every row of the MLP input is zero,
-    so the offset is one constant 3-vector evaluated on a single row."""
+    no_grad code only).  When the Hann window is fully closed (every training iteration before
+    kick_in_iter, network.py:579-583, where the condition code is zero as well) every row of the MLP input is the same
+    [cond69, 0], so the offset is one constant 3-vector evaluated on a single row -- decided on the host from the
+    window alone, the condition tensor is never inspected (no device->host sync, CUDA-graph capturable)."""
     m, dev = xyz.shape[0], xyz.device
     if const_off is not None:
         return xyz + const_off
     w = [t.detach().contiguous() for t in nr_w]
     b = [t.detach().contiguous() for t in nr_b]
-    zero_in = all(v == 0.0 for v in window) and cond is None
+    zero_in = all(v == 0.0 for v in window)
     rows = 1 if zero_in else m
-    if zero_in:
-        pe = torch.zeros(1, 36, device=dev, dtype=f32)
+    pe = torch.zeros(1, 36, device=dev, dtype=f32) if zero_in else ops.hann_pe(xyz, window)
+    if cond is None:
         cond = torch.zeros(1, 69, device=dev, dtype=f32)
-    else:
-        pe = ops.hann_pe(xyz, window)
-        if cond is None:
-            cond = torch.zeros(1, 69, device=dev, dtype=f32)
-        cond = cond.reshape(1, 69).contiguous().float()
+    cond = cond.reshape(1, 69).contiguous().float()
     # layer 0: fold the (row-independent) condition code into the bias
     b0 = torch.empty(1, 128, device=dev, dtype=f32)
     _gemm(cond.data_ptr(), 69, 1, w[0].data_ptr(), 1, 105, b0.data_ptr(), 128, 1, 128, 69, bias=b[0].data_ptr())

@@ -435,19 +435,25 @@ class Network(nn.Module):
             if not hasattr(non_rigid_pos_embed_fn, "window"):
                 raise TypeError("non_rigid_pos_embed_fn must be the HannEmbedder returned by get_non_rigid_embedder()")
             window = non_rigid_pos_embed_fn.window
-            if non_rigid_mlp_input is not None and bool((non_rigid_mlp_input != 0).any()):
+            # the condition tensor is never inspected on the device (that would be a host sync per call and cannot be
+            # captured in a CUDA graph): `forward` passes None before kick_in_iter, the reference passes zeros
+            # (network.py:579-583); both give the same offsets
+            if non_rigid_mlp_input is not None:
                 cond = non_rigid_mlp_input.reshape(1, -1).float()
-        # closed Hann window + zero condition code (all of training before kick_in_iter): the offset is one constant
-        # 3-vector, evaluated once per call instead of once per chunk
+        # closed Hann window (all of training before kick_in_iter): every sample sees the same MLP input [cond, 0], so the
+        # offset is one constant 3-vector, evaluated once per call instead of once per chunk
         self._nr_const = None
-        if window is not None and cond is None and all(v == 0.0 for v in window):
+        if window is not None and all(v == 0.0 for v in window):
             nw, nb = self.non_rigid_mlp.module.flat()
-            # ... and only when the non-rigid MLP's tensors have changed (they get no gradient before kick_in_iter)
-            key = tuple((t.data_ptr(), t._version) for t in nw + nb)
-            if getattr(self, "_nr_const_key", None) != key:
-                self._nr_const_val = M.nonrigid_offsets(pos_flat[:1].detach().contiguous().float(), None, window, nw, nb, return_const=True)
-                self._nr_const_key = key
-            self._nr_const = self._nr_const_val
+            if cond is None:
+                # ... and only when the non-rigid MLP's tensors have changed (they get no gradient before kick_in_iter)
+                key = tuple((t.data_ptr(), t._version) for t in nw + nb)
+                if getattr(self, "_nr_const_key", None) != key:
+                    self._nr_const_val = M.nonrigid_offsets(pos_flat[:1].detach().contiguous().float(), None, window, nw, nb, return_const=True)
+                    self._nr_const_key = key
+                self._nr_const = self._nr_const_val
+            else:                       # a caller-supplied condition code may change between calls: one-row evaluation per call
+                self._nr_const = M.nonrigid_offsets(pos_flat[:1].detach().contiguous().float(), cond, window, nw, nb, return_const=True)
         # non-rigid offsets (network.py:225-232) and the multi-scale neighbour search (network.py:236-255) run under no_grad
         # in the reference and do not depend on the chunking: one search over all points keeps the SMs full (per-chunk
         # launches of ~2 waves lose a third of their time to the tail), the memory-heavy part below stays chunked

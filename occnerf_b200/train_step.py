@@ -68,7 +68,7 @@ class GraphedTrainStep:
 
     def needs_recapture(self, iter_val: int) -> bool:
         cfg = self.net.cfg
-        marks = (cfg.non_rigid_kick_in_iter, cfg.non_rigid_full_band_iter)
+        marks = (cfg.non_rigid_kick_in_iter, cfg.non_rigid_full_band_iter, getattr(self.net, "_pose_kick_in_iter", float("inf")))
         return any((self.iter_val < m) != (iter_val < m) for m in marks) or \
             (cfg.non_rigid_kick_in_iter <= iter_val < cfg.non_rigid_full_band_iter and iter_val != self.iter_val)
 

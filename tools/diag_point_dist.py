@@ -1,0 +1,84 @@
+"""Diagnostic (GPU): where does the per-entry difference of d loss / d point_dist between the CUDA path (fp32 engine) and the
+oracle come from?  Compares, on the golden case `train_dense`, the gradient arriving at the per-vertex feature table
+(V,35), the gradient w.r.t. the vertices' hash-grid inputs, and the final point_dist gradient, vertex by vertex."""
+import copy, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from occnerf_b200 import synthetic as S, ops
+from occnerf_b200.network import RenderConfig
+from oracle import make_golden, occnerf_oracle as O
+from tests.helpers import load_case
+
+sub, w, fr, vol, t_rand, rk, g = load_case("train_dense")
+dev = torch.device("cuda:0")
+# ---- oracle with the intermediate gradients retained
+cap = {}
+orig_vb, orig_he = O.vertex_block, O.hash_encode
+def vb(*a, **k):
+    pc, kb, dist = orig_vb(*a, **k)
+    for n, t in (("pc", pc), ("kb", kb), ("dist", dist)):
+        t.retain_grad(); cap[n] = t
+    return pc, kb, dist
+def he(x4, ww, ls=None):
+    out = orig_he(x4, ww, ls)
+    if x4.shape[0] == 6890:
+        out.retain_grad(); cap["hv"] = out; cap["v_in"] = x4
+    return out
+O.vertex_block, O.hash_encode = vb, he
+sub_g, w_g = copy.deepcopy(sub), copy.deepcopy(w)
+for t in [w_g.embeddings, sub_g.point_dist]:
+    t.requires_grad_(True)
+o = O.render_rays(fr, vol.clone().requires_grad_(True), sub_g, w_g, iter_val=rk["iter_val"], training=True, t_rand=t_rand)
+make_golden.scalar_loss(o).backward()
+O.vertex_block, O.hash_encode = orig_vb, orig_he
+g_pd_o = sub_g.point_dist.grad.reshape(-1)
+# ---- CUDA path, fp32 engine
+net = S.network_from_synthetic(sub, w, RenderConfig(perturb=1.0, mlp_engine="fp32"), device=dev).train(True)
+hook = {}
+orig_vf = net.vertex_features
+def vf():
+    f, pc = orig_vf()
+    f.register_hook(lambda gr: hook.__setitem__("g_feats", gr.detach().clone()))
+    hook["feats"] = f.detach().clone()
+    return f, pc
+net.vertex_features = vf
+frd = S.frame_to(fr, dev)
+emb_fn, _ = net.get_non_rigid_embedder(6, 0, rk["iter_val"])
+packed = torch.cat([frd.rays_o, frd.rays_d, frd.near, frd.far], -1)
+out = net._batchify_rays(packed, pos_embed_fn=None, non_rigid_pos_embed_fn=emb_fn, non_rigid_mlp_input=frd.dst_posevec[None],
+                         motion_scale_Rs=frd.motion_scale_Rs[None], motion_Ts=frd.motion_Ts[None], motion_weights_vol=vol.to(dev).requires_grad_(True),
+                         cnl_bbox_min_xyz=frd.cnl_bbox_min_xyz, cnl_bbox_scale_xyz=frd.cnl_bbox_scale_xyz, bgcolor=frd.bgcolor, t_rand=t_rand.to(dev))
+make_golden.scalar_loss({k: out[k] for k in ("rgb", "alpha", "depth", "comp_loss")}).backward()
+g_pd = net.point_dist.grad.reshape(-1).cpu()
+gf = hook["g_feats"].cpu()
+
+def mx(a, b): return float((a - b).abs().max() / b.abs().max())
+def fro(a, b): return float((a - b).norm() / b.norm())
+print("feats (V,32) hash values  max", mx(hook["feats"][:, :32].cpu(), cap["hv"].detach()))
+print("g_feats[:, :32] (d/d hash feats of vertices): max", mx(gf[:, :32], cap["hv"].grad), "fro", fro(gf[:, :32], cap["hv"].grad))
+print("g_feats[:, 32:35] (d/d pc via aggregation): max", mx(gf[:, 32:35], cap["pc"].grad), "fro", fro(gf[:, 32:35], cap["pc"].grad),
+      " [oracle pc.grad also holds the vertex-block part]")
+print("g_point_dist: max", mx(g_pd, g_pd_o), "fro", fro(g_pd, g_pd_o), " vs golden: max", mx(g_pd, torch.from_numpy(g["g_point_dist"]).reshape(-1)))
+err = (g_pd - g_pd_o).abs()
+top = torch.topk(err, 8)[1]
+st = net._static()
+pc = (sub.point_base + sub.point_dist)
+kidx = O.knn_bruteforce(pc, sub.point_base, 3)
+for v in top.tolist():
+    d = pc[v][None] - sub.point_base[kidx[v]]
+    print(f"v={v} err={float(err[v]):.3e} ours={float(g_pd[v]):.4e} oracle={float(g_pd_o[v]):.4e} |g|max={float(g_pd_o.abs().max()):.3e} "
+          f"kidx={kidx[v].tolist()} |d|={d.norm(dim=1).tolist()} v_in={cap['v_in'][v].tolist()}")
+# gradient w.r.t. the vertices' hash-grid input from OUR dy_dx path with the ORACLE's upstream gradient
+enc = net.cnl_mlp.module.encoder
+scales = ops.level_scales(float(np.log2(enc.per_level_scale)), enc.base_resolution, enc.num_levels, dev)
+v_in_d = cap["v_in"].detach().to(dev).contiguous()
+feats_tmp = torch.empty(6890, 32, device=dev)
+_, dy_dx, _, _ = ops.hashgrid_forward(v_in_d, enc.embeddings.detach().contiguous(), enc.offsets, scales, out_ptr=feats_tmp.data_ptr(), ld=32, want_dy_dx=True)
+up = cap["hv"].grad.to(dev).contiguous()
+g_v_in = ops.hashgrid_input_backward(up.data_ptr(), 32, 0, dy_dx, 6890, 4, 2, 16).cpu()
+# oracle's: chain kb/dist grads are not directly d/d v_in; recompute with autograd in fp64 through the C oracle is not available,
+# so compare against a float64 evaluation of sum_l g * dy_dx from the same dy_dx
+dd = dy_dx.cpu().double().reshape(6890, 16, 4, 2)
+g64 = (dd * up.cpu().double().reshape(6890, 16, 1, 2)).sum((1, 3))
+print("hashgrid_input_backward vs fp64 sum of the same terms: max", mx(g_v_in.double(), g64), "fro", fro(g_v_in.double(), g64))
