@@ -66,10 +66,33 @@ int occnerf_warp_forward(const float *rays, const float *t_lin, const float *t_r
                          int N, int S, int nb, int vd, int vh, int vw, float *z, float *x_skel, float *mask,
                          int32_t *bins, occnerf_stream_t stream);
 /* d(mask) -> g_vol [nb,vd,vh,vw] (accumulated; caller zeroes).  x_skel has no gradient consumer
- * (network.py:225-299 uses it under no_grad only), Rs/Ts gradients are not produced. */
+ * (network.py:225-299 uses it under no_grad only); Rs/Ts gradients: see occnerf_warp_backward_packed. */
 int occnerf_warp_backward(const float *rays, const float *t_lin, const float *t_rand, const float *Rs,
                           const float *Ts, const float *bbox_min, const float *bbox_scale, const float *g_mask,
                           int N, int S, int nb, int vd, int vh, int vw, float *g_vol, occnerf_stream_t stream);
+
+/* Corner-packed variant (what the Python operator layer uses).  The 24 bones are sampled at 24 different positions, so
+ * what one lookup's 8 corners share is the floor voxel: occnerf_warp_pack_volume re-lays the per-frame volume out as
+ * vol8 [nb][vd+1][vh+1][vw+1][8] (cell (z0+1,y0+1,x0+1) = the 8 corners of floor voxel (x0,y0,z0), k = dz*4+dy*2+dx, zero
+ * padding baked in; occnerf_warp_packed_floats() floats, 16-byte aligned) and the kernels read one 32-byte sector per
+ * (sample, bone).  Block inputs (bone table, rays, jitter tile) are staged by TMA bulk copies.  Same z / x_skel / mask as
+ * occnerf_warp_forward, bit for bit. */
+long occnerf_warp_packed_floats(int nb, int vd, int vh, int vw);
+int occnerf_warp_pack_volume(const float *vol, int nb, int vd, int vh, int vw, float *vol8, occnerf_stream_t stream);
+int occnerf_warp_forward_packed(const float *rays, const float *t_lin, const float *t_rand, const float *Rs,
+                                const float *Ts, const float *vol8, const float *bbox_min, const float *bbox_scale,
+                                int N, int S, int nb, int vd, int vh, int vw, float *z, float *x_skel, float *mask,
+                                occnerf_stream_t stream);
+/* d(mask) -> g_vol8 (packed layout, accumulated with vector reductions; caller zeroes), folded back into the reference
+ * layout g_vol [channels >= nb, vd,vh,vw] (overwritten; channels >= nb get 0) by occnerf_warp_unpack_grad.
+ * g_Rs [nb,9] / g_Ts [nb,3] (both or neither; accumulated, caller zeroes): d mask / d motion_scale_Rs, motion_Ts -- what
+ * F.grid_sample's grid gradient gives the reference (network.py:367-370) once the pose decoder trains; needs vol8. */
+int occnerf_warp_backward_packed(const float *rays, const float *t_lin, const float *t_rand, const float *Rs,
+                                 const float *Ts, const float *vol8, const float *bbox_min, const float *bbox_scale,
+                                 const float *g_mask, int N, int S, int nb, int vd, int vh, int vw, float *g_vol8,
+                                 float *g_Rs, float *g_Ts, occnerf_stream_t stream);
+int occnerf_warp_unpack_grad(const float *g_vol8, int nb, int channels, int vd, int vh, int vw, float *g_vol,
+                             occnerf_stream_t stream);
 
 /* ---- exact k-nearest-neighbour search (knn.py:33-85; network.py:236-255,265,508) --------------------
  * queries [m,3]; supports4 [ns,4] = (x,y,z,unused); the support set is split into n_levels contiguous

@@ -25,6 +25,10 @@ class MlpParams(C.Structure):
 _SIGNATURES = {
     "occnerf_warp_forward": [_vp] * 8 + [_i] * 6 + [_vp] * 4 + [_vp],
     "occnerf_warp_backward": [_vp] * 8 + [_i] * 6 + [_vp, _vp],
+    "occnerf_warp_pack_volume": [_vp, _i, _i, _i, _i, _vp, _vp],
+    "occnerf_warp_forward_packed": [_vp] * 8 + [_i] * 6 + [_vp] * 3 + [_vp],
+    "occnerf_warp_backward_packed": [_vp] * 9 + [_i] * 6 + [_vp, _vp, _vp, _vp],
+    "occnerf_warp_unpack_grad": [_vp, _i, _i, _i, _i, _i, _vp, _vp],
     "occnerf_knn": [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "occnerf_knn_hier": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp],
     "occnerf_knn_tree": [_vp, _i, _i, _i] + [_vp] * 11 + [_i] * 5 + [_vp, _vp],
@@ -57,7 +61,7 @@ _SIGNATURES = {
     "occnerf_unpack_image": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
 }
 EXPORTED = sorted(list(_SIGNATURES) + ["occnerf_last_error", "occnerf_abi_version", "occnerf_mlp_packed_bytes",
-                                           "occnerf_rays_scratch_bytes"])
+                                           "occnerf_rays_scratch_bytes", "occnerf_warp_packed_floats"])
 
 GEMM_BIAS, GEMM_RELU, GEMM_ACCUM, GEMM_RELUMASK = 1, 2, 4, 8
 LAYOUT_BLC, LAYOUT_LBC = 0, 1
@@ -81,6 +85,7 @@ def load(build_if_missing: bool = True):
     lib.occnerf_abi_version.restype = _i
     lib.occnerf_mlp_packed_bytes.argtypes, lib.occnerf_mlp_packed_bytes.restype = [_i, _i], _l
     lib.occnerf_rays_scratch_bytes.argtypes, lib.occnerf_rays_scratch_bytes.restype = [_i, _i], _l
+    lib.occnerf_warp_packed_floats.argtypes, lib.occnerf_warp_packed_floats.restype = [_i, _i, _i, _i], _l
     _lib = lib
     return lib
 

@@ -399,15 +399,37 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
                 if (args.debug) dbg_wait += clk() - t0;
                 const int kc = min(KC, K - c * KC);
                 const uint32_t bytes = (uint32_t)N * kc * EB;      // per part; the k-slab-outer image is contiguous
-                mbar_arrive_expect_tx(sm.bar_w_full + 8 * s, bytes * NP);   // what lands in MY slot (from both CTAs)
+                const uint32_t all = bytes * NP;                   // what lands in MY slot (from both CTAs of the pair)
                 const uint32_t dst = smem_u32(sm.W + s * kStageBytes);
+                const uint32_t bar = sm.bar_w_full + 8 * s;
+                if (args.debug & 14) {
+                    // TIMING EXPERIMENTS (OCCNERF_MLP_DEBUG bits 1..3; results are garbage except for bit 3): they separate the
+                    // L2-output bound from the peer-delivery bound of the weight stream.
+                    //   bit 1: both CTAs fetch a quarter and multicast it -> half of the bytes everywhere
+                    //   bit 2: every CTA fetches its own half only, nothing is multicast (normal L2 output, no peer traffic)
+                    //   bit 3: every CTA fetches the whole chunk itself, nothing is multicast (2x L2 output; numerically valid)
+                    const unsigned char *chunk = src + (long)c * NP * pb;
+                    if (args.debug & 8) {
+                        mbar_arrive_expect_tx(bar, all);
+                        bulk_g2s(dst, chunk, bytes, bar);
+                        if (NP == 2) bulk_g2s(dst + kStageBytes / 2, chunk + pb, bytes, bar);
+                    } else if (args.debug & 4) {
+                        mbar_arrive_expect_tx(bar, all / 2);
+                        bulk_g2s(dst + rank * (all / 2), chunk + rank * (all / 2), all / 2, bar);
+                    } else {
+                        mbar_arrive_expect_tx(bar, all / 2);
+                        bulk_g2s_mc(dst + rank * (all / 4), chunk + rank * (all / 4), all / 4, bar, 3);
+                    }
+                    continue;
+                }
+                mbar_arrive_expect_tx(bar, all);
                 // the two CTAs of a cluster walk the same weight stream: each fetches one half from L2 and multicasts
                 // it into both shared memories, halving the L2 -> SM weight traffic
                 if (NP == 2) {
-                    bulk_g2s_mc(dst + rank * (kStageBytes / 2), src + ((long)c * 2 + rank) * pb, bytes, sm.bar_w_full + 8 * s, 3);
+                    bulk_g2s_mc(dst + rank * (kStageBytes / 2), src + ((long)c * 2 + rank) * pb, bytes, bar, 3);
                 } else {
                     const uint32_t half = bytes / 2;
-                    bulk_g2s_mc(dst + rank * half, src + (long)c * pb + rank * half, half, sm.bar_w_full + 8 * s, 3);
+                    bulk_g2s_mc(dst + rank * half, src + (long)c * pb + rank * half, half, bar, 3);
                 }
             }
         }

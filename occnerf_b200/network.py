@@ -171,23 +171,29 @@ class RenderConfig:
 
 # ----------------------------------------------------------------------------- differentiable stages
 class _WarpFn(torch.autograd.Function):
-    """vol -> (z, x_skel, mask); only mask carries a gradient (to vol), as in the reference."""
+    """(vol, Rs, Ts) -> (z, x_skel, mask); only mask carries a gradient, as in the reference: to the weight
+    volume, and -- through F.grid_sample's grid gradient upstream, network.py:367-370 -- to motion_scale_Rs / motion_Ts
+    (consumed only when the pose decoder trains, i.e. iter >= pose_decoder.kick_in_iter)."""
 
     @staticmethod
-    def forward(ctx, vol, rays, t_rand, Rs, Ts, bmin, bscale, S):
-        vol_c = vol.detach().contiguous().float()
-        z, x_skel, mask = ops.warp_forward(rays, t_rand, Rs, Ts, vol_c, bmin, bscale, S)
-        ctx.save_for_backward(rays, t_rand if t_rand is not None else torch.empty(0, device=rays.device), Rs, Ts, bmin, bscale)
+    def forward(ctx, vol, rays, t_rand, Rs, Ts, bmin, bscale, S, vol8):
+        if vol8 is None:
+            vol8 = ops.warp_pack_volume(vol.detach().contiguous().float(), Rs.shape[0])
+        z, x_skel, mask = ops.warp_forward(rays, t_rand, Rs.detach(), Ts.detach(), vol.detach(), bmin, bscale, S, vol8=vol8)
+        ctx.save_for_backward(rays, t_rand if t_rand is not None else torch.empty(0, device=rays.device), Rs.detach(), Ts.detach(), bmin, bscale, vol8)
         ctx.meta = (S, tuple(vol.shape), t_rand is not None)
         ctx.mark_non_differentiable(z, x_skel)
         return z, x_skel, mask
 
     @staticmethod
     def backward(ctx, _gz, _gx, g_mask):
-        rays, t_rand, Rs, Ts, bmin, bscale = ctx.saved_tensors
+        rays, t_rand, Rs, Ts, bmin, bscale, vol8 = ctx.saved_tensors
         S, vol_shape, has_rand = ctx.meta
-        g_vol = ops.warp_backward(rays, t_rand if has_rand else None, Rs, Ts, bmin, bscale, g_mask.contiguous(), S, vol_shape)
-        return g_vol, None, None, None, None, None, None, None
+        want_pose = ctx.needs_input_grad[3] or ctx.needs_input_grad[4]
+        r = ops.warp_backward(rays, t_rand if has_rand else None, Rs, Ts, bmin, bscale, g_mask.contiguous(), S, vol_shape, vol8=vol8,
+                              want_pose=want_pose)
+        g_vol, g_Rs, g_Ts = r if want_pose else (r, None, None)
+        return g_vol, None, None, g_Rs, g_Ts, None, None, None, None
 
 
 class _CompositeFn(torch.autograd.Function):
@@ -510,7 +516,7 @@ class Network(nn.Module):
     # -- reference API: network.py:435-525
     def _render_rays(self, ray_batch, motion_scale_Rs, motion_Ts, motion_weights_vol, cnl_bbox_min_xyz,
                      cnl_bbox_scale_xyz, pos_embed_fn, non_rigid_pos_embed_fn, non_rigid_mlp_input=None, bgcolor=None,
-                     t_rand=None, _feats=None, **_):
+                     t_rand=None, _feats=None, _vol8=None, **_):
         cfg = self.cfg
         S = cfg.N_samples
         rays = ray_batch.contiguous().float()
@@ -523,7 +529,7 @@ class Network(nn.Module):
         Rs = motion_scale_Rs.reshape(-1, 3, 3).contiguous().float()
         Ts = motion_Ts.reshape(-1, 3).contiguous().float()
         z, x_skel, mask = _WarpFn.apply(motion_weights_vol, rays, t_rand.contiguous() if t_rand is not None else None, Rs, Ts,
-                                        cnl_bbox_min_xyz.contiguous().float(), cnl_bbox_scale_xyz.contiguous().float(), S)
+                                        cnl_bbox_min_xyz.contiguous().float(), cnl_bbox_scale_xyz.contiguous().float(), S, _vol8)
         feats36, pc = _feats if _feats is not None else self.vertex_features()
         q = self._query_mlp(pos_xyz=x_skel, rays_d=None, pos_embed_fn=pos_embed_fn,
                             non_rigid_pos_embed_fn=non_rigid_pos_embed_fn, non_rigid_mlp_input=non_rigid_mlp_input,
@@ -540,10 +546,13 @@ class Network(nn.Module):
         """network.py:307-317."""
         t_rand = kwargs.pop("t_rand", None)
         feats = self.vertex_features()
+        # the per-frame weight volume in the corner-packed layout of K1 (csrc/warp.cu): once per frame, not once per ray chunk
+        vol = kwargs["motion_weights_vol"]
+        vol8 = ops.warp_pack_volume(vol.detach().contiguous().float(), self.cfg.total_bones) if vol.shape[0] >= self.cfg.total_bones else None
         all_ret = {}
         for i in range(0, rays_flat.shape[0], self.cfg.chunk):
             tr = t_rand[i:i + self.cfg.chunk] if t_rand is not None else None
-            ret = self._render_rays(rays_flat[i:i + self.cfg.chunk], t_rand=tr, _feats=feats, **kwargs)
+            ret = self._render_rays(rays_flat[i:i + self.cfg.chunk], t_rand=tr, _feats=feats, _vol8=vol8, **kwargs)
             for k, v in ret.items():
                 all_ret.setdefault(k, []).append(v)
         out = {}

@@ -29,8 +29,20 @@ def t_lin(S: int, device) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- K1 warp
-def warp_forward(rays, t_rand, Rs, Ts, vol, bbox_min, bbox_scale, S, want_bins=False):
-    """rays (N,8) -> z (N,S), x_skel (N,S,3), mask (N,S) [, bins (N,S,nb,3) int32]."""
+def warp_pack_volume(vol, nb):
+    """[>=nb, D,H,W] reference-layout weight volume -> corner-packed vol8 [nb, D+1, H+1, W+1, 8] (csrc/warp.cu): once per frame."""
+    vd, vh, vw = vol.shape[-3:]
+    if vol.shape[0] < nb:
+        raise RuntimeError(f"warp_pack_volume: the weight volume has {vol.shape[0]} channels for {nb} bones")
+    vol8 = torch.empty(nb, vd + 1, vh + 1, vw + 1, 8, device=vol.device, dtype=f32)
+    call("occnerf_warp_pack_volume", ptr(vol, f32), nb, vd, vh, vw, ptr(vol8), stream())
+    return vol8
+
+
+def warp_forward(rays, t_rand, Rs, Ts, vol, bbox_min, bbox_scale, S, want_bins=False, vol8=None):
+    """rays (N,8) -> z (N,S), x_skel (N,S,3), mask (N,S) [, bins (N,S,nb,3) int32].
+    Default: the corner-packed kernel (`vol8` = warp_pack_volume(vol), built here when not given).  With `want_bins` the
+    scalar-gather kernel on the reference layout runs (it is the one that can dump the voxel bins; same outputs)."""
     N, nb = rays.shape[0], Rs.shape[0]
     dev = rays.device
     z = torch.empty(N, S, device=dev, dtype=f32)
@@ -40,17 +52,38 @@ def warp_forward(rays, t_rand, Rs, Ts, vol, bbox_min, bbox_scale, S, want_bins=F
     vd, vh, vw = vol.shape[-3:]
     if vol.shape[0] < nb:
         raise RuntimeError(f"warp_forward: the weight volume has {vol.shape[0]} channels for {nb} bones")
+    if not want_bins:
+        if vol8 is None:
+            vol8 = warp_pack_volume(vol, nb)
+        call("occnerf_warp_forward_packed", ptr(rays, f32), ptr(t_lin(S, dev), f32), ptr(t_rand, f32), ptr(Rs, f32), ptr(Ts, f32),
+             ptr(vol8, f32), ptr(bbox_min, f32), ptr(bbox_scale, f32), N, S, nb, vd, vh, vw, ptr(z), ptr(x_skel), ptr(mask), stream())
+        return z, x_skel, mask
     call("occnerf_warp_forward", ptr(rays, f32), ptr(t_lin(S, dev), f32), ptr(t_rand, f32), ptr(Rs, f32), ptr(Ts, f32),
          ptr(vol, f32), ptr(bbox_min, f32), ptr(bbox_scale, f32), N, S, nb, vd, vh, vw, ptr(z), ptr(x_skel), ptr(mask),
          ptr(bins), stream())
     return (z, x_skel, mask, bins) if want_bins else (z, x_skel, mask)
 
 
-def warp_backward(rays, t_rand, Rs, Ts, bbox_min, bbox_scale, g_mask, S, vol_shape):
-    """d mask (N,S) -> g_vol with the shape of the reference's motion_weights_vol (channels >= nb stay 0)."""
+def warp_backward(rays, t_rand, Rs, Ts, bbox_min, bbox_scale, g_mask, S, vol_shape, vol8=None, want_pose=False, packed=True):
+    """d mask (N,S) -> g_vol with the shape of the reference's motion_weights_vol (channels >= nb stay 0)
+    [, g_Rs (nb,3,3), g_Ts (nb,3) with want_pose: the gradient F.grid_sample gives the reference w.r.t. its grid, chained
+    through q = R p + T].  packed=False runs the scalar-reduction kernel on the reference layout (cross-check)."""
     N, nb = rays.shape[0], Rs.shape[0]
-    g_vol = torch.zeros(vol_shape, device=rays.device, dtype=f32)
     vd, vh, vw = vol_shape[-3:]
+    dev = rays.device
+    if packed:
+        if want_pose and vol8 is None:
+            raise RuntimeError("warp_backward: the pose gradients need the packed volume (vol8)")
+        g_vol8 = torch.zeros(nb, vd + 1, vh + 1, vw + 1, 8, device=dev, dtype=f32)
+        g_Rs = torch.zeros(nb, 3, 3, device=dev, dtype=f32) if want_pose else None
+        g_Ts = torch.zeros(nb, 3, device=dev, dtype=f32) if want_pose else None
+        call("occnerf_warp_backward_packed", ptr(rays, f32), ptr(t_lin(S, dev), f32), ptr(t_rand, f32), ptr(Rs, f32), ptr(Ts, f32),
+             ptr(vol8, f32), ptr(bbox_min, f32), ptr(bbox_scale, f32), ptr(g_mask, f32), N, S, nb, vd, vh, vw, ptr(g_vol8), ptr(g_Rs),
+             ptr(g_Ts), stream())
+        g_vol = torch.empty(vol_shape, device=dev, dtype=f32)
+        call("occnerf_warp_unpack_grad", ptr(g_vol8), nb, int(vol_shape[0]), vd, vh, vw, ptr(g_vol), stream())
+        return (g_vol, g_Rs, g_Ts) if want_pose else g_vol
+    g_vol = torch.zeros(vol_shape, device=rays.device, dtype=f32)
     call("occnerf_warp_backward", ptr(rays, f32), ptr(t_lin(S, rays.device), f32), ptr(t_rand, f32), ptr(Rs, f32),
          ptr(Ts, f32), ptr(bbox_min, f32), ptr(bbox_scale, f32), ptr(g_mask, f32), N, S, nb, vd, vh, vw, ptr(g_vol),
          stream())

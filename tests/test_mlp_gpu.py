@@ -65,7 +65,7 @@ def test_forward_against_torch(engine, tol, m):
     assert float(raw[:, 4].min()) == 7.0 and float(raw[:, 4].max()) == 7.0      # the dist channel is not touched
 
 
-@pytest.mark.parametrize("engine,rel", [("fp32", 1e-4), ("tc3", 1e-2), ("tf32", 2e-2), ("tc1", 3e-1)])
+@pytest.mark.parametrize("engine,rel", [("fp32", 1e-4), ("tc3", 1e-2), ("tf32", 8e-2), ("tc1", 3e-1)])
 def test_backward_against_torch(engine, rel):
     m = 3000
     w = _weights(seed=2)

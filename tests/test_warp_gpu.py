@@ -74,3 +74,68 @@ def test_no_jitter_and_odd_sizes():
     z, x_skel, mask = ops.warp_forward(rays[:0].contiguous(), None, fr.motion_scale_Rs.to(d).contiguous(), fr.motion_Ts.to(d).contiguous(),
                                        vol.to(d).contiguous(), fr.cnl_bbox_min_xyz.to(d), fr.cnl_bbox_scale_xyz.to(d), 128)
     assert z.shape == (0, 128)
+
+
+def test_packed_kernels_equal_the_scalar_kernels_bitwise():
+    """The corner-packed path (vol8 + TMA-staged block inputs, what Network uses) against the scalar-gather kernel on the
+    reference layout: the same rounding sequence, so z / x_skel / mask are bit-identical -- with and without jitter, for S that
+    takes the bulk-copy path (multiple of 4) and S that does not."""
+    sub = S.make_subject(seed=0)
+    vol = S.make_motion_weights_vol(sub.priors, seed=2)
+    d = dev()
+    for mode, kw, Sn in (("patch", dict(n_patches=6, patch=32), 128), ("image", dict(img=64, max_rays=301), 33), ("image", dict(img=64, max_rays=77), 130)):
+        fr = S.make_frame(sub, mode=mode, seed=21, **kw)
+        N = fr.rays_o.shape[0]
+        rays = torch.cat([fr.rays_o, fr.rays_d, fr.near, fr.far], -1).to(d).contiguous()
+        args = (fr.motion_scale_Rs.to(d).contiguous(), fr.motion_Ts.to(d).contiguous(), vol.to(d).contiguous(), fr.cnl_bbox_min_xyz.to(d),
+                fr.cnl_bbox_scale_xyz.to(d), Sn)
+        for t_rand in (None, torch.rand(N, Sn, generator=torch.Generator().manual_seed(5)).to(d)):
+            a = ops.warp_forward(rays, t_rand, *args)
+            b = ops.warp_forward(rays, t_rand, *args, want_bins=True)
+            for x, y, nm in zip(a, b[:3], ("z", "x_skel", "mask")):
+                assert torch.equal(x, y), (nm, mode, Sn, t_rand is not None)
+    # backward: packed (vector reductions + fold) vs scalar reductions
+    fr = S.make_frame(sub, mode="patch", n_patches=6, patch=32, seed=21)
+    N = fr.rays_o.shape[0]
+    rays = torch.cat([fr.rays_o, fr.rays_d, fr.near, fr.far], -1).to(d).contiguous()
+    t_rand = torch.rand(N, 128, generator=torch.Generator().manual_seed(5)).to(d)
+    gm = torch.randn(N, 128, generator=torch.Generator().manual_seed(6)).to(d)
+    bw = (rays, t_rand, fr.motion_scale_Rs.to(d).contiguous(), fr.motion_Ts.to(d).contiguous(), fr.cnl_bbox_min_xyz.to(d),
+          fr.cnl_bbox_scale_xyz.to(d), gm, 128, tuple(vol.shape))
+    g1, g0 = ops.warp_backward(*bw), ops.warp_backward(*bw, packed=False)
+    assert normwise_close(g1.cpu().numpy(), g0.cpu().numpy(), 1e-5)
+    assert float(g1[24].abs().max()) == 0.0
+
+
+def test_pose_gradients_against_autograd():
+    """d mask / d (motion_scale_Rs, motion_Ts): what F.grid_sample's grid gradient gives the reference (network.py:367-370)."""
+    sub = S.make_subject(seed=0)
+    fr = S.make_frame(sub, mode="patch", n_patches=2, patch=16, seed=8)
+    vol = S.make_motion_weights_vol(sub.priors, seed=2)
+    N = fr.rays_o.shape[0]
+    t_rand = torch.rand(N, 128, generator=torch.Generator().manual_seed(5))
+    Rs, Ts = fr.motion_scale_Rs.clone().requires_grad_(True), fr.motion_Ts.clone().requires_grad_(True)
+    volr = vol.clone().requires_grad_(True)
+    zo = O.z_samples(fr.near, fr.far, 128, t_rand)
+    pts = O.sample_points(fr.rays_o, fr.rays_d, zo).reshape(-1, 3)
+    _, mo = O.lbs_warp(pts, Rs, Ts, volr, fr.cnl_bbox_min_xyz, fr.cnl_bbox_scale_xyz, exact=False)
+    gm = torch.randn(N, 128, generator=torch.Generator().manual_seed(6))
+    (mo * gm.reshape(-1)).sum().backward()
+    d = dev()
+    rays = torch.cat([fr.rays_o, fr.rays_d, fr.near, fr.far], -1).to(d).contiguous()
+    vol8 = ops.warp_pack_volume(vol.to(d).contiguous(), 24)
+    g_vol, g_Rs, g_Ts = ops.warp_backward(rays, t_rand.to(d), fr.motion_scale_Rs.to(d).contiguous(), fr.motion_Ts.to(d).contiguous(),
+                                          fr.cnl_bbox_min_xyz.to(d), fr.cnl_bbox_scale_xyz.to(d), gm.to(d), 128, tuple(vol.shape), vol8=vol8,
+                                          want_pose=True)
+    eR = maxabs(g_Rs, Rs.grad) / float(Rs.grad.abs().max())
+    eT = maxabs(g_Ts, Ts.grad) / float(Ts.grad.abs().max())
+    report("warp_pose_grads", g_Rs_rel=eR, g_Ts_rel=eT, scale_R=float(Rs.grad.abs().max()))
+    assert eR < 2e-4 and eT < 2e-4
+    assert normwise_close(g_vol.cpu().numpy(), volr.grad.numpy(), 1e-4)
+    # and through the autograd node of the network path
+    from occnerf_b200.network import _WarpFn
+    Rd, Td = fr.motion_scale_Rs.to(d).clone().requires_grad_(True), fr.motion_Ts.to(d).clone().requires_grad_(True)
+    vd_ = vol.to(d).clone().requires_grad_(True)
+    z, xs, mask = _WarpFn.apply(vd_, rays, t_rand.to(d), Rd, Td, fr.cnl_bbox_min_xyz.to(d), fr.cnl_bbox_scale_xyz.to(d), 128, None)
+    (mask * gm.to(d)).sum().backward()
+    assert normwise_close(Rd.grad.cpu().numpy(), Rs.grad.numpy(), 2e-4) and normwise_close(Td.grad.cpu().numpy(), Ts.grad.numpy(), 2e-4)
