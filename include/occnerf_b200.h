@@ -231,7 +231,9 @@ long occnerf_mlp_packed_bytes(int n_pass, int chain);
 int occnerf_mlp_debug_counters(unsigned long long *host8, int reset);
 /* Debug only: `iters` back-to-back tcgen05.mma (M=128, N=n, K=16, bf16, shared-memory operands) on `ctas` CTAs (one per
  * SM) at once; out_dev[cta] = cycles from the first issue to the completion of the last (tools/mma_rate.py). */
-int occnerf_mlp_debug_mma_rate(int iters, int n, unsigned long long *out_dev, int ctas, occnerf_stream_t stream);
+int occnerf_mlp_debug_mma_rate(int iters, int n, int tf32, unsigned long long *out_dev, int ctas, occnerf_stream_t stream);
+/* debug only: per-layer clock64 stamps of one tile of CTA 0 (OCCNERF_MLP_DEBUG bit 4): 16 x 12 u64, see csrc/mlp_tc.cu */
+int occnerf_mlp_debug_trace(unsigned long long *host192);
 /* Debug only: cudaOccupancyMaxActiveClusters of the tc3 forward chain kernel for clusters of `cluster_size` CTAs (< 0: error). */
 int occnerf_mlp_debug_max_clusters(int cluster_size);
 int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, void *packed, occnerf_stream_t stream);

@@ -365,6 +365,12 @@ struct ChainArgs {
 // [4] MMA thread total, [5] epilogue thread total, [6] CTAs.
 __device__ unsigned long long g_dbg[16];
 __device__ __forceinline__ long long clk() { return clock64(); }
+// Per-layer time stamps (OCCNERF_MLP_DEBUG bit 4) of CTA 0's third tile, clock64 of one SM: [layer][event]
+//  0 MMA thread enters the layer   1 first MMA issued   2 last MMA issued   3 epilogue warp 0: accumulator ready
+//  4 warp 0: first group published   5 warp 0: last group published   6 warp 15: accumulator ready   7 warp 15: last group published
+//  8 producer: last chunk of the layer issued   10 MMA thread: cycles waiting for A in the layer   11 ... for weights
+__device__ unsigned long long g_trace[16][12];
+#define TRACE(cond, l, e) do { if (cond) g_trace[l][e] = (unsigned long long)clock64(); } while (0)
 
 // bf16 activations / gradients saved for the weight-gradient kernel use a CHUNK-MAJOR layout [slot][k8 = col/8][row][8]:
 // the 32 lanes of an epilogue warp (32 consecutive rows, one 8-column chunk) then write 512 contiguous bytes instead of
@@ -387,6 +393,7 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
     long long dbg_wait = 0;
     const uint32_t rank = cluster_ctarank();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const bool tr = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x;
         for (int l = 0; l < n_layers(args.chain); ++l) {
             const int K = chain_K(args.chain, l), N = chain_N(args.chain, l);
             const int nch = (K + KC - 1) / KC;
@@ -432,6 +439,7 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
                     bulk_g2s_mc(dst + rank * half, src + (long)c * pb + rank * half, half, bar, 3);
                 }
             }
+            TRACE(tr, l, 8);
         }
     }
     if (args.debug) atomicAdd(&g_dbg[3], (unsigned long long)dbg_wait);
@@ -449,7 +457,10 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
     const long long dbg_t0 = args.debug ? clk() : 0;
     const uint32_t a_base = smem_u32(sm.A);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const bool tr = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x;
         for (int l = 0; l < n_layers(args.chain); ++l) {
+            TRACE(tr, l, 0);
+            const long long w0 = dbg_w, a0 = dbg_a;
             const int K = chain_K(args.chain, l), N = chain_N(args.chain, l);
             const int nch = (K + KC - 1) / KC;
             const uint32_t idesc = NPASS == 2 ? instr_desc_tf32(N) : instr_desc(N);
@@ -480,6 +491,7 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
                     const uint64_t da_hi = smem_desc(a_hi, 2048, 128), db_hi = smem_desc(b_hi, b_lbo, 128);
                     if (NPASS == 2) tc_mma_tf32(d_tmem, da_hi, db_hi, idesc, first ? 0u : 1u);
                     else tc_mma(d_tmem, da_hi, db_hi, idesc, first ? 0u : 1u);
+                    TRACE(tr && first, l, 1);
                     first = 0;
                     if (NPASS == 3) {
                         const uint64_t da_lo = smem_desc(a_hi + kAPartBytes, 2048, 128);
@@ -490,6 +502,8 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
                 }
                 tc_commit_mc(sm.bar_w_empty + 8 * s, 3);  // frees the ring slot in both CTAs of the pair once these MMAs have read it
             }
+            TRACE(tr, l, 2);
+            if (tr) { g_trace[l][10] = (unsigned long long)(dbg_a - a0); g_trace[l][11] = (unsigned long long)(dbg_w - w0); }
             tc_commit(sm.bar_acc_full);                  // accumulator of GEMM l complete
         }
     }
@@ -526,6 +540,8 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long grow = (long)tile * kTileM + row;
         const bool valid = grow < args.m;
+        const bool tr0 = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x && threadIdx.x == 0;
+        const bool tr15 = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x && threadIdx.x == 15 * 32;
         const float *xrow = args.XB + grow * 132 + 64;
         __nv_bfloat16 *sv = (valid && args.act_dtype == 2) ? reinterpret_cast<__nv_bfloat16 *>(args.act_save) : nullptr;
         {   // GEMM 0 operand A[:, 0:80) = (agg35, var, h32, pad): chunks 0..9 -> A groups 0, 1, 2
@@ -543,6 +559,8 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                 mbar_wait(sm.bar_acc_full, acc_cnt & 1);
                 if (dbg_on) dbg_acc += clk() - t0;
             }
+            TRACE(tr0, l, 3);
+            TRACE(tr15, l, 6);
             tc_fence_after();
             const uint32_t t_acc = t_lane + (uint32_t)(l & 1) * 256;
             const float *bias = bias_all + l * 256;
@@ -616,6 +634,9 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                     const long long c0 = dbg_on ? clk() : 0;
                     publish(sm, cg);
                     if (dbg_on) dbg_pub += clk() - c0;
+                    TRACE(tr0 && cg == 0, l, 4);
+                    TRACE(tr0 && cg == 7, l, 5);
+                    TRACE(tr15 && cg == 7, l, 7);
                     if (valid) {
                         if (args.act_dtype == 1) {
                             const long e = ((long)slot * args.slot_stride + grow) * 256 + k8 * 8;
@@ -948,7 +969,7 @@ int launch_chain(const ChainArgs &a, cudaStream_t st) {
 // Debug micro-benchmark: `iters` back-to-back tcgen05.mma (M=128, N=n, K=16, bf16, SS operands at fixed shared-memory
 // addresses, one accumulator) per CTA, timed with clock64 between the first issue and the arrival of the final commit.
 // Gives the issue-to-completion rate of the tensor pipe for exactly the instruction shape the chain kernels use.
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int n, unsigned long long *out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int n, int tf32, unsigned long long *out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 65536 + 32768);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 2);
@@ -965,12 +986,13 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int n, unsi
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) {
         const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 65536);
-        const uint32_t idesc = instr_desc(n), b_lbo = (uint32_t)(n / 8) * 128;
+        const uint32_t idesc = tf32 ? instr_desc_tf32(n) : instr_desc(n), b_lbo = (uint32_t)(n / 8) * 128;
         const long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
             const uint64_t da = smem_desc(a_base + (uint32_t)(i & 15) * 4096, 2048, 128);
             const uint64_t db = smem_desc(b_base + (uint32_t)(i & 1) * 2 * b_lbo, b_lbo, 128);
-            tc_mma(tmem_base + (uint32_t)(i & 1) * 256, da, db, idesc, i > 1 ? 1u : 0u);
+            if (tf32) tc_mma_tf32(tmem_base + (uint32_t)(i & 1) * 256, da, db, idesc, i > 1 ? 1u : 0u);
+            else tc_mma(tmem_base + (uint32_t)(i & 1) * 256, da, db, idesc, i > 1 ? 1u : 0u);
         }
         tc_commit(smem_u32(bar));
         mbar_wait(smem_u32(bar), 0);
@@ -1012,16 +1034,24 @@ extern "C" int occnerf_mlp_debug_max_clusters(int cluster_size) {
 }
 
 // debug only: cycles per tcgen05.mma (M=128, N=n, K=16) measured on every SM at once; out_dev [148+] device u64
-extern "C" int occnerf_mlp_debug_mma_rate(int iters, int n, unsigned long long *out_dev, int ctas, occnerf_stream_t stream) {
+extern "C" int occnerf_mlp_debug_mma_rate(int iters, int n, int tf32, unsigned long long *out_dev, int ctas, occnerf_stream_t stream) {
     OCC_CHECK_ARG(out_dev && iters >= 2 && n >= 16 && n <= 256 && n % 16 == 0 && ctas >= 1, "mlp_debug_mma_rate: bad arguments");
     const int smem_bytes = 65536 + 32768 + 64;
     OCC_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    mma_rate_kernel<<<ctas, 128, smem_bytes, (cudaStream_t)stream>>>(iters, n, out_dev);
+    mma_rate_kernel<<<ctas, 128, smem_bytes, (cudaStream_t)stream>>>(iters, n, tf32, out_dev);
     OCC_LAUNCH_CHECK();
     return OCCNERF_OK;
 }
 
 // debug only: reads (and optionally clears) the stall counters described at g_dbg
+// debug only: the per-layer time stamps of g_trace (16 x 12 u64)
+extern "C" int occnerf_mlp_debug_trace(unsigned long long *host192) {
+    OCC_CUDA(cudaDeviceSynchronize());
+    OCC_CHECK_ARG(host192, "mlp_debug_trace: null pointer");
+    OCC_CUDA(cudaMemcpyFromSymbol(host192, g_trace, sizeof(unsigned long long) * 16 * 12));
+    return OCCNERF_OK;
+}
+
 extern "C" int occnerf_mlp_debug_counters(unsigned long long *host8, int reset) {
     OCC_CUDA(cudaDeviceSynchronize());
     if (host8) OCC_CUDA(cudaMemcpyFromSymbol(host8, g_dbg, sizeof(unsigned long long) * 16));

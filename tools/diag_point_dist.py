@@ -24,6 +24,8 @@ def he(x4, ww, ls=None):
     out = orig_he(x4, ww, ls)
     if x4.shape[0] == 6890:
         out.retain_grad(); cap["hv"] = out; cap["v_in"] = x4
+        if x4.requires_grad:
+            x4.retain_grad()
     return out
 O.vertex_block, O.hash_encode = vb, he
 sub_g, w_g = copy.deepcopy(sub), copy.deepcopy(w)
@@ -69,6 +71,25 @@ for v in top.tolist():
     d = pc[v][None] - sub.point_base[kidx[v]]
     print(f"v={v} err={float(err[v]):.3e} ours={float(g_pd[v]):.4e} oracle={float(g_pd_o[v]):.4e} |g|max={float(g_pd_o.abs().max()):.3e} "
           f"kidx={kidx[v].tolist()} |d|={d.norm(dim=1).tolist()} v_in={cap['v_in'][v].tolist()}")
+# ---- per-vertex pieces for the worst vertices: ours (recomputed from OUR upstream gradient) vs the oracle's
+enc0 = net.cnl_mlp.module.encoder
+sc0 = ops.level_scales(float(np.log2(enc0.per_level_scale)), enc0.base_resolution, enc0.num_levels, dev)
+pd_d = net.point_dist.detach().reshape(-1).contiguous()
+pc_d = st["point_base"] + pd_d[:, None]
+kidx_d = ops.knn(pc_d.contiguous(), st["base4"], [0, 6890], 3)[:, 0].contiguous()
+v_in_ours = torch.empty(6890, 4, device=dev)
+ftmp = torch.empty(6890, 36, device=dev)
+ops.vertex_block_forward(st["point_base"], pd_d, st["point_norms"], kidx_d, net.bound, v_in_ours, ftmp.data_ptr() + 4 * 32, 36)
+_, dy_ours, _, _ = ops.hashgrid_forward(v_in_ours, enc0.embeddings.detach().contiguous(), enc0.offsets, sc0, out_ptr=ftmp.data_ptr(), ld=36, want_dy_dx=True)
+gfd = hook["g_feats"].contiguous()
+g_v_in_ours = ops.hashgrid_input_backward(gfd.data_ptr(), 36, 0, dy_ours, 6890, 4, 2, 16).cpu()
+g_v_in_or = cap["v_in"].grad
+print("v_in ours vs oracle: max abs", float((v_in_ours.cpu() - cap["v_in"].detach()).abs().max()), " kidx equal:", bool(torch.equal(kidx_d.cpu().long(), kidx)))
+print("g_v_in ours vs oracle: max", mx(g_v_in_ours, g_v_in_or), "fro", fro(g_v_in_ours, g_v_in_or))
+for v in top.tolist()[:4]:
+    print(f"v={v} g_v_in ours={g_v_in_ours[v].tolist()} oracle={g_v_in_or[v].tolist()}")
+    print(f"      v_in ours={v_in_ours[v].cpu().tolist()} oracle={cap['v_in'][v].tolist()}")
+    print(f"      g_feats[:32] rel row err={float((gf[v,:32]-cap['hv'].grad[v]).norm()/cap['hv'].grad[v].norm()):.3e} row norm={float(cap['hv'].grad[v].norm()):.3e} tail ours={gf[v,32:35].tolist()}")
 # gradient w.r.t. the vertices' hash-grid input from OUR dy_dx path with the ORACLE's upstream gradient
 enc = net.cnl_mlp.module.encoder
 scales = ops.level_scales(float(np.log2(enc.per_level_scale)), enc.base_resolution, enc.num_levels, dev)
