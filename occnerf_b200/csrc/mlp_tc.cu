@@ -39,7 +39,11 @@ constexpr int kStages = 3;                  // (6 x 16 KB with half-size chunks 
 constexpr int kStageBytes = 32768;
 constexpr int kLayers = 10;
 constexpr int kAPartBytes = 65536;          // 128 rows x 256 K x bf16
-constexpr int kGroups = 8;                  // 32-column groups of the A operand
+constexpr int kGroupCols = 64;              // hand-off granularity of the A operand: columns per a_ready group.  32 = one publish
+                                            // (2 fences + arrive, ~250 cycles of latency per warp) per 8-column chunk of a thread;
+                                            // 64 = one per two chunks: the epilogue then outruns the MMAs (trace: tools/mlp_trace.py)
+constexpr int kGroups = 256 / kGroupCols;
+constexpr int kGroupK8 = kGroupCols / 8;    // 8-column chunks per group
 constexpr uint32_t kSpinLimit = 1u << 27;
 
 // (Tried and reverted: evaluating the 256 -> 3 output layer -- 16 K-steps of at least 67 cycles each for 3 useful columns --
@@ -451,7 +455,6 @@ template <int NPASS>
 __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base) {
     constexpr int KC = (NPASS == 1) ? 64 : 32;
     constexpr int KS = (NPASS == 2) ? 8 : 16;          // K per MMA instruction (32 bytes of operand row)
-    constexpr int SPG = 32 / KS;                       // MMA steps per 32-column A group
     uint32_t it = 0, a_phase = 0;      // a_phase: one parity bit per A group
     long long dbg_w = 0, dbg_a = 0;
     const long long dbg_t0 = args.debug ? clk() : 0;
@@ -466,7 +469,12 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
             const uint32_t idesc = NPASS == 2 ? instr_desc_tf32(N) : instr_desc(N);
             const uint32_t b_lbo = (uint32_t)(N / 8) * 128;
             const uint32_t d_tmem = tmem_base + (uint32_t)(l & 1) * 256;
+            // operand descriptors advance by a constant per K-step (the start-address field holds addr >> 4): A by two k-slabs
+            // (4096 B), B by two k-slabs of the chunk image (2 * b_lbo)
+            uint64_t da = smem_desc(a_base, 2048, 128);
+            const uint64_t db_step = (uint64_t)((2 * b_lbo) >> 4);
             uint32_t first = 1;
+            int t = 0;                                             // global K-step of this GEMM
             for (int c = 0; c < nch; ++c, ++it) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                 {
@@ -474,31 +482,28 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
                     mbar_wait(sm.bar_w_full + 8 * s, ph);
                     if (args.debug) dbg_w += clk() - t0;
                 }
+                tc_fence_after();
                 const int kc = min(KC, K - c * KC);
-                const uint32_t wbase = smem_u32(sm.W + s * kStageBytes);
-                for (int k16 = 0; k16 < kc / KS; ++k16) {
-                    const int t = c * (KC / KS) + k16;             // global K-step of this GEMM
-                    if ((t % SPG) == 0) {                          // first step of a 32-column group: wait for the epilogue
-                        const int g = t / SPG;
+                uint64_t db = smem_desc(smem_u32(sm.W + s * kStageBytes), b_lbo, 128);
+                for (int ks = 0; ks < kc / KS; ++ks, ++t) {
+                    if ((t % (kGroupCols / KS)) == 0) {            // first step of an A group: wait for the epilogue
+                        const int g = t / (kGroupCols / KS);
                         const long long t0 = args.debug ? clk() : 0;
                         mbar_wait(sm.bar_a_ready + 8 * g, (a_phase >> g) & 1);
                         if (args.debug) dbg_a += clk() - t0;
                         a_phase ^= 1u << g;
+                        tc_fence_after();
                     }
-                    tc_fence_after();
-                    const uint32_t a_hi = a_base + (uint32_t)t * 4096;
-                    const uint32_t b_hi = wbase + (uint32_t)k16 * 2 * b_lbo;
-                    const uint64_t da_hi = smem_desc(a_hi, 2048, 128), db_hi = smem_desc(b_hi, b_lbo, 128);
-                    if (NPASS == 2) tc_mma_tf32(d_tmem, da_hi, db_hi, idesc, first ? 0u : 1u);
-                    else tc_mma(d_tmem, da_hi, db_hi, idesc, first ? 0u : 1u);
+                    if (NPASS == 2) tc_mma_tf32(d_tmem, da, db, idesc, first ? 0u : 1u);
+                    else tc_mma(d_tmem, da, db, idesc, first ? 0u : 1u);
                     TRACE(tr && first, l, 1);
                     first = 0;
                     if (NPASS == 3) {
-                        const uint64_t da_lo = smem_desc(a_hi + kAPartBytes, 2048, 128);
-                        const uint64_t db_lo = smem_desc(b_hi + kStageBytes / 2, b_lbo, 128);
-                        tc_mma(d_tmem, da_hi, db_lo, idesc, 1u);
-                        tc_mma(d_tmem, da_lo, db_hi, idesc, 1u);
+                        tc_mma(d_tmem, da, db + (uint64_t)((kStageBytes / 2) >> 4), idesc, 1u);       // hi . Wlo
+                        tc_mma(d_tmem, da + (uint64_t)(kAPartBytes >> 4), db, idesc, 1u);             // lo . Whi
                     }
+                    da += 4096 >> 4;
+                    db += db_step;
                 }
                 tc_commit_mc(sm.bar_w_empty + 8 * s, 3);  // frees the ring slot in both CTAs of the pair once these MMAs have read it
             }
@@ -519,6 +524,11 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
 // it owns in that group -- if any -- is in shared memory and after all of its TMEM reads of older accumulators: a group
 // therefore completes only when all 512 threads are past the previous layer, which is what makes it safe for GEMM l+2 to
 // overwrite the TMEM buffer of GEMM l.
+// (with 64-column groups a thread owns two chunks per group; pub_after(cg) says whether chunk index cg = k8 / 4 of the
+//  thread's sequence k8 = set, set + 4, ... closes a group, pub_group(cg) which one)
+__device__ __forceinline__ constexpr bool pub_after(int cg) { return ((cg + 1) * 32) % kGroupCols == 0; }
+__device__ __forceinline__ constexpr int pub_group(int cg) { return (cg * 32) / kGroupCols; }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void publish(const Smem &sm, int g) {
     tc_fence_before();
     fence_proxy_async();
@@ -547,13 +557,16 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
         {   // GEMM 0 operand A[:, 0:80) = (agg35, var, h32, pad): chunks 0..9 -> A groups 0, 1, 2
             auto sv8 = [&](int g) { return sv ? sv + saved_off(8, g, args.slot_stride, grow) : nullptr; };
             stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 0, set, sv8(set));
-            publish(sm, 0);
+            if (kGroupCols == 32) publish(sm, 0);
             stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 0, set + 4, sv8(set + 4));
-            publish(sm, 1);
+            publish(sm, kGroupCols == 32 ? 1 : 0);
             if (set < 2) stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 0, set + 8, sv8(set + 8));
-            publish(sm, 2);
+            publish(sm, kGroupCols == 32 ? 2 : 1);
         }
         for (int l = 0; l < kLayers; ++l, ++acc_cnt) {
+            // the layer's 1 KB of bias into L1 while the GEMM runs: the first chunk of the epilogue sits on the critical path
+            // of the chain and used to start with an L2 round trip
+            if (set == 0 && (threadIdx.x & 31) < 8) prefetch_l1(bias_all + l * 256 + (threadIdx.x & 31) * 32);
             {
                 const long long t0 = dbg_on ? clk() : 0;
                 mbar_wait(sm.bar_acc_full, acc_cnt & 1);
@@ -599,7 +612,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) + bj[i];
                     const uint4 hi = store_a8<NPASS>(sm.A, row, k8, v);
-                    publish(sm, cg);
+                    if (kGroupCols == 32 || cg == 1) publish(sm, kGroupCols == 32 ? cg : 0);
                     if (valid && args.act_dtype != 0) {
                         float4 *dst = reinterpret_cast<float4 *>(args.XB + grow * 132 + k8 * 8);
                         dst[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -610,11 +623,11 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                 // A[:, 64:144) = (agg35, var, h32, pad): chunks 8..17 -> A groups 2, 3, 4
                 auto sv9 = [&](int g) { return sv ? sv + saved_off(9, 8 + g, args.slot_stride, grow) : nullptr; };
                 stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 8, set, sv9(set));
-                publish(sm, 2);
+                if (kGroupCols == 32) publish(sm, 2);
                 stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 8, set + 4, sv9(set + 4));
-                publish(sm, 3);
+                publish(sm, kGroupCols == 32 ? 3 : 1);
                 if (set < 2) stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 8, set + 8, sv9(set + 8));
-                publish(sm, 4);
+                publish(sm, kGroupCols == 32 ? 4 : 2);
             } else {
                 // hidden layer: +bias, ReLU -> next A operand (and the saved activation / ReLU mask for the backward pass)
                 const int slot = l < 4 ? l : l - 1;                  // 0..3 = pts1..4, 4..7 = rgb1..4
@@ -632,9 +645,9 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                     // publish FIRST: the arrive has release semantics and would otherwise wait for the global stores below
                     // (measured: 21-25 % of the epilogue's time with them in front of it)
                     const long long c0 = dbg_on ? clk() : 0;
-                    publish(sm, cg);
+                    if (pub_after(cg)) publish(sm, pub_group(cg));
                     if (dbg_on) dbg_pub += clk() - c0;
-                    TRACE(tr0 && cg == 0, l, 4);
+                    TRACE(tr0 && cg == kGroupK8 / 4 - 1, l, 4);
                     TRACE(tr0 && cg == 7, l, 5);
                     TRACE(tr15 && cg == 7, l, 7);
                     if (valid) {
@@ -756,7 +769,7 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
                     const uint4 hi = store_a8<NPASS>(sm.A, row, k8, v);
-                    publish(sm, cg);
+                    if (kGroupCols == 32 || cg == 1) publish(sm, kGroupCols == 32 ? cg : 0);
                     if (valid) *reinterpret_cast<uint4 *>(args.g_save + saved_off(4, k8, args.slot_stride, grow)) = hi;
                 }
                 if (set < 2) {   // A[:, 64:80) = (d sigma, 0...): chunk 8 by set 0, chunk 9 (zeros) by set 1
@@ -764,7 +777,7 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
                     store_a8<NPASS>(sm.A, row, 8 + set, v);
                     if (valid) *reinterpret_cast<uint4 *>(args.g_save + saved_off(4, 8 + set, args.slot_stride, grow)) = pack_bf16x8(v);
                 }
-                publish(sm, 2);
+                publish(sm, kGroupCols == 32 ? 2 : 1);
             } else {
                 // through a ReLU: G = acc * (saved activation > 0) -> next A operand, and saved for the weight gradient
                 const int gslot = d;                                 // g_save: 0..3 rgb3..rgb0, 4 geo, 5..8 pts3..pts0
@@ -776,7 +789,7 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = ((bits >> i) & 1u) ? __uint_as_float(r[i]) : 0.f;
                     const uint4 hi = store_a8<NPASS>(sm.A, row, k8, v);
-                    publish(sm, cg);                                 // before the global store (see the forward epilogue)
+                    if (pub_after(cg)) publish(sm, pub_group(cg));   // before the global store (see the forward epilogue)
                     if (valid) *reinterpret_cast<uint4 *>(args.g_save + saved_off(gslot, k8, args.slot_stride, grow)) = hi;
                 };
                 tmem_ld8_issue(t_acc + set * 8, ra);
@@ -834,9 +847,9 @@ __device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Sm
         pe_chunk(x, win, set + 4, pe1);                  // (all zeros for sets 2, 3: indices >= 48)
         // GEMM 0 operand A[:, 0:48) = (pe36, pad): chunks 0..5 -> A groups 0, 1
         store_a8<NPASS>(sm.A, row, set, pe0);
-        publish(sm, 0);
+        if (kGroupCols == 32) publish(sm, 0);
         if (set < 2) store_a8<NPASS>(sm.A, row, set + 4, pe1);
-        publish(sm, 1);
+        publish(sm, kGroupCols == 32 ? 1 : 0);
         for (int l = 0; l < 7; ++l, ++acc_cnt) {
             mbar_wait(sm.bar_acc_full, acc_cnt & 1);
             tc_fence_after();
@@ -864,7 +877,7 @@ __device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Sm
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[i]) + bj[i], 0.f);
                     store_a8<NPASS>(sm.A, row, k8, v);
-                    publish(sm, cg);
+                    if (pub_after(cg)) publish(sm, pub_group(cg));
                 };
                 tmem_ld8_issue(t_acc + set * 8, ra);
 #pragma unroll 1
@@ -878,9 +891,9 @@ __device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Sm
                 }
                 if (l == 3) {   // skip connection: A[:, 128:176) = (pe36, pad): chunks 16..21 -> A groups 4, 5
                     store_a8<NPASS>(sm.A, row, 16 + set, pe0);
-                    publish(sm, 4);
+                    if (kGroupCols == 32) publish(sm, 4);
                     if (set < 2) store_a8<NPASS>(sm.A, row, 20 + set, pe1);
-                    publish(sm, 5);
+                    publish(sm, kGroupCols == 32 ? 5 : 2);
                 }
             }
         }
