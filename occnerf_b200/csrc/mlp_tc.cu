@@ -298,8 +298,11 @@ __device__ __forceinline__ uint4 store_a8(unsigned char *a_base, int row, int k8
     if (NPASS == 2) {
         // tf32 engine: the operand is fp32-sized, 4 columns per 16-byte core-matrix row -> k-slabs 2*k8 and 2*k8+1
         const uint32_t off = (uint32_t)(k8 * 32 + (row >> 3)) * 128 + (row & 7) * 16;
-        *reinterpret_cast<uint4 *>(a_base + off) = make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
-        *reinterpret_cast<uint4 *>(a_base + off + 2048) = make_uint4(to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7]));
+        // round to nearest tf32, ties away (= cvt.rna.tf32.f32 for finite values, which ptxas expands to 5 instructions with
+        // the inf/nan handling): add half an ulp of the 10-bit mantissa to the magnitude, clear the 13 low bits
+        auto rna = [](float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; };
+        *reinterpret_cast<uint4 *>(a_base + off) = make_uint4(rna(v[0]), rna(v[1]), rna(v[2]), rna(v[3]));
+        *reinterpret_cast<uint4 *>(a_base + off + 2048) = make_uint4(rna(v[4]), rna(v[5]), rna(v[6]), rna(v[7]));
         return pack_bf16x8(v);
     }
 #pragma unroll
@@ -384,6 +387,7 @@ __device__ __forceinline__ long saved_off(int slot, int k8, long stride, long ro
 
 struct Smem {
     unsigned char *A, *W;
+    float *bias;                     // 2 x 256 floats: the bias of the layer in flight and of the next one (double buffer)
     uint32_t bar_w_full, bar_w_empty, bar_a_ready, bar_acc_full;
 };
 
@@ -451,16 +455,42 @@ __device__ __forceinline__ void producer_loop(const ChainArgs &args, const Smem 
 
 // ---- MMA issuer: GEMM l accumulates into TMEM buffer (l & 1); it consumes the A operand group by group as the
 //      epilogue of GEMM l-1 publishes it
+// one lane of a converged warp (the warp-uniform way to issue single-thread instructions: everything around it stays in the
+// uniform datapath, no per-operand R2UR / ELECT loops as from a divergent `if (lane == 0)` region)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0;
+}
+
+template <int NPASS>
+__device__ __forceinline__ void mma_step(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    if (NPASS == 2) {
+        tc_mma_tf32(d_tmem, da, db, idesc, accumulate);
+    } else {
+        tc_mma(d_tmem, da, db, idesc, accumulate);
+        if (NPASS == 3) {
+            tc_mma(d_tmem, da, db + (uint64_t)((kStageBytes / 2) >> 4), idesc, 1u);       // hi . Wlo
+            tc_mma(d_tmem, da + (uint64_t)(kAPartBytes >> 4), db, idesc, 1u);             // lo . Whi
+        }
+    }
+}
+
+// ---- MMA issuer (ALL 32 lanes of the MMA warp run this loop, one elected lane issues): GEMM l accumulates into TMEM buffer
+//      (l & 1); it consumes the A operand group by group as the epilogue of GEMM l-1 publishes it
 template <int NPASS>
 __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base) {
     constexpr int KC = (NPASS == 1) ? 64 : 32;
     constexpr int KS = (NPASS == 2) ? 8 : 16;          // K per MMA instruction (32 bytes of operand row)
+    constexpr int CPG = kGroupCols / KC;               // weight chunks per A group (kGroupCols >= KC)
+    static_assert(kGroupCols % KC == 0, "an A group is a whole number of weight chunks");
     uint32_t it = 0, a_phase = 0;      // a_phase: one parity bit per A group
     long long dbg_w = 0, dbg_a = 0;
     const long long dbg_t0 = args.debug ? clk() : 0;
     const uint32_t a_base = smem_u32(sm.A);
+    const bool lane0 = (threadIdx.x & 31) == 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const bool tr = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x;
+        const bool tr = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x && lane0;
         for (int l = 0; l < n_layers(args.chain); ++l) {
             TRACE(tr, l, 0);
             const long long w0 = dbg_w, a0 = dbg_a;
@@ -473,8 +503,6 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
             // (4096 B), B by two k-slabs of the chunk image (2 * b_lbo)
             uint64_t da = smem_desc(a_base, 2048, 128);
             const uint64_t db_step = (uint64_t)((2 * b_lbo) >> 4);
-            uint32_t first = 1;
-            int t = 0;                                             // global K-step of this GEMM
             for (int c = 0; c < nch; ++c, ++it) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                 {
@@ -482,37 +510,38 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
                     mbar_wait(sm.bar_w_full + 8 * s, ph);
                     if (args.debug) dbg_w += clk() - t0;
                 }
+                if (c % CPG == 0) {                                // first chunk of an A group: wait for the epilogue
+                    const int g = c / CPG;
+                    const long long t0 = args.debug ? clk() : 0;
+                    mbar_wait(sm.bar_a_ready + 8 * g, (a_phase >> g) & 1);
+                    if (args.debug) dbg_a += clk() - t0;
+                    a_phase ^= 1u << g;
+                }
                 tc_fence_after();
+                TRACE(tr && c == 0, l, 1);
                 const int kc = min(KC, K - c * KC);
                 uint64_t db = smem_desc(smem_u32(sm.W + s * kStageBytes), b_lbo, 128);
-                for (int ks = 0; ks < kc / KS; ++ks, ++t) {
-                    if ((t % (kGroupCols / KS)) == 0) {            // first step of an A group: wait for the epilogue
-                        const int g = t / (kGroupCols / KS);
-                        const long long t0 = args.debug ? clk() : 0;
-                        mbar_wait(sm.bar_a_ready + 8 * g, (a_phase >> g) & 1);
-                        if (args.debug) dbg_a += clk() - t0;
-                        a_phase ^= 1u << g;
-                        tc_fence_after();
+                if (elect_one()) {
+                    if (kc == KC) {
+#pragma unroll
+                        for (int ks = 0; ks < KC / KS; ++ks)
+                            mma_step<NPASS>(d_tmem, da + (uint64_t)(ks * (4096 >> 4)), db + ks * db_step, idesc, (c | ks) ? 1u : 0u);
+                    } else {
+                        for (int ks = 0; ks < kc / KS; ++ks)
+                            mma_step<NPASS>(d_tmem, da + (uint64_t)(ks * (4096 >> 4)), db + ks * db_step, idesc, (c | ks) ? 1u : 0u);
                     }
-                    if (NPASS == 2) tc_mma_tf32(d_tmem, da, db, idesc, first ? 0u : 1u);
-                    else tc_mma(d_tmem, da, db, idesc, first ? 0u : 1u);
-                    TRACE(tr && first, l, 1);
-                    first = 0;
-                    if (NPASS == 3) {
-                        tc_mma(d_tmem, da, db + (uint64_t)((kStageBytes / 2) >> 4), idesc, 1u);       // hi . Wlo
-                        tc_mma(d_tmem, da + (uint64_t)(kAPartBytes >> 4), db, idesc, 1u);             // lo . Whi
-                    }
-                    da += 4096 >> 4;
-                    db += db_step;
+                    tc_commit_mc(sm.bar_w_empty + 8 * s, 3);  // frees the ring slot in both CTAs of the pair once these MMAs have read it
                 }
-                tc_commit_mc(sm.bar_w_empty + 8 * s, 3);  // frees the ring slot in both CTAs of the pair once these MMAs have read it
+                __syncwarp();
+                da += (uint64_t)((KC / KS) * (4096 >> 4));
             }
             TRACE(tr, l, 2);
             if (tr) { g_trace[l][10] = (unsigned long long)(dbg_a - a0); g_trace[l][11] = (unsigned long long)(dbg_w - w0); }
-            tc_commit(sm.bar_acc_full);                  // accumulator of GEMM l complete
+            if (elect_one()) tc_commit(sm.bar_acc_full);   // accumulator of GEMM l complete
+            __syncwarp();
         }
     }
-    if (args.debug) {
+    if (args.debug && lane0) {
         atomicAdd(&g_dbg[0], (unsigned long long)dbg_w);
         atomicAdd(&g_dbg[1], (unsigned long long)dbg_a);
         atomicAdd(&g_dbg[4], (unsigned long long)(clk() - dbg_t0));
@@ -528,7 +557,8 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
 //  thread's sequence k8 = set, set + 4, ... closes a group, pub_group(cg) which one)
 __device__ __forceinline__ constexpr bool pub_after(int cg) { return ((cg + 1) * 32) % kGroupCols == 0; }
 __device__ __forceinline__ constexpr int pub_group(int cg) { return (cg * 32) / kGroupCols; }
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// named barrier of the 512 epilogue threads (the two role warps never join it)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 __device__ __forceinline__ void publish(const Smem &sm, int g) {
     tc_fence_before();
     fence_proxy_async();
@@ -541,12 +571,19 @@ template <int NPASS>
 __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base, int warp) {
     const int quarter = warp & 3, set = warp >> 2;
     const int row = quarter * 32 + (threadIdx.x & 31);
+    const int tid = threadIdx.x;                                   // 0 .. 511
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float *bias_all = reinterpret_cast<const float *>(args.packed + args.bias_off);
-    uint32_t acc_cnt = 0;
+    uint32_t acc_cnt = 0, bl = 0;                                  // bl: running layer count = parity of the bias buffer
     const bool dbg_on = args.debug && threadIdx.x == 0;
-    long long dbg_acc = 0, dbg_ld = 0, dbg_pub = 0;
+    long long dbg_acc = 0;
     const long long dbg_t0 = dbg_on ? clk() : 0;
+    // Biases live in shared memory, one layer ahead: thread t < 256 fetches element t of the NEXT layer's bias into a register
+    // when it starts a layer and parks it in the other buffer when it is done; a named barrier of the epilogue threads (in
+    // the window in which they would wait for the next accumulator anyway) publishes it.  The ncu source view had shown a
+    // quarter of the epilogue's active time in the first FADD of every chunk, waiting for its two bias LDG.128.
+    if (tid < 256) sm.bias[tid] = __ldg(bias_all + tid);
+    epi_bar_sync();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long grow = (long)tile * kTileM + row;
         const bool valid = grow < args.m;
@@ -554,7 +591,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
         const bool tr15 = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x && threadIdx.x == 15 * 32;
         const float *xrow = args.XB + grow * 132 + 64;
         __nv_bfloat16 *sv = (valid && args.act_dtype == 2) ? reinterpret_cast<__nv_bfloat16 *>(args.act_save) : nullptr;
-        {   // GEMM 0 operand A[:, 0:80) = (agg35, var, h32, pad): chunks 0..9 -> A groups 0, 1, 2
+        {   // GEMM 0 operand A[:, 0:80) = (agg35, var, h32, pad): chunks 0..9
             auto sv8 = [&](int g) { return sv ? sv + saved_off(8, g, args.slot_stride, grow) : nullptr; };
             stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 0, set, sv8(set));
             if (kGroupCols == 32) publish(sm, 0);
@@ -563,10 +600,10 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
             if (set < 2) stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 0, set + 8, sv8(set + 8));
             publish(sm, kGroupCols == 32 ? 2 : 1);
         }
-        for (int l = 0; l < kLayers; ++l, ++acc_cnt) {
-            // the layer's 1 KB of bias into L1 while the GEMM runs: the first chunk of the epilogue sits on the critical path
-            // of the chain and used to start with an L2 round trip
-            if (set == 0 && (threadIdx.x & 31) < 8) prefetch_l1(bias_all + l * 256 + (threadIdx.x & 31) * 32);
+        for (int l = 0; l < kLayers; ++l, ++acc_cnt, ++bl) {
+            const int l_next = l + 1 == kLayers ? 0 : l + 1;
+            float bias_next = 0.f;
+            if (tid < 256) bias_next = __ldg(bias_all + l_next * 256 + tid);
             {
                 const long long t0 = dbg_on ? clk() : 0;
                 mbar_wait(sm.bar_acc_full, acc_cnt & 1);
@@ -576,7 +613,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
             TRACE(tr15, l, 6);
             tc_fence_after();
             const uint32_t t_acc = t_lane + (uint32_t)(l & 1) * 256;
-            const float *bias = bias_all + l * 256;
+            const float *bias = sm.bias + (bl & 1) * 256;
             if (l == 9) {
                 if (set == 0) {
                     uint32_t r[8];
@@ -584,9 +621,9 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                     tmem_ld_wait();
                     if (valid) {
                         float *o = args.raw + grow * args.ldr;
-                        o[0] = __uint_as_float(r[0]) + __ldg(bias + 0);
-                        o[1] = __uint_as_float(r[1]) + __ldg(bias + 1);
-                        o[2] = __uint_as_float(r[2]) + __ldg(bias + 2);
+                        o[0] = __uint_as_float(r[0]) + bias[0];
+                        o[1] = __uint_as_float(r[1]) + bias[1];
+                        o[2] = __uint_as_float(r[2]) + bias[2];
                     }
                 }
                 tc_fence_before();
@@ -597,15 +634,15 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                     uint32_t r[8];
                     tmem_ld8_issue(t_acc + 64, r);
                     tmem_ld_wait();
-                    if (valid) args.raw[grow * args.ldr + 3] = __uint_as_float(r[0]) + __ldg(bias + 64);
+                    if (valid) args.raw[grow * args.ldr + 3] = __uint_as_float(r[0]) + bias[64];
                 }
 #pragma unroll 1
                 for (int cg = 0; cg < 2; ++cg) {
                     const int k8 = cg * 4 + set;
                     uint32_t r[8];
                     tmem_ld8_issue(t_acc + k8 * 8, r);
-                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + k8 * 8));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + k8 * 8 + 4));
+                    const float4 b0 = *reinterpret_cast<const float4 *>(bias + k8 * 8);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(bias + k8 * 8 + 4);
                     tmem_ld_wait();
                     const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                     float v[8];
@@ -635,8 +672,8 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                 uint32_t ra[8], rb[8];
                 auto process = [&](int cg, const uint32_t (&r)[8]) {
                     const int k8 = cg * 4 + set;
-                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + k8 * 8));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + k8 * 8 + 4));
+                    const float4 b0 = *reinterpret_cast<const float4 *>(bias + k8 * 8);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(bias + k8 * 8 + 4);
                     const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                     float v[8];
 #pragma unroll
@@ -644,9 +681,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                     const uint4 hi = store_a8<NPASS>(sm.A, row, k8, v);
                     // publish FIRST: the arrive has release semantics and would otherwise wait for the global stores below
                     // (measured: 21-25 % of the epilogue's time with them in front of it)
-                    const long long c0 = dbg_on ? clk() : 0;
                     if (pub_after(cg)) publish(sm, pub_group(cg));
-                    if (dbg_on) dbg_pub += clk() - c0;
                     TRACE(tr0 && cg == kGroupK8 / 4 - 1, l, 4);
                     TRACE(tr0 && cg == 7, l, 5);
                     TRACE(tr15 && cg == 7, l, 7);
@@ -670,22 +705,21 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                 tmem_ld8_issue(t_acc + set * 8, ra);
 #pragma unroll 1
                 for (int cg = 0; cg < 8; cg += 2) {
-                    long long c0 = dbg_on ? clk() : 0;
                     tmem_ld_wait();
-                    if (dbg_on) dbg_ld += clk() - c0;
                     tmem_ld8_issue(t_acc + ((cg + 1) * 4 + set) * 8, rb);
                     process(cg, ra);
-                    c0 = dbg_on ? clk() : 0;
                     tmem_ld_wait();
-                    if (dbg_on) dbg_ld += clk() - c0;
                     if (cg + 2 < 8) tmem_ld8_issue(t_acc + ((cg + 2) * 4 + set) * 8, ra);
                     process(cg + 1, rb);
                 }
             }
+            // park the next layer's bias (fetched at the top of this layer) in the other buffer; the barrier sits where the
+            // threads would otherwise wait for the next accumulator
+            if (tid < 256) sm.bias[((bl + 1) & 1) * 256 + tid] = bias_next;
+            epi_bar_sync();
         }
     }
-    if (dbg_on) { atomicAdd(&g_dbg[2], (unsigned long long)dbg_acc); atomicAdd(&g_dbg[5], (unsigned long long)(clk() - dbg_t0));
-                  atomicAdd(&g_dbg[8], (unsigned long long)dbg_ld); atomicAdd(&g_dbg[9], (unsigned long long)dbg_pub); }
+    if (dbg_on) { atomicAdd(&g_dbg[2], (unsigned long long)dbg_acc); atomicAdd(&g_dbg[5], (unsigned long long)(clk() - dbg_t0)); }
 }
 
 // ---- backward (data-gradient) epilogue.  Chain position d: 0 out^T, 1..3 rgb3..1^T, 4 rgb0^T, 5 geo^T, 6..8 pts3..1^T, 9 pts0^T
@@ -909,6 +943,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
     Smem sm;
     sm.A = smem;
     sm.W = smem + kABytes;
+    sm.bias = reinterpret_cast<float *>(smem + kABytes + kStages * kStageBytes + 256);
     sm.bar_w_full = smem_u32(bars);
     sm.bar_w_empty = smem_u32(bars + kStages);
     sm.bar_a_ready = smem_u32(bars + 2 * kStages);
@@ -937,7 +972,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
     if (warp == 4 * kEpiSets) {
         if (lane == 0) producer_loop<NPASS>(args, sm, num_tiles);
     } else if (warp == 4 * kEpiSets + 1) {
-        if (lane == 0) mma_loop<NPASS>(args, sm, num_tiles, tmem_base);
+        mma_loop<NPASS>(args, sm, num_tiles, tmem_base);          // whole warp, one elected lane issues
     } else {
         if (CHAIN == 0) fwd_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
         else if (CHAIN == 1) bwd_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
@@ -952,7 +987,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
 template <int NPASS, int CHAIN>
 int launch_chain(const ChainArgs &a, cudaStream_t st) {
     constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);
-    const int smem_bytes = kABytes + kStages * kStageBytes + 256;
+    const int smem_bytes = kABytes + kStages * kStageBytes + 256 + 2048;     // + barriers + the bias double buffer
     static bool configured = false;
     if (!configured) {
         OCC_CUDA(cudaFuncSetAttribute(mlp_chain_tc_kernel<NPASS, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -1030,7 +1065,7 @@ void fill_layout(ChainArgs &a, int n_pass, int chain, const void *packed) {
 
 // debug only: how many clusters of `cluster_size` CTAs of the tc3 forward chain kernel the device can hold at once
 extern "C" int occnerf_mlp_debug_max_clusters(int cluster_size) {
-    constexpr int smem_bytes = 2 * kAPartBytes + kStages * kStageBytes + 256;
+    constexpr int smem_bytes = 2 * kAPartBytes + kStages * kStageBytes + 256 + 2048;
     if (cudaFuncSetAttribute(mlp_chain_tc_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return -1;
     if (cluster_size > 8 && cudaFuncSetAttribute(mlp_chain_tc_kernel<3, 0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -2;
     cudaLaunchConfig_t cfg = {};
