@@ -216,7 +216,10 @@ int occnerf_colsum(const float *A, long lda, const float *mask, long ldmask, int
 /* ---- fused canonical MLP on tcgen05/TMEM (occnerf_mlp.py:183-199) ------------------------------------
  * Layer table (10 layers): pts 68->256,256,256,256 ; geo 256->65 ; rgb 131->256,256,256,256 ; out 256->3.
  * occnerf_mlp_pack_weights re-lays the fp32 nn.Linear weights out as bf16 (hi[,lo]) UMMA operand images.
- * n_pass = 1: bf16 x bf16 -> fp32 ; n_pass = 3: split-bf16 (hi*hi + hi*lo + lo*hi), fp32-grade accuracy. */
+ * n_pass = 1: bf16 x bf16 -> fp32 ; n_pass = 3: split-bf16 (hi*hi + hi*lo + lo*hi), fp32-grade accuracy ;
+ * n_pass = 2: kind::tf32 (fp32 operands rounded to tf32, 10-bit mantissa, two tensor units per product).
+ * cta_pair = 1: the chain runs as cta_group::2 CTA pairs (one M = 256 UMMA over two 128-sample tiles, each CTA streams and holds
+ * half of the weight rows); the packed image is split by weight-row halves, so pack and run with the same flag. */
 typedef struct {
     const float *w[10]; /* pts0..3, geo, rgb0..3, out : [out,in] row-major (nn.Linear.weight) */
     const float *b[10];
@@ -236,7 +239,7 @@ int occnerf_mlp_debug_mma_rate(int iters, int n, int tf32, unsigned long long *o
 int occnerf_mlp_debug_trace(unsigned long long *host192);
 /* Debug only: cudaOccupancyMaxActiveClusters of the tc3 forward chain kernel for clusters of `cluster_size` CTAs (< 0: error). */
 int occnerf_mlp_debug_max_clusters(int cluster_size);
-int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, void *packed, occnerf_stream_t stream);
+int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, int cta_pair, void *packed, occnerf_stream_t stream);
 /* XB [m,132]: columns 64..131 = (agg35, var1, h32) are read; columns 0..63 receive the 64 geometry features when
  * act_dtype != 0.  raw [m, ldr]: columns 0..3 = (rgb_pre3, sigma_pre1) are written.
  * act_save: NULL (act_dtype 0, inference) or a buffer receiving the post-ReLU activations of the 8 hidden layers
@@ -245,7 +248,7 @@ int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int c
  * row)*8 + col%8; slot 8 = input of pts0 (80 columns), slot 9 = input of rgb0 (144 columns)) -- the layout in which a
  * warp's stores are contiguous and which the weight-gradient kernel's TMA consumes directly.
  * relu_mask: NULL or [8][32][slot_stride] bytes: bit i of byte (slot, k8, row) = [hidden unit 8*k8+i > 0]. */
-int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, float *raw, int ldr, void *act_save,
+int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, int cta_pair, float *raw, int ldr, void *act_save,
                            int act_dtype, long slot_stride, void *relu_mask, occnerf_stream_t stream);
 
 /* Fused data-gradient chain (the transposed layers in reverse order, ReLU masks from the saved bf16 activations).
@@ -253,7 +256,7 @@ int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, flo
  * Writes gXB [m,132] columns 64..131 = d(agg35, var1, h32) summed over both trunks, and g_save, bf16 chunk-major
  * [10][32][slot_stride][8] like act_save = gradients w.r.t. the pre-activations: slots 0..3 = rgb3, rgb2, rgb1, rgb0;
  * 4 = geo (columns 0..63 features, 64 sigma); 5..8 = pts3, pts2, pts1, pts0; 9 = d raw[:, :3]. */
-int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, const void *relu_mask, float *gXB,
+int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, int cta_pair, const void *relu_mask, float *gXB,
                             void *g_save, long slot_stride, occnerf_stream_t stream);
 
 /* Weight and bias gradients dW_l = G_l^T X_l, db_l = colsum(G_l) of all 10 layers from the two bf16 buffers above

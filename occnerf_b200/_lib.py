@@ -45,9 +45,9 @@ _SIGNATURES = {
     "occnerf_hann_pe": [_vp, _i, _vp, _i, _vp, _i, _vp],
     "occnerf_sgemm": [_vp, _l, _l, _vp, _l, _l, _vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp],
     "occnerf_colsum": [_vp, _l, _vp, _l, _i, _i, _vp, _vp],
-    "occnerf_mlp_pack_weights": [C.POINTER(MlpParams), _i, _i, _vp, _vp],
-    "occnerf_mlp_forward_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _l, _vp, _vp],
-    "occnerf_mlp_backward_tc": [_vp, _i, _vp, _i, _vp, _vp, _vp, _l, _vp],
+    "occnerf_mlp_pack_weights": [C.POINTER(MlpParams), _i, _i, _i, _vp, _vp],
+    "occnerf_mlp_forward_tc": [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _l, _vp, _vp],
+    "occnerf_mlp_backward_tc": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _l, _vp],
     "occnerf_mlp_debug_counters": [_vp, _i],
     "occnerf_mlp_debug_mma_rate": [_i, _i, _i, _vp, _i, _vp],
     "occnerf_mlp_debug_trace": [_vp],

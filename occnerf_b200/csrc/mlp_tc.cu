@@ -123,11 +123,19 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {       // round to nearest
 // element (n, k) of a padded N x K weight matrix -> its place in the packed operand image of layer `base`:
 // per K-chunk of KC columns [part][k-slab][n/8][n%8][16 B] (K-major, no swizzle: 8 rows x 16 B core matrices, a k-slab =
 // 8 bf16 / 4 tf32 columns of all N rows)
-__device__ __forceinline__ void pack_store(unsigned char *out, long base, int n_pass, int N, int n, int k, float w) {
+// With cta_pair the chunk image is split by weight-row HALVES, [half][part][k-slab][...]: CTA r of a pair streams half r.
+__device__ __forceinline__ void pack_store(unsigned char *out, long base, int n_pass, int N, int n, int k, float w, int cta_pair = 0) {
     const int KC = chunk_K(n_pass), np = parts(n_pass);
     const int chunk = k / KC, kk = k % KC;
+    long half_off = 0;
+    if (cta_pair) {
+        const int Nh = N / 2, h = n / Nh;
+        half_off = (long)h * np * Nh * KC * elem_bytes(n_pass);
+        n -= h * Nh;
+        N = Nh;
+    }
     if (n_pass == 2) {
-        const long cb = base + (long)chunk * N * KC * 4;
+        const long cb = base + (long)chunk * (cta_pair ? 2 : 1) * N * KC * 4 + half_off;
         const long inner = ((long)(kk / 4) * (N / 8) + n / 8) * 128 + (n % 8) * 16 + (kk % 4) * 4;
         *reinterpret_cast<uint32_t *>(out + cb + inner) = to_tf32(w);
         return;
@@ -135,20 +143,20 @@ __device__ __forceinline__ void pack_store(unsigned char *out, long base, int n_
     const __nv_bfloat16 hi = __float2bfloat16_rn(w);
     const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
     const long pb = (long)N * KC * 2;
-    const long cb = base + (long)chunk * np * pb;
+    const long cb = base + (long)chunk * (cta_pair ? 2 : 1) * np * pb + half_off;
     const long inner = ((long)(kk / 8) * (N / 8) + n / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2;
     *reinterpret_cast<__nv_bfloat16 *>(out + cb + inner) = hi;
     if (np == 2) *reinterpret_cast<__nv_bfloat16 *>(out + cb + pb + inner) = lo;
 }
 
-__global__ void pack_weights_kernel(occnerf_mlp_params P, DevLayout L, int n_pass, int chain, unsigned char *out) {
+__global__ void pack_weights_kernel(occnerf_mlp_params P, DevLayout L, int n_pass, int chain, int cta_pair, unsigned char *out) {
     const int l = blockIdx.y;
     const int K = chain_K(chain, l), N = chain_N(chain, l);
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < (long)N * K) {
         const int n = (int)(idx / K), k = (int)(idx % K);
         const float w = chain == 0 ? fwd_weight(P, l, n, k) : fwd_weight(P, 9 - l, k, n);     // backward chain: W^T
-        pack_store(out, L.w_off[l], n_pass, N, n, k, w);
+        pack_store(out, L.w_off[l], n_pass, N, n, k, w, cta_pair);
     }
     if (chain == 0 && blockIdx.x == 0 && threadIdx.x < 256) {
         float *b = reinterpret_cast<float *>(out + L.bias_off) + l * 256;
@@ -242,18 +250,54 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
     asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- CTA-pair mode (cta_group::2): one UMMA of M = 256 spans both CTAs of a cluster -- each CTA holds its own 128 rows of A and
+// HALF of the B operand (N/2 weight rows), the leader CTA's elected thread issues for both, the accumulator rows land in each
+// CTA's own TMEM.  Per CTA that halves the weight bytes streamed into shared memory and the B bytes the tensor core reads.
+__device__ __forceinline__ void tc_mma_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p; }"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p; }"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of all prior MMAs of this thread -> one arrival on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_cg2_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a LOCAL mbarrier whose arrivals come from the peer CTA as well (cluster-scope acquire)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+
 // K-major, no-swizzle shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout, version 1 = Blackwell)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
-__device__ __forceinline__ uint32_t instr_desc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+__device__ __forceinline__ uint32_t instr_desc(int n, int m = kTileM) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // kind::tf32 instruction descriptor: D=f32, A=B=tf32 (format 2), both K-major, M=128
-__device__ __forceinline__ uint32_t instr_desc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+__device__ __forceinline__ uint32_t instr_desc_tf32(int n, int m = kTileM) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -389,6 +433,9 @@ struct Smem {
     unsigned char *A, *W;
     float *bias;                     // 2 x 256 floats: the bias of the layer in flight and of the next one (double buffer)
     uint32_t bar_w_full, bar_w_empty, bar_a_ready, bar_acc_full;
+    uint32_t bar_w_peer;             // pair mode, leader: "the peer's half of the chunk has landed" (arrived by the peer's relay)
+    uint32_t a_ready_arrive;         // where the epilogue warps arrive: the local a_ready, or the leader's (cluster address)
+    bool pair;
 };
 
 // ---- weight producer: streams every K-chunk of every GEMM of every tile through the ring, running ahead freely
@@ -549,6 +596,143 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
     }
 }
 
+// ================================================================== CTA-pair mode (cta_group::2) role loops
+// Ring: 6 x 16 KB per CTA (a K-chunk of HALF the weight rows, hi [+ lo]); packed image per chunk = [half][part][k-slab][n/8][8][16 B]
+// (occnerf_mlp_pack_weights with cta_pair = 1), so a CTA's half of a chunk is one contiguous piece.
+constexpr int kPairStages = 6;
+constexpr int kPairStageBytes = 16384;
+
+// both CTAs: stream MY half of every chunk (plain bulk copies, no multicast)
+template <int NPASS>
+__device__ __forceinline__ void producer_loop_pair(const ChainArgs &args, const Smem &sm, int num_tiles) {
+    constexpr int KC = (NPASS == 1) ? 64 : 32;
+    constexpr int NP = (NPASS == 3) ? 2 : 1;
+    constexpr int EB = (NPASS == 2) ? 4 : 2;
+    uint32_t it = 0;
+    const uint32_t rank = cluster_ctarank();
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int l = 0; l < n_layers(args.chain); ++l) {
+            const int K = chain_K(args.chain, l), Nh = chain_N(args.chain, l) / 2;
+            const int nch = (K + KC - 1) / KC;
+            const uint32_t pbh = (uint32_t)Nh * KC * EB;                         // one part of one half of a full chunk
+            const unsigned char *src = args.packed + args.w_off[l] + (long)rank * NP * pbh;
+            for (int c = 0; c < nch; ++c, ++it) {
+                const uint32_t s = it % kPairStages, ph = (it / kPairStages) & 1;
+                mbar_wait(sm.bar_w_empty + 8 * s, ph ^ 1);
+                const int kc = min(KC, K - c * KC);
+                const uint32_t bytes = (uint32_t)Nh * kc * EB;
+                const uint32_t dst = smem_u32(sm.W + s * kPairStageBytes);
+                const uint32_t bar = sm.bar_w_full + 8 * s;
+                mbar_arrive_expect_tx(bar, bytes * NP);
+                const unsigned char *chunk = src + (long)c * 2 * NP * pbh;
+                bulk_g2s(dst, chunk, bytes, bar);
+                if (NP == 2) bulk_g2s(dst + kPairStageBytes / 2, chunk + pbh, bytes, bar);
+            }
+        }
+    }
+}
+
+// peer CTA (rank 1): tell the leader's MMA thread that MY half of chunk `it` has landed in MY shared memory
+template <int NPASS>
+__device__ __forceinline__ void relay_loop_pair(const ChainArgs &args, const Smem &sm, int num_tiles) {
+    constexpr int KC = (NPASS == 1) ? 64 : 32;
+    uint32_t it = 0;
+    const uint32_t leader_w_peer = map_to_cta(sm.bar_w_peer, 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int l = 0; l < n_layers(args.chain); ++l) {
+            const int nch = (chain_K(args.chain, l) + KC - 1) / KC;
+            for (int c = 0; c < nch; ++c, ++it) {
+                const uint32_t s = it % kPairStages, ph = (it / kPairStages) & 1;
+                mbar_wait(sm.bar_w_full + 8 * s, ph);
+                mbar_arrive_cluster(leader_w_peer + 8 * s);
+            }
+        }
+    }
+}
+
+template <int NPASS>
+__device__ __forceinline__ void mma_step_pair(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    if (NPASS == 2) {
+        tc_mma_tf32_cg2(d_tmem, da, db, idesc, accumulate);
+    } else {
+        tc_mma_cg2(d_tmem, da, db, idesc, accumulate);
+        if (NPASS == 3) {
+            tc_mma_cg2(d_tmem, da, db + (uint64_t)((kPairStageBytes / 2) >> 4), idesc, 1u);   // hi . Wlo
+            tc_mma_cg2(d_tmem, da + (uint64_t)(kAPartBytes >> 4), db, idesc, 1u);             // lo . Whi
+        }
+    }
+}
+
+// leader CTA (rank 0), whole MMA warp: M = 256 UMMAs over both CTAs' A tiles and B halves
+template <int NPASS>
+__device__ __forceinline__ void mma_loop_pair(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base) {
+    constexpr int KC = (NPASS == 1) ? 64 : 32;
+    constexpr int KS = (NPASS == 2) ? 8 : 16;
+    constexpr int CPG = kGroupCols / KC;
+    uint32_t it = 0, a_phase = 0;
+    long long dbg_w = 0, dbg_a = 0;
+    const long long dbg_t0 = args.debug ? clk() : 0;
+    const uint32_t a_base = smem_u32(sm.A);
+    const bool lane0 = (threadIdx.x & 31) == 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const bool tr = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x && lane0;
+        for (int l = 0; l < n_layers(args.chain); ++l) {
+            TRACE(tr, l, 0);
+            const long long w0 = dbg_w, a0 = dbg_a;
+            const int K = chain_K(args.chain, l), N = chain_N(args.chain, l);
+            const int nch = (K + KC - 1) / KC;
+            const uint32_t idesc = NPASS == 2 ? instr_desc_tf32(N, 256) : instr_desc(N, 256);
+            const uint32_t b_lbo = (uint32_t)(N / 16) * 128;                   // k-slab stride of MY half (N/2 rows)
+            const uint32_t d_tmem = tmem_base + (uint32_t)(l & 1) * 256;
+            uint64_t da = smem_desc(a_base, 2048, 128);
+            const uint64_t db_step = (uint64_t)((2 * b_lbo) >> 4);
+            for (int c = 0; c < nch; ++c, ++it) {
+                const uint32_t s = it % kPairStages, ph = (it / kPairStages) & 1;
+                {
+                    const long long t0 = args.debug ? clk() : 0;
+                    mbar_wait(sm.bar_w_full + 8 * s, ph);                       // my half
+                    mbar_wait_cluster(sm.bar_w_peer + 8 * s, ph);               // the peer's half
+                    if (args.debug) dbg_w += clk() - t0;
+                }
+                if (c % CPG == 0) {
+                    const int g = c / CPG;
+                    const long long t0 = args.debug ? clk() : 0;
+                    mbar_wait_cluster(sm.bar_a_ready + 8 * g, (a_phase >> g) & 1);   // 16 warps of each CTA
+                    if (args.debug) dbg_a += clk() - t0;
+                    a_phase ^= 1u << g;
+                }
+                tc_fence_after();
+                TRACE(tr && c == 0, l, 1);
+                const int kc = min(KC, K - c * KC);
+                uint64_t db = smem_desc(smem_u32(sm.W + s * kPairStageBytes), b_lbo, 128);
+                if (elect_one()) {
+                    if (kc == KC) {
+#pragma unroll
+                        for (int ks = 0; ks < KC / KS; ++ks)
+                            mma_step_pair<NPASS>(d_tmem, da + (uint64_t)(ks * (4096 >> 4)), db + ks * db_step, idesc, (c | ks) ? 1u : 0u);
+                    } else {
+                        for (int ks = 0; ks < kc / KS; ++ks)
+                            mma_step_pair<NPASS>(d_tmem, da + (uint64_t)(ks * (4096 >> 4)), db + ks * db_step, idesc, (c | ks) ? 1u : 0u);
+                    }
+                    tc_commit_cg2_mc(sm.bar_w_empty + 8 * s, 3);                // frees the slot in BOTH CTAs
+                }
+                __syncwarp();
+                da += (uint64_t)((KC / KS) * (4096 >> 4));
+            }
+            TRACE(tr, l, 2);
+            if (tr) { g_trace[l][10] = (unsigned long long)(dbg_a - a0); g_trace[l][11] = (unsigned long long)(dbg_w - w0); }
+            if (elect_one()) tc_commit_cg2_mc(sm.bar_acc_full, 3);             // accumulator rows of BOTH CTAs complete
+            __syncwarp();
+        }
+    }
+    if (args.debug && lane0) {
+        atomicAdd(&g_dbg[0], (unsigned long long)dbg_w);
+        atomicAdd(&g_dbg[1], (unsigned long long)dbg_a);
+        atomicAdd(&g_dbg[4], (unsigned long long)(clk() - dbg_t0));
+        atomicAdd(&g_dbg[6], 1ull);
+    }
+}
+
 // one arrival of this thread's WARP on A group g.  EVERY epilogue warp arrives exactly once per group and GEMM, after the chunk
 // it owns in that group -- if any -- is in shared memory and after all of its TMEM reads of older accumulators: a group
 // therefore completes only when all 512 threads are past the previous layer, which is what makes it safe for GEMM l+2 to
@@ -563,7 +747,10 @@ __device__ __forceinline__ void publish(const Smem &sm, int g) {
     tc_fence_before();
     fence_proxy_async();
     __syncwarp();                                    // the warp's 32 fenced writes are ordered before lane 0's release-arrive:
-    if ((threadIdx.x & 31) == 0) mbar_arrive(sm.bar_a_ready + 8 * g);   // 16 arrivals per group instead of 512
+    if ((threadIdx.x & 31) == 0) {                   // 16 arrivals per group (and CTA) instead of 512
+        if (sm.pair) mbar_arrive_cluster(sm.a_ready_arrive + 8 * g);     // both CTAs report to the leader's barrier
+        else mbar_arrive(sm.bar_a_ready + 8 * g);
+    }
 }
 
 // ---- forward epilogue.  Thread = (row, set): the 8-column chunks k8 = set, set+4, ... of every layer.
@@ -934,45 +1121,69 @@ __device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Sm
     }
 }
 
-template <int NPASS, int CHAIN>
+template <int NPASS, int CHAIN, int CG>
 __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_constant__ ChainArgs args) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);     // bf16: 64 KB; hi+lo or tf32: 128 KB
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kABytes + kStages * kStageBytes);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
+    constexpr int kRingBytes = kStages * kStageBytes;               // = kPairStages * kPairStageBytes
+    static_assert(kStages * kStageBytes == kPairStages * kPairStageBytes, "both ring geometries use the same bytes");
+    constexpr int kNStages = CG == 2 ? kPairStages : kStages;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kABytes + kRingBytes);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 30);
     Smem sm;
     sm.A = smem;
     sm.W = smem + kABytes;
-    sm.bias = reinterpret_cast<float *>(smem + kABytes + kStages * kStageBytes + 256);
+    sm.bias = reinterpret_cast<float *>(smem + kABytes + kRingBytes + 256);
     sm.bar_w_full = smem_u32(bars);
-    sm.bar_w_empty = smem_u32(bars + kStages);
-    sm.bar_a_ready = smem_u32(bars + 2 * kStages);
-    sm.bar_acc_full = smem_u32(bars + 2 * kStages + kGroups);
+    sm.bar_w_empty = smem_u32(bars + kNStages);
+    sm.bar_w_peer = smem_u32(bars + 2 * kNStages);                  // (pair mode only)
+    sm.bar_a_ready = smem_u32(bars + 3 * kNStages);
+    sm.bar_acc_full = smem_u32(bars + 3 * kNStages + kGroups);
+    static_assert(3 * kPairStages + kGroups + 1 <= 30, "barrier block");
+    sm.pair = CG == 2;
+    sm.a_ready_arrive = CG == 2 ? map_to_cta(sm.bar_a_ready, 0) : sm.bar_a_ready;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // both CTAs of a cluster must walk weight streams of equal length: the tile count is padded to an even number and
     // a padding tile simply has no valid rows
     const int num_tiles = ((args.m + kTileM - 1) / kTileM + 1) & ~1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(sm.bar_w_full + 8 * s, 1); mbar_init(sm.bar_w_empty + 8 * s, 2); }
-        for (int g = 0; g < kGroups; ++g) mbar_init(sm.bar_a_ready + 8 * g, kEpiThreads / 32);
+        for (int s = 0; s < kNStages; ++s) {
+            mbar_init(sm.bar_w_full + 8 * s, 1);
+            mbar_init(sm.bar_w_empty + 8 * s, CG == 2 ? 1 : 2);     // pair mode: one multicast commit of the leader covers both smems
+            if (CG == 2) mbar_init(sm.bar_w_peer + 8 * s, 1);
+        }
+        for (int g = 0; g < kGroups; ++g) mbar_init(sm.bar_a_ready + 8 * g, (CG == 2 ? 2 : 1) * (kEpiThreads / 32));
         mbar_init(sm.bar_acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                       // the peer's barriers are initialised before anything is multicast to them
+    cluster_sync_all();                       // the peer's barriers are initialised before anything is signalled to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 4 * kEpiSets) {
-        if (lane == 0) producer_loop<NPASS>(args, sm, num_tiles);
+        if (lane == 0) {
+            if (CG == 2) producer_loop_pair<NPASS>(args, sm, num_tiles);
+            else producer_loop<NPASS>(args, sm, num_tiles);
+        }
     } else if (warp == 4 * kEpiSets + 1) {
-        mma_loop<NPASS>(args, sm, num_tiles, tmem_base);          // whole warp, one elected lane issues
+        if (CG == 2) {
+            if (cluster_ctarank() == 0) mma_loop_pair<NPASS>(args, sm, num_tiles, tmem_base);
+            else if (lane == 0) relay_loop_pair<NPASS>(args, sm, num_tiles);
+        } else {
+            mma_loop<NPASS>(args, sm, num_tiles, tmem_base);      // whole warp, one elected lane issues
+        }
     } else {
         if (CHAIN == 0) fwd_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
         else if (CHAIN == 1) bwd_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
@@ -981,16 +1192,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                       // nobody leaves while the peer may still signal into this CTA
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    if (warp == 0) {
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
 }
 
-template <int NPASS, int CHAIN>
-int launch_chain(const ChainArgs &a, cudaStream_t st) {
+template <int NPASS, int CHAIN, int CG>
+int launch_chain_cg(const ChainArgs &a, cudaStream_t st) {
     constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);
     const int smem_bytes = kABytes + kStages * kStageBytes + 256 + 2048;     // + barriers + the bias double buffer
     static bool configured = false;
     if (!configured) {
-        OCC_CUDA(cudaFuncSetAttribute(mlp_chain_tc_kernel<NPASS, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        OCC_CUDA(cudaFuncSetAttribute(mlp_chain_tc_kernel<NPASS, CHAIN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured = true;
     }
     int dev = 0, sms = 148;
@@ -1010,8 +1224,15 @@ int launch_chain(const ChainArgs &a, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OCC_CUDA(cudaLaunchKernelEx(&cfg, mlp_chain_tc_kernel<NPASS, CHAIN>, a));
+    OCC_CUDA(cudaLaunchKernelEx(&cfg, mlp_chain_tc_kernel<NPASS, CHAIN, CG>, a));
     return OCCNERF_OK;
+}
+
+// cta_pair: 0 = cta_group::1 CTAs sharing the weight stream by multicast, 1 = cta_group::2 (weights packed with cta_pair = 1)
+template <int NPASS, int CHAIN>
+int launch_chain(const ChainArgs &a, cudaStream_t st, int cta_pair = 0) {
+    if (CHAIN != 2 && cta_pair) return launch_chain_cg<NPASS, CHAIN == 2 ? 0 : CHAIN, 2>(a, st);
+    return launch_chain_cg<NPASS, CHAIN, 1>(a, st);
 }
 
 // Debug micro-benchmark: `iters` back-to-back tcgen05.mma (M=128, N=n, K=16, bf16, SS operands at fixed shared-memory
@@ -1066,8 +1287,8 @@ void fill_layout(ChainArgs &a, int n_pass, int chain, const void *packed) {
 // debug only: how many clusters of `cluster_size` CTAs of the tc3 forward chain kernel the device can hold at once
 extern "C" int occnerf_mlp_debug_max_clusters(int cluster_size) {
     constexpr int smem_bytes = 2 * kAPartBytes + kStages * kStageBytes + 256 + 2048;
-    if (cudaFuncSetAttribute(mlp_chain_tc_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return -1;
-    if (cluster_size > 8 && cudaFuncSetAttribute(mlp_chain_tc_kernel<3, 0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(mlp_chain_tc_kernel<3, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return -1;
+    if (cluster_size > 8 && cudaFuncSetAttribute(mlp_chain_tc_kernel<3, 0, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(148 / cluster_size * cluster_size);
     cfg.blockDim = dim3(kThreads);
@@ -1077,7 +1298,7 @@ extern "C" int occnerf_mlp_debug_max_clusters(int cluster_size) {
     attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, mlp_chain_tc_kernel<3, 0>, &cfg) != cudaSuccess) { cudaGetLastError(); return -3; }
+    if (cudaOccupancyMaxActiveClusters(&n, mlp_chain_tc_kernel<3, 0, 1>, &cfg) != cudaSuccess) { cudaGetLastError(); return -3; }
     return n;
 }
 
@@ -1115,7 +1336,7 @@ extern "C" long occnerf_mlp_packed_bytes(int n_pass, int chain) {
     return packed_layout(n_pass, chain).total;
 }
 
-extern "C" int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, void *packed,
+extern "C" int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, int cta_pair, void *packed,
                                         occnerf_stream_t stream) {
     OCC_CHECK_ARG(p_host && packed, "mlp_pack_weights: null pointer");
     OCC_CHECK_ARG(valid_pass(n_pass), "mlp_pack_weights: n_pass=%d (supported: 1 bf16, 2 tf32, 3 split-bf16)", n_pass);
@@ -1126,12 +1347,12 @@ extern "C" int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_
     for (int l = 0; l < kLayers; ++l) L.w_off[l] = pl.w_off[l];
     L.bias_off = pl.bias_off;
     dim3 grid(occ_div_up(256 * 256, 256), kLayers);
-    pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p_host, L, n_pass, chain, (unsigned char *)packed);
+    pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p_host, L, n_pass, chain, cta_pair ? 1 : 0, (unsigned char *)packed);
     OCC_LAUNCH_CHECK();
     return OCCNERF_OK;
 }
 
-extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, float *raw, int ldr, void *act_save,
+extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, int cta_pair, float *raw, int ldr, void *act_save,
                                       int act_dtype, long slot_stride, void *relu_mask, occnerf_stream_t stream) {
     if (m == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(XB && packed && raw, "mlp_forward_tc: null pointer");
@@ -1147,10 +1368,11 @@ extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int 
     a.XB = XB; a.raw = raw; a.ldr = ldr; a.act_save = act_save; a.act_dtype = act_dtype; a.slot_stride = slot_stride;
     a.relu_mask = (uint8_t *)relu_mask;
     OCC_CHECK_ARG(((uintptr_t)relu_mask & 15) == 0, "mlp_forward_tc: relu_mask must be 16-byte aligned");
-    return n_pass == 1 ? launch_chain<1, 0>(a, (cudaStream_t)stream) : n_pass == 2 ? launch_chain<2, 0>(a, (cudaStream_t)stream) : launch_chain<3, 0>(a, (cudaStream_t)stream);
+    return n_pass == 1 ? launch_chain<1, 0>(a, (cudaStream_t)stream, cta_pair) : n_pass == 2 ? launch_chain<2, 0>(a, (cudaStream_t)stream, cta_pair)
+                                                                                : launch_chain<3, 0>(a, (cudaStream_t)stream, cta_pair);
 }
 
-extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, const void *relu_mask,
+extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *packed_bwd, int n_pass, int cta_pair, const void *relu_mask,
                                        float *gXB, void *g_save, long slot_stride, occnerf_stream_t stream) {
     if (m == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(g_raw && packed_bwd && relu_mask && gXB && g_save, "mlp_backward_tc: null pointer");
@@ -1162,7 +1384,8 @@ extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *pa
     fill_layout(a, n_pass, 1, packed_bwd);
     OCC_CHECK_ARG(slot_stride >= m, "mlp_backward_tc: slot_stride=%ld < m=%d", slot_stride, m);
     a.g_raw = g_raw; a.relu_mask = (uint8_t *)relu_mask; a.gXB = gXB; a.g_save = (__nv_bfloat16 *)g_save; a.slot_stride = slot_stride;
-    return n_pass == 1 ? launch_chain<1, 1>(a, (cudaStream_t)stream) : n_pass == 2 ? launch_chain<2, 1>(a, (cudaStream_t)stream) : launch_chain<3, 1>(a, (cudaStream_t)stream);
+    return n_pass == 1 ? launch_chain<1, 1>(a, (cudaStream_t)stream, cta_pair) : n_pass == 2 ? launch_chain<2, 1>(a, (cudaStream_t)stream, cta_pair)
+                                                                                : launch_chain<3, 1>(a, (cudaStream_t)stream, cta_pair);
 }
 
 // ---- non-rigid motion MLP on the same chain machinery (chain 2)

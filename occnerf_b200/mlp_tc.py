@@ -9,6 +9,7 @@ backward: data gradients by the fused transposed chain (occnerf_mlp_backward_tc)
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -19,13 +20,15 @@ f32, bf16 = torch.float32, torch.bfloat16
 
 
 class MlpTc:
-    def __init__(self, n_pass: int = 3, wgrad: str = "tc", bwd_pass: int | None = None):
+    def __init__(self, n_pass: int = 3, wgrad: str = "tc", bwd_pass: int | None = None, pair: bool | None = None):
         assert n_pass in (1, 2, 3) and wgrad in ("tc", "lib") and bwd_pass in (None, 1, 2, 3)
         self.n_pass = n_pass
         # precision of the data-gradient chain: by default that of the forward chain; 1 = bf16 operands (what the
         # weight-gradient kernel uses anyway), independent of a split-bf16 forward
         self.bwd_pass = n_pass if bwd_pass is None else bwd_pass
         self.wgrad = wgrad      # "tc": hand-written tcgen05 kernel; "lib": cuBLAS (test cross-check only)
+        # cta_group::2 CTA pairs (each CTA streams / holds half of the weight rows) or cta_group::1 CTAs sharing the stream by multicast
+        self.pair = int(os.environ.get("OCCNERF_MLP_PAIR", "1")) != 0 if pair is None else bool(pair)
         self.name = "tf32" if n_pass == 2 else f"tc{n_pass}"      # 1 bf16 | 2 tf32 (kind::tf32) | 3 split-bf16
 
     def pack(self, W: M.MlpWeights, device, chain: int):
@@ -36,12 +39,12 @@ class MlpTc:
         bs = W.pts_b + [W.geo_b] + W.rgb_b + [W.out_b]
         for i in range(10):
             P.w[i], P.b[i] = ws[i].data_ptr(), bs[i].data_ptr()
-        call("occnerf_mlp_pack_weights", ctypes.byref(P), self.n_pass, chain, packed.data_ptr(), stream())
+        call("occnerf_mlp_pack_weights", ctypes.byref(P), self.n_pass, chain, int(self.pair), packed.data_ptr(), stream())
         return packed
 
     def _packed(self, W, dev, chain, n_pass, shared):
         """Packed operand images of the current weights; built once per _query_mlp call (`shared`) instead of once per chunk."""
-        key = ("packed", chain, n_pass)
+        key = ("packed", chain, n_pass, self.pair)
         if shared is not None and key in shared:
             return shared[key]
         keep, self.n_pass = self.n_pass, n_pass
@@ -62,7 +65,7 @@ class MlpTc:
             mask = torch.empty(8, 32, stride, device=dev, dtype=torch.uint8)      # one bit per hidden unit: ReLU'(x)
             if stride > m:
                 acts[:, :, m:].zero_()
-        call("occnerf_mlp_forward_tc", XB.data_ptr(), m, packed.data_ptr(), self.n_pass, raw.data_ptr(), raw.shape[1],
+        call("occnerf_mlp_forward_tc", XB.data_ptr(), m, packed.data_ptr(), self.n_pass, int(self.pair), raw.data_ptr(), raw.shape[1],
              acts.data_ptr() if save else None, 2 if save else 0, stride, mask.data_ptr() if save else None, stream(),
              work=M.FLOP_FWD * m)
         return {"acts": acts, "mask": mask} if save else None
@@ -79,7 +82,7 @@ class MlpTc:
         g_save = torch.empty(10, 32, stride, 8, device=dev, dtype=bf16)
         if stride > m:
             g_save[:, :, m:].zero_()
-        call("occnerf_mlp_backward_tc", g_raw.data_ptr(), m, packed.data_ptr(), self.bwd_pass, saved["mask"].data_ptr(), gXB.data_ptr(),
+        call("occnerf_mlp_backward_tc", g_raw.data_ptr(), m, packed.data_ptr(), self.bwd_pass, int(self.pair), saved["mask"].data_ptr(), gXB.data_ptr(),
              g_save.data_ptr(), stride, stream(), work=M.FLOP_FWD * m)
         if self.wgrad == "lib":
             with _lib.region("lib:wgrad(cuBLAS bf16)+bias sums"):

@@ -11,7 +11,7 @@ W = _flat(_weights(seed=2), d)
 XB = torch.randn(m, 132, device=d) * 0.3
 raw = torch.zeros(m, 5, device=d)
 res = {}
-for name, eng in [("tc1", mlp_tc.MlpTc(1)), ("tf32", mlp_tc.MlpTc(2)), ("tc3", mlp_tc.MlpTc(3))] + ([] if once else [("fp32", M.MlpSimt())]):
+for name, eng in [("tc1", mlp_tc.MlpTc(1)), ("tf32", mlp_tc.MlpTc(2)), ("tc3", mlp_tc.MlpTc(3)), ("tf32_cg1", mlp_tc.MlpTc(2, pair=False)), ("tc3_cg1", mlp_tc.MlpTc(3, pair=False))] + ([] if once else [("fp32", M.MlpSimt())]):
     for save in (False, True):
         if once and save: continue
         for _ in range(1 if once else 3):
@@ -27,7 +27,7 @@ for name, eng in [("tc1", mlp_tc.MlpTc(1)), ("tf32", mlp_tc.MlpTc(2)), ("tc3", m
         res[f"{name}_save{int(save)}"] = dict(ms=ms, tflops=m * M.FLOP_FWD / ms / 1e9)
 if not once:
     g_raw = torch.randn(m, 5, device=d)
-    for name, eng in [("tc1", mlp_tc.MlpTc(1)), ("tf32", mlp_tc.MlpTc(2)), ("tc3", mlp_tc.MlpTc(3))]:
+    for name, eng in [("tc1", mlp_tc.MlpTc(1)), ("tf32", mlp_tc.MlpTc(2)), ("tc3", mlp_tc.MlpTc(3)), ("tf32_cg1", mlp_tc.MlpTc(2, pair=False)), ("tc3_cg1", mlp_tc.MlpTc(3, pair=False))]:
         saved = eng.forward(XB, raw, W, save=True)
         for _ in range(2): eng.backward(XB, g_raw, W, saved)
         torch.cuda.synchronize()
