@@ -43,7 +43,6 @@ constexpr int kGroupCols = 64;              // hand-off granularity of the A ope
                                             // (2 fences + arrive, ~250 cycles of latency per warp) per 8-column chunk of a thread;
                                             // 64 = one per two chunks: the epilogue then outruns the MMAs (trace: tools/mlp_trace.py)
 constexpr int kGroups = 256 / kGroupCols;
-static_assert(kGroupCols == kGroupColsDecl, "pair_geom uses the group width");
 constexpr int kGroupK8 = kGroupCols / 8;    // 8-column chunks per group
 constexpr uint32_t kSpinLimit = 1u << 27;
 
@@ -67,53 +66,12 @@ __host__ __device__ inline int chunk_K(int n_pass) { return n_pass == 1 ? 64 : 3
 __host__ __device__ inline int parts(int n_pass) { return n_pass == 3 ? 2 : 1; }
 __host__ __device__ inline int elem_bytes(int n_pass) { return n_pass == 2 ? 4 : 2; }
 __host__ __device__ inline bool valid_pass(int n_pass) { return n_pass >= 1 && n_pass <= 3; }
-constexpr int kGroupColsDecl = 64;           // (= kGroupCols, needed here before its definition)
-
-// ---- CTA-pair mode geometry (cta_group::2 + N-split, see "CTA-pair mode" further down).  A layer's padded output width is cut
-// into nq column halves (two for the 256-wide layers) and every half into the two CTAs' shares of R weight rows; the weight stream
-// consists of UNITS (q, c) = (column half, K-chunk), R rows x KC columns per CTA, in the order the MMA issuer consumes them:
-//     (q0, part A) (q1, part A) (q0, part B) (q1, part B),   part A = the K-chunks of the first half of the A groups
-// so that the accumulator of column half 0 completes a quarter of the layer's MMAs before that of half 1 and its epilogue -- which
-// produces exactly part A of the NEXT layer's operand -- overlaps the rest.
-struct PairGeom { int K, N, Npad, nq, R, nch, cA, nunits; };
-__host__ __device__ inline int pair_pad_N(int N) { return N == 144 ? 160 : N; }          // 144 = 2 x 72: 72 / 2 is no multiple of 8
-__host__ __device__ inline PairGeom pair_geom(int n_pass, int chain, int l);
 
 struct PackedLayout {
     long w_off[kLayers];
     long bias_off;
     long total;
 };
-
-__host__ __device__ inline PairGeom pair_geom(int n_pass, int chain, int l) {
-    PairGeom g;
-    const int KC = chunk_K(n_pass);
-    g.K = chain_K(chain, l);
-    g.N = chain_N(chain, l);
-    g.Npad = pair_pad_N(g.N);
-    g.nq = g.Npad > 128 ? 2 : 1;
-    g.R = g.Npad / (2 * g.nq);
-    g.nch = (g.K + KC - 1) / KC;
-    const int groups = (g.K + kGroupColsDecl - 1) / kGroupColsDecl;
-    const int cA = ((groups + 1) / 2) * (kGroupColsDecl / KC);
-    g.cA = cA < g.nch ? cA : g.nch;
-    g.nunits = g.nq * g.nch;
-    return g;
-}
-// position of unit (q, c) in the stream of its layer
-__host__ __device__ inline int pair_unit_index(const PairGeom &g, int q, int c) {
-    if (g.nq == 1) return c;
-    return c < g.cA ? q * g.cA + c : 2 * g.cA + q * (g.nch - g.cA) + (c - g.cA);
-}
-// inverse: unit u -> (q, c)
-__host__ __device__ inline void pair_unit(const PairGeom &g, int u, int &q, int &c) {
-    if (g.nq == 1) { q = 0; c = u; return; }
-    if (u < 2 * g.cA) { q = u / g.cA; c = u % g.cA; return; }
-    const int nb = g.nch - g.cA;
-    u -= 2 * g.cA;
-    q = u / nb;
-    c = g.cA + u % nb;
-}
 
 inline PackedLayout packed_layout(int n_pass, int chain) {
     PackedLayout p;
@@ -123,7 +81,7 @@ inline PackedLayout packed_layout(int n_pass, int chain) {
     for (int l = 0; l < n_layers(chain); ++l) {
         p.w_off[l] = off;
         const int K = chain_K(chain, l), N = chain_N(chain, l);
-        off += (long)((K + KC - 1) / KC) * parts(n_pass) * pair_pad_N(N) * KC * elem_bytes(n_pass);
+        off += (long)((K + KC - 1) / KC) * parts(n_pass) * N * KC * elem_bytes(n_pass);
     }
     p.bias_off = off;
     off += kLayers * 256 * 4;
@@ -165,34 +123,19 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {       // round to nearest
 // element (n, k) of a padded N x K weight matrix -> its place in the packed operand image of layer `base`:
 // per K-chunk of KC columns [part][k-slab][n/8][n%8][16 B] (K-major, no swizzle: 8 rows x 16 B core matrices, a k-slab =
 // 8 bf16 / 4 tf32 columns of all N rows)
-// With cta_pair (= 1 + cA of the layer's PairGeom) the image is the unit stream of the pair mode: [unit][CTA share][part][k-slab][...].
-__device__ __forceinline__ void pack_store(unsigned char *out, long base, int n_pass, int N, int n, int k, float w, int cta_pair = 0,
-                                           int pack_nch = 0) {
+// With cta_pair the chunk image is split by weight-row HALVES, [half][part][k-slab][...]: CTA r of a pair streams half r.
+__device__ __forceinline__ void pack_store(unsigned char *out, long base, int n_pass, int N, int n, int k, float w, int cta_pair = 0) {
     const int KC = chunk_K(n_pass), np = parts(n_pass);
     const int chunk = k / KC, kk = k % KC;
+    long half_off = 0;
     if (cta_pair) {
-        // unit (q, c) of the stream, CTA share r, row i of the share (see PairGeom); `N` = padded width, `cta_pair` - 1 = cA
-        const int nq = N > 128 ? 2 : 1, R = N / (2 * nq), EB = elem_bytes(n_pass);
-        const int q = n / (2 * R), r = (n % (2 * R)) / R, i = n % R;
-        PairGeom g;
-        g.nq = nq; g.cA = cta_pair - 1; g.nch = pack_nch;
-        const long unit = (long)2 * np * R * KC * EB;
-        const long ub = base + pair_unit_index(g, q, chunk) * unit + (long)r * np * R * KC * EB;
-        const long pbh = (long)R * KC * EB;
-        if (n_pass == 2) {
-            const long inner = ((long)(kk / 4) * (R / 8) + i / 8) * 128 + (i % 8) * 16 + (kk % 4) * 4;
-            *reinterpret_cast<uint32_t *>(out + ub + inner) = to_tf32(w);
-            return;
-        }
-        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-        const long inner = ((long)(kk / 8) * (R / 8) + i / 8) * 128 + (i % 8) * 16 + (kk % 8) * 2;
-        *reinterpret_cast<__nv_bfloat16 *>(out + ub + inner) = hi;
-        if (np == 2) *reinterpret_cast<__nv_bfloat16 *>(out + ub + pbh + inner) = lo;
-        return;
+        const int Nh = N / 2, h = n / Nh;
+        half_off = (long)h * np * Nh * KC * elem_bytes(n_pass);
+        n -= h * Nh;
+        N = Nh;
     }
     if (n_pass == 2) {
-        const long cb = base + (long)chunk * N * KC * 4;
+        const long cb = base + (long)chunk * (cta_pair ? 2 : 1) * N * KC * 4 + half_off;
         const long inner = ((long)(kk / 4) * (N / 8) + n / 8) * 128 + (n % 8) * 16 + (kk % 4) * 4;
         *reinterpret_cast<uint32_t *>(out + cb + inner) = to_tf32(w);
         return;
@@ -200,7 +143,7 @@ __device__ __forceinline__ void pack_store(unsigned char *out, long base, int n_
     const __nv_bfloat16 hi = __float2bfloat16_rn(w);
     const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
     const long pb = (long)N * KC * 2;
-    const long cb = base + (long)chunk * np * pb;
+    const long cb = base + (long)chunk * (cta_pair ? 2 : 1) * np * pb + half_off;
     const long inner = ((long)(kk / 8) * (N / 8) + n / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2;
     *reinterpret_cast<__nv_bfloat16 *>(out + cb + inner) = hi;
     if (np == 2) *reinterpret_cast<__nv_bfloat16 *>(out + cb + pb + inner) = lo;
@@ -210,17 +153,10 @@ __global__ void pack_weights_kernel(occnerf_mlp_params P, DevLayout L, int n_pas
     const int l = blockIdx.y;
     const int K = chain_K(chain, l), N = chain_N(chain, l);
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cta_pair) {
-        const PairGeom g = pair_geom(n_pass, chain, l);
-        if (idx < (long)g.Npad * K) {
-            const int n = (int)(idx / K), k = (int)(idx % K);
-            const float w = n >= N ? 0.f : (chain == 0 ? fwd_weight(P, l, n, k) : fwd_weight(P, 9 - l, k, n));
-            pack_store(out, L.w_off[l], n_pass, g.Npad, n, k, w, 1 + g.cA, g.nch);
-        }
-    } else if (idx < (long)N * K) {
+    if (idx < (long)N * K) {
         const int n = (int)(idx / K), k = (int)(idx % K);
         const float w = chain == 0 ? fwd_weight(P, l, n, k) : fwd_weight(P, 9 - l, k, n);     // backward chain: W^T
-        pack_store(out, L.w_off[l], n_pass, N, n, k, w);
+        pack_store(out, L.w_off[l], n_pass, N, n, k, w, cta_pair);
     }
     if (chain == 0 && blockIdx.x == 0 && threadIdx.x < 256) {
         float *b = reinterpret_cast<float *>(out + L.bias_off) + l * 256;
@@ -663,17 +599,13 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
     }
 }
 
-// ================================================================== CTA-pair mode (cta_group::2 + N-split) role loops
-// One UMMA spans both CTAs of a cluster (M = 256: each CTA's own 128-sample tile) and one COLUMN HALF q of the layer (N <= 128:
-// each CTA holds R = N/2 weight rows of it).  Units (q, K-chunk) stream through a ring of 12 x 8 KB per CTA in the order
-// (q0, part A) (q1, part A) (q0, part B) (q1, part B) (PairGeom): the accumulator of half 0 is committed while half 1 still has a
-// quarter of the layer's MMAs to go, its epilogue produces part A of the next operand meanwhile, and the next layer starts on
-// part A with both halves while the epilogue of half 1 delivers part B -- the tensor pipe no longer idles for a whole epilogue
-// hand-off per layer (trace before: 1.8 k of 7.4 k cycles per layer).
-constexpr int kPairStages = 12;
-constexpr int kPairStageBytes = 8192;
+// ================================================================== CTA-pair mode (cta_group::2) role loops
+// Ring: 6 x 16 KB per CTA (a K-chunk of HALF the weight rows, hi [+ lo]); packed image per chunk = [half][part][k-slab][n/8][8][16 B]
+// (occnerf_mlp_pack_weights with cta_pair = 1), so a CTA's half of a chunk is one contiguous piece.
+constexpr int kPairStages = 6;
+constexpr int kPairStageBytes = 16384;
 
-// both CTAs: stream MY share (R rows) of every unit (plain bulk copies, no multicast)
+// both CTAs: stream MY half of every chunk (plain bulk copies, no multicast)
 template <int NPASS>
 __device__ __forceinline__ void producer_loop_pair(const ChainArgs &args, const Smem &sm, int num_tiles) {
     constexpr int KC = (NPASS == 1) ? 64 : 32;
@@ -683,36 +615,36 @@ __device__ __forceinline__ void producer_loop_pair(const ChainArgs &args, const 
     const uint32_t rank = cluster_ctarank();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int l = 0; l < n_layers(args.chain); ++l) {
-            const PairGeom g = pair_geom(NPASS, args.chain, l);
-            const uint32_t pbh = (uint32_t)g.R * KC * EB;                        // one part of one CTA's share of a full unit
+            const int K = chain_K(args.chain, l), Nh = chain_N(args.chain, l) / 2;
+            const int nch = (K + KC - 1) / KC;
+            const uint32_t pbh = (uint32_t)Nh * KC * EB;                         // one part of one half of a full chunk
             const unsigned char *src = args.packed + args.w_off[l] + (long)rank * NP * pbh;
-            for (int u = 0; u < g.nunits; ++u, ++it) {
-                int q, c;
-                pair_unit(g, u, q, c);
+            for (int c = 0; c < nch; ++c, ++it) {
                 const uint32_t s = it % kPairStages, ph = (it / kPairStages) & 1;
                 mbar_wait(sm.bar_w_empty + 8 * s, ph ^ 1);
-                const int kc = min(KC, g.K - c * KC);
-                const uint32_t bytes = (uint32_t)g.R * kc * EB;
+                const int kc = min(KC, K - c * KC);
+                const uint32_t bytes = (uint32_t)Nh * kc * EB;
                 const uint32_t dst = smem_u32(sm.W + s * kPairStageBytes);
                 const uint32_t bar = sm.bar_w_full + 8 * s;
                 mbar_arrive_expect_tx(bar, bytes * NP);
-                const unsigned char *unit = src + (long)u * 2 * NP * pbh;
-                bulk_g2s(dst, unit, bytes, bar);
-                if (NP == 2) bulk_g2s(dst + kPairStageBytes / 2, unit + pbh, bytes, bar);
+                const unsigned char *chunk = src + (long)c * 2 * NP * pbh;
+                bulk_g2s(dst, chunk, bytes, bar);
+                if (NP == 2) bulk_g2s(dst + kPairStageBytes / 2, chunk + pbh, bytes, bar);
             }
         }
     }
 }
 
-// peer CTA (rank 1): tell the leader's MMA thread that MY share of unit `it` has landed in MY shared memory
+// peer CTA (rank 1): tell the leader's MMA thread that MY half of chunk `it` has landed in MY shared memory
 template <int NPASS>
 __device__ __forceinline__ void relay_loop_pair(const ChainArgs &args, const Smem &sm, int num_tiles) {
+    constexpr int KC = (NPASS == 1) ? 64 : 32;
     uint32_t it = 0;
     const uint32_t leader_w_peer = map_to_cta(sm.bar_w_peer, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int l = 0; l < n_layers(args.chain); ++l) {
-            const int nunits = pair_geom(NPASS, args.chain, l).nunits;
-            for (int u = 0; u < nunits; ++u, ++it) {
+            const int nch = (chain_K(args.chain, l) + KC - 1) / KC;
+            for (int c = 0; c < nch; ++c, ++it) {
                 const uint32_t s = it % kPairStages, ph = (it / kPairStages) & 1;
                 mbar_wait(sm.bar_w_full + 8 * s, ph);
                 mbar_arrive_cluster(leader_w_peer + 8 * s);
@@ -734,7 +666,7 @@ __device__ __forceinline__ void mma_step_pair(uint32_t d_tmem, uint64_t da, uint
     }
 }
 
-// leader CTA (rank 0), whole MMA warp: M = 256 UMMAs over both CTAs' A tiles and weight shares, one column half at a time
+// leader CTA (rank 0), whole MMA warp: M = 256 UMMAs over both CTAs' A tiles and B halves
 template <int NPASS>
 __device__ __forceinline__ void mma_loop_pair(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base) {
     constexpr int KC = (NPASS == 1) ? 64 : 32;
@@ -750,34 +682,32 @@ __device__ __forceinline__ void mma_loop_pair(const ChainArgs &args, const Smem 
         for (int l = 0; l < n_layers(args.chain); ++l) {
             TRACE(tr, l, 0);
             const long long w0 = dbg_w, a0 = dbg_a;
-            const PairGeom g = pair_geom(NPASS, args.chain, l);
-            const uint32_t idesc = NPASS == 2 ? instr_desc_tf32(2 * g.R, 256) : instr_desc(2 * g.R, 256);
-            const uint32_t b_lbo = (uint32_t)(g.R / 8) * 128;                   // k-slab stride of MY share of a unit
-            const uint64_t da0 = smem_desc(a_base, 2048, 128);
+            const int K = chain_K(args.chain, l), N = chain_N(args.chain, l);
+            const int nch = (K + KC - 1) / KC;
+            const uint32_t idesc = NPASS == 2 ? instr_desc_tf32(N, 256) : instr_desc(N, 256);
+            const uint32_t b_lbo = (uint32_t)(N / 16) * 128;                   // k-slab stride of MY half (N/2 rows)
+            const uint32_t d_tmem = tmem_base + (uint32_t)(l & 1) * 256;
+            uint64_t da = smem_desc(a_base, 2048, 128);
             const uint64_t db_step = (uint64_t)((2 * b_lbo) >> 4);
-            for (int u = 0; u < g.nunits; ++u, ++it) {
-                int q, c;
-                pair_unit(g, u, q, c);
+            for (int c = 0; c < nch; ++c, ++it) {
                 const uint32_t s = it % kPairStages, ph = (it / kPairStages) & 1;
                 {
                     const long long t0 = args.debug ? clk() : 0;
-                    mbar_wait(sm.bar_w_full + 8 * s, ph);                       // my share
-                    mbar_wait_cluster(sm.bar_w_peer + 8 * s, ph);               // the peer's share
+                    mbar_wait(sm.bar_w_full + 8 * s, ph);                       // my half
+                    mbar_wait_cluster(sm.bar_w_peer + 8 * s, ph);               // the peer's half
                     if (args.debug) dbg_w += clk() - t0;
                 }
-                if (q == 0 && c % CPG == 0) {                       // first touch of an A group (half 1 follows half 0 on every chunk)
-                    const int grp = c / CPG;
+                if (c % CPG == 0) {
+                    const int g = c / CPG;
                     const long long t0 = args.debug ? clk() : 0;
-                    mbar_wait_cluster(sm.bar_a_ready + 8 * grp, (a_phase >> grp) & 1);   // 16 warps of each CTA
+                    mbar_wait_cluster(sm.bar_a_ready + 8 * g, (a_phase >> g) & 1);   // 16 warps of each CTA
                     if (args.debug) dbg_a += clk() - t0;
-                    a_phase ^= 1u << grp;
+                    a_phase ^= 1u << g;
                 }
                 tc_fence_after();
-                TRACE(tr && u == 0, l, 1);
-                const int kc = min(KC, g.K - c * KC);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(l & 1) * 256 + (uint32_t)q * 128;
-                const uint64_t da = da0 + (uint64_t)(c * (KC / KS) * (4096 >> 4));
-                const uint64_t db = smem_desc(smem_u32(sm.W + s * kPairStageBytes), b_lbo, 128);
+                TRACE(tr && c == 0, l, 1);
+                const int kc = min(KC, K - c * KC);
+                uint64_t db = smem_desc(smem_u32(sm.W + s * kPairStageBytes), b_lbo, 128);
                 if (elect_one()) {
                     if (kc == KC) {
 #pragma unroll
@@ -788,15 +718,14 @@ __device__ __forceinline__ void mma_loop_pair(const ChainArgs &args, const Smem 
                             mma_step_pair<NPASS>(d_tmem, da + (uint64_t)(ks * (4096 >> 4)), db + ks * db_step, idesc, (c | ks) ? 1u : 0u);
                     }
                     tc_commit_cg2_mc(sm.bar_w_empty + 8 * s, 3);                // frees the slot in BOTH CTAs
-                    // column half q of BOTH CTAs' accumulators complete (one barrier per half: a parity wait tolerates one phase
-                    // of lag only, and the two commits of a layer are less than a thousand cycles apart)
-                    if (c == g.nch - 1) tc_commit_cg2_mc(sm.bar_acc_full + 8 * q, 3);
                 }
                 __syncwarp();
-                TRACE(tr && q == 0 && c == g.nch - 1, l, 9);
+                da += (uint64_t)((KC / KS) * (4096 >> 4));
             }
             TRACE(tr, l, 2);
             if (tr) { g_trace[l][10] = (unsigned long long)(dbg_a - a0); g_trace[l][11] = (unsigned long long)(dbg_w - w0); }
+            if (elect_one()) tc_commit_cg2_mc(sm.bar_acc_full, 3);             // accumulator rows of BOTH CTAs complete
+            __syncwarp();
         }
     }
     if (args.debug && lane0) {
@@ -806,9 +735,6 @@ __device__ __forceinline__ void mma_loop_pair(const ChainArgs &args, const Smem 
         atomicAdd(&g_dbg[6], 1ull);
     }
 }
-
-// how many accumulator commits the epilogue sees for a layer of padded width N in pair mode (one per column half)
-__device__ __forceinline__ int pair_halves(bool pair, int N) { return (pair && pair_pad_N(N) > 128) ? 2 : 1; }
 
 // one arrival of this thread's WARP on A group g.  EVERY epilogue warp arrives exactly once per group and GEMM, after the chunk
 // it owns in that group -- if any -- is in shared memory and after all of its TMEM reads of older accumulators: a group
@@ -838,7 +764,7 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
     const int tid = threadIdx.x;                                   // 0 .. 511
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float *bias_all = reinterpret_cast<const float *>(args.packed + args.bias_off);
-    uint32_t acc_cnt[2] = {0u, 0u}, bl = 0;                        // bl: running layer count = parity of the bias buffer
+    uint32_t acc_cnt = 0, bl = 0;                                  // bl: running layer count = parity of the bias buffer
     const bool dbg_on = args.debug && threadIdx.x == 0;
     long long dbg_acc = 0;
     const long long dbg_t0 = dbg_on ? clk() : 0;
@@ -864,21 +790,18 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
             if (set < 2) stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 0, set + 8, sv8(set + 8));
             publish(sm, kGroupCols == 32 ? 2 : 1);
         }
-        // accumulator of column half q complete (pair mode commits the two halves of a 256-wide layer separately)
-        auto wait_acc = [&](int q) {
-            const long long t0 = dbg_on ? clk() : 0;
-            mbar_wait(sm.bar_acc_full + 8 * q, acc_cnt[q] & 1);
-            ++acc_cnt[q];
-            if (dbg_on) dbg_acc += clk() - t0;
-            tc_fence_after();
-        };
-        for (int l = 0; l < kLayers; ++l, ++bl) {
+        for (int l = 0; l < kLayers; ++l, ++acc_cnt, ++bl) {
             const int l_next = l + 1 == kLayers ? 0 : l + 1;
             float bias_next = 0.f;
             if (tid < 256) bias_next = __ldg(bias_all + l_next * 256 + tid);
-            wait_acc(0);
+            {
+                const long long t0 = dbg_on ? clk() : 0;
+                mbar_wait(sm.bar_acc_full, acc_cnt & 1);
+                if (dbg_on) dbg_acc += clk() - t0;
+            }
             TRACE(tr0, l, 3);
             TRACE(tr15, l, 6);
+            tc_fence_after();
             const uint32_t t_acc = t_lane + (uint32_t)(l & 1) * 256;
             const float *bias = sm.bias + (bl & 1) * 256;
             if (l == 9) {
@@ -969,20 +892,15 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                         }
                     }
                 };
+                tmem_ld8_issue(t_acc + set * 8, ra);
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {            // columns 0..127, then 128..255
-                    if (half == 1 && sm.pair) wait_acc(1);
-                    const int c0 = half * 4;
-                    tmem_ld8_issue(t_acc + (c0 * 4 + set) * 8, ra);
-#pragma unroll 1
-                    for (int cg = c0; cg < c0 + 4; cg += 2) {
-                        tmem_ld_wait();
-                        tmem_ld8_issue(t_acc + ((cg + 1) * 4 + set) * 8, rb);
-                        process(cg, ra);
-                        tmem_ld_wait();
-                        if (cg + 2 < c0 + 4) tmem_ld8_issue(t_acc + ((cg + 2) * 4 + set) * 8, ra);
-                        process(cg + 1, rb);
-                    }
+                for (int cg = 0; cg < 8; cg += 2) {
+                    tmem_ld_wait();
+                    tmem_ld8_issue(t_acc + ((cg + 1) * 4 + set) * 8, rb);
+                    process(cg, ra);
+                    tmem_ld_wait();
+                    if (cg + 2 < 8) tmem_ld8_issue(t_acc + ((cg + 2) * 4 + set) * 8, ra);
+                    process(cg + 1, rb);
                 }
             }
             // park the next layer's bias (fetched at the top of this layer) in the other buffer; the barrier sits where the
@@ -1000,17 +918,10 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
     const int quarter = warp & 3, set = warp >> 2;
     const int row = quarter * 32 + (threadIdx.x & 31);
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t acc_cnt[2] = {0u, 0u};
+    uint32_t acc_cnt = 0;
     const bool dbg_on = args.debug && threadIdx.x == 0;
     long long dbg_acc = 0;
     const long long dbg_t0 = dbg_on ? clk() : 0;
-    auto wait_acc = [&](int q) {                                   // (see the forward epilogue)
-        const long long t0 = dbg_on ? clk() : 0;
-        mbar_wait(sm.bar_acc_full + 8 * q, acc_cnt[q] & 1);
-        ++acc_cnt[q];
-        if (dbg_on) dbg_acc += clk() - t0;
-        tc_fence_after();
-    };
     // 8 accumulator columns [col, col+8) -> gXB[:, 64 + c*8 ...) (chunk c of the 68 (agg,var,h) columns; chunk 8 has 4)
     auto gxb_chunk = [&](uint32_t t_acc, int col, int c, long grow, bool valid, bool accumulate) {
         uint32_t r[8];
@@ -1043,7 +954,7 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
             }
             publish(sm, 0);
         }
-        for (int d = 0; d < kLayers; ++d) {
+        for (int d = 0; d < kLayers; ++d, ++acc_cnt) {
             uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};        // this thread's 8 ReLU-mask bytes of the layer, fetched before the wait
             if (valid && d != 9 && d != 4) {
                 const int slot = d < 4 ? 7 - d : 8 - d;              // d0..3 -> R4..R1 (slots 7..4); d5..8 -> H4..H1 (slots 3..0)
@@ -1051,7 +962,12 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
 #pragma unroll
                 for (int cg = 0; cg < 8; ++cg) mw[cg] = __ldg(mp + (long)cg * 4 * args.slot_stride);
             }
-            wait_acc(0);
+            {
+                const long long t0 = dbg_on ? clk() : 0;
+                mbar_wait(sm.bar_acc_full, acc_cnt & 1);
+                if (dbg_on) dbg_acc += clk() - t0;
+            }
+            tc_fence_after();
             const uint32_t t_acc = t_lane + (uint32_t)(d & 1) * 256;
             if (d == 9) {
                 // pts0^T: 68 (+12 pad) columns, accumulated onto the colour trunk's share of d(agg,var,h)
@@ -1064,12 +980,9 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
                 // Every TMEM read of a thread comes BEFORE its last publish: GEMM d+2 overwrites this buffer as soon as some
                 // threads have published the first group of layer d+1, which they can only do after GEMM d+1 has consumed
                 // everything published here.
-                // (pair mode: the 144 outputs are padded to 2 x 80; column half 1 = outputs 80..159 sits at TMEM columns 128..207)
-                if (sm.pair) wait_acc(1);
-                auto tcol = [&](int j) { return (sm.pair && j >= 80) ? j + 48 : j; };
-                gxb_chunk(t_acc, tcol(64 + set * 8), set, grow, valid, false);
-                gxb_chunk(t_acc, tcol(64 + (set + 4) * 8), set + 4, grow, valid, false);
-                if (set == 0) gxb_chunk(t_acc, tcol(128), 8, grow, valid, false);
+                gxb_chunk(t_acc, 64 + set * 8, set, grow, valid, false);
+                gxb_chunk(t_acc, 64 + (set + 4) * 8, set + 4, grow, valid, false);
+                if (set == 0) gxb_chunk(t_acc, 128, 8, grow, valid, false);
 #pragma unroll 1
                 for (int cg = 0; cg < 2; ++cg) {
                     const int k8 = cg * 4 + set;
@@ -1103,20 +1016,15 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
                     if (pub_after(cg)) publish(sm, pub_group(cg));   // before the global store (see the forward epilogue)
                     if (valid) *reinterpret_cast<uint4 *>(args.g_save + saved_off(gslot, k8, args.slot_stride, grow)) = hi;
                 };
+                tmem_ld8_issue(t_acc + set * 8, ra);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {            // columns 0..127, then 128..255
-                    if (half == 1 && sm.pair) wait_acc(1);
-                    const int c0 = half * 4;
-                    tmem_ld8_issue(t_acc + (c0 * 4 + set) * 8, ra);
-#pragma unroll
-                    for (int cg = c0; cg < c0 + 4; cg += 2) {
-                        tmem_ld_wait();
-                        tmem_ld8_issue(t_acc + ((cg + 1) * 4 + set) * 8, rb);
-                        process(cg, ra, mw[cg]);
-                        tmem_ld_wait();
-                        if (cg + 2 < c0 + 4) tmem_ld8_issue(t_acc + ((cg + 2) * 4 + set) * 8, ra);
-                        process(cg + 1, rb, mw[cg + 1]);
-                    }
+                for (int cg = 0; cg < 8; cg += 2) {
+                    tmem_ld_wait();
+                    tmem_ld8_issue(t_acc + ((cg + 1) * 4 + set) * 8, rb);
+                    process(cg, ra, mw[cg]);
+                    tmem_ld_wait();
+                    if (cg + 2 < 8) tmem_ld8_issue(t_acc + ((cg + 2) * 4 + set) * 8, ra);
+                    process(cg + 1, rb, mw[cg + 1]);
                 }
             }
         }
@@ -1224,17 +1132,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
     static_assert(kStages * kStageBytes == kPairStages * kPairStageBytes, "both ring geometries use the same bytes");
     constexpr int kNStages = CG == 2 ? kPairStages : kStages;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kABytes + kRingBytes);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 46);      // barrier block: 46 x 8 B, then the TMEM base
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 30);
     Smem sm;
     sm.A = smem;
     sm.W = smem + kABytes;
-    sm.bias = reinterpret_cast<float *>(smem + kABytes + kRingBytes + 512);
+    sm.bias = reinterpret_cast<float *>(smem + kABytes + kRingBytes + 256);
     sm.bar_w_full = smem_u32(bars);
     sm.bar_w_empty = smem_u32(bars + kNStages);
     sm.bar_w_peer = smem_u32(bars + 2 * kNStages);                  // (pair mode only)
     sm.bar_a_ready = smem_u32(bars + 3 * kNStages);
     sm.bar_acc_full = smem_u32(bars + 3 * kNStages + kGroups);
-    static_assert(3 * kPairStages + kGroups + 2 <= 46, "barrier block");
+    static_assert(3 * kPairStages + kGroups + 1 <= 30, "barrier block");
     sm.pair = CG == 2;
     sm.a_ready_arrive = CG == 2 ? map_to_cta(sm.bar_a_ready, 0) : sm.bar_a_ready;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1250,7 +1158,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
         }
         for (int g = 0; g < kGroups; ++g) mbar_init(sm.bar_a_ready + 8 * g, (CG == 2 ? 2 : 1) * (kEpiThreads / 32));
         mbar_init(sm.bar_acc_full, 1);
-        mbar_init(sm.bar_acc_full + 8, 1);                          // (pair mode: column half 1)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -1297,7 +1204,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
 template <int NPASS, int CHAIN, int CG>
 int launch_chain_cg(const ChainArgs &a, cudaStream_t st) {
     constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);
-    const int smem_bytes = kABytes + kStages * kStageBytes + 512 + 2048;     // + barriers + the bias double buffer
+    const int smem_bytes = kABytes + kStages * kStageBytes + 256 + 2048;     // + barriers + the bias double buffer
     static bool configured = false;
     if (!configured) {
         OCC_CUDA(cudaFuncSetAttribute(mlp_chain_tc_kernel<NPASS, CHAIN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -1382,7 +1289,7 @@ void fill_layout(ChainArgs &a, int n_pass, int chain, const void *packed) {
 
 // debug only: how many clusters of `cluster_size` CTAs of the tc3 forward chain kernel the device can hold at once
 extern "C" int occnerf_mlp_debug_max_clusters(int cluster_size) {
-    constexpr int smem_bytes = 2 * kAPartBytes + kStages * kStageBytes + 512 + 2048;
+    constexpr int smem_bytes = 2 * kAPartBytes + kStages * kStageBytes + 256 + 2048;
     if (cudaFuncSetAttribute(mlp_chain_tc_kernel<3, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return -1;
     if (cluster_size > 8 && cudaFuncSetAttribute(mlp_chain_tc_kernel<3, 0, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -2;
     cudaLaunchConfig_t cfg = {};
