@@ -29,6 +29,7 @@ _SIGNATURES = {
     "occnerf_warp_forward_packed": [_vp] * 8 + [_i] * 6 + [_vp] * 3 + [_vp],
     "occnerf_warp_backward_packed": [_vp] * 9 + [_i] * 6 + [_vp, _vp, _vp, _vp],
     "occnerf_warp_unpack_grad": [_vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "occnerf_clip_adam_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _vp, _vp],
     "occnerf_knn": [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "occnerf_knn_hier": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp],
     "occnerf_knn_tree": [_vp, _i, _i, _i] + [_vp] * 11 + [_i] * 5 + [_vp, _vp],
@@ -114,7 +115,7 @@ def ptr(t, dtype=None):
 
 
 # kernels launched per C call (for the bench's `gpu_launches` claim); entries not listed launch exactly one
-KERNELS_PER_CALL = {"occnerf_visibility_hits": 3, "occnerf_generate_rays": 3, "occnerf_unpack_image": 2}
+KERNELS_PER_CALL = {"occnerf_clip_adam_step": 3, "occnerf_visibility_hits": 3, "occnerf_generate_rays": 3, "occnerf_unpack_image": 2}
 COUNTERS = {"calls": 0, "launches": 0}
 PROFILE = None   # set to {} to record (start_event, end_event, work) per C call on the current stream
 
