@@ -147,8 +147,11 @@ class Workload:
         self.packed = torch.cat([self.fr.rays_o, self.fr.rays_d, self.fr.near, self.fr.far], -1).contiguous()
         path_params = [p for n, p in self.net.named_parameters() if p.requires_grad and not n.startswith(("mweight_vol_decoder", "pose_decoder", "non_rigid_mlp"))]
         self.path_params = path_params
-        self.opt_path = torch.optim.Adam(path_params, lr=5e-4, fused=True)
-        self.opt_all = torch.optim.Adam([p for p in self.net.parameters() if p.requires_grad], lr=5e-4, fused=True)
+        from occnerf_b200.optim import ClipAdam
+        from occnerf_b200.distributed import GradReducer
+        self.opt_path = ClipAdam(path_params, lr=5e-4, max_norm=1.0)          # native clip + Adam (csrc/optim.cu), trainer.py:248-249
+        self.opt_all = ClipAdam([p for p in self.net.parameters() if p.requires_grad], lr=5e-4, max_norm=1.0)
+        self.reducer, self.reducer_e2e = GradReducer(), GradReducer()
         # pinned host copies of everything `Network.forward` receives per frame (trainer.py:223-229)
         h = self.fr_host
         self.host = {k: v.pin_memory() for k, v in dict(rays_o=h.rays_o, rays_d=h.rays_d, near=h.near, far=h.far, dst_Rs=h.dst_Rs,
@@ -157,8 +160,9 @@ class Workload:
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
         self.loss_host = torch.zeros(1).pin_memory()
 
-    def loss(self, out, target):
-        return 0.2 * torch.mean((out["rgb"] - target) ** 2) + out["comp_loss"].mean()
+    def loss(self, out, target, world=1):
+        # (data parallel: 1 / world folded into the loss, so that the SUM all-reduce of the gradients is their average)
+        return (0.2 * torch.mean((out["rgb"] - target) ** 2) + out["comp_loss"].mean()) * (1.0 / world)
 
     def grads_to_reduce(self):
         return [p.grad for p in self.path_params if p.grad is not None] + ([self.vol.grad] if self.vol.grad is not None else [])
@@ -169,20 +173,17 @@ class Workload:
         out = net._batchify_rays(self.packed, pos_embed_fn=None, non_rigid_pos_embed_fn=self.emb_fn, non_rigid_mlp_input=None,
                                  motion_scale_Rs=fr.motion_scale_Rs[None], motion_Ts=fr.motion_Ts[None], motion_weights_vol=self.vol,
                                  cnl_bbox_min_xyz=fr.cnl_bbox_min_xyz, cnl_bbox_scale_xyz=fr.cnl_bbox_scale_xyz, bgcolor=fr.bgcolor)
-        self.loss(out, self.target).backward()
+        self.loss(out, self.target, world).backward()
         hits = out["hits"]
         if world > 1:
-            # one bucket for the 22 small tensors (MLP, point_dist, weight volume), the 59 MiB table gradient on its own
+            # one flat bucket for the 22 small tensors (MLP, point_dist, weight volume), the 59 MiB table gradient in place
             from occnerf_b200 import distributed as D
-            D.allreduce_gradients(self.path_params, extra=[self.vol.grad])
+            self.reducer([p.grad for p in self.path_params] + [self.vol.grad])
             D.allreduce_visibility(hits)
-        from occnerf_b200 import _lib
-        with _lib.region("lib:clip+adam+zero_grad"):
-            torch.nn.utils.clip_grad_norm_(self.path_params, 1.0)
-            self.opt_path.step()
-            self.opt_path.zero_grad(set_to_none=True)
-            self.vol.grad = None
-            net.apply_visibility(hits)
+        self.opt_path.step()                             # occnerf_clip_adam_step: global-norm clip + Adam, 3 launches
+        self.opt_path.zero_grad(set_to_none=True)
+        self.vol.grad = None
+        net.apply_visibility(hits)
 
     def make_graphed(self, world):
         """The e2e step as one CUDA graph (occnerf_b200/train_step.py); under data parallelism the NCCL all-reduces of the
@@ -190,10 +191,9 @@ class Workload:
         from occnerf_b200 import distributed as D
         from occnerf_b200.train_step import GraphedTrainStep
         params = [p for p in self.net.parameters() if p.requires_grad]
-        opt = torch.optim.Adam(params, lr=5e-4, fused=True, capturable=True)
-        sync = (lambda ps, hits: (D.allreduce_gradients(ps), D.allreduce_visibility(hits))) if world > 1 else None
-        self.graphed = GraphedTrainStep(self.net, opt, lambda out, d: self.loss({"rgb": out["rgb"], "comp_loss": out["comp_loss"]}, d["target"]),
-                                        self.host, self.iter_val, params=params, grad_sync=sync)
+        sync = (lambda grads, hits: (self.reducer_e2e(grads), D.allreduce_visibility(hits))) if world > 1 else None
+        self.graphed = GraphedTrainStep(self.net, self.opt_all, lambda out, d: self.loss({"rgb": out["rgb"], "comp_loss": out["comp_loss"]}, d["target"], world),
+                                        self.host, self.iter_val, params=params, max_norm=None, grad_sync=sync)
         return self.graphed
 
     def step_e2e_graphed(self, world):
@@ -207,14 +207,13 @@ class Workload:
         out = net.forward((d["rays_o"], d["rays_d"]), d["dst_Rs"], d["dst_Ts"], d["cnl_gtfms"], d["priors"], dst_posevec=d["posevec"],
                           near=d["near"], far=d["far"], iter_val=self.iter_val, cnl_bbox_min_xyz=d["bmin"], cnl_bbox_scale_xyz=d["bscale"],
                           bgcolor=d["bg"])
-        loss = self.loss({"rgb": out["rgb"], "comp_loss": out["comp_loss"]}, d["target"])
+        loss = self.loss({"rgb": out["rgb"], "comp_loss": out["comp_loss"]}, d["target"], world)
         loss.backward()
         params = [p for p in net.parameters() if p.requires_grad]
         if world > 1:
             from occnerf_b200 import distributed as D
-            D.allreduce_gradients(params)
+            self.reducer_e2e([p.grad for p in params])
             D.allreduce_visibility(out["hits"])
-        torch.nn.utils.clip_grad_norm_(params, 1.0)
         self.opt_all.step()
         self.opt_all.zero_grad(set_to_none=True)
         net.apply_visibility(out["hits"])
@@ -260,9 +259,43 @@ def forward_frame(wl, flush, repeats=3):
     net.cfg.perturb = perturb
     ms = tot / repeats
     n = packed.shape[0]
+    peaks = load_peaks()
+    t_mlp = dict((name, t) for t, name in top).get("occnerf_mlp_forward_tc")
+    roof = None
+    if t_mlp:
+        ach = FLOP_MLP_FWD * n * S_SAMPLES / (t_mlp * 1e-3) / 1e12
+        roof = {"kernel": "occnerf_mlp_forward_tc", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None}
     return {"workload": "forward render of one 512x512 view, all bbox-hitting pixels, 128 samples/ray, non-rigid MLP active (iter 1e7)",
             "rays": n, "ms_per_frame": ms, "rays_per_sec": n / (ms * 1e-3), "finite": bool(torch.isfinite(out["rgb"]).all()),
-            "top_calls_ms": [[name, round(t, 2)] for t, name in top]}
+            "top_calls_ms": [[name, round(t, 2)] for t, name in top], "roofline": roof}
+
+
+def cpu_forward_reference(sample_rays: int):
+    """BASELINE configs[0]'s own measurement: the reference's pure-PyTorch forward on the host cores (oracle port), bounded sample."""
+    from occnerf_b200 import synthetic as S
+    from oracle import hashgrid_c, occnerf_oracle as O
+    import dataclasses
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hashgrid_c.set_threads(cores)
+    sub = S.make_subject(seed=0)
+    w = S.make_weights(sub.bound, seed=0)
+    fr = S.make_frame(sub, mode="full", img=512, seed=3)
+    vol = S.make_motion_weights_vol(sub.priors, seed=0)
+    pick = torch.arange(0, fr.rays_o.shape[0], max(1, fr.rays_o.shape[0] // sample_rays))[:sample_rays]
+    sl = {f.name: (getattr(fr, f.name)[pick] if f.name in ("rays_o", "rays_d", "near", "far") else getattr(fr, f.name)) for f in dataclasses.fields(fr)}
+    frs = S.Frame(**sl)
+    times = []
+    with torch.no_grad():
+        for it in range(3):
+            t0 = time.perf_counter()
+            O.render_rays(frs, vol, sub, w, iter_val=10 ** 7, training=False)
+            times.append(time.perf_counter() - t0)
+    hashgrid_c.set_threads(1)
+    t = float(np.mean(times[1:]))
+    n = int(pick.numel())
+    return {"value": n / t, "unit": "rays/s", "cores": cores, "kind": "port", "sample": f"{n} of {fr.rays_o.shape[0]} rays of the frame x {S_SAMPLES} samples, forward only, 2 timed repeats"}
 
 
 def timed_loop(fn, steps, warmup, world, flush):
@@ -315,11 +348,13 @@ def roofline_for(row, peaks, M, engine="tc3"):
     per_launch_samples = M / max(row["launches_per_step"], 1.0) if name.startswith(("occnerf_mlp", "occnerf_aggregate", "occnerf_hashgrid", "occnerf_sample")) else M
     traffic = NCU_TRAFFIC_PER_SAMPLE.get(name)
     traffic = traffic * per_launch_samples if traffic is not None else None
-    hbm = {"occnerf_warp_forward": 20.25, "occnerf_warp_backward": 4.0, "occnerf_composite_forward": 28.0 + 28.0 / S_SAMPLES,
+    hbm = {"occnerf_warp_forward": 20.25, "occnerf_warp_backward": 4.0, "occnerf_warp_forward_packed": 20.25, "occnerf_warp_backward_packed": 4.0,
+           # weight gradients: the bf16 operands read once = (8 x 256 + 80 + 144) + (8 x 256 + 80 + 16) columns x 2 B per sample
+           "occnerf_mlp_wgrad_tc": 8832.0, "occnerf_composite_forward": 28.0 + 28.0 / S_SAMPLES,
            "occnerf_composite_backward": 52.0, "occnerf_hashgrid_forward": 144.0, "occnerf_hashgrid_backward": 128.0,
            "occnerf_aggregate_forward": 160.0 + 144.0, "occnerf_aggregate_backward": 160.0 + 144.0, "occnerf_knn": 12.0 + 160.0,
            "occnerf_knn_grid": 12.0 + 160.0, "occnerf_knn_tree": 12.0 + 160.0, "occnerf_sample_geometry": 12.0 + 40.0 + 20.0}
-    if name in ("occnerf_sgemm", "occnerf_mlp_forward_tc", "occnerf_mlp_backward_tc", "occnerf_mlp_wgrad_tc"):
+    if name in ("occnerf_sgemm", "occnerf_mlp_forward_tc", "occnerf_mlp_backward_tc"):
         flops = row["work_per_step"] / max(row["launches_per_step"], 1e-9)
         ach = flops / (ms * 1e-3) / 1e12
         out = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -329,6 +364,11 @@ def roofline_for(row, peaks, M, engine="tc3"):
             out["issued_mma_tflops"] = ach * MMA_ISSUE_FACTOR[engine]
             out["issued_mma_frac"] = out["issued_mma_tflops"] / peaks["bf16_tflops_sustained"]
         return out
+    if name == "occnerf_clip_adam_step":                  # 32 B per parameter (g twice, p/m/v read + written)
+        bytes_ = 32.0 * row.get("params", 0.0)
+        ach = bytes_ / (ms * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                "traffic": None, "peak_source": peaks["source"] + " copy bandwidth"}
     bytes_ = hbm.get(name, 0.0) * per_launch_samples
     ach = bytes_ / (ms * 1e-3) / 1e9
     return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
@@ -384,19 +424,23 @@ def main():
     profile, _lib.PROFILE = _lib.PROFILE, None
     clocks = sampler.stop()
     table = kernel_table(profile, args.steps)
+    n_path_params = float(sum(p.numel() for p in wl.path_params))
+    for r in table:
+        if r["call"] == "occnerf_clip_adam_step":
+            r["params"] = n_path_params
     # ---- e2e: public API with host buffers
     if args.profile_mode:
         if rank == 0:
             print(json.dumps({"profile_mode": True, "ms_per_step": ms, "kernels": [(r["call"], round(r["ms_per_step"], 4)) for r in table]}))
         return
     e2e_mode, e2e_launches = "eager", None
-    # (capturing the NCCL all-reduces with the step hung at N=2 in round 1: multi-GPU runs time the eager step unless
-    #  OCCNERF_GRAPH_NCCL=1 asks for the experiment)
-    if not args.no_graph and (world == 1 or os.environ.get("OCCNERF_GRAPH_NCCL", "0") == "1"):
+    # one CUDA graph per step on one GPU; with data parallelism two graphs (forward+backward | clip+Adam) around the eagerly
+    # launched NCCL all-reduces -- the same launch mode at every rank count
+    if not args.no_graph:
         ok = 1
         try:
             g = wl.make_graphed(world)
-            e2e_mode, e2e_launches = "cuda_graph", g.launches
+            e2e_mode, e2e_launches = ("cuda_graph" if world == 1 else "2 cuda graphs + eager nccl"), g.launches
         except Exception as exc:                                   # capture is an optimisation, never a requirement
             import traceback
             traceback.print_exc(file=sys.stderr)
@@ -408,8 +452,18 @@ def main():
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()) == 0:
                 e2e_mode, e2e_launches = "eager", None
-    step = wl.step_e2e_graphed if e2e_mode == "cuda_graph" else wl.step_e2e
+    step = wl.step_e2e_graphed if e2e_mode != "eager" else wl.step_e2e
     ms_e2e = timed_loop(lambda: step(world), args.steps, args.warmup, world, flush)
+    # the same K steps by the wall clock (host gaps between steps included; L2 flushes included too, hence a little above the event time)
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        step(world)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3 / args.steps
 
     if rank == 0:
         peaks = load_peaks()
@@ -420,11 +474,13 @@ def main():
             "dtype": {"fp32": "f32", "tf32": "tf32->f32", "tc3": "bf16x3(split)->f32", "tc3b1": "bf16x3(split)->f32 fwd, bf16->f32 dgrad", "tc1": "bf16->f32"}[args.engine], "data": "synthetic",
             "config": {"workload": "zju387_train_step_6x32x32_rays_128spr_fwd_bwd", "rays_per_step_per_gpu": RAYS_PER_STEP, "samples_per_ray": S_SAMPLES,
                        "mlp_engine": args.engine, "l2": "256 MiB flush write between timed steps", "timing": "cuda events per step, max over ranks",
-                       "optimizer": "grad-clip + fused Adam (library) inside the step", "parallelism": f"dp{world}"},
+                       "optimizer": "global-norm clip + Adam inside the step (occnerf_clip_adam_step)", "parallelism": f"dp{world}",
+                       "knn": "exact; pykeops' own reduction is un-vendored upstream (parity unpinned for that one call), ids checked against brute force"},
             "clocks": clocks,
             "e2e": {"value": world * RAYS_PER_STEP / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": wl.h2d_bytes,
                     "d2h_bytes_per_step": 4, "api": "Network.forward (prologue + ray path) + loss + backward + optimizer",
-                    "launch": e2e_mode, "our_launches_per_step": e2e_launches},
+                    "launch": e2e_mode, "our_launches_per_step": e2e_launches, "wall_ms_per_step": wall_ms,
+                    "wall_note": "K back-to-back steps by the host clock, no L2 flush between them"},
             "gpu_launches": launches,
             "roofline": roof_all[0] if roof_all else None,
             "kernels": [{"call": r["call"], "ms_per_step": round(r["ms_per_step"], 4), "launches_per_step": r["launches_per_step"]} for r in table],
@@ -432,6 +488,8 @@ def main():
         }
         if world == 1:
             line["forward_only"] = forward_frame(wl, flush)
+            if not args.no_cpu_baseline:
+                line["forward_only"]["cpu_baseline"] = cpu_forward_reference(args.ref_rays)
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference(args.ref_rays, 2, 1)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "rays/s", "cores": cb["cores"], "kind": "port", "sample": cb["sample"]}

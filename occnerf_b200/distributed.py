@@ -61,6 +61,42 @@ def allreduce_gradients(params, extra=(), average: bool = True, bucket_bytes: in
                 t.div_(world)
 
 
+class GradReducer:
+    """Sum-all-reduce of a fixed list of gradient tensors with the fewest launches: tensors below `bucket_bytes` travel through ONE
+    persistent flat buffer (a multi-tensor copy in, one collective, a multi-tensor copy out -- no torch.cat, no per-tensor
+    copy-back, no division pass: the caller folds 1 / world_size into the loss), the large ones (hash table, decoder weights)
+    are reduced in place.  All collectives are issued asynchronously and waited for together, so NCCL pipelines them."""
+
+    def __init__(self, bucket_bytes: int = 4 << 20):
+        self.bucket_bytes = bucket_bytes
+        self.flat, self.views, self.key = None, None, None
+
+    def __call__(self, grads):
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        grads = [g for g in grads if g is not None]
+        small = [g for g in grads if g.numel() * g.element_size() < self.bucket_bytes]
+        large = [g for g in grads if g.numel() * g.element_size() >= self.bucket_bytes]
+        work = []
+        if small:
+            key = tuple((tuple(g.shape), g.dtype, g.device) for g in small)
+            if key != self.key:
+                self.flat = torch.empty(sum(g.numel() for g in small), dtype=small[0].dtype, device=small[0].device)
+                self.views, off = [], 0
+                for g in small:
+                    self.views.append(self.flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+                self.key = key
+            torch._foreach_copy_(self.views, small)
+            work.append(dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True))
+        for g in large:
+            work.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True))
+        for w in work:
+            w.wait()
+        if small:
+            torch._foreach_copy_(small, self.views)
+
+
 def allreduce_visibility(hits: torch.Tensor) -> torch.Tensor:
     """A point is voted for if any rank's rays voted for it (duplicates collapse upstream too)."""
     if dist.is_initialized() and dist.get_world_size() > 1:

@@ -44,6 +44,15 @@ def _worker(rank, world, port, tmp):
         for p, f in zip(params, full):
             assert torch.allclose(p.grad, f * scale, rtol=1e-6)
         assert torch.allclose(extra, torch.full((25, 4), sum(range(world)) / world))
+        # GradReducer: the persistent flat bucket for the small tensors, in-place reduction of the large one, twice (buffer reuse)
+        red = D.GradReducer(bucket_bytes=1 << 20)
+        for rep in range(2):
+            grads = [f * (rank + 1 + rep) for f in full] + [None]
+            red(grads)
+            tot = sum(r + 1 + rep for r in range(world))
+            for gr, f in zip(grads, full):
+                assert torch.allclose(gr, f * tot, rtol=1e-6)
+        assert red.flat is not None and red.flat.numel() == 256 * 68 + 256
         hits = torch.zeros(100)
         hits[rank * 10:rank * 10 + 5] = 1.0
         D.allreduce_visibility(hits)

@@ -44,7 +44,7 @@ def test_graph_replay_matches_eager_steps():
     eager = GraphedTrainStep.__new__(GraphedTrainStep)
     eager.net, eager.opt, eager.loss_fn, eager.iter_val, eager.max_norm, eager.params = net_e, opt_e, _loss, 500, 1.0, params_e
     eager.static = {k: v.to(d) for k, v in host.items()}
-    eager.loss_dev, eager.grad_sync = torch.zeros(1, device=d), None
+    eager.loss_dev, eager.grad_sync, eager._hits = torch.zeros(1, device=d), None, None
     # the graphed step warms up with 3 real iterations before capture: give the eager model the same head start
     losses_e = []
     for i in range(3 + steps):
@@ -70,3 +70,47 @@ def test_graph_replay_matches_eager_steps():
             continue
         assert torch.allclose(pe, pg, rtol=1e-2, atol=2 * 5e-4 * (3 + steps)), n     # within a couple of Adam steps (lr = 5e-4)
     assert not gs.needs_recapture(501) and gs.needs_recapture(net_g.cfg.non_rigid_kick_in_iter)
+
+
+def test_two_graph_step_with_sync_hook_and_native_optimizer():
+    """Data-parallel shape of the step on one GPU: forward+backward graph, an eager hook on the static gradient tensors (what the
+    NCCL all-reduce does between the graphs), optimizer graph with the native clip + Adam (occnerf_clip_adam_step)."""
+    from occnerf_b200.optim import ClipAdam
+    net_a, host = _setup()
+    net_b = copy.deepcopy(net_a)
+    net_b._cache = None
+    calls = []
+
+    def hook(grads, hits):                        # a "collective" that leaves the values alone (world size 1)
+        calls.append(len([g for g in grads if g is not None]))
+        for g in grads:
+            if g is not None:
+                g.mul_(1.0)
+
+    pa = [p for p in net_a.parameters() if p.requires_grad]
+    pb = [p for p in net_b.parameters() if p.requires_grad]
+    one = GraphedTrainStep(net_a, ClipAdam(pa, lr=5e-4, max_norm=1.0), _loss, host, 500, params=pa, max_norm=None)
+    two = GraphedTrainStep(net_b, ClipAdam(pb, lr=5e-4, max_norm=1.0), _loss, host, 500, params=pb, max_norm=None, grad_sync=hook)
+    assert two.graph_opt is not None and one.graph_opt is None
+    la, lb = [], []
+    for _ in range(3):
+        a, b = one.step(host), two.step(host)
+        torch.cuda.synchronize()
+        la.append(float(a)); lb.append(float(b))
+    assert len(calls) >= 3 + 3 and calls[-1] > 20
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 5e-3 * max(abs(a), 1e-6), (la, lb)
+    assert lb[-1] != lb[0]
+
+
+def test_capture_after_non_rigid_kick_in():
+    """with iter_val >= non_rigid_kick_in_iter `forward` hands the pose vector to `_query_mlp`; nothing on that path may
+    synchronise with the host, or the step cannot be captured."""
+    net, host = _setup()
+    it = net.cfg.non_rigid_kick_in_iter + 1000
+    params = [p for p in net.parameters() if p.requires_grad]
+    from occnerf_b200.optim import ClipAdam
+    gs = GraphedTrainStep(net, ClipAdam(params, lr=5e-4), _loss, host, it, params=params, max_norm=None, warmup=2)
+    lh = gs.step(host); torch.cuda.synchronize(); l0 = float(lh)
+    lh = gs.step(host); torch.cuda.synchronize(); l1 = float(lh)
+    assert l0 == l0 and l1 == l1 and gs.needs_recapture(it + 1) and not gs.needs_recapture(it)
