@@ -98,11 +98,12 @@ int occnerf_warp_unpack_grad(const float *g_vol8, int nb, int channels, int vd, 
  * n tensors given as HOST arrays of device pointers (params, grads, exp_avg, exp_avg_sq: fp32, numel[t] elements each) with
  * one learning rate per tensor.  clip_grad_norm_ semantics: coef = min(1, max_norm / (||g||_2 + 1e-6)) over ALL tensors
  * (max_norm <= 0: no clipping), applied on the fly; torch.optim.Adam semantics (no weight decay, no amsgrad).
- * state2: two doubles in device memory {squared norm of the last step, step count}; the count is incremented by the call.
+ * steps[t]: one fp32 step counter per tensor in device memory (torch keeps one per parameter), incremented by the call;
+ * sumsq: one double in device memory, receives the squared gradient norm.
  * Nothing is read back to the host: CUDA-graph capturable.  Gradients are not modified. */
 int occnerf_clip_adam_step(void *const *params, const void *const *grads, void *const *exp_avg, void *const *exp_avg_sq,
-                           const long *numel, const float *lr, int n, float beta1, float beta2, float eps, float max_norm,
-                           double *state2, occnerf_stream_t stream);
+                           void *const *steps, const long *numel, const float *lr, int n, float beta1, float beta2, float eps,
+                           float max_norm, double *sumsq, occnerf_stream_t stream);
 
 /* ---- exact k-nearest-neighbour search (knn.py:33-85; network.py:236-255,265,508) --------------------
  * queries [m,3]; supports4 [ns,4] = (x,y,z,unused); the support set is split into n_levels contiguous

@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int kMaxTensors = 64;          // 64 x 44 B + prefix table = 3.1 KB of kernel parameters
+constexpr int kMaxTensors = 64;          // 64 x 52 B + prefix table = 3.6 KB of kernel parameters
 constexpr int kChunk = 4096;             // elements per block
 
 struct TensorList {
@@ -28,6 +28,8 @@ struct TensorList {
     const float *g[kMaxTensors];
     float *m[kMaxTensors];
     float *v[kMaxTensors];
+    float *step[kMaxTensors];            // per-tensor step count (torch keeps one per parameter: a tensor without gradient in
+                                         // some iteration is skipped and its bias correction lags behind)
     int chunk_begin[kMaxTensors + 1];    // prefix sums of ceil(numel / kChunk)
     int numel[kMaxTensors];
     float lr[kMaxTensors];
@@ -72,9 +74,7 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(const __grid_constant__
 
 struct AdamHyper { float beta1, beta2, eps, max_norm; };
 
-// sumsq / step: the two doubles of `state2` (squared gradient norm of this step, written by pass 1; step count)
-__global__ void __launch_bounds__(256) clip_adam_kernel(const __grid_constant__ TensorList L, const double *__restrict__ sumsq,
-                                                        const double *__restrict__ step, AdamHyper h) {
+__global__ void __launch_bounds__(256) clip_adam_kernel(const __grid_constant__ TensorList L, const double *__restrict__ sumsq, AdamHyper h) {
     const int t = find_tensor(L, blockIdx.x);
     const int base = (blockIdx.x - L.chunk_begin[t]) * kChunk;
     const int n = min(kChunk, L.numel[t] - base);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(const __grid_constant__ 
     const float norm = (float)sqrt(*sumsq);
     const float coef = h.max_norm > 0.f ? fminf(h.max_norm / (norm + 1e-6f), 1.0f) : 1.0f;
     // torch.optim.Adam (single-tensor formulation): step_size = lr / (1 - beta1^t); denom = sqrt(v) / sqrt(1 - beta2^t) + eps
-    const double tstep = *step;
+    const double tstep = (double)*L.step[t];
     const float bc1 = 1.0f - (float)pow((double)h.beta1, tstep);
     const float bc2_sqrt = sqrtf(1.0f - (float)pow((double)h.beta2, tstep));
     const float step_size = L.lr[t] / bc1;
@@ -102,21 +102,24 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(const __grid_constant__ 
 
 }  // namespace
 
-// One optimisation step over n tensors (host arrays of device pointers).  state2 = {squared norm, step count} as two doubles in
-// device memory; the step count is incremented FIRST (a one-thread kernel), as torch does.  max_norm <= 0 disables the clipping.
-__global__ void adam_prologue_kernel(double *state2) { state2[0] = 0.0; state2[1] += 1.0; }
+// One optimisation step over n tensors (host arrays of device pointers).  sumsq: one double in device memory (squared gradient
+// norm of this step); every listed tensor's step count is incremented FIRST, as torch does.  max_norm <= 0 disables the clipping.
+__global__ void adam_count_kernel(const __grid_constant__ TensorList L, double *sumsq, int clear) {
+    if (clear && threadIdx.x == 0) *sumsq = 0.0;
+    if ((int)threadIdx.x < L.n) *L.step[threadIdx.x] += 1.0f;
+}
 
 extern "C" int occnerf_clip_adam_step(void *const *params, const void *const *grads, void *const *exp_avg, void *const *exp_avg_sq,
-                                      const long *numel, const float *lr, int n, float beta1, float beta2, float eps, float max_norm,
-                                      double *state2, occnerf_stream_t stream) {
-    OCC_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && numel && lr && state2, "clip_adam_step: null pointer");
+                                      void *const *steps, const long *numel, const float *lr, int n, float beta1, float beta2, float eps,
+                                      float max_norm, double *sumsq, occnerf_stream_t stream) {
+    OCC_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && steps && numel && lr && sumsq, "clip_adam_step: null pointer");
     OCC_CHECK_ARG(n >= 0, "clip_adam_step: n=%d", n);
     cudaStream_t st = (cudaStream_t)stream;
-    adam_prologue_kernel<<<1, 1, 0, st>>>(state2);
-    OCC_LAUNCH_CHECK();
+    double *state2 = sumsq;
     AdamHyper h = {beta1, beta2, eps, max_norm};
+    bool cleared = false;
     // (the squared norm spans ALL tensors, so every batch of the list runs pass 1 before any batch runs pass 2)
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = -1; pass < 2; ++pass) {                 // -1: step counters (+ clear the norm), 0: norm, 1: update
         for (int t0 = 0; t0 < n; t0 += kMaxTensors) {
             TensorList L;
             L.n = 0;
@@ -127,14 +130,17 @@ extern "C" int occnerf_clip_adam_step(void *const *params, const void *const *gr
                 OCC_CHECK_ARG(numel[t] > 0 && numel[t] < (1l << 31), "clip_adam_step: tensor %d has %ld elements", t, numel[t]);
                 const int k = L.n++;
                 L.p[k] = (float *)params[t]; L.g[k] = (const float *)grads[t]; L.m[k] = (float *)exp_avg[t]; L.v[k] = (float *)exp_avg_sq[t];
+                OCC_CHECK_ARG(steps[t], "clip_adam_step: tensor %d has no step counter", t);
+                L.step[k] = (float *)steps[t];
                 L.numel[k] = (int)numel[t]; L.lr[k] = lr[t];
                 L.chunk_begin[k] = chunks;
                 chunks += (int)((numel[t] + kChunk - 1) / kChunk);
             }
             L.chunk_begin[L.n] = chunks;
             if (chunks == 0) continue;
-            if (pass == 0) grad_sumsq_kernel<<<chunks, 256, 0, st>>>(L, state2);
-            else clip_adam_kernel<<<chunks, 256, 0, st>>>(L, state2, state2 + 1, h);
+            if (pass < 0) { adam_count_kernel<<<1, kMaxTensors, 0, st>>>(L, state2, cleared ? 0 : 1); cleared = true; }
+            else if (pass == 0) grad_sumsq_kernel<<<chunks, 256, 0, st>>>(L, state2);
+            else clip_adam_kernel<<<chunks, 256, 0, st>>>(L, state2, h);
             OCC_LAUNCH_CHECK();
         }
     }

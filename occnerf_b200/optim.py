@@ -32,14 +32,14 @@ class ClipAdam:
             self.param_groups.append(g)
         self.betas, self.eps, self.max_norm = betas, eps, max_norm
         self.state = {}
-        self._state2 = None          # device doubles: {squared grad norm of the last step, step count}
+        self._state2 = None          # device double: squared gradient norm of the last step
 
     def _params(self):
         return [(p, g["lr"]) for g in self.param_groups for p in g["params"]]
 
     def _init(self, dev):
         if self._state2 is None:
-            self._state2 = torch.zeros(2, device=dev, dtype=torch.float64)
+            self._state2 = torch.zeros(1, device=dev, dtype=torch.float64)
 
     def zero_grad(self, set_to_none: bool = True):
         for p, _ in self._params():
@@ -57,7 +57,7 @@ class ClipAdam:
         dev = todo[0][0].device
         self._init(dev)
         n = len(todo)
-        P, G, M, V = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
+        P, G, M, V, T = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
         numel, lrs = (C.c_long * n)(), (C.c_float * n)()
         keep = []
         for i, (p, lr) in enumerate(todo):
@@ -69,12 +69,13 @@ class ClipAdam:
                 keep.append(g)
             st = self.state.get(p)
             if st is None:
-                st = self.state[p] = {"exp_avg": torch.zeros_like(p, memory_format=torch.contiguous_format),
+                st = self.state[p] = {"step": torch.zeros((), device=dev, dtype=f32),
+                                      "exp_avg": torch.zeros_like(p, memory_format=torch.contiguous_format),
                                       "exp_avg_sq": torch.zeros_like(p, memory_format=torch.contiguous_format)}
-            P[i], G[i], M[i], V[i] = p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+            P[i], G[i], M[i], V[i], T[i] = p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), st["step"].data_ptr()
             numel[i], lrs[i] = p.numel(), float(lr)
         call("occnerf_clip_adam_step", C.cast(P, C.c_void_p), C.cast(G, C.c_void_p), C.cast(M, C.c_void_p), C.cast(V, C.c_void_p),
-             C.cast(numel, C.c_void_p), C.cast(lrs, C.c_void_p), n, float(self.betas[0]), float(self.betas[1]), float(self.eps),
+             C.cast(T, C.c_void_p), C.cast(numel, C.c_void_p), C.cast(lrs, C.c_void_p), n, float(self.betas[0]), float(self.betas[1]), float(self.eps),
              float(self.max_norm if self.max_norm is not None else 0.0), self._state2.data_ptr(), stream())
 
     def grad_norm(self) -> torch.Tensor:
@@ -84,12 +85,12 @@ class ClipAdam:
     # -- torch.optim.Adam checkpoint format
     def state_dict(self):
         idx, packed_groups, state = 0, [], {}
-        step = float(self._state2[1].item()) if self._state2 is not None else 0.0
         for g in self.param_groups:
             ids = []
             for p in g["params"]:
                 if p in self.state:
-                    state[idx] = {"step": torch.tensor(step), "exp_avg": self.state[p]["exp_avg"], "exp_avg_sq": self.state[p]["exp_avg_sq"]}
+                    state[idx] = {"step": self.state[p]["step"].detach().cpu().clone(), "exp_avg": self.state[p]["exp_avg"],
+                                  "exp_avg_sq": self.state[p]["exp_avg_sq"]}
                 ids.append(idx)
                 idx += 1
             pg = {k: v for k, v in g.items() if k != "params"}
@@ -103,12 +104,10 @@ class ClipAdam:
             for k, v in sg.items():
                 if k != "params":
                     g[k] = v
-        step = 0.0
         for i, st in sd["state"].items():
             p = flat[int(i)]
-            self.state[p] = {"exp_avg": st["exp_avg"].to(p.device, f32).contiguous().clone(),
+            self.state[p] = {"step": torch.as_tensor(float(st["step"]), dtype=f32).to(p.device),
+                             "exp_avg": st["exp_avg"].to(p.device, f32).contiguous().clone(),
                              "exp_avg_sq": st["exp_avg_sq"].to(p.device, f32).contiguous().clone()}
-            step = max(step, float(st["step"]))
         if flat:
             self._init(flat[0].device)
-            self._state2[1] = step
