@@ -88,4 +88,4 @@ def test_capturable_in_a_cuda_graph():
     before = p.detach().clone()
     g.replay()
     torch.cuda.synchronize()
-    assert float((p - before).abs().max()) > 0.0 and float(opt.state[p]["step"]) == 3.0
+    assert float((p - before).abs().max()) > 0.0 and float(opt.state[p]["step"]) == 2.0      # one eager step + one replay (the capture itself does not execute)
