@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the OccNeRF per-ray rendering path (BASELINE.json metric: rays/s at 128 samples/ray, fwd+bwd).
 
-    python bench.py --gpus N --steps K --warmup W [--engine fp32|tc3|tc1] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--engine tf32|tc3|fp32|tc1] [--impl reference]
 
 Workload (BASELINE.json configs[1]): one ZJU-Mocap-387-shaped training step = 6 patches of 32x32 rays
 (6144 rays, 786 432 samples), synthetic SMPL-like subject, random-init network, stratified jitter,
@@ -381,7 +381,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("OCCNERF_ENGINE", "tc3"), choices=["fp32", "tf32", "tc3", "tc3b1", "tc1"])
+    ap.add_argument("--engine", default=os.environ.get("OCCNERF_ENGINE", "tf32"), choices=["fp32", "tf32", "tc3", "tc3b1", "tc1"])
     ap.add_argument("--ref-rays", type=int, default=96, help="rays per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the e2e step eagerly instead of as one CUDA graph")
