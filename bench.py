@@ -76,16 +76,17 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- reference arm / CPU baseline
-def cpu_reference(sample_rays: int, steps: int, warmup: int, seed: int = 0):
+def cpu_reference(sample_rays: int, steps: int, warmup: int, seed: int = 0, workload: str = "zju387"):
     """Forward + backward of the oracle restatement on `sample_rays` rays of the bench workload, all host cores."""
     from occnerf_b200 import synthetic as S
     from oracle import hashgrid_c, make_golden, occnerf_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     hashgrid_c.set_threads(cores)
-    sub = S.make_subject(seed=0)
+    spec = WORKLOADS[workload]
+    sub = S.make_subject(seed=0, bbox_offset=spec["bbox_offset"])
     w = S.make_weights(sub.bound, seed=0)
-    fr = S.make_frame(sub, mode="patch", n_patches=6, patch=32, seed=seed)
+    fr = S.make_frame(sub, mode="patch", n_patches=6, patch=32, seed=seed, bbox_offset=spec["bbox_offset"], occlusion_band=spec["occlusion_band"])
     vol = S.make_motion_weights_vol(sub.priors, seed=0).requires_grad_(True)
     for t in [w.embeddings, sub.point_dist, w.geo_w, w.geo_b, w.out_w, w.out_b] + w.pts_w + w.pts_b + w.rgb_w + w.rgb_b:
         t.requires_grad_(True)
@@ -113,29 +114,40 @@ def cpu_reference(sample_rays: int, steps: int, warmup: int, seed: int = 0):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    r = cpu_reference(args.ref_rays, max(1, args.steps), max(0, min(args.warmup, 1)))
+    r = cpu_reference(args.ref_rays, max(1, args.steps), max(0, min(args.warmup, 1)), workload=args.workload)
     line = {"impl": "reference", "metric": "rays_per_sec_fwd_bwd_128spr", "value": r["value"], "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "zju387_train_step_6x32x32_rays_128spr_fwd_bwd", "rays_per_step": args.ref_rays, "samples_per_ray": S_SAMPLES},
+            "config": {"workload": WORKLOADS[args.workload]["name"], "rays_per_step": args.ref_rays, "samples_per_ray": S_SAMPLES},
             "cpu_baseline": {"value": r["value"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------- our arm
+WORKLOADS = {
+    # BASELINE configs[1]: ZJU-Mocap-387-shaped training step
+    "zju387": dict(name="zju387_train_step_6x32x32_rays_128spr_fwd_bwd", bbox_offset=0.3, occlusion_band=None),
+    # BASELINE configs[3]: OcMotion-shaped occluded training (configs/occnerf/ocmotion/*/occnerf.yaml: bbox_offset 2.0; the dataset
+    # blanks a column band of the alpha mask, train.py:286-287; completeness loss + visibility counter update as in every training step)
+    "ocmotion": dict(name="ocmotion_shaped_occluded_train_step_6x32x32_rays_128spr_fwd_bwd", bbox_offset=2.0, occlusion_band=(256, 60)),
+}
+
+
 class Workload:
-    def __init__(self, device, rank, engine):
+    def __init__(self, device, rank, engine, workload="zju387"):
         from occnerf_b200 import synthetic as S
         from occnerf_b200.network import RenderConfig
         self.S = S
-        sub = S.make_subject(seed=0)
+        self.spec = WORKLOADS[workload]
+        sub = S.make_subject(seed=0, bbox_offset=self.spec["bbox_offset"])
         w = S.make_weights(sub.bound, seed=0)
         self.sub = sub
         self.net = S.network_from_synthetic(sub, w, RenderConfig(perturb=1.0, mlp_engine=engine), device=device)
         self.net.train(True)
         self.net.install_prologue()
-        self.fr_host = S.make_frame(sub, mode="patch", n_patches=6, patch=32, seed=100 + rank)
+        self.fr_host = S.make_frame(sub, mode="patch", n_patches=6, patch=32, seed=100 + rank, bbox_offset=self.spec["bbox_offset"],
+                                    occlusion_band=self.spec["occlusion_band"])
         self.fr = S.frame_to(self.fr_host, device)
         self.vol = S.make_motion_weights_vol(sub.priors, seed=0).to(device).requires_grad_(True)
         self.priors = sub.priors.to(device)
@@ -382,6 +394,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default=os.environ.get("OCCNERF_ENGINE", "tf32"), choices=["fp32", "tf32", "tc3", "tc3b1", "tc1"])
+    ap.add_argument("--workload", default="zju387", choices=list(WORKLOADS), help="zju387 = BASELINE configs[1] (the headline); ocmotion = configs[3]")
     ap.add_argument("--ref-rays", type=int, default=96, help="rays per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the e2e step eagerly instead of as one CUDA graph")
@@ -403,7 +416,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from occnerf_b200 import _lib
     _lib.load()
-    wl = Workload(device, rank, args.engine)
+    wl = Workload(device, rank, args.engine, args.workload)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=device)
     M = RAYS_PER_STEP * S_SAMPLES
 
@@ -472,7 +485,7 @@ def main():
             "metric": "rays_per_sec_fwd_bwd_128spr", "value": world * RAYS_PER_STEP / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "tf32": "tf32->f32", "tc3": "bf16x3(split)->f32", "tc3b1": "bf16x3(split)->f32 fwd, bf16->f32 dgrad", "tc1": "bf16->f32"}[args.engine], "data": "synthetic",
-            "config": {"workload": "zju387_train_step_6x32x32_rays_128spr_fwd_bwd", "rays_per_step_per_gpu": RAYS_PER_STEP, "samples_per_ray": S_SAMPLES,
+            "config": {"workload": wl.spec["name"], "rays_per_step_per_gpu": RAYS_PER_STEP, "samples_per_ray": S_SAMPLES,
                        "mlp_engine": args.engine, "l2": "256 MiB flush write between timed steps", "timing": "cuda events per step, max over ranks",
                        "optimizer": "global-norm clip + Adam inside the step (occnerf_clip_adam_step)", "parallelism": f"dp{world}",
                        "knn": "exact; pykeops' own reduction is un-vendored upstream (parity unpinned for that one call), ids checked against brute force"},
@@ -491,7 +504,7 @@ def main():
             if not args.no_cpu_baseline:
                 line["forward_only"]["cpu_baseline"] = cpu_forward_reference(args.ref_rays)
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reference(args.ref_rays, 2, 1)
+            cb = cpu_reference(args.ref_rays, 2, 1, workload=args.workload)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "rays/s", "cores": cb["cores"], "kind": "port", "sample": cb["sample"]}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -368,7 +368,10 @@ class Frame:
 
 def make_frame(subject: Subject, mode: str = "patch", img: int = 512, n_patches: int = 6, patch: int = 32,
                seed: int = 0, yaw: float = 0.0, pose_std: float = 0.2, max_rays: int | None = None,
-               subject_ratio: float = 0.8) -> Frame:
+               subject_ratio: float = 0.8, bbox_offset: float = 0.3, occlusion_band: tuple | None = None) -> Frame:
+    """bbox_offset: margin of the posed box the rays are clipped to (cfg.bbox_offset: 0.3 for ZJU-Mocap, 2.0 in the OcMotion yamls);
+    occlusion_band = (mid, width) in pixels: the column band the dataset blanks in the alpha mask (core/data/occnerf/train.py:286-287),
+    patches are not placed on it."""
     rng = np.random.default_rng(seed + 7)
     pose = np.zeros(72, dtype=np.float32)
     pose[3:] = rng.normal(0.0, pose_std, 69).astype(np.float32)
@@ -376,7 +379,7 @@ def make_frame(subject: Subject, mode: str = "patch", img: int = 512, n_patches:
     G = canonical_global_tfms(subject.joints)
     mRs, mTs, glob = motion_basis(Rs, Ts, G)
     posed_joints = glob[:, :3, 3].numpy()
-    dmin, dmax = skeleton_bbox(posed_joints, 0.3)
+    dmin, dmax = skeleton_bbox(posed_joints, bbox_offset)
     K, R, T = lookat_camera(img, yaw=yaw)
     o, d = pixel_rays(img, img, K, R, T)
     o, d = o.reshape(-1, 3), d.reshape(-1, 3)
@@ -403,6 +406,8 @@ def make_frame(subject: Subject, mode: str = "patch", img: int = 512, n_patches:
             if y0 < 0 or x0 < 0 or y0 + patch > img or x0 + patch > img:
                 continue
             if not hit2d[y0:y0 + patch, x0:x0 + patch].all() or sel[y0:y0 + patch, x0:x0 + patch].any():
+                continue
+            if occlusion_band is not None and abs(cx - occlusion_band[0]) < occlusion_band[1] // 2:
                 continue
             sel[y0:y0 + patch, x0:x0 + patch] = True
             order[y0:y0 + patch, x0:x0 + patch] = count * patch * patch + np.arange(patch * patch).reshape(patch, patch)

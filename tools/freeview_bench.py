@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--views", type=int, default=10)
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--engine", default="tc3")
+    ap.add_argument("--engine", default="tf32")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
