@@ -94,6 +94,23 @@ int occnerf_warp_backward_packed(const float *rays, const float *t_lin, const fl
 int occnerf_warp_unpack_grad(const float *g_vol8, int nb, int channels, int vd, int vh, int vw, float *g_vol,
                              occnerf_stream_t stream);
 
+/* ---- per-frame prologue of Network.forward (network.py:556-597) ------------------------------------------------------
+ * occnerf_pose_refine: BodyPoseRefiner (pose_decoders/mlp_delta_body_pose.py:35-41) + Rodrigues (network_util.py:98-127) +
+ *   dst_Rs[1:] . R_delta (network.py:558-570).  w5/b5: HOST arrays of the 5 nn.Linear weight / bias device pointers
+ *   (69->256, 256->256 x3, 256->69; [out,in] row-major); posevec69 [69]; dst_Rs [24,3,3] -> Rs_out [24,3,3] (root unchanged).
+ * occnerf_motion_basis: MotionBasisComputer (network_util.py:138-200): dst_Rs [24,3,3], dst_Ts [24,3], cnl_gtfms [24,4,4] ->
+ *   motion_scale_Rs [24,3,3], motion_Ts [24,3] (forward-kinematics chain along SMPL_PARENT, affine inverse, cnl . inverse).
+ * occnerf_weight_volume_forward: vol = softmax_channels(logits + log(priors)) per voxel (deconv_vol_decoder.py:25-33), all
+ *   [channels, voxels]; _backward: g_logits = vol * (g_vol - sum_c g_vol * vol).  Forward-only entry points carry no gradient. */
+int occnerf_pose_refine(const void *const *w5_host, const void *const *b5_host, const float *posevec69, const float *dst_Rs,
+                        int n_bones, float *Rs_out, occnerf_stream_t stream);
+int occnerf_motion_basis(const float *dst_Rs, const float *dst_Ts, const float *cnl_gtfms, int n_bones, float *Rs_out,
+                         float *Ts_out, occnerf_stream_t stream);
+int occnerf_weight_volume_forward(const float *logits, const float *priors, int channels, long voxels, float *vol,
+                                  occnerf_stream_t stream);
+int occnerf_weight_volume_backward(const float *vol, const float *g_vol, int channels, long voxels, float *g_logits,
+                                   occnerf_stream_t stream);
+
 /* ---- loss epilogue: global grad-norm clip + Adam over all trainable tensors (trainer.py:248-249, optimizer.py:12-43) ----
  * n tensors given as HOST arrays of device pointers (params, grads, exp_avg, exp_avg_sq: fp32, numel[t] elements each) with
  * one learning rate per tensor.  clip_grad_norm_ semantics: coef = min(1, max_norm / (||g||_2 + 1e-6)) over ALL tensors

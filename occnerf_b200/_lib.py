@@ -29,6 +29,10 @@ _SIGNATURES = {
     "occnerf_warp_forward_packed": [_vp] * 8 + [_i] * 6 + [_vp] * 3 + [_vp],
     "occnerf_warp_backward_packed": [_vp] * 9 + [_i] * 6 + [_vp, _vp, _vp, _vp],
     "occnerf_warp_unpack_grad": [_vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "occnerf_pose_refine": [_vp, _vp, _vp, _vp, _i, _vp, _vp],
+    "occnerf_motion_basis": [_vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "occnerf_weight_volume_forward": [_vp, _vp, _i, _l, _vp, _vp],
+    "occnerf_weight_volume_backward": [_vp, _vp, _i, _l, _vp, _vp],
     "occnerf_clip_adam_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _vp, _vp],
     "occnerf_knn": [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "occnerf_knn_hier": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp],

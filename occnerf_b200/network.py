@@ -357,9 +357,7 @@ class Network(nn.Module):
     def _run_prologue(self, dst_Rs, dst_Ts, cnl_gtfms, priors, dst_posevec, iter_val):
         dst_Rs = dst_Rs[None]
         if iter_val >= self._pose_kick_in_iter:
-            refined = self.pose_decoder(dst_posevec[None])["Rs"]
-            no_root = torch.matmul(dst_Rs[:, 1:].reshape(-1, 3, 3), refined.reshape(-1, 3, 3)).reshape(-1, 23, 3, 3)
-            dst_Rs = torch.cat([dst_Rs[:, 0:1], no_root], dim=1)
+            dst_Rs = self.pose_decoder.refine(dst_Rs, dst_posevec[None])
         Rs, Ts = self.motion_basis_computer(dst_Rs, dst_Ts[None], cnl_gtfms[None])
         return Rs, Ts, self.mweight_vol_decoder(motion_weights_priors=priors[None])[0]
 

@@ -90,6 +90,39 @@ def warp_backward(rays, t_rand, Rs, Ts, bbox_min, bbox_scale, g_mask, S, vol_sha
     return g_vol
 
 
+# ----------------------------------------------------------------------------- per-frame prologue (csrc/prologue.cu)
+def motion_basis(dst_Rs, dst_Ts, cnl_gtfms):
+    """(24,3,3), (24,3), (24,4,4) -> motion_scale_Rs (24,3,3), motion_Ts (24,3)  (network_util.py:138-200)."""
+    nb = dst_Rs.shape[0]
+    Rs = torch.empty(nb, 3, 3, device=dst_Rs.device, dtype=f32)
+    Ts = torch.empty(nb, 3, device=dst_Rs.device, dtype=f32)
+    call("occnerf_motion_basis", ptr(dst_Rs, f32), ptr(dst_Ts, f32), ptr(cnl_gtfms, f32), nb, ptr(Rs), ptr(Ts), stream())
+    return Rs, Ts
+
+
+def pose_refine(weights5, biases5, posevec69, dst_Rs):
+    """BodyPoseRefiner + Rodrigues + dst_Rs[1:] . R_delta in one launch (forward only)."""
+    wp = (C.c_void_p * 5)(*[ptr(w.detach().contiguous(), f32) for w in weights5])
+    bp = (C.c_void_p * 5)(*[ptr(b.detach().contiguous(), f32) for b in biases5])
+    out = torch.empty_like(dst_Rs)
+    call("occnerf_pose_refine", C.cast(wp, C.c_void_p), C.cast(bp, C.c_void_p), ptr(posevec69, f32), ptr(dst_Rs, f32), dst_Rs.shape[0],
+         ptr(out), stream())
+    return out
+
+
+def weight_volume_forward(logits, priors):
+    """softmax over the channels of logits + log(priors), [channels, D, H, W]."""
+    vol = torch.empty_like(logits)
+    call("occnerf_weight_volume_forward", ptr(logits, f32), ptr(priors, f32), logits.shape[0], logits[0].numel(), ptr(vol), stream())
+    return vol
+
+
+def weight_volume_backward(vol, g_vol):
+    g = torch.empty_like(vol)
+    call("occnerf_weight_volume_backward", ptr(vol, f32), ptr(g_vol, f32), vol.shape[0], vol[0].numel(), ptr(g), stream())
+    return g
+
+
 # ----------------------------------------------------------------------------- KNN
 def to_float4(points: torch.Tensor) -> torch.Tensor:
     out = torch.zeros(points.shape[0], 4, device=points.device, dtype=f32)

@@ -1,8 +1,10 @@
 """Per-frame prologue of `Network.forward` (network.py:558-597): pose refinement, motion basis, motion-weight
 volume decoder.  It runs once per frame and produces the ray path's inputs (`motion_scale_Rs`, `motion_Ts`,
-`motion_weights_vol`); SURVEY.md section 8(f) lists it as the NEXT row after the ray path, so for now it is
-plain library code (torch/cuDNN) with the reference's module and parameter names -- it is not claimed as a
-native kernel and is not inside the timed ray path of bench.py's `value`.
+`motion_weights_vol`); SURVEY.md section 8(f) rank 1.  The modules keep the reference's names and parameters (checkpoints load).
+On a CUDA device the small stages are native kernels (csrc/prologue.cu): the 24-bone motion basis (one launch instead of ~50),
+the pose refiner MLP + Rodrigues (one launch), and the decoder's softmax(logits + log prior) with its gradient.  The decoder's
+five ConvTranspose3d (4.5 GMAC per frame at batch 1) remain library calls (cuDNN): not claimed as native, inside `e2e` only.
+When the inputs of the first two require gradients (pose refinement training) they fall back to the differentiable torch form.
 
   MotionBasisComputer         core/utils/network_util.py:138-200   (FK chain evaluated level by level of the SMPL tree)
   MotionWeightVolumeDecoder   mweight_vol_decoders/deconv_vol_decoder.py:8-33 + network_util.py:12-50
@@ -63,8 +65,29 @@ def _affine_inverse(T):
     return out
 
 
+class _VolumeSoftmax(torch.autograd.Function):
+    """softmax_channels(logits + log prior) per voxel (occnerf_weight_volume_forward / _backward)."""
+
+    @staticmethod
+    def forward(ctx, logits, priors):
+        from occnerf_b200 import ops
+        vol = ops.weight_volume_forward(logits.detach().contiguous().float(), priors.contiguous().float())
+        ctx.save_for_backward(vol)
+        return vol
+
+    @staticmethod
+    def backward(ctx, g):
+        from occnerf_b200 import ops
+        (vol,) = ctx.saved_tensors
+        return ops.weight_volume_backward(vol, g.contiguous().float()), None
+
+
 class MotionBasisComputer(nn.Module):
     def forward(self, dst_Rs, dst_Ts, cnl_gtfms):
+        if dst_Rs.is_cuda and dst_Rs.shape[0] == 1 and not (dst_Rs.requires_grad or dst_Ts.requires_grad):
+            from occnerf_b200 import ops
+            Rs, Ts = ops.motion_basis(dst_Rs[0].contiguous().float(), dst_Ts[0].contiguous().float(), cnl_gtfms[0].contiguous().float())
+            return Rs[None], Ts[None]
         B = dst_Rs.shape[0]
         G = torch.zeros(B, 24, 4, 4, dtype=dst_Rs.dtype, device=dst_Rs.device)
         G[:, :, :3, :3] = dst_Rs
@@ -111,7 +134,10 @@ class MotionWeightVolumeDecoder(nn.Module):
         self.decoder = ConvDecoder3D(embedding_size, volume_size, total_bones + 1)
 
     def forward(self, motion_weights_priors, **_):
-        return F.softmax(self.decoder(self.const_embedding[None]) + torch.log(motion_weights_priors), dim=1)
+        logits = self.decoder(self.const_embedding[None])                  # library (cuDNN) transposed convolutions
+        if logits.is_cuda and logits.shape[0] == 1:
+            return _VolumeSoftmax.apply(logits[0], motion_weights_priors[0])[None]
+        return F.softmax(logits + torch.log(motion_weights_priors), dim=1)
 
 
 def rodrigues(rvec):
@@ -141,6 +167,19 @@ class BodyPoseRefiner(nn.Module):
     def forward(self, pose_input):
         return {"Rs": rodrigues(self.block_mlps(pose_input).view(-1, 3)).view(-1, self.total_bones, 3, 3)}
 
+    def refine(self, dst_Rs, pose_input):
+        """dst_Rs (1,24,3,3), pose_input (1,69) -> dst_Rs with the non-root rotations multiplied by the predicted corrections
+        (network.py:558-570); one native launch when nothing here needs a gradient, the torch form otherwise."""
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if dst_Rs.is_cuda and dst_Rs.shape[0] == 1 and not needs_grad:
+            from occnerf_b200 import ops
+            lin = [m for m in self.block_mlps if isinstance(m, nn.Linear)]
+            return ops.pose_refine([l.weight for l in lin], [l.bias for l in lin], pose_input.reshape(-1).contiguous().float(),
+                                   dst_Rs[0].contiguous().float())[None]
+        refined = self.forward(pose_input)["Rs"]
+        no_root = torch.matmul(dst_Rs[:, 1:].reshape(-1, 3, 3), refined.reshape(-1, 3, 3)).reshape(-1, 23, 3, 3)
+        return torch.cat([dst_Rs[:, 0:1], no_root], dim=1)
+
 
 class Prologue(nn.Module):
     """callable(dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec, iter_val) -> (Rs, Ts, vol)
@@ -157,9 +196,7 @@ class Prologue(nn.Module):
     def forward(self, dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec, iter_val):
         dst_Rs = dst_Rs[None]
         if iter_val >= self.pose_kick_in_iter:
-            refined = self.pose_decoder(dst_posevec[None])["Rs"]
-            no_root = torch.matmul(dst_Rs[:, 1:].reshape(-1, 3, 3), refined.reshape(-1, 3, 3)).reshape(-1, 23, 3, 3)
-            dst_Rs = torch.cat([dst_Rs[:, 0:1], no_root], dim=1)
+            dst_Rs = self.pose_decoder.refine(dst_Rs, dst_posevec[None])
         Rs, Ts = self.motion_basis_computer(dst_Rs, dst_Ts[None], cnl_gtfms[None])
         vol = self.mweight_vol_decoder(motion_weights_priors=motion_weights_priors[None])[0]
         return Rs, Ts, vol
