@@ -395,7 +395,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default=os.environ.get("OCCNERF_ENGINE", "tf32"), choices=["fp32", "tf32", "tc3", "tc3b1", "tc1"])
     ap.add_argument("--workload", default="zju387", choices=list(WORKLOADS), help="zju387 = BASELINE configs[1] (the headline); ocmotion = configs[3]")
-    ap.add_argument("--ref-rays", type=int, default=96, help="rays per step of the CPU reference arm / cpu_baseline sample")
+    ap.add_argument("--ref-rays", type=int, default=1024, help="rays per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the e2e step eagerly instead of as one CUDA graph")
     ap.add_argument("--profile-mode", action="store_true", help="device-resident steps only (no e2e, no CPU baseline): for ncu runs")
