@@ -163,7 +163,9 @@ class Workload:
         from occnerf_b200.distributed import GradReducer
         self.opt_path = ClipAdam(path_params, lr=5e-4, max_norm=1.0)          # native clip + Adam (csrc/optim.cu), trainer.py:248-249
         self.opt_all = ClipAdam([p for p in self.net.parameters() if p.requires_grad], lr=5e-4, max_norm=1.0)
-        self.reducer, self.reducer_e2e = GradReducer(), GradReducer()
+        from occnerf_b200.distributed import structural_zero_slices
+        self.reducer = GradReducer()
+        self.reducer_e2e = GradReducer(active=structural_zero_slices([p for p in self.net.parameters() if p.requires_grad]))
         # pinned host copies of everything `Network.forward` receives per frame (trainer.py:223-229)
         h = self.fr_host
         self.host = {k: v.pin_memory() for k, v in dict(rays_o=h.rays_o, rays_d=h.rays_d, near=h.near, far=h.far, dst_Rs=h.dst_Rs,
@@ -189,9 +191,7 @@ class Workload:
         hits = out["hits"]
         if world > 1:
             # one flat bucket for the 22 small tensors (MLP, point_dist, weight volume), the 59 MiB table gradient in place
-            from occnerf_b200 import distributed as D
-            self.reducer([p.grad for p in self.path_params] + [self.vol.grad])
-            D.allreduce_visibility(hits)
+            self.reducer([p.grad for p in self.path_params] + [self.vol.grad], hits=hits)
         self.opt_path.step()                             # occnerf_clip_adam_step: global-norm clip + Adam, 3 launches
         self.opt_path.zero_grad(set_to_none=True)
         self.vol.grad = None
@@ -203,7 +203,7 @@ class Workload:
         from occnerf_b200 import distributed as D
         from occnerf_b200.train_step import GraphedTrainStep
         params = [p for p in self.net.parameters() if p.requires_grad]
-        sync = (lambda grads, hits: (self.reducer_e2e(grads), D.allreduce_visibility(hits))) if world > 1 else None
+        sync = (lambda grads, hits: self.reducer_e2e(grads, hits=hits)) if world > 1 else None
         self.graphed = GraphedTrainStep(self.net, self.opt_all, lambda out, d: self.loss({"rgb": out["rgb"], "comp_loss": out["comp_loss"]}, d["target"], world),
                                         self.host, self.iter_val, params=params, max_norm=None, grad_sync=sync)
         return self.graphed
@@ -223,9 +223,7 @@ class Workload:
         loss.backward()
         params = [p for p in net.parameters() if p.requires_grad]
         if world > 1:
-            from occnerf_b200 import distributed as D
-            self.reducer_e2e([p.grad for p in params])
-            D.allreduce_visibility(out["hits"])
+            self.reducer_e2e([p.grad for p in params], hits=out["hits"])
         self.opt_all.step()
         self.opt_all.zero_grad(set_to_none=True)
         net.apply_visibility(out["hits"])

@@ -62,22 +62,39 @@ def allreduce_gradients(params, extra=(), average: bool = True, bucket_bytes: in
 
 
 class GradReducer:
-    """Sum-all-reduce of a fixed list of gradient tensors with the fewest launches: tensors below `bucket_bytes` travel through ONE
-    persistent flat buffer (a multi-tensor copy in, one collective, a multi-tensor copy out -- no torch.cat, no per-tensor
-    copy-back, no division pass: the caller folds 1 / world_size into the loss), the large ones (hash table, decoder weights)
-    are reduced in place.  All collectives are issued asynchronously and waited for together, so NCCL pipelines them."""
+    """Sum-all-reduce of a fixed list of gradient tensors with the fewest bytes and launches:
+      * tensors below `bucket_bytes` travel through ONE persistent flat buffer (a multi-tensor copy in, one collective, a
+        multi-tensor copy out -- no torch.cat, no per-tensor copy-back, no division pass: the caller folds 1 / world_size into
+        the loss); the 0/1 visibility votes ride in the same buffer (their sum > 0 <=> some rank voted, network.py:517);
+      * the large ones (hash table, decoder weights) are reduced in place;
+      * `active` maps a tensor (by position in the list) to the index expression of the only entries that can be non-zero on
+        ANY rank; only that compact block is exchanged.  Used for the decoder's first ConvTranspose3d(1024, 512, 4, 2, 1): its
+        input is 1x1x1, so 56 of its 64 taps never receive a gradient (117 of the 134 MB of that tensor are structural zeros);
+      * all collectives of a step are issued as ONE NCCL group (a single launch) and waited for together."""
 
-    def __init__(self, bucket_bytes: int = 4 << 20):
+    def __init__(self, bucket_bytes: int = 4 << 20, active: dict | None = None):
         self.bucket_bytes = bucket_bytes
+        self.active = dict(active or {})
         self.flat, self.views, self.key = None, None, None
 
-    def __call__(self, grads):
+    def __call__(self, grads, hits=None):
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return
-        grads = [g for g in grads if g is not None]
-        small = [g for g in grads if g.numel() * g.element_size() < self.bucket_bytes]
-        large = [g for g in grads if g.numel() * g.element_size() >= self.bucket_bytes]
-        work = []
+        compact = {}
+        items = []
+        for i, g in enumerate(grads):
+            if g is None:
+                continue
+            if i in self.active:
+                c = g[self.active[i]].contiguous()
+                compact[i] = c
+                items.append(c)
+            else:
+                items.append(g)
+        if hits is not None:
+            items.append(hits)
+        small = [g for g in items if g.numel() * g.element_size() < self.bucket_bytes]
+        large = [g for g in items if g.numel() * g.element_size() >= self.bucket_bytes]
         if small:
             key = tuple((tuple(g.shape), g.dtype, g.device) for g in small)
             if key != self.key:
@@ -88,13 +105,31 @@ class GradReducer:
                     off += g.numel()
                 self.key = key
             torch._foreach_copy_(self.views, small)
-            work.append(dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True))
-        for g in large:
-            work.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True))
-        for w in work:
-            w.wait()
+        tensors = ([self.flat] if small else []) + large
+        if dist.get_backend() == "nccl" and hasattr(dist, "_coalescing_manager") and len(tensors) > 1:
+            with dist._coalescing_manager(device=tensors[0].device, async_ops=True) as cm:     # one NCCL group = one launch
+                for t in tensors:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            cm.wait()
+        else:                                                  # (gloo in the CPU tests: no coalescing)
+            for w in [dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True) for t in tensors]:
+                w.wait()
         if small:
             torch._foreach_copy_(small, self.views)
+        for i, c in compact.items():
+            grads[i][self.active[i]] = c
+        if hits is not None:
+            hits.clamp_(max=1.0)                               # votes are 0/1: any rank's vote counts once
+
+
+def structural_zero_slices(params):
+    """{position: index expression} for GradReducer(active=...): parameters whose gradient is structurally zero outside a block.
+    A ConvTranspose3d(k=4, s=2, p=1) weight [Cin, Cout, 4, 4, 4] fed by a 1x1x1 input only ever uses taps 1..2 per axis."""
+    out = {}
+    for i, p in enumerate(params):
+        if p.dim() == 5 and tuple(p.shape[2:]) == (4, 4, 4) and p.shape[0] == 1024:
+            out[i] = (slice(None), slice(None), slice(1, 3), slice(1, 3), slice(1, 3))
+    return out
 
 
 def allreduce_visibility(hits: torch.Tensor) -> torch.Tensor:

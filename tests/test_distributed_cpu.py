@@ -53,6 +53,20 @@ def _worker(rank, world, port, tmp):
             for gr, f in zip(grads, full):
                 assert torch.allclose(gr, f * tot, rtol=1e-6)
         assert red.flat is not None and red.flat.numel() == 256 * 68 + 256
+        # structural zeros: only the active block of a 5-D "first deconvolution" gradient is exchanged; votes ride along as a sum
+        conv = torch.zeros(1024, 4, 4, 4, 4)
+        conv[:, :, 1:3, 1:3, 1:3] = float(rank + 1)
+        params5 = [torch.nn.Parameter(torch.zeros(1024, 4, 4, 4, 4)), torch.nn.Parameter(torch.zeros(3))]
+        act = D.structural_zero_slices(params5)
+        assert list(act) == [0]
+        red2 = D.GradReducer(bucket_bytes=1 << 10, active=act)
+        votes = torch.zeros(50)
+        votes[rank * 5:rank * 5 + 10] = 1.0
+        small = torch.full((3,), float(rank))
+        red2([conv, small], hits=votes)
+        assert float(conv[:, :, 1:3, 1:3, 1:3].min()) == float(sum(r + 1 for r in range(world))) and float(conv[:, :, 0].abs().max()) == 0.0
+        assert torch.equal(small, torch.full((3,), float(sum(range(world)))))
+        assert float(votes.max()) == 1.0 and int(votes.sum()) == 15
         hits = torch.zeros(100)
         hits[rank * 10:rank * 10 + 5] = 1.0
         D.allreduce_visibility(hits)
