@@ -75,7 +75,9 @@ class GridEncoder(nn.Module):
     def reset_parameters(self):
         self.embeddings.data.uniform_(-1e-4, 1e-4)
 
-    def forward(self, inputs, bound=None):
+    def forward(self, inputs, bound=1):
+        """gridencoder/grid.py:146-170: inputs in [-bound, bound] are mapped to [0, 1] (bound = 1 by default, a tensor bound
+        broadcasts); pass bound=None for inputs that already are in [0, 1]."""
         if bound is not None:
             inputs = (inputs + bound) / (2 * bound)
         prefix = list(inputs.shape[:-1])
@@ -405,12 +407,24 @@ class Network(nn.Module):
             lb = np.cumsum([0, base.shape[0]] + [int(f.shape[0]) for f in fps]).tolist()
             self._cache = dict(device=dev, key=key, supports4=ops.to_float4(sup), support_gid=gid.contiguous(), level_begin=lb,
                                base4=ops.to_float4(base), point_base=base.contiguous().float(),
-                               point_norms=self.point_norms.contiguous().float(),
-                               # cluster hierarchies for the pruned exact search: level 0 around level 2, level 1 around level 3
-                               hier0=ops.build_knn_hierarchy(base, base[fps[1]]), gid2=fps[1].to(i32).contiguous(),
-                               hier1=ops.build_knn_hierarchy(base[fps[0]], base[fps[2]]), gid1=fps[0].to(i32).contiguous(),
-                               gid3=fps[2].to(i32).contiguous(), tree=ops.build_knn_tree(base, fps))
+                               point_norms=self.point_norms.contiguous().float(), fps=fps)
         return self._cache
+
+    def _knn_structure(self, name):
+        """Acceleration structures of the exact searches, built on first use (each is a few hundred library launches once per
+        subject): 'grid' = per-cell candidate lists, 'tree' = 3-level cluster tree, 'hier' = the two 2-level hierarchies."""
+        st = self._static()
+        if name not in st:
+            base, fps = st["point_base"], st["fps"]
+            if name == "grid":
+                st["grid"] = ops.build_knn_grid(base, fps)
+            elif name == "tree":
+                st["tree"] = ops.build_knn_tree(base, fps)
+            else:       # cluster hierarchies for the pruned exact search: level 0 around level 2, level 1 around level 3
+                st["hier"] = dict(hier0=ops.build_knn_hierarchy(base, base[fps[1]]), gid2=fps[1].to(i32).contiguous(),
+                                  hier1=ops.build_knn_hierarchy(base[fps[0]], base[fps[2]]), gid1=fps[0].to(i32).contiguous(),
+                                  gid3=fps[2].to(i32).contiguous())
+        return st[name]
 
     def _engine(self):
         e = self.cfg.mlp_engine
@@ -497,14 +511,13 @@ class Network(nn.Module):
         if self.cfg.knn_mode == "brute":
             return ops.knn(xyz, st["supports4"], st["level_begin"], 10, support_gid=st["support_gid"])
         if self.cfg.knn_mode == "grid":
-            if "grid" not in st:
-                st["grid"] = ops.build_knn_grid(st["point_base"], [f.to(xyz.device) for f in self.fps_index])
-            return ops.knn_grid(xyz, gs, st["grid"])
+            return ops.knn_grid(xyz, gs, self._knn_structure("grid"))
         if self.cfg.knn_mode == "tree":
-            return ops.knn_tree(xyz, gs, st["tree"])
+            return ops.knn_tree(xyz, gs, self._knn_structure("tree"))
+        h = self._knn_structure("hier")
         knn_idx = torch.empty(xyz.shape[0], 4, 10, device=xyz.device, dtype=i32)
-        ops.knn_hier(xyz, gs, *st["hier0"], knn_idx, 0, 2, None, st["gid2"])
-        ops.knn_hier(xyz, gs, *st["hier1"], knn_idx, 1, 3, st["gid1"], st["gid3"])
+        ops.knn_hier(xyz, gs, *h["hier0"], knn_idx, 0, 2, None, h["gid2"])
+        ops.knn_hier(xyz, gs, *h["hier1"], knn_idx, 1, 3, h["gid1"], h["gid3"])
         return knn_idx
 
     def get_non_rigid_embedder(self, multires, is_identity, iter_val):
@@ -556,9 +569,12 @@ class Network(nn.Module):
         out = {}
         for k, v in all_ret.items():
             if k == "hits":
-                out[k] = torch.stack(v, 0).amax(0)
+                # the reference increments point_counter once per ray chunk (network.py:502-517, inside _render_rays): the 0/1
+                # votes of the chunks add up.  (It also lets later chunks see the updated counter; here all chunks of a call
+                # see the counter as it was at the start -- documented difference, only for calls with more than cfg.chunk rays.)
+                out[k] = torch.stack(v, 0).sum(0)
             elif k == "comp_loss" and not self.training:
-                out[k] = v[0]
+                out[k] = torch.cat([c.reshape(-1) for c in v], 0) if len(v) > 1 else v[0]   # (n_chunks,) placeholders as upstream
             else:
                 out[k] = v[0] if len(v) == 1 else torch.cat(v, 0)
         return out
@@ -566,7 +582,7 @@ class Network(nn.Module):
     def apply_visibility(self, hits):
         """The reference's in-place `point_counter[knn_index] += 1.` (network.py:517)."""
         with torch.no_grad():
-            self.point_counter += (hits > 0).to(self.point_counter.dtype)
+            self.point_counter += hits.to(self.point_counter.dtype)
 
     # -- reference API: network.py:542-623
     def forward(self, rays, dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec=None, near=None, far=None,

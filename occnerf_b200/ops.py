@@ -409,7 +409,7 @@ class _GridEncode(torch.autograd.Function):
         inputs = inputs.contiguous().float()
         S = float(np.log2(per_level_scale))
         scales = level_scales(S, base_resolution, offsets.shape[0] - 1, inputs.device)
-        need_in = inputs.requires_grad
+        need_in = bool(ctx.needs_input_grad[0])       # (of the caller's tensor: the contiguous fp32 copy above never requires grad)
         out, dy_dx, _, _ = hashgrid_forward(inputs.detach(), embeddings.detach().contiguous(), offsets, scales,
                                             want_dy_dx=need_in)
         ctx.save_for_backward(inputs.detach(), offsets, scales, dy_dx if need_in else torch.empty(0, device=inputs.device))

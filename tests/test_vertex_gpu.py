@@ -26,7 +26,7 @@ def _torch_vertex_features(net):
     dist = direction.norm(dim=-1).mean(1, keepdim=True)
     dist = torch.where(inside[:, None], -dist, dist)
     v_in = torch.cat([(knn_base + net.bound) / (2 * net.bound), torch.clamp((dist + 0.2) / 0.8, 0.0, 1.0)], -1)
-    hv = net.cnl_mlp.module.encoder(v_in)
+    hv = net.cnl_mlp.module.encoder(v_in, bound=None)      # already in [0, 1]
     return torch.cat([hv, pc, torch.zeros(V, 1, device=pc.device, dtype=pc.dtype)], -1), pc, knn_base, dist, v_in, kidx
 
 
