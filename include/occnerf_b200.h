@@ -265,8 +265,12 @@ int occnerf_mlp_debug_counters(unsigned long long *host8, int reset);
 int occnerf_mlp_debug_mma_rate(int iters, int n, int tf32, unsigned long long *out_dev, int ctas, occnerf_stream_t stream);
 /* debug only: per-layer clock64 stamps of one tile of CTA 0 (OCCNERF_MLP_DEBUG bit 4): 16 x 12 u64, see csrc/mlp_tc.cu */
 int occnerf_mlp_debug_trace(unsigned long long *host192);
+/* debug only: weight-stream round-trip stamps of layers 2 and 3 of the same tile: 2 x 8 chunks x 6 events u64 */
+int occnerf_mlp_debug_trace_w(unsigned long long *host96);
 /* Debug only: cudaOccupancyMaxActiveClusters of the tc3 forward chain kernel for clusters of `cluster_size` CTAs (< 0: error). */
 int occnerf_mlp_debug_max_clusters(int cluster_size);
+/* debug only: override OCCNERF_MLP_DEBUG for the following launches (debug < 0: back to the environment's value) */
+int occnerf_mlp_debug_set(int debug);
 int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, int cta_pair, void *packed, occnerf_stream_t stream);
 /* XB [m,132]: columns 64..131 = (agg35, var1, h32) are read; columns 0..63 receive the 64 geometry features when
  * act_dtype != 0.  raw [m, ldr]: columns 0..3 = (rgb_pre3, sigma_pre1) are written.

@@ -56,7 +56,9 @@ _SIGNATURES = {
     "occnerf_mlp_debug_counters": [_vp, _i],
     "occnerf_mlp_debug_mma_rate": [_i, _i, _i, _vp, _i, _vp],
     "occnerf_mlp_debug_trace": [_vp],
+    "occnerf_mlp_debug_trace_w": [_vp],
     "occnerf_mlp_debug_max_clusters": [_i],
+    "occnerf_mlp_debug_set": [_i],
     "occnerf_nonrigid_pack_weights": [_vp, _vp, _vp, _i, _vp, _vp],
     "occnerf_nonrigid_forward_tc": [_vp, _vp, _i, _vp, _i, _vp, _vp],
     "occnerf_mlp_wgrad_tc": [_vp, _vp, _i, _l, _vp, _vp, _vp],

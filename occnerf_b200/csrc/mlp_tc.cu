@@ -62,7 +62,9 @@ __host__ __device__ inline int nr_N(int l) { return l == 6 ? 16 : 128; }
 __host__ __device__ inline int n_layers(int chain) { return chain == 2 ? 7 : 10; }
 __host__ __device__ inline int chain_K(int chain, int l) { return chain == 0 ? fwd_K(l) : (chain == 1 ? fwd_N(9 - l) : nr_K(l)); }
 __host__ __device__ inline int chain_N(int chain, int l) { return chain == 0 ? fwd_N(l) : (chain == 1 ? fwd_K(9 - l) : nr_N(l)); }
-__host__ __device__ inline int chunk_K(int n_pass) { return n_pass == 1 ? 64 : 32; }
+// K columns per weight chunk (= one ring slot).  Pair mode streams half of the weight rows per CTA, so the same slot bytes hold twice
+// the K: 64 columns for every engine (the MMA thread pays its per-chunk cost -- barrier polls, loop, commit -- half as often)
+__host__ __device__ inline int chunk_K(int n_pass, int pair = 0) { return (n_pass == 1 || pair) ? 64 : 32; }
 __host__ __device__ inline int parts(int n_pass) { return n_pass == 3 ? 2 : 1; }
 __host__ __device__ inline int elem_bytes(int n_pass) { return n_pass == 2 ? 4 : 2; }
 __host__ __device__ inline bool valid_pass(int n_pass) { return n_pass >= 1 && n_pass <= 3; }
@@ -73,10 +75,10 @@ struct PackedLayout {
     long total;
 };
 
-inline PackedLayout packed_layout(int n_pass, int chain) {
+inline PackedLayout packed_layout(int n_pass, int chain, int pair) {
     PackedLayout p;
     long off = 0;
-    const int KC = chunk_K(n_pass);
+    const int KC = chunk_K(n_pass, pair);
     for (int l = 0; l < kLayers; ++l) p.w_off[l] = 0;
     for (int l = 0; l < n_layers(chain); ++l) {
         p.w_off[l] = off;
@@ -125,7 +127,7 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {       // round to nearest
 // 8 bf16 / 4 tf32 columns of all N rows)
 // With cta_pair the chunk image is split by weight-row HALVES, [half][part][k-slab][...]: CTA r of a pair streams half r.
 __device__ __forceinline__ void pack_store(unsigned char *out, long base, int n_pass, int N, int n, int k, float w, int cta_pair = 0) {
-    const int KC = chunk_K(n_pass), np = parts(n_pass);
+    const int KC = chunk_K(n_pass, cta_pair), np = parts(n_pass);
     const int chunk = k / KC, kk = k % KC;
     long half_off = 0;
     if (cta_pair) {
@@ -346,8 +348,10 @@ __device__ __forceinline__ uint4 store_a8(unsigned char *a_base, int row, int k8
         // tf32 engine: the operand is fp32-sized, 4 columns per 16-byte core-matrix row -> k-slabs 2*k8 and 2*k8+1
         const uint32_t off = (uint32_t)(k8 * 32 + (row >> 3)) * 128 + (row & 7) * 16;
         // round to nearest tf32, ties away (= cvt.rna.tf32.f32 for finite values, which ptxas expands to 5 instructions with
-        // the inf/nan handling): add half an ulp of the 10-bit mantissa to the magnitude, clear the 13 low bits
-        auto rna = [](float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; };
+        // the inf/nan handling): add half an ulp of the 10-bit mantissa to the magnitude.  The 13 low mantissa bits stay as they
+        // are: kind::tf32 ignores them (measured on B200: outputs bitwise identical with and without clearing them,
+        // tools/mlp_exp.py `nomask`, gpurun_out/r2o_mlp_exp.json), which saves one LOP3 per value in the epilogue
+        auto rna = [](float x) { return __float_as_uint(x) + 0x1000u; };
         *reinterpret_cast<uint4 *>(a_base + off) = make_uint4(rna(v[0]), rna(v[1]), rna(v[2]), rna(v[3]));
         *reinterpret_cast<uint4 *>(a_base + off + 2048) = make_uint4(rna(v[4]), rna(v[5]), rna(v[6]), rna(v[7]));
         return pack_bf16x8(v);
@@ -424,6 +428,10 @@ __device__ __forceinline__ long long clk() { return clock64(); }
 //  4 warp 0: first group published   5 warp 0: last group published   6 warp 15: accumulator ready   7 warp 15: last group published
 //  8 producer: last chunk of the layer issued   10 MMA thread: cycles waiting for A in the layer   11 ... for weights
 __device__ unsigned long long g_trace[16][12];
+// Weight-stream round trip (same tile, layer 2 and 3): [layer - 2][chunk][event]  0 producer: slot seen empty  1 producer: copy issued
+//  2 MMA thread: starts waiting for the chunk  3 own half landed  4 peer's half reported  5 MMAs + commit issued
+__device__ unsigned long long g_trace_w[2][8][6];
+#define TRACEW(cond, l, c, e) do { if ((cond) && ((l) == 2 || (l) == 3)) g_trace_w[(l) - 2][c][e] = (unsigned long long)clock64(); } while (0)
 #define TRACE(cond, l, e) do { if (cond) g_trace[l][e] = (unsigned long long)clock64(); } while (0)
 
 // bf16 activations / gradients saved for the weight-gradient kernel use a CHUNK-MAJOR layout [slot][k8 = col/8][row][8]:
@@ -600,36 +608,50 @@ __device__ __forceinline__ void mma_loop(const ChainArgs &args, const Smem &sm, 
 }
 
 // ================================================================== CTA-pair mode (cta_group::2) role loops
-// Ring: 6 x 16 KB per CTA (a K-chunk of HALF the weight rows, hi [+ lo]); packed image per chunk = [half][part][k-slab][n/8][8][16 B]
-// (occnerf_mlp_pack_weights with cta_pair = 1), so a CTA's half of a chunk is one contiguous piece.
-constexpr int kPairStages = 6;
-constexpr int kPairStageBytes = 16384;
+// Packed image per chunk = [half][part][k-slab][n/8][8][16 B] (occnerf_mlp_pack_weights with cta_pair = 1), so a CTA's half of a chunk is
+// one contiguous piece.
+// Ring geometry per engine: bf16 6 x 16 KB, tf32 / split-bf16 3 x 32 KB (a K-chunk of 64 columns of HALF the weight rows, hi [+ lo]).
+// Round-2 measurement behind the 64-column chunks (tools/mlp_trace_w.py, profiles/r02_mlp_trace_w.txt): with 32-column chunks the
+// weights sat in the ring ~4 k cycles before they were used -- the "weight wait" of the MMA thread was not waiting at all but the
+// latency of its own two barrier polls (~120 cycles each, even on a completed phase), and together with ~75 cycles of issue per UMMA
+// one chunk of four cost the thread 620-700 cycles against 412 cycles of tensor time.  The issuing thread was the bottleneck of the
+// MMA phase, neither L2 bandwidth (fetching half of the bytes changed nothing) nor a same-address hot spot (replicated weight images
+// changed nothing).
+constexpr int kPairKC = 64;
+template <int NPASS> struct PairRing {
+    static constexpr int kStagesN = NPASS == 1 ? 6 : 3;
+    static constexpr int kBytes = NPASS == 1 ? 16384 : 32768;
+};
 
 // both CTAs: stream MY half of every chunk (plain bulk copies, no multicast)
 template <int NPASS>
 __device__ __forceinline__ void producer_loop_pair(const ChainArgs &args, const Smem &sm, int num_tiles) {
-    constexpr int KC = (NPASS == 1) ? 64 : 32;
+    constexpr int KC = kPairKC;
     constexpr int NP = (NPASS == 3) ? 2 : 1;
     constexpr int EB = (NPASS == 2) ? 4 : 2;
+    constexpr int NS = PairRing<NPASS>::kStagesN, SB = PairRing<NPASS>::kBytes;
     uint32_t it = 0;
     const uint32_t rank = cluster_ctarank();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const bool tr = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x;
         for (int l = 0; l < n_layers(args.chain); ++l) {
             const int K = chain_K(args.chain, l), Nh = chain_N(args.chain, l) / 2;
             const int nch = (K + KC - 1) / KC;
             const uint32_t pbh = (uint32_t)Nh * KC * EB;                         // one part of one half of a full chunk
             const unsigned char *src = args.packed + args.w_off[l] + (long)rank * NP * pbh;
             for (int c = 0; c < nch; ++c, ++it) {
-                const uint32_t s = it % kPairStages, ph = (it / kPairStages) & 1;
+                const uint32_t s = it % NS, ph = (it / NS) & 1;
                 mbar_wait(sm.bar_w_empty + 8 * s, ph ^ 1);
+                TRACEW(tr, l, c, 0);
                 const int kc = min(KC, K - c * KC);
                 const uint32_t bytes = (uint32_t)Nh * kc * EB;
-                const uint32_t dst = smem_u32(sm.W + s * kPairStageBytes);
+                const uint32_t dst = smem_u32(sm.W + s * SB);
                 const uint32_t bar = sm.bar_w_full + 8 * s;
                 mbar_arrive_expect_tx(bar, bytes * NP);
                 const unsigned char *chunk = src + (long)c * 2 * NP * pbh;
                 bulk_g2s(dst, chunk, bytes, bar);
-                if (NP == 2) bulk_g2s(dst + kPairStageBytes / 2, chunk + pbh, bytes, bar);
+                if (NP == 2) bulk_g2s(dst + SB / 2, chunk + pbh, bytes, bar);
+                TRACEW(tr, l, c, 1);
             }
         }
     }
@@ -638,14 +660,15 @@ __device__ __forceinline__ void producer_loop_pair(const ChainArgs &args, const 
 // peer CTA (rank 1): tell the leader's MMA thread that MY half of chunk `it` has landed in MY shared memory
 template <int NPASS>
 __device__ __forceinline__ void relay_loop_pair(const ChainArgs &args, const Smem &sm, int num_tiles) {
-    constexpr int KC = (NPASS == 1) ? 64 : 32;
+    constexpr int KC = kPairKC;
+    constexpr int NS = PairRing<NPASS>::kStagesN;
     uint32_t it = 0;
     const uint32_t leader_w_peer = map_to_cta(sm.bar_w_peer, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int l = 0; l < n_layers(args.chain); ++l) {
             const int nch = (chain_K(args.chain, l) + KC - 1) / KC;
             for (int c = 0; c < nch; ++c, ++it) {
-                const uint32_t s = it % kPairStages, ph = (it / kPairStages) & 1;
+                const uint32_t s = it % NS, ph = (it / NS) & 1;
                 mbar_wait(sm.bar_w_full + 8 * s, ph);
                 mbar_arrive_cluster(leader_w_peer + 8 * s);
             }
@@ -660,26 +683,39 @@ __device__ __forceinline__ void mma_step_pair(uint32_t d_tmem, uint64_t da, uint
     } else {
         tc_mma_cg2(d_tmem, da, db, idesc, accumulate);
         if (NPASS == 3) {
-            tc_mma_cg2(d_tmem, da, db + (uint64_t)((kPairStageBytes / 2) >> 4), idesc, 1u);   // hi . Wlo
-            tc_mma_cg2(d_tmem, da + (uint64_t)(kAPartBytes >> 4), db, idesc, 1u);             // lo . Whi
+            tc_mma_cg2(d_tmem, da, db + (uint64_t)((PairRing<3>::kBytes / 2) >> 4), idesc, 1u);   // hi . Wlo
+            tc_mma_cg2(d_tmem, da + (uint64_t)(kAPartBytes >> 4), db, idesc, 1u);                 // lo . Whi
         }
     }
 }
 
-// leader CTA (rank 0), whole MMA warp: M = 256 UMMAs over both CTAs' A tiles and B halves
+// non-blocking poll of one phase of a local mbarrier: the result arrives ~100 cycles later, so it is issued one chunk AHEAD of its use
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+
+// leader CTA (rank 0), whole MMA warp: M = 256 UMMAs over both CTAs' A tiles and B halves.
+// Software-pipelined barrier polls: the three barriers chunk i+1 depends on (my half, the peer's half, its A group) are polled BEFORE
+// the MMAs of chunk i are issued and the answers are looked at after them; only a negative answer falls back to the blocking wait.
 template <int NPASS>
 __device__ __forceinline__ void mma_loop_pair(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base) {
-    constexpr int KC = (NPASS == 1) ? 64 : 32;
+    constexpr int KC = kPairKC;
     constexpr int KS = (NPASS == 2) ? 8 : 16;
-    constexpr int CPG = kGroupCols / KC;
+    constexpr int NS = PairRing<NPASS>::kStagesN, SB = PairRing<NPASS>::kBytes;
+    static_assert(kGroupCols == KC, "pair mode: one A group per weight chunk");
     uint32_t it = 0, a_phase = 0;
     long long dbg_w = 0, dbg_a = 0;
     const long long dbg_t0 = args.debug ? clk() : 0;
     const uint32_t a_base = smem_u32(sm.A);
     const bool lane0 = (threadIdx.x & 31) == 0;
+    const int nl = n_layers(args.chain);
+    uint32_t ok_w = 0, ok_a = 0;                       // early answers for the chunk about to be issued
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const bool tr = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x && lane0;
-        for (int l = 0; l < n_layers(args.chain); ++l) {
+        for (int l = 0; l < nl; ++l) {
             TRACE(tr, l, 0);
             const long long w0 = dbg_w, a0 = dbg_a;
             const int K = chain_K(args.chain, l), N = chain_N(args.chain, l);
@@ -690,24 +726,33 @@ __device__ __forceinline__ void mma_loop_pair(const ChainArgs &args, const Smem 
             uint64_t da = smem_desc(a_base, 2048, 128);
             const uint64_t db_step = (uint64_t)((2 * b_lbo) >> 4);
             for (int c = 0; c < nch; ++c, ++it) {
-                const uint32_t s = it % kPairStages, ph = (it / kPairStages) & 1;
-                {
+                const uint32_t s = it % NS, ph = (it / NS) & 1;
+                TRACEW(tr, l, c, 2);
+                if (!ok_w) {
                     const long long t0 = args.debug ? clk() : 0;
                     mbar_wait(sm.bar_w_full + 8 * s, ph);                       // my half
+                    TRACEW(tr, l, c, 3);
                     mbar_wait_cluster(sm.bar_w_peer + 8 * s, ph);               // the peer's half
                     if (args.debug) dbg_w += clk() - t0;
                 }
-                if (c % CPG == 0) {
-                    const int g = c / CPG;
+                TRACEW(tr, l, c, 4);
+                if (!ok_a) {
                     const long long t0 = args.debug ? clk() : 0;
-                    mbar_wait_cluster(sm.bar_a_ready + 8 * g, (a_phase >> g) & 1);   // 16 warps of each CTA
+                    mbar_wait_cluster(sm.bar_a_ready + 8 * c, (a_phase >> c) & 1);   // A group c: 16 warps of each CTA
                     if (args.debug) dbg_a += clk() - t0;
-                    a_phase ^= 1u << g;
                 }
+                a_phase ^= 1u << c;
                 tc_fence_after();
                 TRACE(tr && c == 0, l, 1);
+                // polls for the NEXT chunk (the next layer's first one after the last of this layer)
+                {
+                    const uint32_t it1 = it + 1, s1 = it1 % NS, ph1 = (it1 / NS) & 1;
+                    const int c1 = c + 1 < nch ? c + 1 : 0;
+                    ok_w = mbar_test(sm.bar_w_full + 8 * s1, ph1) & mbar_test(sm.bar_w_peer + 8 * s1, ph1);
+                    ok_a = mbar_test(sm.bar_a_ready + 8 * c1, (a_phase >> c1) & 1);
+                }
                 const int kc = min(KC, K - c * KC);
-                uint64_t db = smem_desc(smem_u32(sm.W + s * kPairStageBytes), b_lbo, 128);
+                uint64_t db = smem_desc(smem_u32(sm.W + s * SB), b_lbo, 128);
                 if (elect_one()) {
                     if (kc == KC) {
 #pragma unroll
@@ -718,14 +763,14 @@ __device__ __forceinline__ void mma_loop_pair(const ChainArgs &args, const Smem 
                             mma_step_pair<NPASS>(d_tmem, da + (uint64_t)(ks * (4096 >> 4)), db + ks * db_step, idesc, (c | ks) ? 1u : 0u);
                     }
                     tc_commit_cg2_mc(sm.bar_w_empty + 8 * s, 3);                // frees the slot in BOTH CTAs
+                    if (c + 1 == nch) tc_commit_cg2_mc(sm.bar_acc_full, 3);     // accumulator rows of BOTH CTAs complete
                 }
                 __syncwarp();
+                TRACEW(tr, l, c, 5);
                 da += (uint64_t)((KC / KS) * (4096 >> 4));
             }
             TRACE(tr, l, 2);
             if (tr) { g_trace[l][10] = (unsigned long long)(dbg_a - a0); g_trace[l][11] = (unsigned long long)(dbg_w - w0); }
-            if (elect_one()) tc_commit_cg2_mc(sm.bar_acc_full, 3);             // accumulator rows of BOTH CTAs complete
-            __syncwarp();
         }
     }
     if (args.debug && lane0) {
@@ -1128,9 +1173,9 @@ template <int NPASS, int CHAIN, int CG>
 __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_constant__ ChainArgs args) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);     // bf16: 64 KB; hi+lo or tf32: 128 KB
-    constexpr int kRingBytes = kStages * kStageBytes;               // = kPairStages * kPairStageBytes
-    static_assert(kStages * kStageBytes == kPairStages * kPairStageBytes, "both ring geometries use the same bytes");
-    constexpr int kNStages = CG == 2 ? kPairStages : kStages;
+    constexpr int kRingBytes = kStages * kStageBytes;
+    static_assert(kStages * kStageBytes == PairRing<NPASS>::kStagesN * PairRing<NPASS>::kBytes, "both ring geometries use the same bytes");
+    constexpr int kNStages = CG == 2 ? PairRing<NPASS>::kStagesN : kStages;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kABytes + kRingBytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 30);
     Smem sm;
@@ -1142,7 +1187,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
     sm.bar_w_peer = smem_u32(bars + 2 * kNStages);                  // (pair mode only)
     sm.bar_a_ready = smem_u32(bars + 3 * kNStages);
     sm.bar_acc_full = smem_u32(bars + 3 * kNStages + kGroups);
-    static_assert(3 * kPairStages + kGroups + 1 <= 30, "barrier block");
+    static_assert(3 * 6 + kGroups + 1 <= 30, "barrier block");
     sm.pair = CG == 2;
     sm.a_ready_arrive = CG == 2 ? map_to_cta(sm.bar_a_ready, 0) : sm.bar_a_ready;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1275,10 +1320,12 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int n, int 
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
-void fill_layout(ChainArgs &a, int n_pass, int chain, const void *packed) {
+int g_host_debug = -1;
+
+void fill_layout(ChainArgs &a, int n_pass, int chain, const void *packed, int pair = 0) {
     static const int debug = getenv("OCCNERF_MLP_DEBUG") ? atoi(getenv("OCCNERF_MLP_DEBUG")) : 0;
-    a.debug = debug;
-    const PackedLayout pl = packed_layout(n_pass, chain);
+    a.debug = g_host_debug >= 0 ? g_host_debug : debug;
+    const PackedLayout pl = packed_layout(n_pass, chain, pair);
     for (int l = 0; l < kLayers; ++l) a.w_off[l] = pl.w_off[l];
     a.bias_off = pl.bias_off;
     a.chain = chain;
@@ -1315,12 +1362,26 @@ extern "C" int occnerf_mlp_debug_mma_rate(int iters, int n, int tf32, unsigned l
     return OCCNERF_OK;
 }
 
+// debug only: overrides OCCNERF_MLP_DEBUG for the following launches (debug < 0: back to the environment's value)
+extern "C" int occnerf_mlp_debug_set(int debug) {
+    g_host_debug = debug;
+    return OCCNERF_OK;
+}
+
 // debug only: reads (and optionally clears) the stall counters described at g_dbg
 // debug only: the per-layer time stamps of g_trace (16 x 12 u64)
 extern "C" int occnerf_mlp_debug_trace(unsigned long long *host192) {
     OCC_CUDA(cudaDeviceSynchronize());
     OCC_CHECK_ARG(host192, "mlp_debug_trace: null pointer");
     OCC_CUDA(cudaMemcpyFromSymbol(host192, g_trace, sizeof(unsigned long long) * 16 * 12));
+    return OCCNERF_OK;
+}
+
+// debug only: the weight-stream round-trip stamps of g_trace_w (2 x 8 x 6 u64)
+extern "C" int occnerf_mlp_debug_trace_w(unsigned long long *host96) {
+    OCC_CUDA(cudaDeviceSynchronize());
+    OCC_CHECK_ARG(host96, "mlp_debug_trace_w: null pointer");
+    OCC_CUDA(cudaMemcpyFromSymbol(host96, g_trace_w, sizeof(unsigned long long) * 96));
     return OCCNERF_OK;
 }
 
@@ -1336,7 +1397,8 @@ extern "C" int occnerf_mlp_debug_counters(unsigned long long *host8, int reset) 
 
 extern "C" long occnerf_mlp_packed_bytes(int n_pass, int chain) {
     if (!valid_pass(n_pass) || chain < 0 || chain > 2) return -1;
-    return packed_layout(n_pass, chain).total;
+    const long a = packed_layout(n_pass, chain, 0).total, b = packed_layout(n_pass, chain, 1).total;
+    return a > b ? a : b;                       // (the pair-mode image pads K to its larger chunks)
 }
 
 extern "C" int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int chain, int cta_pair, void *packed,
@@ -1345,7 +1407,7 @@ extern "C" int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_
     OCC_CHECK_ARG(valid_pass(n_pass), "mlp_pack_weights: n_pass=%d (supported: 1 bf16, 2 tf32, 3 split-bf16)", n_pass);
     OCC_CHECK_ARG(chain == 0 || chain == 1, "mlp_pack_weights: chain=%d (0 forward, 1 backward)", chain);
     for (int l = 0; l < kLayers; ++l) OCC_CHECK_ARG(p_host->w[l] && p_host->b[l], "mlp_pack_weights: layer %d has a null pointer", l);
-    const PackedLayout pl = packed_layout(n_pass, chain);
+    const PackedLayout pl = packed_layout(n_pass, chain, cta_pair ? 1 : 0);
     DevLayout L;
     for (int l = 0; l < kLayers; ++l) L.w_off[l] = pl.w_off[l];
     L.bias_off = pl.bias_off;
@@ -1366,7 +1428,7 @@ extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int 
                   "mlp_forward_tc: XB/packed/act_save must be 16-byte aligned");
     ChainArgs a = {};
     a.m = m;
-    fill_layout(a, n_pass, 0, packed);
+    fill_layout(a, n_pass, 0, packed, cta_pair ? 1 : 0);
     OCC_CHECK_ARG(act_dtype == 0 || slot_stride >= m, "mlp_forward_tc: slot_stride=%ld < m=%d", slot_stride, m);
     a.XB = XB; a.raw = raw; a.ldr = ldr; a.act_save = act_save; a.act_dtype = act_dtype; a.slot_stride = slot_stride;
     a.relu_mask = (uint8_t *)relu_mask;
@@ -1384,7 +1446,7 @@ extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *pa
                   ((uintptr_t)g_save & 15) == 0, "mlp_backward_tc: buffers must be 16-byte aligned");
     ChainArgs a = {};
     a.m = m;
-    fill_layout(a, n_pass, 1, packed_bwd);
+    fill_layout(a, n_pass, 1, packed_bwd, cta_pair ? 1 : 0);
     OCC_CHECK_ARG(slot_stride >= m, "mlp_backward_tc: slot_stride=%ld < m=%d", slot_stride, m);
     a.g_raw = g_raw; a.relu_mask = (uint8_t *)relu_mask; a.gXB = gXB; a.g_save = (__nv_bfloat16 *)g_save; a.slot_stride = slot_stride;
     return n_pass == 1 ? launch_chain<1, 1>(a, (cudaStream_t)stream, cta_pair) : n_pass == 2 ? launch_chain<2, 1>(a, (cudaStream_t)stream, cta_pair)
@@ -1403,7 +1465,7 @@ extern "C" int occnerf_nonrigid_pack_weights(const void *const *w7_host, const v
         P.b[l] = (const float *)b7_host[l];
     }
     P.cond = cond_dev;
-    const PackedLayout pl = packed_layout(n_pass, 2);
+    const PackedLayout pl = packed_layout(n_pass, 2, 0);
     DevLayout L;
     for (int l = 0; l < kLayers; ++l) L.w_off[l] = pl.w_off[l];
     L.bias_off = pl.bias_off;
