@@ -275,11 +275,12 @@ int occnerf_mlp_pack_weights(const occnerf_mlp_params *p_host, int n_pass, int c
 /* XB [m,132]: columns 64..131 = (agg35, var1, h32) are read; columns 0..63 receive the 64 geometry features when
  * act_dtype != 0.  raw [m, ldr]: columns 0..3 = (rgb_pre3, sigma_pre1) are written.
  * act_save: NULL (act_dtype 0, inference) or a buffer receiving the post-ReLU activations of the 8 hidden layers
- * (slots 0..3 = pts1..4, 4..7 = rgb1..4) for the backward pass: fp32 row-major [8][slot_stride][256] (act_dtype 1) or
+ * (slots 0..3 = pts1..4, 4..7 = rgb1..4) for the backward pass:
  * bf16 CHUNK-MAJOR [10][32][slot_stride][8] (act_dtype 2; element (slot, row, col) at ((slot*32 + col/8)*slot_stride +
  * row)*8 + col%8; slot 8 = input of pts0 (80 columns), slot 9 = input of rgb0 (144 columns)) -- the layout in which a
  * warp's stores are contiguous and which the weight-gradient kernel's TMA consumes directly.
- * relu_mask: NULL or [8][32][slot_stride] bytes: bit i of byte (slot, k8, row) = [hidden unit 8*k8+i > 0]. */
+ * relu_mask (required with act_dtype 2): [8][32][slot_stride] bytes; byte (slot, k8, row) holds [hidden unit 8*k8+c > 0] of columns
+ * c = 0..7 at bit (c >> 1) + 4 * (c & 1) (the order in which the packed bf16 pairs are compared). */
 int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int n_pass, int cta_pair, float *raw, int ldr, void *act_save,
                            int act_dtype, long slot_stride, void *relu_mask, occnerf_stream_t stream);
 

@@ -329,6 +329,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// (a0, a1) += (b0, b1) as one packed fp32x2 add (FADD2 on sm_100): halves the bias adds of the epilogue
+__device__ __forceinline__ void add2(float &a0, float &a1, float b0, float b1) {
+    asm("{ .reg .b64 x, y; mov.b64 x, {%0, %1}; mov.b64 y, {%2, %3}; add.rn.f32x2 x, x, y; mov.b64 {%0, %1}, x; }"
+        : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+
 __device__ __forceinline__ uint4 pack_bf16x8(const float (&v)[8]) {
     uint32_t pk[4];
 #pragma unroll
@@ -370,22 +376,6 @@ __device__ __forceinline__ uint4 store_a8(unsigned char *a_base, int row, int k8
     *reinterpret_cast<uint4 *>(a_base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     if (NPASS == 3) *reinterpret_cast<uint4 *>(a_base + kAPartBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     return make_uint4(hi[0], hi[1], hi[2], hi[3]);
-}
-
-// chunk g (8 columns) of the (agg35, var, h32) part of a sample's input row -> A chunk k8_0 + g, zero padded beyond column 68
-template <int NPASS>
-__device__ __forceinline__ void stage_x0_chunk(unsigned char *a_base, int row, const float *__restrict__ xrow, bool valid, int k8_0,
-                                               int g, __nv_bfloat16 *save_chunk) {
-    float v[8];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int c = g * 8 + h * 4;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && c < 68) x = __ldg(reinterpret_cast<const float4 *>(xrow + c));
-        v[h * 4 + 0] = x.x; v[h * 4 + 1] = x.y; v[h * 4 + 2] = x.z; v[h * 4 + 3] = x.w;
-    }
-    const uint4 hi = store_a8<NPASS>(a_base, row, k8_0 + g, v);
-    if (save_chunk) *reinterpret_cast<uint4 *>(save_chunk) = hi;       // (few per tile: not worth reordering after the publish)
 }
 
 struct ChainArgs {
@@ -751,15 +741,15 @@ __device__ __forceinline__ void mma_loop_pair(const ChainArgs &args, const Smem 
                     ok_w = mbar_test(sm.bar_w_full + 8 * s1, ph1) & mbar_test(sm.bar_w_peer + 8 * s1, ph1);
                     ok_a = mbar_test(sm.bar_a_ready + 8 * c1, (a_phase >> c1) & 1);
                 }
-                const int kc = min(KC, K - c * KC);
+                const int nks = min(KC, K - c * KC) / KS;
                 uint64_t db = smem_desc(smem_u32(sm.W + s * SB), b_lbo, 128);
                 if (elect_one()) {
-                    if (kc == KC) {
+                    if (nks == KC / KS) {
 #pragma unroll
                         for (int ks = 0; ks < KC / KS; ++ks)
                             mma_step_pair<NPASS>(d_tmem, da + (uint64_t)(ks * (4096 >> 4)), db + ks * db_step, idesc, (c | ks) ? 1u : 0u);
                     } else {
-                        for (int ks = 0; ks < kc / KS; ++ks)
+                        for (int ks = 0; ks < nks; ++ks)
                             mma_step_pair<NPASS>(d_tmem, da + (uint64_t)(ks * (4096 >> 4)), db + ks * db_step, idesc, (c | ks) ? 1u : 0u);
                     }
                     tc_commit_cg2_mc(sm.bar_w_empty + 8 * s, 3);                // frees the slot in BOTH CTAs
@@ -801,8 +791,24 @@ __device__ __forceinline__ void publish(const Smem &sm, int g) {
     }
 }
 
+// (Tried and reverted in round 2: publishing the first 32 columns of the next operand on a barrier of their own, so that the first four
+//  UMMAs of a layer start one epilogue chunk earlier.  The MMAs did start ~0.5 k cycles earlier, but the extra publish -- fences +
+//  remote arrive on every warp's critical path -- slowed the epilogue, which is what the MMAs of the rest of the layer wait for:
+//  tf32 forward 0.479 -> 0.531 ms per 262 144 samples, trace period 7.0 k -> 7.6 k cycles per layer.)
+// ReLU-mask byte of an 8-column chunk from its packed bf16 activations (4 words of 2): bit i = [column 2i != 0], bit 4+i =
+// [column 2i+1 != 0] for i < 4 -- 4 packed compares + 4 LOP3 + 2 instead of ~28 scalar instructions.  (v >= 0 here; bf16 keeps the
+// fp32 exponent range, so bf16(v) != 0 <=> v > 0 down to 2^-134.)
+__device__ __forceinline__ uint32_t relu_mask_byte(const uint4 &h) {
+    const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+    auto nz = [&](uint32_t w) { return __hne2_mask(*reinterpret_cast<const __nv_bfloat162 *>(&w), z); };
+    const uint32_t m = (nz(h.x) & 0x00100001u) | (nz(h.y) & 0x00200002u) | (nz(h.z) & 0x00400004u) | (nz(h.w) & 0x00800008u);
+    return (m & 0xFu) | ((m >> 16) & 0xF0u);
+}
+// position of column i (0..7) of a chunk in that byte
+__device__ __forceinline__ constexpr int relu_mask_bit(int i) { return (i >> 1) + 4 * (i & 1); }
+
 // ---- forward epilogue.  Thread = (row, set): the 8-column chunks k8 = set, set+4, ... of every layer.
-template <int NPASS>
+template <int NPASS, bool SAVE>
 __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const Smem &sm, int num_tiles, uint32_t tmem_base, int warp) {
     const int quarter = warp & 3, set = warp >> 2;
     const int row = quarter * 32 + (threadIdx.x & 31);
@@ -819,24 +825,65 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
     // quarter of the epilogue's active time in the first FADD of every chunk, waiting for its two bias LDG.128.
     if (tid < 256) sm.bias[tid] = __ldg(bias_all + tid);
     epi_bar_sync();
+    // x0: the (agg35, var, h32) input columns of the tile, zero padded to 80 -- the operand of GEMM 0 and the tail of the operand of
+    // GEMM 5 --, fetched ONE TILE AHEAD (during layer 6 of the previous tile): the round-2 trace showed layers 0 and 5, the two with
+    // the least arithmetic, taking 11 k cycles each against 6.8 k for a 256 x 256 layer, all of it the latency of these loads in front
+    // of the first UMMA.  For this staging a thread owns chunks cs, cs + 4, cs + 8 (cs = lane & 3) of row 8 * warp + lane / 4 -- NOT
+    // its TMEM row: a warp instruction then touches 8 rows x 64 B instead of 32 rows (528 B apart) x 16 B.  With lane = row the
+    // 2.7 k uncoalesced line requests per tile slowed the UMMAs running beside them from ~100 to ~270 cycles each (trace: the MMA
+    // phase of the layer during which the loads are in flight took 6.8-9 k cycles instead of 3 k; L1::no_allocate made it worse).
+    const int row_s = warp * 8 + ((threadIdx.x & 31) >> 2), cs = threadIdx.x & 3;
+    float x0[3][8];
+    auto load_x0 = [&](int t) {
+        const long g = (long)t * kTileM + row_s;
+        const bool ok = t < num_tiles && g < args.m;
+        const float *xr = args.XB + g * 132 + 64;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = (cs + 4 * j) * 8 + h * 4;
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok && c < 68) x = __ldg(reinterpret_cast<const float4 *>(xr + c));
+                x0[j][h * 4 + 0] = x.x; x0[j][h * 4 + 1] = x.y; x0[j][h * 4 + 2] = x.z; x0[j][h * 4 + 3] = x.w;
+            }
+    };
+    load_x0(blockIdx.x);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long grow = (long)tile * kTileM + row;
         const bool valid = grow < args.m;
         const bool tr0 = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x && threadIdx.x == 0;
         const bool tr15 = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x && threadIdx.x == 15 * 32;
-        const float *xrow = args.XB + grow * 132 + 64;
-        __nv_bfloat16 *sv = (valid && args.act_dtype == 2) ? reinterpret_cast<__nv_bfloat16 *>(args.act_save) : nullptr;
+        __nv_bfloat16 *sv = (SAVE && valid) ? reinterpret_cast<__nv_bfloat16 *>(args.act_save) : nullptr;
+        // chunk cs + 4 j of x0 -> A chunk k8_0 + cs + 4 j of row row_s (and its bf16 copy into slot `slot` of the saved activations)
+        const long grow_s = (long)tile * kTileM + row_s;
+        const bool save_s = SAVE && grow_s < args.m;
+        // (the global stores of the bf16 copies come AFTER the publishes: fence.proxy.async is a MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in
+        //  SASS and would wait for them)
+        static_assert(kGroupCols == 64, "staging below publishes 64-column groups");
+        auto stage_x0 = [&](int j, int k8_0) { return store_a8<NPASS>(sm.A, row_s, k8_0 + cs + 4 * j, x0[j]); };
+        auto save_x0 = [&](int slot, int k8_0, const uint4 &h0, const uint4 &h1, const uint4 &h2) {
+            if (!save_s) return;
+            uint4 *dst = reinterpret_cast<uint4 *>(args.act_save) + ((long)(slot * 32 + k8_0 + cs) * args.slot_stride + grow_s);
+            dst[0] = h0;
+            dst[4 * args.slot_stride] = h1;
+            if (cs < 2) dst[8 * args.slot_stride] = h2;
+        };
         {   // GEMM 0 operand A[:, 0:80) = (agg35, var, h32, pad): chunks 0..9
-            auto sv8 = [&](int g) { return sv ? sv + saved_off(8, g, args.slot_stride, grow) : nullptr; };
-            stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 0, set, sv8(set));
-            if (kGroupCols == 32) publish(sm, 0);
-            stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 0, set + 4, sv8(set + 4));
-            publish(sm, kGroupCols == 32 ? 1 : 0);
-            if (set < 2) stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 0, set + 8, sv8(set + 8));
-            publish(sm, kGroupCols == 32 ? 2 : 1);
+            const uint4 h0 = stage_x0(0, 0), h1 = stage_x0(1, 0);
+            publish(sm, 0);
+            uint4 h2 = make_uint4(0u, 0u, 0u, 0u);
+            if (cs < 2) h2 = stage_x0(2, 0);
+            publish(sm, 1);
+            save_x0(8, 0, h0, h1, h2);
         }
         for (int l = 0; l < kLayers; ++l, ++acc_cnt, ++bl) {
             const int l_next = l + 1 == kLayers ? 0 : l + 1;
+            // The next tile's inputs (x0 is dead from layer 5 on).  While these loads are outstanding the MMA warp stalls for ~4-6 k
+            // cycles wherever they are placed (measured at layers 5, 6 and 9: the issue span of that layer's UMMAs grows by that much,
+            // independent of their number and shape -- the LSU path the MMA warp's barrier polls share with the epilogue warps' misses);
+            // layer 6 was the cheapest of the three (tf32 forward with saves 0.544 / 0.559 / 0.553 ms per 262 144 samples).
+            if (l == 6) load_x0(tile + (int)gridDim.x);
             float bias_next = 0.f;
             if (tid < 256) bias_next = __ldg(bias_all + l_next * 256 + tid);
             {
@@ -864,81 +911,78 @@ __device__ __forceinline__ void fwd_epilogue_loop(const ChainArgs &args, const S
                 tc_fence_before();
             } else if (l == 4) {
                 // geometry head: columns 0..63 = features (-> A[:, 0:64) of the colour trunk), column 64 = sigma.
-                // All TMEM reads of a thread come before its last publish (see the backward chain, d == 4).
-                if (set == 0) {
-                    uint32_t r[8];
-                    tmem_ld8_issue(t_acc + 64, r);
+                // All TMEM reads of a thread come before its last publish (see the backward chain, d == 4); all of its global
+                // stores come after it.
+                uint32_t rs[8], ra[8], rb[8];
+                if (set == 0) tmem_ld8_issue(t_acc + 64, rs);
+                tmem_ld8_issue(t_acc + set * 8, ra);
+                tmem_ld8_issue(t_acc + (4 + set) * 8, rb);
+                float va[8], vb[8];
+                {
+                    const float4 a0 = *reinterpret_cast<const float4 *>(bias + set * 8), a1 = *reinterpret_cast<const float4 *>(bias + set * 8 + 4);
+                    const float4 c0 = *reinterpret_cast<const float4 *>(bias + (4 + set) * 8), c1 = *reinterpret_cast<const float4 *>(bias + (4 + set) * 8 + 4);
+                    const float ba[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bb[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
                     tmem_ld_wait();
-                    if (valid) args.raw[grow * args.ldr + 3] = __uint_as_float(r[0]) + bias[64];
-                }
-#pragma unroll 1
-                for (int cg = 0; cg < 2; ++cg) {
-                    const int k8 = cg * 4 + set;
-                    uint32_t r[8];
-                    tmem_ld8_issue(t_acc + k8 * 8, r);
-                    const float4 b0 = *reinterpret_cast<const float4 *>(bias + k8 * 8);
-                    const float4 b1 = *reinterpret_cast<const float4 *>(bias + k8 * 8 + 4);
-                    tmem_ld_wait();
-                    const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                    float v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) + bj[i];
-                    const uint4 hi = store_a8<NPASS>(sm.A, row, k8, v);
-                    if (kGroupCols == 32 || cg == 1) publish(sm, kGroupCols == 32 ? cg : 0);
-                    if (valid && args.act_dtype != 0) {
-                        float4 *dst = reinterpret_cast<float4 *>(args.XB + grow * 132 + k8 * 8);
-                        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                        if (sv) *reinterpret_cast<uint4 *>(sv + saved_off(9, k8, args.slot_stride, grow)) = hi;
+                    for (int i = 0; i < 8; ++i) { va[i] = __uint_as_float(ra[i]) + ba[i]; vb[i] = __uint_as_float(rb[i]) + bb[i]; }
+                }
+                const uint4 fa = store_a8<NPASS>(sm.A, row, set, va), fb = store_a8<NPASS>(sm.A, row, 4 + set, vb);
+                publish(sm, 0);
+                // A[:, 64:144) = (agg35, var, h32, pad): chunks 8..17 -> A groups 1, 2
+                const uint4 h0 = stage_x0(0, 8), h1 = stage_x0(1, 8);
+                publish(sm, 1);
+                uint4 h2 = make_uint4(0u, 0u, 0u, 0u);
+                if (cs < 2) h2 = stage_x0(2, 8);
+                publish(sm, 2);
+                if (valid) {
+                    if (set == 0) args.raw[grow * args.ldr + 3] = __uint_as_float(rs[0]) + bias[64];
+                    if (SAVE) {
+                        float4 *dst = reinterpret_cast<float4 *>(args.XB + grow * 132 + set * 8);
+                        dst[0] = make_float4(va[0], va[1], va[2], va[3]);
+                        dst[1] = make_float4(va[4], va[5], va[6], va[7]);
+                        dst[8] = make_float4(vb[0], vb[1], vb[2], vb[3]);
+                        dst[9] = make_float4(vb[4], vb[5], vb[6], vb[7]);
+                        uint4 *sd = reinterpret_cast<uint4 *>(args.act_save) + ((long)(9 * 32 + set) * args.slot_stride + grow);
+                        sd[0] = fa;
+                        sd[4 * args.slot_stride] = fb;
                     }
                 }
-                // A[:, 64:144) = (agg35, var, h32, pad): chunks 8..17 -> A groups 2, 3, 4
-                auto sv9 = [&](int g) { return sv ? sv + saved_off(9, 8 + g, args.slot_stride, grow) : nullptr; };
-                stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 8, set, sv9(set));
-                if (kGroupCols == 32) publish(sm, 2);
-                stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 8, set + 4, sv9(set + 4));
-                publish(sm, kGroupCols == 32 ? 3 : 1);
-                if (set < 2) stage_x0_chunk<NPASS>(sm.A, row, xrow, valid, 8, set + 8, sv9(set + 8));
-                publish(sm, kGroupCols == 32 ? 4 : 2);
+                save_x0(9, 8, h0, h1, h2);
             } else {
-                // hidden layer: +bias, ReLU -> next A operand (and the saved activation / ReLU mask for the backward pass)
+                // hidden layer: +bias, ReLU -> next A operand (and the saved activation / ReLU mask for the backward pass).
+                // Fully unrolled over the thread's 8 chunks k8 = set, set + 4, ...: TMEM columns, bias and operand offsets become
+                // immediates (round 2: the epilogue is what the MMAs of the next layer wait for -- ~120 instructions per chunk in
+                // the rolled loop with its 64-bit index arithmetic, ~60 now).
                 const int slot = l < 4 ? l : l - 1;                  // 0..3 = pts1..4, 4..7 = rgb1..4
-                uint8_t *mask_row = args.relu_mask ? args.relu_mask + ((long)slot * 32 * args.slot_stride + grow) : nullptr;   // + k8 * stride
+                const long step4 = 4 * args.slot_stride;             // per chunk: 16-byte units of the bf16 save, bytes of the mask
+                uint4 *sv_p = reinterpret_cast<uint4 *>(args.act_save) + ((long)(slot * 32 + set) * args.slot_stride + grow);
+                uint8_t *mk_p = args.relu_mask + ((long)(slot * 32 + set) * args.slot_stride + grow);
+                const float *bias_t = bias + set * 8;
                 uint32_t ra[8], rb[8];
-                auto process = [&](int cg, const uint32_t (&r)[8]) {
-                    const int k8 = cg * 4 + set;
-                    const float4 b0 = *reinterpret_cast<const float4 *>(bias + k8 * 8);
-                    const float4 b1 = *reinterpret_cast<const float4 *>(bias + k8 * 8 + 4);
-                    const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                auto process = [&](int cg, uint32_t (&r)[8]) {
+                    const float4 b0 = *reinterpret_cast<const float4 *>(bias_t + cg * 32);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(bias_t + cg * 32 + 4);
                     float v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[i]) + bj[i], 0.f);
-                    const uint4 hi = store_a8<NPASS>(sm.A, row, k8, v);
+                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+                    add2(v[0], v[1], b0.x, b0.y); add2(v[2], v[3], b0.z, b0.w);
+                    add2(v[4], v[5], b1.x, b1.y); add2(v[6], v[7], b1.z, b1.w);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                    const uint4 hi = store_a8<NPASS>(sm.A, row, cg * 4 + set, v);
                     // publish FIRST: the arrive has release semantics and would otherwise wait for the global stores below
                     // (measured: 21-25 % of the epilogue's time with them in front of it)
                     if (pub_after(cg)) publish(sm, pub_group(cg));
                     TRACE(tr0 && cg == kGroupK8 / 4 - 1, l, 4);
                     TRACE(tr0 && cg == 7, l, 5);
                     TRACE(tr15 && cg == 7, l, 7);
-                    if (valid) {
-                        if (args.act_dtype == 1) {
-                            const long e = ((long)slot * args.slot_stride + grow) * 256 + k8 * 8;
-                            float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(args.act_save) + e);
-                            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                        } else if (args.act_dtype == 2) {
-                            *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(args.act_save) + saved_off(slot, k8, args.slot_stride, grow)) = hi;
-                        }
-                        if (mask_row) {                               // ReLU'(x) = [x > 0]; v >= 0 here, so > 0 <=> any bit set
-                            uint32_t bits = 0;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) bits += min(__float_as_uint(v[i]), 1u) << i;
-                            mask_row[(long)k8 * args.slot_stride] = (uint8_t)bits;
-                        }
+                    if (SAVE && valid) {
+                        sv_p[cg * step4] = hi;
+                        mk_p[cg * step4] = (uint8_t)relu_mask_byte(hi);      // ReLU'(x) = [x > 0], from the packed bf16 words
                     }
                 };
                 tmem_ld8_issue(t_acc + set * 8, ra);
-#pragma unroll 1
+#pragma unroll
                 for (int cg = 0; cg < 8; cg += 2) {
                     tmem_ld_wait();
                     tmem_ld8_issue(t_acc + ((cg + 1) * 4 + set) * 8, rb);
@@ -967,37 +1011,30 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
     const bool dbg_on = args.debug && threadIdx.x == 0;
     long long dbg_acc = 0;
     const long long dbg_t0 = dbg_on ? clk() : 0;
-    // 8 accumulator columns [col, col+8) -> gXB[:, 64 + c*8 ...) (chunk c of the 68 (agg,var,h) columns; chunk 8 has 4)
-    auto gxb_chunk = [&](uint32_t t_acc, int col, int c, long grow, bool valid, bool accumulate) {
-        uint32_t r[8];
-        tmem_ld8_issue(t_acc + col, r);
-        tmem_ld_wait();
-        if (!valid) return;
-        float4 *dst = reinterpret_cast<float4 *>(args.gXB + grow * 132 + 64 + c * 8);
-        const int n4 = c < 8 ? 2 : 1;
-        for (int i = 0; i < n4; ++i) {
-            float4 o = accumulate ? dst[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            o.x += __uint_as_float(r[4 * i + 0]); o.y += __uint_as_float(r[4 * i + 1]);
-            o.z += __uint_as_float(r[4 * i + 2]); o.w += __uint_as_float(r[4 * i + 3]);
-            dst[i] = o;
-        }
+    // d raw of this thread's row (set 0 only), fetched one tile ahead: it is the operand of GEMM 0, in front of the first UMMA of a tile
+    float gr[4] = {0.f, 0.f, 0.f, 0.f};
+    auto load_gr = [&](int t) {
+        const long g = (long)t * kTileM + row;
+        const bool ok = set == 0 && t < num_tiles && g < args.m;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gr[i] = ok ? __ldg(args.g_raw + g * 5 + i) : 0.f;
     };
+    load_gr(blockIdx.x);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long grow = (long)tile * kTileM + row;
         const bool valid = grow < args.m;
-        float g_sigma = 0.f;
-        {   // GEMM 0 operand: d raw[:, 0:3] in A[:, 0:16): chunk 0 by set 0, chunk 1 (zeros) by set 1
-            if (set < 2) {
-                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (valid && set == 0) {
-                    const float *gr = args.g_raw + grow * 5;
-                    v[0] = __ldg(gr + 0); v[1] = __ldg(gr + 1); v[2] = __ldg(gr + 2);
-                    g_sigma = __ldg(gr + 3);
-                }
-                store_a8<NPASS>(sm.A, row, set, v);
-                if (valid) *reinterpret_cast<uint4 *>(args.g_save + saved_off(9, set, args.slot_stride, grow)) = pack_bf16x8(v);
-            }
+        const bool tr0 = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x && threadIdx.x == 0;
+        const bool tr15 = (args.debug & 16) && blockIdx.x == 0 && tile == 2 * (int)gridDim.x && threadIdx.x == 15 * 32;
+        const float g_sigma = gr[3];
+        // the colour trunk's share of d(agg, var, h) (position 4) waits in registers for the geometry trunk's (position 9): chunks
+        // set and set + 4 of the 68 columns, and columns 64..67 in set 0 -- one gXB store instead of store + load + store
+        float gx[3][8];
+        {   // GEMM 0 operand: d raw[:, 0:3] in A[:, 0:16): chunk 0 by set 0, chunk 1 (zeros) by set 1.  (The global store of the bf16
+            // copy comes after the publish: fence.proxy.async would wait for it.)
+            float v[8] = {gr[0], gr[1], gr[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (set < 2) store_a8<NPASS>(sm.A, row, set, v);
             publish(sm, 0);
+            if (valid && set < 2) *reinterpret_cast<uint4 *>(args.g_save + saved_off(9, set, args.slot_stride, grow)) = pack_bf16x8(v);
         }
         for (int d = 0; d < kLayers; ++d, ++acc_cnt) {
             uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};        // this thread's 8 ReLU-mask bytes of the layer, fetched before the wait
@@ -1012,54 +1049,79 @@ __device__ __forceinline__ void bwd_epilogue_loop(const ChainArgs &args, const S
                 mbar_wait(sm.bar_acc_full, acc_cnt & 1);
                 if (dbg_on) dbg_acc += clk() - t0;
             }
+            TRACE(tr0, d, 3);
+            TRACE(tr15, d, 6);
             tc_fence_after();
             const uint32_t t_acc = t_lane + (uint32_t)(d & 1) * 256;
+            if (d == 8) load_gr(tile + (int)gridDim.x);
             if (d == 9) {
-                // pts0^T: 68 (+12 pad) columns, accumulated onto the colour trunk's share of d(agg,var,h)
-                gxb_chunk(t_acc, set * 8, set, grow, valid, true);
-                gxb_chunk(t_acc, (set + 4) * 8, set + 4, grow, valid, true);
-                if (set == 0) gxb_chunk(t_acc, 64, 8, grow, valid, true);
+                // pts0^T: 68 (+12 pad) columns, added to the colour trunk's share of d(agg,var,h) kept in gx since position 4
+                uint32_t r0[8], r1[8], r2[8];
+                tmem_ld8_issue(t_acc + set * 8, r0);
+                tmem_ld8_issue(t_acc + (set + 4) * 8, r1);
+                if (set == 0) tmem_ld8_issue(t_acc + 64, r2);
+                tmem_ld_wait();
                 tc_fence_before();
+                if (valid) {
+                    float4 *dst = reinterpret_cast<float4 *>(args.gXB + grow * 132 + 64 + set * 8);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { gx[0][i] += __uint_as_float(r0[i]); gx[1][i] += __uint_as_float(r1[i]); }
+                    dst[0] = make_float4(gx[0][0], gx[0][1], gx[0][2], gx[0][3]);
+                    dst[1] = make_float4(gx[0][4], gx[0][5], gx[0][6], gx[0][7]);
+                    dst[8] = make_float4(gx[1][0], gx[1][1], gx[1][2], gx[1][3]);
+                    dst[9] = make_float4(gx[1][4], gx[1][5], gx[1][6], gx[1][7]);
+                    if (set == 0)
+                        dst[16] = make_float4(gx[2][0] + __uint_as_float(r2[0]), gx[2][1] + __uint_as_float(r2[1]),
+                                              gx[2][2] + __uint_as_float(r2[2]), gx[2][3] + __uint_as_float(r2[3]));
+                }
             } else if (d == 4) {
                 // rgb0^T: columns 0..63 = d geo features (-> operand of geo^T together with d sigma), 64..131 = d(agg,var,h).
                 // Every TMEM read of a thread comes BEFORE its last publish: GEMM d+2 overwrites this buffer as soon as some
                 // threads have published the first group of layer d+1, which they can only do after GEMM d+1 has consumed
-                // everything published here.
-                gxb_chunk(t_acc, 64 + set * 8, set, grow, valid, false);
-                gxb_chunk(t_acc, 64 + (set + 4) * 8, set + 4, grow, valid, false);
-                if (set == 0) gxb_chunk(t_acc, 128, 8, grow, valid, false);
-#pragma unroll 1
-                for (int cg = 0; cg < 2; ++cg) {
-                    const int k8 = cg * 4 + set;
-                    uint32_t r[8];
-                    tmem_ld8_issue(t_acc + k8 * 8, r);
-                    tmem_ld_wait();
-                    float v[8];
+                // everything published here.  Every global store comes after it.
+                uint32_t r0[8], r1[8], r2[8], fa[8], fb[8];
+                tmem_ld8_issue(t_acc + set * 8, fa);
+                tmem_ld8_issue(t_acc + (4 + set) * 8, fb);
+                tmem_ld8_issue(t_acc + 64 + set * 8, r0);
+                tmem_ld8_issue(t_acc + 64 + (set + 4) * 8, r1);
+                if (set == 0) tmem_ld8_issue(t_acc + 128, r2);
+                tmem_ld_wait();
+                float va[8], vb[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-                    const uint4 hi = store_a8<NPASS>(sm.A, row, k8, v);
-                    if (kGroupCols == 32 || cg == 1) publish(sm, kGroupCols == 32 ? cg : 0);
-                    if (valid) *reinterpret_cast<uint4 *>(args.g_save + saved_off(4, k8, args.slot_stride, grow)) = hi;
+                for (int i = 0; i < 8; ++i) {
+                    va[i] = __uint_as_float(fa[i]); vb[i] = __uint_as_float(fb[i]);
+                    gx[0][i] = __uint_as_float(r0[i]); gx[1][i] = __uint_as_float(r1[i]);
+                    gx[2][i] = set == 0 ? __uint_as_float(r2[i]) : 0.f;
                 }
-                if (set < 2) {   // A[:, 64:80) = (d sigma, 0...): chunk 8 by set 0, chunk 9 (zeros) by set 1
-                    float v[8] = {set == 0 ? g_sigma : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    store_a8<NPASS>(sm.A, row, 8 + set, v);
-                    if (valid) *reinterpret_cast<uint4 *>(args.g_save + saved_off(4, 8 + set, args.slot_stride, grow)) = pack_bf16x8(v);
+                const uint4 ha = store_a8<NPASS>(sm.A, row, set, va), hb = store_a8<NPASS>(sm.A, row, 4 + set, vb);
+                publish(sm, 0);
+                // A[:, 64:80) = (d sigma, 0...): chunk 8 by set 0, chunk 9 (zeros) by set 1
+                float vs[8] = {set == 0 ? g_sigma : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (set < 2) store_a8<NPASS>(sm.A, row, 8 + set, vs);
+                publish(sm, 1);
+                if (valid) {
+                    uint4 *gs = reinterpret_cast<uint4 *>(args.g_save) + ((long)(4 * 32 + set) * args.slot_stride + grow);
+                    gs[0] = ha;
+                    gs[4 * args.slot_stride] = hb;
+                    if (set < 2) gs[8 * args.slot_stride] = pack_bf16x8(vs);
                 }
-                publish(sm, kGroupCols == 32 ? 2 : 1);
             } else {
                 // through a ReLU: G = acc * (saved activation > 0) -> next A operand, and saved for the weight gradient
                 const int gslot = d;                                 // g_save: 0..3 rgb3..rgb0, 4 geo, 5..8 pts3..pts0
+                uint4 *gs_p = reinterpret_cast<uint4 *>(args.g_save) + ((long)(gslot * 32 + set) * args.slot_stride + grow);
+                const long step4 = 4 * args.slot_stride;             // 16-byte chunks per step of this thread's k8 = set, set + 4, ...
                 uint32_t ra[8], rb[8];
                 auto process = [&](int cg, const uint32_t (&r)[8], uint32_t word) {
-                    const int k8 = cg * 4 + set;
                     const uint32_t bits = word;
                     float v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = ((bits >> i) & 1u) ? __uint_as_float(r[i]) : 0.f;
-                    const uint4 hi = store_a8<NPASS>(sm.A, row, k8, v);
+                    for (int i = 0; i < 8; ++i) v[i] = (bits & (1u << relu_mask_bit(i))) ? __uint_as_float(r[i]) : 0.f;
+                    const uint4 hi = store_a8<NPASS>(sm.A, row, cg * 4 + set, v);
                     if (pub_after(cg)) publish(sm, pub_group(cg));   // before the global store (see the forward epilogue)
-                    if (valid) *reinterpret_cast<uint4 *>(args.g_save + saved_off(gslot, k8, args.slot_stride, grow)) = hi;
+                    TRACE(tr0 && cg == kGroupK8 / 4 - 1, d, 4);
+                    TRACE(tr0 && cg == 7, d, 5);
+                    TRACE(tr15 && cg == 7, d, 7);
+                    if (valid) gs_p[cg * step4] = hi;
                 };
                 tmem_ld8_issue(t_acc + set * 8, ra);
 #pragma unroll
@@ -1169,7 +1231,7 @@ __device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Sm
     }
 }
 
-template <int NPASS, int CHAIN, int CG>
+template <int NPASS, int CHAIN, int CG, bool SAVE = false>
 __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_constant__ ChainArgs args) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);     // bf16: 64 KB; hi+lo or tf32: 128 KB
@@ -1233,7 +1295,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
             mma_loop<NPASS>(args, sm, num_tiles, tmem_base);      // whole warp, one elected lane issues
         }
     } else {
-        if (CHAIN == 0) fwd_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
+        if (CHAIN == 0) fwd_epilogue_loop<NPASS, SAVE>(args, sm, num_tiles, tmem_base, warp);
         else if (CHAIN == 1) bwd_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
         else nr_epilogue_loop<NPASS>(args, sm, num_tiles, tmem_base, warp);
     }
@@ -1246,13 +1308,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_tc_kernel(const __grid_
     }
 }
 
-template <int NPASS, int CHAIN, int CG>
+template <int NPASS, int CHAIN, int CG, bool SAVE = false>
 int launch_chain_cg(const ChainArgs &a, cudaStream_t st) {
     constexpr int kABytes = kAPartBytes * (NPASS == 1 ? 1 : 2);
     const int smem_bytes = kABytes + kStages * kStageBytes + 256 + 2048;     // + barriers + the bias double buffer
     static bool configured = false;
     if (!configured) {
-        OCC_CUDA(cudaFuncSetAttribute(mlp_chain_tc_kernel<NPASS, CHAIN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        OCC_CUDA(cudaFuncSetAttribute(mlp_chain_tc_kernel<NPASS, CHAIN, CG, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured = true;
     }
     int dev = 0, sms = 148;
@@ -1272,13 +1334,17 @@ int launch_chain_cg(const ChainArgs &a, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OCC_CUDA(cudaLaunchKernelEx(&cfg, mlp_chain_tc_kernel<NPASS, CHAIN, CG>, a));
+    OCC_CUDA(cudaLaunchKernelEx(&cfg, mlp_chain_tc_kernel<NPASS, CHAIN, CG, SAVE>, a));
     return OCCNERF_OK;
 }
 
 // cta_pair: 0 = cta_group::1 CTAs sharing the weight stream by multicast, 1 = cta_group::2 (weights packed with cta_pair = 1)
 template <int NPASS, int CHAIN>
 int launch_chain(const ChainArgs &a, cudaStream_t st, int cta_pair = 0) {
+    if (CHAIN == 0) {      // the forward chain comes with and without the activation / ReLU-mask saves compiled in
+        if (a.act_dtype) return cta_pair ? launch_chain_cg<NPASS, 0, 2, true>(a, st) : launch_chain_cg<NPASS, 0, 1, true>(a, st);
+        return cta_pair ? launch_chain_cg<NPASS, 0, 2, false>(a, st) : launch_chain_cg<NPASS, 0, 1, false>(a, st);
+    }
     if (CHAIN != 2 && cta_pair) return launch_chain_cg<NPASS, CHAIN == 2 ? 0 : CHAIN, 2>(a, st);
     return launch_chain_cg<NPASS, CHAIN, 1>(a, st);
 }
@@ -1423,7 +1489,8 @@ extern "C" int occnerf_mlp_forward_tc(float *XB, int m, const void *packed, int 
     OCC_CHECK_ARG(XB && packed && raw, "mlp_forward_tc: null pointer");
     OCC_CHECK_ARG(valid_pass(n_pass), "mlp_forward_tc: n_pass=%d (supported: 1 bf16, 2 tf32, 3 split-bf16)", n_pass);
     OCC_CHECK_ARG(m > 0 && ldr >= 4, "mlp_forward_tc: m=%d ldr=%d", m, ldr);
-    OCC_CHECK_ARG(act_dtype >= 0 && act_dtype <= 2 && (act_dtype == 0 || act_save), "mlp_forward_tc: act_dtype=%d / act_save mismatch", act_dtype);
+    OCC_CHECK_ARG((act_dtype == 0 || act_dtype == 2) && (act_dtype == 0 || (act_save && relu_mask)),
+                  "mlp_forward_tc: act_dtype=%d (0 none, 2 bf16 chunk-major + ReLU mask; both buffers required)", act_dtype);
     OCC_CHECK_ARG(((uintptr_t)XB & 15) == 0 && ((uintptr_t)packed & 15) == 0 && ((uintptr_t)act_save & 15) == 0,
                   "mlp_forward_tc: XB/packed/act_save must be 16-byte aligned");
     ChainArgs a = {};
