@@ -134,6 +134,21 @@ WORKLOADS = {
 }
 
 
+class _WithActive:
+    """SwitchReducer called with the structural-zero compaction map of a particular gradient list."""
+    capturable = True
+
+    def __init__(self, reducer, active):
+        self.reducer, self.active = reducer, active
+
+    def __call__(self, grads, hits=None):
+        keep, self.reducer.active = self.reducer.active, self.active
+        try:
+            self.reducer(grads, hits=hits)
+        finally:
+            self.reducer.active = keep
+
+
 class Workload:
     def __init__(self, device, rank, engine, workload="zju387"):
         from occnerf_b200 import synthetic as S
@@ -163,9 +178,36 @@ class Workload:
         from occnerf_b200.distributed import GradReducer
         self.opt_path = ClipAdam(path_params, lr=5e-4, max_norm=1.0)          # native clip + Adam (csrc/optim.cu), trainer.py:248-249
         self.opt_all = ClipAdam([p for p in self.net.parameters() if p.requires_grad], lr=5e-4, max_norm=1.0)
-        from occnerf_b200.distributed import structural_zero_slices
-        self.reducer = GradReducer()
-        self.reducer_e2e = GradReducer(active=structural_zero_slices([p for p in self.net.parameters() if p.requires_grad]))
+        from occnerf_b200.distributed import structural_zero_slices, SwitchReducer
+        all_params = [p for p in self.net.parameters() if p.requires_grad]
+        active_e2e = structural_zero_slices(all_params)
+        self.emb = self.net.cnl_mlp.module.encoder.embeddings
+        self.reducer_kind = "none"
+        import torch.distributed as dist
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            self.reducer_kind = "nccl"
+            self.reducer = GradReducer()
+            self.reducer_e2e = GradReducer(active=active_e2e)
+            if os.environ.get("OCCNERF_REDUCER", "switch") == "switch":
+                # gradient all-reduce as one of our kernels over NVSwitch peer memory (csrc/collective.cu); NCCL only if the
+                # symmetric-memory rendezvous is not available on this box (every rank takes the same branch)
+                ok = 1
+                try:
+                    bucket = sum((p[active_e2e[i]].numel() if i in active_e2e else p.numel()) for i, p in enumerate(all_params) if p is not self.emb)
+                    bucket += self.vol.numel() + 6890 + 64
+                    sw = SwitchReducer(self.emb.numel(), bucket, device, active=None)
+                except Exception as exc:
+                    print(f"bench.py: SwitchReducer unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+                    ok = 0
+                flag = torch.tensor([ok], device=device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) == 1:
+                    self.net.bind_emb_grad(sw.table_view)
+                    self.reducer = sw
+                    self.reducer_e2e = _WithActive(sw, active_e2e)
+                    self.reducer_kind = sw.kind
+        else:
+            self.net.bind_emb_grad()                         # one persistent table-gradient buffer: a memset and an add less per step
         # pinned host copies of everything `Network.forward` receives per frame (trainer.py:223-229)
         h = self.fr_host
         self.host = {k: v.pin_memory() for k, v in dict(rays_o=h.rays_o, rays_d=h.rays_d, near=h.near, far=h.far, dst_Rs=h.dst_Rs,
@@ -184,10 +226,12 @@ class Workload:
     def step_device(self, world):
         """One step with inputs resident in HBM: the ray path only (vol is a leaf)."""
         net, fr = self.net, self.fr
+        net.zero_bound_grads()
         out = net._batchify_rays(self.packed, pos_embed_fn=None, non_rigid_pos_embed_fn=self.emb_fn, non_rigid_mlp_input=None,
                                  motion_scale_Rs=fr.motion_scale_Rs[None], motion_Ts=fr.motion_Ts[None], motion_weights_vol=self.vol,
                                  cnl_bbox_min_xyz=fr.cnl_bbox_min_xyz, cnl_bbox_scale_xyz=fr.cnl_bbox_scale_xyz, bgcolor=fr.bgcolor)
         self.loss(out, self.target, world).backward()
+        net.attach_bound_grads()
         hits = out["hits"]
         if world > 1:
             # one flat bucket for the 22 small tensors (MLP, point_dist, weight volume), the 59 MiB table gradient in place
@@ -203,7 +247,7 @@ class Workload:
         from occnerf_b200 import distributed as D
         from occnerf_b200.train_step import GraphedTrainStep
         params = [p for p in self.net.parameters() if p.requires_grad]
-        sync = (lambda grads, hits: self.reducer_e2e(grads, hits=hits)) if world > 1 else None
+        sync = self.reducer_e2e if world > 1 else None       # (SwitchReducer is capturable: one graph; NCCL: two graphs around it)
         self.graphed = GraphedTrainStep(self.net, self.opt_all, lambda out, d: self.loss({"rgb": out["rgb"], "comp_loss": out["comp_loss"]}, d["target"], world),
                                         self.host, self.iter_val, params=params, max_norm=None, grad_sync=sync)
         return self.graphed
@@ -216,11 +260,13 @@ class Workload:
         all-reduce, optimizer, D2H of the loss."""
         d = {k: v.to(self.device, non_blocking=True) for k, v in self.host.items()}
         net = self.net
+        net.zero_bound_grads()
         out = net.forward((d["rays_o"], d["rays_d"]), d["dst_Rs"], d["dst_Ts"], d["cnl_gtfms"], d["priors"], dst_posevec=d["posevec"],
                           near=d["near"], far=d["far"], iter_val=self.iter_val, cnl_bbox_min_xyz=d["bmin"], cnl_bbox_scale_xyz=d["bscale"],
                           bgcolor=d["bg"])
         loss = self.loss({"rgb": out["rgb"], "comp_loss": out["comp_loss"]}, d["target"], world)
         loss.backward()
+        net.attach_bound_grads()
         params = [p for p in net.parameters() if p.requires_grad]
         if world > 1:
             self.reducer_e2e([p.grad for p in params], hits=out["hits"])
@@ -451,7 +497,7 @@ def main():
         ok = 1
         try:
             g = wl.make_graphed(world)
-            e2e_mode, e2e_launches = ("cuda_graph" if world == 1 else "2 cuda graphs + eager nccl"), g.launches
+            e2e_mode, e2e_launches = ("cuda_graph" if g.graph_opt is None else "2 cuda graphs + eager nccl"), g.launches
         except Exception as exc:                                   # capture is an optimisation, never a requirement
             import traceback
             traceback.print_exc(file=sys.stderr)
@@ -485,7 +531,7 @@ def main():
             "dtype": {"fp32": "f32", "tf32": "tf32->f32", "tc3": "bf16x3(split)->f32", "tc3b1": "bf16x3(split)->f32 fwd, bf16->f32 dgrad", "tc1": "bf16->f32"}[args.engine], "data": "synthetic",
             "config": {"workload": wl.spec["name"], "rays_per_step_per_gpu": RAYS_PER_STEP, "samples_per_ray": S_SAMPLES,
                        "mlp_engine": args.engine, "l2": "256 MiB flush write between timed steps", "timing": "cuda events per step, max over ranks",
-                       "optimizer": "global-norm clip + Adam inside the step (occnerf_clip_adam_step)", "parallelism": f"dp{world}",
+                       "optimizer": "global-norm clip + Adam inside the step (occnerf_clip_adam_step)", "parallelism": f"dp{world}", "grad_allreduce": wl.reducer_kind,
                        "knn": "exact; pykeops' own reduction is un-vendored upstream (parity unpinned for that one call), ids checked against brute force"},
             "clocks": clocks,
             "e2e": {"value": world * RAYS_PER_STEP / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": wl.h2d_bytes,

@@ -360,6 +360,17 @@ int occnerf_unpack_image(const float *rgb, const float *alpha, const int *pixel_
                          const float *bgcolor_host, int fill, uint8_t *rgb8, uint8_t *alpha8, int *bad,
                          occnerf_stream_t stream);
 
+/* ---- data-parallel training: gradient all-reduce as one kernel over NVSwitch peer memory (csrc/collective.cu) ----------------
+ * Replaces the gradient reduction that nn.DataParallel / a NCCL all-reduce performs between backward() and the optimizer step
+ * (core/train/trainers/occnerf/trainer.py:246-248).  In-place SUM over `world` ranks of a flat fp32 buffer that every rank holds in
+ * symmetric (peer-mapped) memory.  peer_bufs_host / peer_pads_host: HOST arrays of `world` device pointers to every rank's buffer /
+ * signal pad (entry `rank` is the local one); multicast: the NVLS multicast mapping of the buffer (multimem.ld_reduce / multimem.st
+ * through the switch) or NULL (peer loads and stores); n_floats % 4 == 0; pad: >= blocks * world u32 per rank and epochs: [blocks] u32
+ * of local device memory, both zeroed once before the first call; blocks: 1..148, identical on all ranks.  Ranks synchronise inside
+ * the kernel (epoch counters in device memory), so the launch is CUDA-graph replayable. */
+int occnerf_allreduce_sum_f32(const void *const *peer_bufs_host, const void *const *peer_pads_host, void *multicast, long n_floats,
+                              int rank, int world, int blocks, void *epochs, occnerf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "occnerf_visibility_hits": [_vp, _vp, _vp, _i, _i, _f, _vp, _i, _i, _vp, _vp, _vp],
     "occnerf_generate_rays": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "occnerf_unpack_image": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
+    "occnerf_allreduce_sum_f32": [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp],
 }
 EXPORTED = sorted(list(_SIGNATURES) + ["occnerf_last_error", "occnerf_abi_version", "occnerf_mlp_packed_bytes",
                                            "occnerf_rays_scratch_bytes", "occnerf_warp_packed_floats"])

@@ -122,6 +122,103 @@ class GradReducer:
             hits.clamp_(max=1.0)                               # votes are 0/1: any rank's vote counts once
 
 
+class SwitchReducer:
+    """GradReducer's job as ONE hand-written kernel over NVSwitch peer memory (csrc/collective.cu, occnerf_allreduce_sum_f32)
+    instead of NCCL calls: a two-shot sum in which the switch itself adds the ranks' copies (multimem.ld_reduce / multimem.st on the
+    NVLS multicast mapping; peer loads and stores where no multicast mapping exists).
+
+    All gradients of a step live in one flat fp32 buffer in symmetric memory (torch.distributed._symmetric_memory does the
+    allocation and the handle exchange -- plumbing; the data path is the kernel):
+        [ table | bucket ]
+      * `table_view` is bound as `Network.emb_grad_out`: occnerf_hashgrid_backward scatters the 59 MiB table gradient straight into
+        it (no copy in, no copy out; the owner zeroes it at the start of a step);
+      * every other gradient (MLP, point_dist, weight volume / decoder weights, compacted where structurally zero) and the 0/1
+        visibility votes are copied into the bucket by one multi-tensor copy and back by another.
+    The ranks synchronise inside the kernel, not on the host and not through a communicator stream, so the launch sits in the
+    compute stream like any other kernel and the whole training step -- collective included -- replays from ONE CUDA graph at
+    every rank count."""
+
+    capturable = True
+
+    def __init__(self, table_numel: int, bucket_numel: int, device, group=None, blocks: int = 64, active: dict | None = None):
+        import torch.distributed._symmetric_memory as symm
+        from occnerf_b200 import _lib
+        _lib.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 8:
+            raise RuntimeError("SwitchReducer: at most 8 ranks (one NVSwitch domain)")
+        self.active = dict(active or {})
+        self.blocks = blocks
+        self.table_numel = (table_numel + 3) // 4 * 4
+        self.capacity = self.table_numel + (bucket_numel + 3) // 4 * 4
+        self.flat = symm.empty(self.capacity, dtype=torch.float32, device=device)
+        self.flat.zero_()
+        self.hdl = symm.rendezvous(self.flat, self.group)
+        self.pad = symm.empty(blocks * 8, dtype=torch.int32, device=device)
+        self.pad.zero_()
+        self.hdl_pad = symm.rendezvous(self.pad, self.group)
+        self.epochs = torch.zeros(blocks, dtype=torch.int32, device=device)
+        self.multicast = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        bufs, pads = list(self.hdl.buffer_ptrs), list(self.hdl_pad.buffer_ptrs)
+        if bufs[self.rank] != self.flat.data_ptr() or pads[self.rank] != self.pad.data_ptr():
+            raise RuntimeError("SwitchReducer: symmetric-memory handle does not start at the tensor (unexpected allocator offset)")
+        import ctypes as C
+        self._bufs = (C.c_void_p * self.world)(*bufs)
+        self._pads = (C.c_void_p * self.world)(*pads)
+        self.table_view = self.flat[:table_numel]
+        self.bucket = self.flat[self.table_numel:]
+        self.views, self.key = None, None
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)                  # every rank's pad and buffer are zeroed before anybody signals into them
+        self.kind = "nvls-multimem" if self.multicast else "p2p"
+
+    def bind_table(self, net):
+        """Routes the embeddings' gradient of `net` into the symmetric buffer (zero it with `zero_table()` before each backward)."""
+        net.emb_grad_out = self.table_view
+
+    def zero_table(self):
+        self.table_view.zero_()
+
+    def __call__(self, grads, hits=None):
+        import ctypes as C
+        from occnerf_b200._lib import call, stream
+        compact, items = {}, []
+        for i, g in enumerate(grads):
+            if g is None:
+                continue
+            if g.data_ptr() == self.table_view.data_ptr():
+                continue                                        # already in place
+            if i in self.active:
+                c = g[self.active[i]].contiguous()
+                compact[i] = c
+                items.append(c)
+            else:
+                items.append(g)
+        if hits is not None:
+            items.append(hits)
+        key = tuple((tuple(g.shape), g.dtype) for g in items)
+        if key != self.key:
+            n = sum(g.numel() for g in items)
+            if n > self.bucket.numel():
+                raise RuntimeError(f"SwitchReducer: bucket of {self.bucket.numel()} floats is too small for {n}")
+            self.views, off = [], 0
+            for g in items:
+                self.views.append(self.bucket[off:off + g.numel()].view_as(g))
+                off += g.numel()
+            self.used, self.key = self.table_numel + (off + 3) // 4 * 4, key
+        if items:
+            torch._foreach_copy_(self.views, items)
+        call("occnerf_allreduce_sum_f32", C.cast(self._bufs, C.c_void_p), C.cast(self._pads, C.c_void_p), self.multicast or None,
+             self.used, self.rank, self.world, self.blocks, self.epochs.data_ptr(), stream())
+        if items:
+            torch._foreach_copy_(items, self.views)
+        for i, c in compact.items():
+            grads[i][self.active[i]] = c
+        if hits is not None:
+            hits.clamp_(max=1.0)                               # votes are 0/1: any rank's vote counts once
+
+
 def structural_zero_slices(params):
     """{position: index expression} for GradReducer(active=...): parameters whose gradient is structurally zero outside a block.
     A ConvTranspose3d(k=4, s=2, p=1) weight [Cin, Cout, 4, 4, 4] fed by a 1x1x1 input only ever uses taps 1..2 per axis."""

@@ -271,8 +271,11 @@ class _QueryFn(torch.autograd.Function):
         # the chunks of one _query_mlp call scatter into ONE table-gradient buffer (and one set of privatised vertex-gradient
         # replicas); the chunk whose backward runs last hands it to autograd, the others contribute None (= zero).  That
         # replaces a 59 MiB memset + a 59 MiB add per chunk by one memset per call.
+        # With `Network.emb_grad_out` bound (a persistent, caller-zeroed buffer -- under data parallelism a view of the symmetric
+        # all-reduce buffer) the table gradient is scattered straight into it and autograd receives None for the embeddings.
+        ext = sh.get("g_emb_ext")
         if "g_emb" not in sh:
-            sh["g_emb"] = torch.zeros(s["emb_shape"], device=g_raw.device, dtype=f32)
+            sh["g_emb"] = ext if ext is not None else torch.zeros(s["emb_shape"], device=g_raw.device, dtype=f32)
             sh["g_priv"] = torch.zeros(ops.AGG_BWD_COPIES, s["V"], 36, device=g_raw.device, dtype=f32)
         ops.hashgrid_backward(gXB.data_ptr() + 4 * M.H_OFF, M.XB_LD, 0, s["enc_in"], s["offsets"], s["scales"], sh["g_emb"],
                               s["emb_shape"][1], run_length=ops.HASH_BWD_RUN)           # samples are ordered along rays
@@ -283,6 +286,8 @@ class _QueryFn(torch.autograd.Function):
         g_emb = g_feats = None
         if sh["pending"] == 0:
             g_emb, g_feats = sh.pop("g_emb"), sh.pop("g_priv").sum(0)
+            if ext is not None:
+                g_emb = None
         return (None, None, g_feats, g_emb, None, None, *g_params)
 
 
@@ -318,8 +323,11 @@ class _VertexFn(torch.autograd.Function):
         g = g_feats.contiguous().float()
         V = g.shape[0]
         L, Cc = s["offsets"].shape[0] - 1, s["emb_shape"][1]
-        g_emb = torch.zeros(s["emb_shape"], device=g.device, dtype=f32)
+        ext = getattr(s["net"], "emb_grad_out", None)
+        g_emb = ext if ext is not None else torch.zeros(s["emb_shape"], device=g.device, dtype=f32)
         ops.hashgrid_backward(g.data_ptr(), 36, 0, s["v_in"], s["offsets"], s["scales"], g_emb, Cc)
+        if ext is not None:
+            g_emb = None
         g_v_in = ops.hashgrid_input_backward(g.data_ptr(), 36, 0, s["dy_dx"], V, 4, Cc, L)
         g_pd = ops.vertex_block_backward(st["point_base"], s["pd"], st["point_norms"], s["kidx"], s["net"].bound, g_v_in,
                                          g.data_ptr() + 4 * 32, 36)
@@ -494,7 +502,7 @@ class Network(nn.Module):
                 xyz_all = moved
         knn_all = self._knn(xyz_all, self._group_stride)
         cm = self.cnl_mlp.module
-        raws, shared = [], {}
+        raws, shared = [], {"g_emb_ext": getattr(self, "emb_grad_out", None)}
         for i in range(0, pos_flat.shape[0], chunk):
             raws.append(_QueryFn.apply(xyz_all[i:i + chunk], knn_all[i:i + chunk], feats36, cm.encoder.embeddings, self, shared,
                                        *cm.flat_params()))
@@ -578,6 +586,29 @@ class Network(nn.Module):
             else:
                 out[k] = v[0] if len(v) == 1 else torch.cat(v, 0)
         return out
+
+    # -- optional persistent destination of the hash-table gradient
+    def bind_emb_grad(self, buf=None):
+        """From now on both hash-grid backward calls of a step (sample chunks, per-vertex block) scatter into ONE persistent buffer
+        and autograd receives None for the embeddings: one 59 MiB memset per step instead of two and no 59 MiB accumulation add.
+        `buf`: flat or table-shaped fp32 tensor of the embeddings' size (data parallel: SwitchReducer.table_view, so that the
+        all-reduce finds the gradient in symmetric memory); None allocates one.  Call `zero_bound_grads()` before every backward
+        and `attach_bound_grads()` after it."""
+        emb = self.cnl_mlp.module.encoder.embeddings
+        if buf is None:
+            buf = torch.zeros(emb.numel(), device=emb.device, dtype=f32)
+        if buf.numel() != emb.numel() or buf.dtype != f32 or not buf.is_contiguous() or buf.device != emb.device:
+            raise RuntimeError("bind_emb_grad: the buffer must be a contiguous fp32 tensor of the embeddings' size on their device")
+        self.emb_grad_out = buf
+
+    def zero_bound_grads(self):
+        if getattr(self, "emb_grad_out", None) is not None:
+            self.emb_grad_out.zero_()
+
+    def attach_bound_grads(self):
+        if getattr(self, "emb_grad_out", None) is not None:
+            emb = self.cnl_mlp.module.encoder.embeddings
+            emb.grad = self.emb_grad_out.view_as(emb)
 
     def apply_visibility(self, hits):
         """The reference's in-place `point_counter[knn_index] += 1.` (network.py:517)."""

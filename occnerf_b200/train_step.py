@@ -23,10 +23,11 @@ class GraphedTrainStep:
         needs (e.g. target).  loss_fn(out_dict, static_batch) -> scalar tensor.
         optimizer: occnerf_b200.optim.ClipAdam (clips inside its step; pass max_norm=None) or a capturable torch optimizer
         (then `max_norm` is applied with clip_grad_norm_ first).
-        grad_sync(grads, hits): data-parallel hook between backward() and the optimizer.  With a hook the iteration is TWO graphs
-        -- forward + backward, and clip + optimizer + visibility update -- with the collectives launched eagerly in between: one
-        graph launch, a handful of NCCL calls, one graph launch per step.  (Capturing NCCL inside the step graph hung at 2 GPUs in
-        round 1; this keeps every rank count on the same launch mode.)"""
+        grad_sync(grads, hits): data-parallel hook between backward() and the optimizer.  A hook with `capturable = True`
+        (distributed.SwitchReducer: the all-reduce is one of our kernels, the ranks meet inside it) is captured with everything else:
+        ONE graph per step at every rank count.  Any other hook (NCCL) splits the iteration into TWO graphs -- forward + backward, and
+        clip + optimizer + visibility update -- with the collectives launched eagerly in between.  (Capturing NCCL inside the step
+        graph hung at 2 GPUs in round 1.)"""
         self.net, self.opt, self.loss_fn, self.iter_val, self.max_norm = net, optimizer, loss_fn, iter_val, max_norm
         self.grad_sync = grad_sync
         self.params = params if params is not None else [p for p in net.parameters() if p.requires_grad]
@@ -51,9 +52,11 @@ class GraphedTrainStep:
         from occnerf_b200 import _lib
         c0 = _lib.COUNTERS["launches"]
         self.graph = torch.cuda.CUDAGraph()
-        if self.grad_sync is None:
+        if self.grad_sync is None or getattr(self.grad_sync, "capturable", False):
             with torch.cuda.graph(self.graph):
                 self._forward_backward()
+                if self.grad_sync is not None:
+                    self.grad_sync([p.grad for p in self.params], self._hits)
                 self._optimize()
                 self.opt.zero_grad(set_to_none=True)
             self.graph_opt = None
@@ -74,11 +77,13 @@ class GraphedTrainStep:
 
     def _forward_backward(self):
         d, net = self.static, self.net
+        net.zero_bound_grads()
         out = net.forward((d["rays_o"], d["rays_d"]), d["dst_Rs"], d["dst_Ts"], d["cnl_gtfms"], d["priors"], dst_posevec=d["posevec"],
                           near=d["near"], far=d["far"], iter_val=self.iter_val, cnl_bbox_min_xyz=d["bmin"], cnl_bbox_scale_xyz=d["bscale"],
                           bgcolor=d["bg"])
         loss = self.loss_fn(out, d)
         loss.backward()
+        net.attach_bound_grads()
         self._hits = out.get("hits")
         self.loss_dev.copy_(loss.detach().reshape(1))
 

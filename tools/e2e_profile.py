@@ -6,9 +6,9 @@ import bench
 from occnerf_b200 import _lib
 _lib.load()
 dev = torch.device("cuda", 0)
-wl = bench.Workload(dev, 0, "tc3")
+wl = bench.Workload(dev, 0, os.environ.get("ENGINE", "tf32"))
 MODE = os.environ.get("MODE", "e2e")
-step = (lambda: wl.step_e2e(1)) if MODE == "e2e" else (lambda: wl.step_device(1))
+step = (lambda: bench.Workload.step_e2e(wl, 1)) if MODE == "e2e" else (lambda: wl.step_device(1))
 wl.step_e2e = lambda _w: step()
 for _ in range(3):
     wl.step_e2e(1)
