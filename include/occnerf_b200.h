@@ -360,6 +360,25 @@ int occnerf_unpack_image(const float *rgb, const float *alpha, const int *pixel_
                          const float *bgcolor_host, int fill, uint8_t *rgb8, uint8_t *alpha8, int *bad,
                          occnerf_stream_t stream);
 
+/* ---- per-frame prologue: the motion-weight volume decoder (deconv_vol_decoder.py:25-33, network_util.py:12-50), csrc/deconv.cu ----
+ * ConvTranspose3d(kernel 4, stride 2, padding 1), batch 1, as tf32 tensor-core GEMMs on the reference's weight layout
+ * W [Cin][Cout][4][4][4].  Activations are PRE-activations [C][D^3] (NCDHW, N = 1); the LeakyReLU(slope) between layers is applied
+ * when a layer loads its input (slope = 1: none).  D (input edge) must be a power of two <= 64.
+ * forward : Yout [Cout][(2D)^3] = bias + deconv(act(Yin)).
+ * backward: from dYout: dW (stored; reduced into a caller-zeroed buffer when accumulate_dw or w_splits > 1), dbias [Cout], and --
+ *           unless dYin is NULL -- dYin [Cin][D^3] = act'(Yin) * (data gradient) (caller-zeroed when d_splits > 1).
+ * splits: how many CTAs share one contraction (split-K with fp32 reductions); 1 = none.
+ * exact: 0 = one tf32 MMA per product (what the library path computes under torch.backends.cudnn.allow_tf32, the default);
+ *        1 = 3 x tf32 on (hi, lo) operand splits, fp32-grade (allow_tf32 = False). */
+int occnerf_deconv3d_forward(const float *W, const float *bias, const float *Yin, int Cin, int Cout, int D, float slope, int splits,
+                             int exact, float *Yout, occnerf_stream_t stream);
+int occnerf_deconv3d_backward(const float *W, const float *Yin, const float *dYout, int Cin, int Cout, int D, float slope, int w_splits,
+                              int d_splits, int accumulate_dw, int exact, float *dW, float *dbias, float *dYin, occnerf_stream_t stream);
+/* the 256 -> 1024 linear layer in front of the stack (pre-activation out; network_util.py:25-28), batch 1, and its gradients */
+int occnerf_decoder_linear_forward(const float *w, const float *b, const float *e, int n_out, int n_in, float *y, occnerf_stream_t stream);
+int occnerf_decoder_linear_backward(const float *w, const float *e, const float *g, int n_out, int n_in, float *dw, float *db, float *de,
+                                    occnerf_stream_t stream);
+
 /* ---- data-parallel training: gradient all-reduce as one kernel over NVSwitch peer memory (csrc/collective.cu) ----------------
  * Replaces the gradient reduction that nn.DataParallel / a NCCL all-reduce performs between backward() and the optimizer step
  * (core/train/trainers/occnerf/trainer.py:246-248).  In-place SUM over `world` ranks of a flat fp32 buffer that every rank holds in

@@ -110,6 +110,57 @@ def pose_refine(weights5, biases5, posevec69, dst_Rs):
     return out
 
 
+def _deconv_splits(tiles: int, k_steps: int) -> int:
+    """Split-K factor that brings a GEMM's grid to about two CTAs per SM (148 SMs), keeping at least 8 K-steps per split."""
+    return max(1, min((296 + tiles - 1) // tiles, k_steps // 8))
+
+
+def deconv3d_forward(W, bias, Yin, D, slope, exact=False):
+    """Yout [Cout, (2D)^3] = bias + ConvTranspose3d(4, 2, 1)(LeakyReLU_slope(Yin)); W [Cin, Cout, 4, 4, 4], Yin [Cin, D^3] (batch 1)."""
+    Cin, Cout = W.shape[0], W.shape[1]
+    V, Q = D ** 3, Cout * 64
+    Yout = torch.empty(Cout, 8 * V, device=W.device, dtype=f32)
+    tiles = ((Q + 127) // 128) if V <= 8 else ((Q + 63) // 64) * ((V + 63) // 64)
+    call("occnerf_deconv3d_forward", ptr(W, f32), ptr(bias, f32), ptr(Yin, f32), Cin, Cout, D, float(slope), _deconv_splits(tiles, Cin // 16),
+         int(exact), ptr(Yout), stream())
+    return Yout
+
+
+def deconv3d_backward(W, Yin, dYout, D, slope, exact=False, need_dyin=True, dW_out=None):
+    """-> (dW [Cin, Cout, 4, 4, 4], dbias [Cout], dYin [Cin, D^3] | None).  dW_out: caller's destination for dW (e.g. a view of the
+    data-parallel all-reduce buffer); it is overwritten."""
+    Cin, Cout = W.shape[0], W.shape[1]
+    V, Q = D ** 3, Cout * 64
+    w_splits = _deconv_splits(((Cin + 63) // 64) * ((Q + 63) // 64), max(V // 16, 1))
+    d_tiles = ((Cin + 127) // 128) if V <= 8 else ((Cin + 63) // 64) * ((V + 63) // 64)
+    d_splits = _deconv_splits(d_tiles, Q // 16)
+    if dW_out is None:
+        dW = torch.zeros_like(W) if w_splits > 1 else torch.empty_like(W)
+    else:
+        dW = dW_out
+        if w_splits > 1:
+            dW.zero_()
+    db = torch.empty(Cout, device=W.device, dtype=f32)
+    dYin = None
+    if need_dyin:
+        dYin = torch.zeros(Cin, V, device=W.device, dtype=f32) if d_splits > 1 else torch.empty(Cin, V, device=W.device, dtype=f32)
+    call("occnerf_deconv3d_backward", ptr(W, f32), ptr(Yin, f32), ptr(dYout, f32), Cin, Cout, D, float(slope), w_splits, d_splits, 0, int(exact),
+         ptr(dW), ptr(db), ptr(dYin) if need_dyin else None, stream())
+    return dW, db, dYin
+
+
+def decoder_linear_forward(w, b, e):
+    y = torch.empty(w.shape[0], device=w.device, dtype=f32)
+    call("occnerf_decoder_linear_forward", ptr(w, f32), ptr(b, f32), ptr(e, f32), w.shape[0], w.shape[1], ptr(y), stream())
+    return y
+
+
+def decoder_linear_backward(w, e, g):
+    dw, db, de = torch.empty_like(w), torch.empty(w.shape[0], device=w.device, dtype=f32), torch.empty(w.shape[1], device=w.device, dtype=f32)
+    call("occnerf_decoder_linear_backward", ptr(w, f32), ptr(e, f32), ptr(g, f32), w.shape[0], w.shape[1], ptr(dw), ptr(db), ptr(de), stream())
+    return dw, db, de
+
+
 def weight_volume_forward(logits, priors):
     """softmax over the channels of logits + log(priors), [channels, D, H, W]."""
     vol = torch.empty_like(logits)

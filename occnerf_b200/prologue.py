@@ -2,8 +2,10 @@
 volume decoder.  It runs once per frame and produces the ray path's inputs (`motion_scale_Rs`, `motion_Ts`,
 `motion_weights_vol`); SURVEY.md section 8(f) rank 1.  The modules keep the reference's names and parameters (checkpoints load).
 On a CUDA device the small stages are native kernels (csrc/prologue.cu): the 24-bone motion basis (one launch instead of ~50),
-the pose refiner MLP + Rodrigues (one launch), and the decoder's softmax(logits + log prior) with its gradient.  The decoder's
-five ConvTranspose3d (4.5 GMAC per frame at batch 1) remain library calls (cuDNN): not claimed as native, inside `e2e` only.
+the pose refiner MLP + Rodrigues (one launch), and the decoder's softmax(logits + log prior) with its gradient.  The decoder's five
+ConvTranspose3d exist natively too -- tf32 tensor-core GEMMs on the reference weight layout with their data and weight gradients
+(csrc/deconv.cu, 3.7 GMAC per pass at batch 1; `MotionWeightVolumeDecoder.native`) -- but the library form (cuDNN) is still the
+faster one and stays the default inside `e2e`.
 When the inputs of the first two require gradients (pose refinement training) they fall back to the differentiable torch form.
 
   MotionBasisComputer         core/utils/network_util.py:138-200   (FK chain evaluated level by level of the SMPL tree)
@@ -13,6 +15,7 @@ When the inputs of the first two require gradients (pose refinement training) th
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -82,6 +85,47 @@ class _VolumeSoftmax(torch.autograd.Function):
         return ops.weight_volume_backward(vol, g.contiguous().float()), None
 
 
+class _DecoderFn(torch.autograd.Function):
+    """MotionWeightVolumeDecoder on its native kernels (csrc/deconv.cu + the softmax of csrc/prologue.cu), batch 1:
+    const_embedding -> Linear(256, 1024) -> LeakyReLU -> 5 x ConvTranspose3d(4, 2, 1) (LeakyReLU between) -> softmax(. + log prior).
+    args: embedding [256], priors [25, 32, 32, 32], lin_w, lin_b, then (w, b) of the five transposed convolutions.
+    Pre-activations are kept for the backward pass; `exact` follows torch.backends.cudnn.allow_tf32 (False -> 3 x tf32)."""
+
+    @staticmethod
+    def forward(ctx, emb, priors, *wb):
+        from occnerf_b200 import ops
+        exact = not torch.backends.cudnn.allow_tf32
+        wb = [t.detach().contiguous().float() for t in wb]
+        e = emb.detach().contiguous().float()
+        ys = [ops.decoder_linear_forward(wb[0], wb[1], e)]                   # [1024] = [1024, 1^3]
+        D = 1
+        for l in range(5):
+            ys.append(ops.deconv3d_forward(wb[2 + 2 * l], wb[3 + 2 * l], ys[-1], D, 0.2, exact))
+            D *= 2
+        logits = ys.pop().view(-1, D, D, D)
+        vol = ops.weight_volume_forward(logits, priors.contiguous().float())
+        ctx.save_for_backward(e, vol, *ys, *wb)
+        ctx.exact = exact
+        ctx.grad_out = getattr(_DecoderFn, "grad_out", None)
+        return vol
+
+    @staticmethod
+    def backward(ctx, g_vol):
+        from occnerf_b200 import ops
+        e, vol, *rest = ctx.saved_tensors
+        ys, wb = rest[:5], rest[5:]
+        g = ops.weight_volume_backward(vol, g_vol.contiguous().float()).view(vol.shape[0], -1)
+        grads = [None] * 12
+        D = 16
+        for l in range(4, -1, -1):
+            dst = ctx.grad_out[2 + 2 * l] if ctx.grad_out is not None else None
+            dW, db, g = ops.deconv3d_backward(wb[2 + 2 * l], ys[l], g, D, 0.2, ctx.exact, need_dyin=True, dW_out=dst)
+            grads[2 + 2 * l], grads[3 + 2 * l] = dW, db
+            D //= 2
+        grads[0], grads[1], de = ops.decoder_linear_backward(wb[0], e, g.view(-1))
+        return (de, None, *grads)
+
+
 class MotionBasisComputer(nn.Module):
     def forward(self, dst_Rs, dst_Ts, cnl_gtfms):
         if dst_Rs.is_cuda and dst_Rs.shape[0] == 1 and not (dst_Rs.requires_grad or dst_Ts.requires_grad):
@@ -133,7 +177,19 @@ class MotionWeightVolumeDecoder(nn.Module):
         self.const_embedding = nn.Parameter(torch.randn(embedding_size))
         self.decoder = ConvDecoder3D(embedding_size, volume_size, total_bones + 1)
 
+    # True: the five transposed convolutions on the native kernels of csrc/deconv.cu (forward, data and weight gradients; parity-tested
+    # in tests/test_deconv_gpu.py).  They are complete and correct but not yet faster than the library at batch 1 (B200, forward +
+    # backward, tf32: 1.47 ms against cuDNN's 1.09 ms incl. its layout passes, gpurun_out/r2t_decoder_bench.json: the scatter-add
+    # epilogue of the two large layers and the register-staged operand loads are what is left to do), so `e2e` keeps the library form
+    # by default; OCCNERF_NATIVE_DECODER=1 switches.
+    native = os.environ.get("OCCNERF_NATIVE_DECODER", "0") != "0"
+
     def forward(self, motion_weights_priors, **_):
+        if self.native and self.const_embedding.is_cuda and motion_weights_priors.shape[0] == 1:
+            d = self.decoder
+            convs = [m for m in d.block_conv if isinstance(m, nn.ConvTranspose3d)]
+            wb = [d.block_mlp[0].weight, d.block_mlp[0].bias] + [t for c in convs for t in (c.weight, c.bias)]
+            return _DecoderFn.apply(self.const_embedding, motion_weights_priors[0], *wb)[None]
         logits = self.decoder(self.const_embedding[None])                  # library (cuDNN) transposed convolutions
         if logits.is_cuda and logits.shape[0] == 1:
             return _VolumeSoftmax.apply(logits[0], motion_weights_priors[0])[None]
