@@ -150,7 +150,13 @@ class _WithActive:
 
 
 class Workload:
-    def __init__(self, device, rank, engine, workload="zju387"):
+    def __init__(self, device, rank, engine, workload="zju387", frame_rank=None):
+        # frame_rank: which synthetic frame (patch placement) this rank renders.  Weak scaling keeps the per-GPU work FIXED: by
+        # default every rank renders the frame of rank 0 -- the workload of the one-GPU line -- with its own stratified jitter and its
+        # own targets, so the gradients differ and the all-reduce is real.  With rank-specific frames (--rank-frames distinct) the
+        # step time of the eight frames spreads over 7.72 .. 8.22 ms on ONE GPU (profiles/r02_frame_variance.json) and a synchronous
+        # data-parallel step follows the slowest frame: that is workload imbalance, not collective cost.
+        frame_rank = rank if frame_rank is None else frame_rank
         from occnerf_b200 import synthetic as S
         from occnerf_b200.network import RenderConfig
         self.S = S
@@ -161,7 +167,7 @@ class Workload:
         self.net = S.network_from_synthetic(sub, w, RenderConfig(perturb=1.0, mlp_engine=engine), device=device)
         self.net.train(True)
         self.net.install_prologue()
-        self.fr_host = S.make_frame(sub, mode="patch", n_patches=6, patch=32, seed=100 + rank, bbox_offset=self.spec["bbox_offset"],
+        self.fr_host = S.make_frame(sub, mode="patch", n_patches=6, patch=32, seed=100 + frame_rank, bbox_offset=self.spec["bbox_offset"],
                                     occlusion_band=self.spec["occlusion_band"])
         self.fr = S.frame_to(self.fr_host, device)
         self.vol = S.make_motion_weights_vol(sub.priors, seed=0).to(device).requires_grad_(True)
@@ -441,7 +447,9 @@ def main():
     ap.add_argument("--workload", default="zju387", choices=list(WORKLOADS), help="zju387 = BASELINE configs[1] (the headline); ocmotion = configs[3]")
     ap.add_argument("--ref-rays", type=int, default=1024, help="rays per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="time the e2e step eagerly instead of as one CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="time the steps eagerly instead of as CUDA graphs")
+    ap.add_argument("--rank-frames", default="same", choices=["same", "distinct"],
+                    help="N > 1: every rank renders the configs[1] frame of the one-GPU line (fixed per-GPU work; default) or its own frame")
     ap.add_argument("--profile-mode", action="store_true", help="device-resident steps only (no e2e, no CPU baseline): for ncu runs")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -460,11 +468,13 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from occnerf_b200 import _lib
     _lib.load()
-    wl = Workload(device, rank, args.engine, args.workload)
+    torch.manual_seed(1234 + rank)                   # rank-specific stratified jitter (torch.rand inside the path)
+    wl = Workload(device, rank, args.engine, args.workload, frame_rank=0 if args.rank_frames == "same" else rank)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=device)
     M = RAYS_PER_STEP * S_SAMPLES
 
-    # ---- value: ray path, inputs resident
+    # ---- value: ray path, inputs resident.  The step is captured ONCE as a CUDA graph and replayed (the data-parallel all-reduce is
+    # one of our kernels and is captured with it); an eager pass with per-call CUDA events feeds the kernel table and the launch count.
     sampler = ClockSampler(local)
     sampler.start()
     _lib.PROFILE = {}
@@ -474,9 +484,40 @@ def main():
     _lib.PROFILE, c0 = {}, dict(_lib.COUNTERS)
     if args.profile_mode:
         torch.cuda.profiler.start()              # `ncu --profile-from-start off` then sees the steady-state steps only
-    ms = timed_loop(lambda: wl.step_device(world), args.steps, 0, world, flush)
+    ms_eager = timed_loop(lambda: wl.step_device(world), args.steps, 0, world, flush)
     if args.profile_mode:
         torch.cuda.profiler.stop()
+    value_launch = "eager"
+    ms = ms_eager
+    if not args.no_graph and not args.profile_mode and getattr(getattr(wl, "reducer", None), "capturable", world == 1):
+        ok = 1
+        try:
+            prof_keep, _lib.PROFILE = _lib.PROFILE, None
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                wl.step_device(world)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g_value = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_value):
+                wl.step_device(world)
+            _lib.PROFILE = prof_keep
+        except Exception as exc:
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            print(f"bench.py: CUDA-graph capture of the device-resident step failed ({type(exc).__name__}: {exc}); keeping the eager timing", file=sys.stderr)
+            ok = 0
+        if world > 1:
+            import torch.distributed as dist
+            flag = torch.tensor([ok], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if ok:
+            prof_keep, _lib.PROFILE = _lib.PROFILE, None
+            ms = timed_loop(lambda: g_value.replay(), args.steps, args.warmup, world, flush)
+            _lib.PROFILE = prof_keep
+            value_launch = "cuda_graph"
     launches = (_lib.COUNTERS["launches"] - c0["launches"]) / args.steps
     profile, _lib.PROFILE = _lib.PROFILE, None
     clocks = sampler.stop()
@@ -532,6 +573,8 @@ def main():
             "config": {"workload": wl.spec["name"], "rays_per_step_per_gpu": RAYS_PER_STEP, "samples_per_ray": S_SAMPLES,
                        "mlp_engine": args.engine, "l2": "256 MiB flush write between timed steps", "timing": "cuda events per step, max over ranks",
                        "optimizer": "global-norm clip + Adam inside the step (occnerf_clip_adam_step)", "parallelism": f"dp{world}", "grad_allreduce": wl.reducer_kind,
+                       "launch": value_launch, "ms_per_step_eager": ms_eager,
+                       "rank_frames": args.rank_frames if world > 1 else "n/a",
                        "knn": "exact; pykeops' own reduction is un-vendored upstream (parity unpinned for that one call), ids checked against brute force"},
             "clocks": clocks,
             "e2e": {"value": world * RAYS_PER_STEP / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": wl.h2d_bytes,

@@ -140,7 +140,7 @@ class SwitchReducer:
 
     capturable = True
 
-    def __init__(self, table_numel: int, bucket_numel: int, device, group=None, blocks: int = 64, active: dict | None = None):
+    def __init__(self, table_numel: int, bucket_numel: int, device, group=None, blocks: int = 16, active: dict | None = None):
         import torch.distributed._symmetric_memory as symm
         from occnerf_b200 import _lib
         _lib.load()
