@@ -433,8 +433,19 @@ def roofline_for(row, peaks, M, engine="tc3"):
                 "traffic": None, "peak_source": peaks["source"] + " copy bandwidth"}
     bytes_ = hbm.get(name, 0.0) * per_launch_samples
     ach = bytes_ / (ms * 1e-3) / 1e9
-    return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-            "traffic": traffic, "peak_source": peaks["source"] + " copy bandwidth"}
+    out = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+           "traffic": traffic, "peak_source": peaks["source"] + " copy bandwidth"}
+    # The gather / scatter stages keep their tables in L2 by design (BASELINE north star: "HBM/L2 GB/s for the gather stages"): their
+    # algorithmic GATHERED bytes per sample (the packed warp kernel reads 24 32-byte cells) against the L2 output cap of
+    # /opt/skills/guides/B300_MICROARCH.md (~6300 B/clk over the chip at the SM clock), next to the HBM figure above.
+    l2 = {"occnerf_warp_forward_packed": 768.0, "occnerf_hashgrid_forward": 2048.0, "occnerf_hashgrid_backward": 2048.0,
+          "occnerf_aggregate_forward": 40 * 144.0, "occnerf_aggregate_backward": 40 * 144.0}
+    if name in l2:
+        cap = 6300.0 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e9
+        g = l2[name] * per_launch_samples / (ms * 1e-3) / 1e9
+        out["l2"] = {"gathered_bytes_per_sample": l2[name], "achieved_gbs": g, "cap_gbs": cap, "frac": g / cap,
+                     "cap_source": "B300_MICROARCH.md LTS throughput cap 6300 B/clk x SM clock"}
+    return out
 
 
 def main():
