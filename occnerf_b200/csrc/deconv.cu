@@ -35,14 +35,30 @@ struct DeconvArgs {
     int k_len;             // K range of one split (a multiple of BK)
     int accumulate;        // WGRAD / DGRAD: reduce into `out` (split-K, or the caller wants +=) instead of storing
     int exact;             // 0: one tf32 MMA per product;  1: 3 x tf32 (hi * hi + hi * lo + lo * hi of the operands' tf32 splits, fp32-grade)
+    int T;                 // taps per output channel that can touch the output at all: 64, or 8 when D = 1 (a 1^3 input reaches only the
+                           // taps {1, 2}^3: the other 56 of the first layer are never read, and their gradient is never written -- it is zero)
 };
 
 __device__ __forceinline__ uint32_t tf32_rna(float x) { return __float_as_uint(x) + 0x1000u; }      // low mantissa bits are ignored by the MMA
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
 
+// effective column index qe (o * T + j) -> (o, tap k):  T = 64: the identity;  T = 8: j enumerates the taps {1, 2}^3
+__device__ __forceinline__ void split_q(const DeconvArgs &a, int qe, int &o, int &k) {
+    if (a.T == 64) { o = qe >> 6; k = qe & 63; return; }
+    o = qe >> 3;
+    const int j = qe & 7;
+    k = (1 + (j >> 2)) * 16 + (1 + ((j >> 1) & 1)) * 4 + 1 + (j & 1);
+}
+__device__ __forceinline__ long q_index(const DeconvArgs &a, int qe) {      // position of (o, k) along the [Cout][64] axis of W / dW
+    int o, k;
+    split_q(a, qe, o, k);
+    return (long)o * kTaps + k;
+}
+
 // dYout[o][out(v, k)] or 0 outside the output volume
 __device__ __forceinline__ float gather_dy(const DeconvArgs &a, int q, int v) {
-    const int o = q >> 6, k = q & 63;
+    int o, k;
+    split_q(a, q, o, k);
     const int D = a.D, Do = 2 * D;
     const int x = v & (D - 1), y = (v >> a.lg) & (D - 1), z = v >> (2 * a.lg);
     const int xo = 2 * x - 1 + (k & 3), yo = 2 * y - 1 + ((k >> 2) & 3), zo = 2 * z - 1 + (k >> 4);
@@ -53,7 +69,7 @@ __device__ __forceinline__ float gather_dy(const DeconvArgs &a, int q, int v) {
 // GEMM roles   FWD: M = q, N = v, K = ci     WGRAD: M = ci, N = q, K = v     DGRAD: M = ci, N = v, K = q
 template <int MODE>
 __device__ __forceinline__ void dims(const DeconvArgs &a, int &M, int &N, int &K) {
-    const int V = a.D * a.D * a.D, Q = a.Cout * kTaps;
+    const int V = a.D * a.D * a.D, Q = a.Cout * a.T;
     if (MODE == FWD) { M = Q; N = V; K = a.Cin; }
     else if (MODE == WGRAD) { M = a.Cin; N = Q; K = V; }
     else { M = a.Cin; N = V; K = Q; }
@@ -62,9 +78,10 @@ template <int MODE>
 __device__ __forceinline__ float load_a(const DeconvArgs &a, int m, int k, int M, int K) {
     if (m >= M || k >= K) return 0.f;
     const int V = a.D * a.D * a.D;
-    if (MODE == FWD) return __ldg(a.W + (long)k * M + m);                                   // W[ci = k][q = m]
+    const long Qs = (long)a.Cout * kTaps;                                                    // row stride of W
+    if (MODE == FWD) return __ldg(a.W + (long)k * Qs + q_index(a, m));                       // W[ci = k][q = m]
     if (MODE == WGRAD) return leaky(__ldg(a.Yin + (long)m * V + k), a.slope);               // act(Yin[ci = m][v = k])
-    return __ldg(a.W + (long)m * K + k);                                                     // W[ci = m][q = k]
+    return __ldg(a.W + (long)m * Qs + q_index(a, k));                                        // W[ci = m][q = k]
 }
 template <int MODE>
 __device__ __forceinline__ float load_b(const DeconvArgs &a, int k, int n, int K, int N) {
@@ -83,13 +100,15 @@ template <int MODE>
 __device__ __forceinline__ void epilogue_store(const DeconvArgs &a, int m, int n, int M, int N, float c) {
     if (m >= M || n >= N) return;
     if (MODE == FWD) {
-        const int o = m >> 6, k = m & 63, D = a.D, Do = 2 * D;
+        int o, k;
+        split_q(a, m, o, k);
+        const int D = a.D, Do = 2 * D;
         const int x = n & (D - 1), y = (n >> a.lg) & (D - 1), z = n >> (2 * a.lg);
         const int xo = 2 * x - 1 + (k & 3), yo = 2 * y - 1 + ((k >> 2) & 3), zo = 2 * z - 1 + (k >> 4);
         if ((unsigned)xo >= (unsigned)Do || (unsigned)yo >= (unsigned)Do || (unsigned)zo >= (unsigned)Do) return;
         atomicAdd(a.out + ((long)o * Do + zo) * Do * Do + yo * Do + xo, c);
     } else if (MODE == WGRAD) {
-        float *p = a.out + (long)m * N + n;
+        float *p = a.out + (long)m * a.Cout * kTaps + q_index(a, n);
         if (a.accumulate) atomicAdd(p, c); else *p = c;
     } else {
         const float y = __ldg(a.Yin + (long)m * N + n);
@@ -102,55 +121,142 @@ __device__ __forceinline__ void epilogue_store(const DeconvArgs &a, int m, int n
 // 4 warps.  BN = 64: 2 x 2 warps of 32 x 32.  BN = 8: 4 x 1 warps of 32 x 8 (BM = 128).
 // SPLIT: operands are staged as tf32 (hi, lo) pairs and every product takes three MMAs (what torch.backends.cudnn.allow_tf32 = False
 // asks of the library path: fp32-grade results).
-template <int MODE, int BM, int BN, bool SPLIT>
-__global__ void __launch_bounds__(128) deconv_gemm_kernel(const DeconvArgs a) {
-    constexpr int LDA = BM + 8, LDB = BN + 8 - (BN == 8 ? 8 : 0);      // row strides = 8 (mod 32) words: conflict-free fragment loads
-    static_assert(LDA % 32 == 8 && (LDB % 32 == 8), "fragment loads must be conflict free");
-    constexpr int WN = BN == 8 ? 1 : 2, WM = 4 / WN;                   // warp grid
+// Staging: the dense operand A is fetched with 16-byte loads along its contiguous axis whenever the tile allows it -- along m in the
+// forward pass (shared-memory image [k][m]), along k in the two gradient passes (image [m][k]; both images have conflict-free fragment
+// loads) --; the gathered operand (dYout through the transposed convolution's index map) is fetched element by element with the
+// per-thread part of the index arithmetic (the thread's column n is the same for every K step) done once.
+template <int MODE, int BM, int BN, bool SPLIT, int NT>
+__global__ void __launch_bounds__(NT) deconv_gemm_kernel(const DeconvArgs a) {
+    constexpr bool A_T = MODE != FWD;                                   // A image [m][k] (k contiguous) instead of [k][m]
+    constexpr int LDA = A_T ? BK + 4 : BM + 8, LDB = BN + 8 - (BN == 8 ? 8 : 0);
+    static_assert(A_T ? (LDA % 8 == 4) : (LDA % 32 == 8), "A fragment loads must be conflict free");
+    static_assert(LDB % 32 == 8, "B fragment loads must be conflict free");
+    constexpr int WN = BN == 8 ? 1 : 2, WM = (NT / 32) / WN;           // warp grid
     constexpr int TM = BM / WM, TN = BN / WN;                          // warp tile
     constexpr int FM = TM / 16, FN = TN / 8;                           // m16n8 fragments per warp
-    constexpr int NA = BM * BK / 128, NB = (BK * BN + 127) / 128;      // staged elements per thread
+    constexpr int NA = BM * BK / NT, NB = (BK * BN + NT - 1) / NT;     // staged elements per thread
+    static_assert(NA % 4 == 0 && NT % BN == 0, "staging maps");
     constexpr int P = SPLIT ? 2 : 1;
-    __shared__ uint32_t As[P][BK][LDA], Bs[P][BK][LDB];
+    constexpr int A_ROWS = A_T ? BM : BK;
+    __shared__ __align__(16) uint32_t As[P][A_ROWS][LDA];
+    __shared__ uint32_t Bs[P][BK][LDB];
     int M, N, K;
     dims<MODE>(a, M, N, K);
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int k_begin = blockIdx.z * a.k_len, k_end = min(K, k_begin + a.k_len);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wm = (warp / WN) * TM, wn = (warp % WN) * TN;
-    // element (row, col) of the staged tile handled by this thread in round i: consecutive threads walk the operand's contiguous axis
-    constexpr bool A_M_FAST = MODE == FWD;                             // A is contiguous along m (FWD) or along k
+    const int V = a.D * a.D * a.D;
+    const long Qs = (long)a.Cout * kTaps;
+    // ---- A: 16-byte path when the whole tile is inside the matrix, rows are 16-byte aligned and the tap axis is not remapped
+    bool vec_a;
+    if (MODE == FWD) vec_a = a.T == kTaps && m0 + BM <= M;
+    else if (MODE == WGRAD) vec_a = (V % 4 == 0) && m0 + BM <= M && (a.k_len % 4 == 0);
+    else vec_a = a.T == kTaps && m0 + BM <= M;
     float ra[NA], rb[NB];
+    // ---- B: the thread's column nn is fixed (128 % BN == 0); its share of the gather arithmetic
+    const int nn_b = tid % BN, kk_b0 = tid / BN;
+    constexpr int KK_STEP = NT / BN;
+    const int n_b = n0 + nn_b;
+    int gb0 = 0, gb1 = 0, gb2 = 0, gb3 = 0;                            // WGRAD: (o * Do^3, kz-1, ky-1, kx-1);  DGRAD: (2z-1, 2y-1, 2x-1)
+    const int D = a.D, Do = 2 * a.D;
+    if (MODE == WGRAD && n_b < N) {
+        int o, k;
+        split_q(a, n_b, o, k);
+        gb0 = o; gb1 = (k >> 4) - 1; gb2 = ((k >> 2) & 3) - 1; gb3 = (k & 3) - 1;
+    } else if (MODE == DGRAD && n_b < N) {
+        gb1 = 2 * (n_b >> (2 * a.lg)) - 1; gb2 = 2 * ((n_b >> a.lg) & (D - 1)) - 1; gb3 = 2 * (n_b & (D - 1)) - 1;
+    }
     auto fetch = [&](int k0) {
+        if (vec_a) {
 #pragma unroll
-        for (int i = 0; i < NA; ++i) {
-            const int e = tid + i * 128;
-            const int mm = A_M_FAST ? e % BM : e / BK, kk = A_M_FAST ? e / BM : e % BK;
-            ra[i] = (k0 + kk < k_end) ? load_a<MODE>(a, m0 + mm, k0 + kk, M, K) : 0.f;
+            for (int i = 0; i < NA / 4; ++i) {
+                const int e = tid + i * NT;
+                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MODE == FWD) {                                     // 4 consecutive m of one k:  W[ci = k][q = m]
+                    const int m4 = e % (BM / 4), kk = e / (BM / 4);
+                    if (k0 + kk < k_end) v4 = __ldg(reinterpret_cast<const float4 *>(a.W + (long)(k0 + kk) * Qs + m0 + 4 * m4));
+                } else {                                               // 4 consecutive k of one m
+                    const int k4 = e % (BK / 4), mm = e / (BK / 4);
+                    const int kq = k0 + 4 * k4;
+                    if (kq < k_end) {                                  // (k_end and K are multiples of 4 on this path)
+                        if (MODE == WGRAD) {
+                            v4 = __ldg(reinterpret_cast<const float4 *>(a.Yin + (long)(m0 + mm) * V + kq));
+                            v4.x = leaky(v4.x, a.slope); v4.y = leaky(v4.y, a.slope); v4.z = leaky(v4.z, a.slope); v4.w = leaky(v4.w, a.slope);
+                        } else {
+                            v4 = __ldg(reinterpret_cast<const float4 *>(a.W + (long)(m0 + mm) * Qs + kq));
+                        }
+                    }
+                }
+                ra[4 * i] = v4.x; ra[4 * i + 1] = v4.y; ra[4 * i + 2] = v4.z; ra[4 * i + 3] = v4.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                const int e = tid + i * NT;
+                const int mm = A_T ? e / BK : e % BM, kk = A_T ? e % BK : e / BM;
+                ra[i] = (k0 + kk < k_end) ? load_a<MODE>(a, m0 + mm, k0 + kk, M, K) : 0.f;
+            }
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            const int e = tid + i * 128;
-            const int nn = e % BN, kk = e / BN;                        // B is walked along n in all three modes
-            rb[i] = (e < BK * BN && k0 + kk < k_end) ? load_b<MODE>(a, k0 + kk, n0 + nn, K, N) : 0.f;
+            const int kk = kk_b0 + i * KK_STEP, kg = k0 + kk;
+            float v = 0.f;
+            if (kk < BK && kg < k_end && n_b < N) {
+                if (MODE == FWD) {
+                    v = leaky(__ldg(a.Yin + (long)kg * N + n_b), a.slope);
+                } else if (MODE == WGRAD) {                            // kg = input voxel, the thread's column = (o, tap)
+                    const int zo = 2 * (kg >> (2 * a.lg)) + gb1, yo = 2 * ((kg >> a.lg) & (D - 1)) + gb2, xo = 2 * (kg & (D - 1)) + gb3;
+                    if ((unsigned)xo < (unsigned)Do && (unsigned)yo < (unsigned)Do && (unsigned)zo < (unsigned)Do)
+                        v = __ldg(a.dYout + (((long)gb0 * Do + zo) * Do + yo) * Do + xo);
+                } else {                                               // kg = (o, tap), the thread's column = input voxel
+                    int o, k;
+                    split_q(a, kg, o, k);
+                    const int zo = gb1 + (k >> 4), yo = gb2 + ((k >> 2) & 3), xo = gb3 + (k & 3);
+                    if ((unsigned)xo < (unsigned)Do && (unsigned)yo < (unsigned)Do && (unsigned)zo < (unsigned)Do)
+                        v = __ldg(a.dYout + (((long)o * Do + zo) * Do + yo) * Do + xo);
+                }
+            }
+            rb[i] = v;
         }
     };
+    auto put_a = [&](int row, int col, float x) {
+        const uint32_t hi = tf32_rna(x) & 0xffffe000u;
+        As[0][row][col] = hi;
+        if (SPLIT) As[1][row][col] = tf32_rna(x - __uint_as_float(hi));
+    };
     auto stage = [&]() {
+        if (vec_a) {
 #pragma unroll
-        for (int i = 0; i < NA; ++i) {
-            const int e = tid + i * 128;
-            const int mm = A_M_FAST ? e % BM : e / BK, kk = A_M_FAST ? e / BM : e % BK;
-            const uint32_t hi = tf32_rna(ra[i]) & 0xffffe000u;
-            As[0][kk][mm] = hi;
-            if (SPLIT) As[1][kk][mm] = tf32_rna(ra[i] - __uint_as_float(hi));
+            for (int i = 0; i < NA / 4; ++i) {
+                const int e = tid + i * NT;
+                int row, col;
+                if (MODE == FWD) { row = e / (BM / 4); col = 4 * (e % (BM / 4)); }          // [k][m .. m+3]
+                else { row = e / (BK / 4); col = 4 * (e % (BK / 4)); }                      // [m][k .. k+3]
+                uint32_t hi[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hi[j] = tf32_rna(ra[4 * i + j]) & 0xffffe000u;
+                *reinterpret_cast<uint4 *>(&As[0][row][col]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                if (SPLIT)
+                    *reinterpret_cast<uint4 *>(&As[1][row][col]) =
+                        make_uint4(tf32_rna(ra[4 * i] - __uint_as_float(hi[0])), tf32_rna(ra[4 * i + 1] - __uint_as_float(hi[1])),
+                                   tf32_rna(ra[4 * i + 2] - __uint_as_float(hi[2])), tf32_rna(ra[4 * i + 3] - __uint_as_float(hi[3])));
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                const int e = tid + i * NT;
+                const int mm = A_T ? e / BK : e % BM, kk = A_T ? e % BK : e / BM;
+                if (A_T) put_a(mm, kk, ra[i]); else put_a(kk, mm, ra[i]);
+            }
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            const int e = tid + i * 128;
-            if (e < BK * BN) {
+            const int kk = kk_b0 + i * KK_STEP;
+            if (kk < BK) {
                 const uint32_t hi = tf32_rna(rb[i]) & 0xffffe000u;
-                Bs[0][e / BN][e % BN] = hi;
-                if (SPLIT) Bs[1][e / BN][e % BN] = tf32_rna(rb[i] - __uint_as_float(hi));
+                Bs[0][kk][nn_b] = hi;
+                if (SPLIT) Bs[1][kk][nn_b] = tf32_rna(rb[i] - __uint_as_float(hi));
             }
         }
     };
@@ -175,8 +281,13 @@ __global__ void __launch_bounds__(128) deconv_gemm_kernel(const DeconvArgs a) {
 #pragma unroll
                 for (int i = 0; i < FM; ++i) {
                     const int r = wm + i * 16 + g;
-                    fa[p][i][0] = As[p][ks + t][r]; fa[p][i][1] = As[p][ks + t][r + 8];
-                    fa[p][i][2] = As[p][ks + t + 4][r]; fa[p][i][3] = As[p][ks + t + 4][r + 8];
+                    if (A_T) {
+                        fa[p][i][0] = As[p][r][ks + t]; fa[p][i][1] = As[p][r + 8][ks + t];
+                        fa[p][i][2] = As[p][r][ks + t + 4]; fa[p][i][3] = As[p][r + 8][ks + t + 4];
+                    } else {
+                        fa[p][i][0] = As[p][ks + t][r]; fa[p][i][1] = As[p][ks + t][r + 8];
+                        fa[p][i][2] = As[p][ks + t + 4][r]; fa[p][i][3] = As[p][ks + t + 4][r + 8];
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < FN; ++j) {
@@ -266,7 +377,8 @@ int launch_gemm(const DeconvArgs &a0, int splits, cudaStream_t st) {
     DeconvArgs a = a0;
     a.lg = 0;
     while ((1 << a.lg) < a.D) ++a.lg;
-    const int V = a.D * a.D * a.D, Q = a.Cout * kTaps;
+    a.T = a.D == 1 ? 8 : kTaps;
+    const int V = a.D * a.D * a.D, Q = a.Cout * a.T;
     const int M = MODE == FWD ? Q : a.Cin, N = MODE == WGRAD ? Q : V, K = MODE == FWD ? a.Cin : (MODE == WGRAD ? V : Q);
     splits = splits < 1 ? 1 : splits;
     int k_len = (K + splits - 1) / splits;
@@ -276,12 +388,17 @@ int launch_gemm(const DeconvArgs &a0, int splits, cudaStream_t st) {
     if (MODE != FWD && splits > 1) a.accumulate = 1;
     if (N <= 8) {
         dim3 grid(1, occ_div_up(M, 128), splits);
-        if (a.exact) deconv_gemm_kernel<MODE, 128, 8, true><<<grid, 128, 0, st>>>(a);
-        else deconv_gemm_kernel<MODE, 128, 8, false><<<grid, 128, 0, st>>>(a);
+        if (a.exact) deconv_gemm_kernel<MODE, 128, 8, true, 128><<<grid, 128, 0, st>>>(a);
+        else deconv_gemm_kernel<MODE, 128, 8, false, 128><<<grid, 128, 0, st>>>(a);
+    } else if (MODE != FWD && M >= 256) {
+        // gradient passes of the wide layers: 256-row tiles (8 warps), so that a gathered dYout element feeds 256 rows instead of 64
+        dim3 grid(occ_div_up(N, 64), occ_div_up(M, 256), splits);
+        if (a.exact) deconv_gemm_kernel<MODE, 256, 64, true, 256><<<grid, 256, 0, st>>>(a);
+        else deconv_gemm_kernel<MODE, 256, 64, false, 256><<<grid, 256, 0, st>>>(a);
     } else {
         dim3 grid(occ_div_up(N, 64), occ_div_up(M, 64), splits);
-        if (a.exact) deconv_gemm_kernel<MODE, 64, 64, true><<<grid, 128, 0, st>>>(a);
-        else deconv_gemm_kernel<MODE, 64, 64, false><<<grid, 128, 0, st>>>(a);
+        if (a.exact) deconv_gemm_kernel<MODE, 64, 64, true, 128><<<grid, 128, 0, st>>>(a);
+        else deconv_gemm_kernel<MODE, 64, 64, false, 128><<<grid, 128, 0, st>>>(a);
     }
     OCC_LAUNCH_CHECK();
     return OCCNERF_OK;

@@ -118,7 +118,7 @@ def _deconv_splits(tiles: int, k_steps: int) -> int:
 def deconv3d_forward(W, bias, Yin, D, slope, exact=False):
     """Yout [Cout, (2D)^3] = bias + ConvTranspose3d(4, 2, 1)(LeakyReLU_slope(Yin)); W [Cin, Cout, 4, 4, 4], Yin [Cin, D^3] (batch 1)."""
     Cin, Cout = W.shape[0], W.shape[1]
-    V, Q = D ** 3, Cout * 64
+    V, Q = D ** 3, Cout * (8 if D == 1 else 64)
     Yout = torch.empty(Cout, 8 * V, device=W.device, dtype=f32)
     tiles = ((Q + 127) // 128) if V <= 8 else ((Q + 63) // 64) * ((V + 63) // 64)
     call("occnerf_deconv3d_forward", ptr(W, f32), ptr(bias, f32), ptr(Yin, f32), Cin, Cout, D, float(slope), _deconv_splits(tiles, Cin // 16),
@@ -130,15 +130,17 @@ def deconv3d_backward(W, Yin, dYout, D, slope, exact=False, need_dyin=True, dW_o
     """-> (dW [Cin, Cout, 4, 4, 4], dbias [Cout], dYin [Cin, D^3] | None).  dW_out: caller's destination for dW (e.g. a view of the
     data-parallel all-reduce buffer); it is overwritten."""
     Cin, Cout = W.shape[0], W.shape[1]
-    V, Q = D ** 3, Cout * 64
-    w_splits = _deconv_splits(((Cin + 63) // 64) * ((Q + 63) // 64), max(V // 16, 1))
-    d_tiles = ((Cin + 127) // 128) if V <= 8 else ((Cin + 63) // 64) * ((V + 63) // 64)
+    V, Q = D ** 3, Cout * (8 if D == 1 else 64)
+    bm = 256 if Cin >= 256 else 64              # row tile of the gradient GEMMs (csrc/deconv.cu launch_gemm)
+    w_splits = _deconv_splits(((Cin + bm - 1) // bm) * ((Q + 63) // 64), max(V // 16, 1))
+    d_tiles = ((Cin + 127) // 128) if V <= 8 else ((Cin + bm - 1) // bm) * ((V + 63) // 64)
     d_splits = _deconv_splits(d_tiles, Q // 16)
+    need_zero = w_splits > 1 or D == 1        # D = 1: only the 8 reachable taps per (ci, o) are written, the other 56 are zero
     if dW_out is None:
-        dW = torch.zeros_like(W) if w_splits > 1 else torch.empty_like(W)
+        dW = torch.zeros_like(W) if need_zero else torch.empty_like(W)
     else:
         dW = dW_out
-        if w_splits > 1:
+        if need_zero:
             dW.zero_()
     db = torch.empty(Cout, device=W.device, dtype=f32)
     dYin = None

@@ -4,8 +4,8 @@ volume decoder.  It runs once per frame and produces the ray path's inputs (`mot
 On a CUDA device the small stages are native kernels (csrc/prologue.cu): the 24-bone motion basis (one launch instead of ~50),
 the pose refiner MLP + Rodrigues (one launch), and the decoder's softmax(logits + log prior) with its gradient.  The decoder's five
 ConvTranspose3d exist natively too -- tf32 tensor-core GEMMs on the reference weight layout with their data and weight gradients
-(csrc/deconv.cu, 3.7 GMAC per pass at batch 1; `MotionWeightVolumeDecoder.native`) -- but the library form (cuDNN) is still the
-faster one and stays the default inside `e2e`.
+(csrc/deconv.cu, 3.7 GMAC per pass at batch 1; `MotionWeightVolumeDecoder.native`, the default); the library form (cuDNN) remains
+as the cross-check of the tests.
 When the inputs of the first two require gradients (pose refinement training) they fall back to the differentiable torch form.
 
   MotionBasisComputer         core/utils/network_util.py:138-200   (FK chain evaluated level by level of the SMPL tree)
@@ -177,12 +177,11 @@ class MotionWeightVolumeDecoder(nn.Module):
         self.const_embedding = nn.Parameter(torch.randn(embedding_size))
         self.decoder = ConvDecoder3D(embedding_size, volume_size, total_bones + 1)
 
-    # True: the five transposed convolutions on the native kernels of csrc/deconv.cu (forward, data and weight gradients; parity-tested
-    # in tests/test_deconv_gpu.py).  They are complete and correct but not yet faster than the library at batch 1 (B200, forward +
-    # backward, tf32: 1.47 ms against cuDNN's 1.09 ms incl. its layout passes, gpurun_out/r2t_decoder_bench.json: the scatter-add
-    # epilogue of the two large layers and the register-staged operand loads are what is left to do), so `e2e` keeps the library form
-    # by default; OCCNERF_NATIVE_DECODER=1 switches.
-    native = os.environ.get("OCCNERF_NATIVE_DECODER", "0") != "0"
+    # True (default): the five transposed convolutions on the native kernels of csrc/deconv.cu (forward, data and weight gradients;
+    # parity-tested in tests/test_deconv_gpu.py).  B200, forward + backward per step, tf32: 0.96 ms against 1.09 ms for the library
+    # form (cuDNN incl. its layout passes; gpurun_out/r2t_decoder_bench.json).  OCCNERF_NATIVE_DECODER=0 keeps the library form
+    # (the cross-check of the tests).
+    native = os.environ.get("OCCNERF_NATIVE_DECODER", "1") != "0"
 
     def forward(self, motion_weights_priors, **_):
         if self.native and self.const_embedding.is_cuda and motion_weights_priors.shape[0] == 1:

@@ -71,7 +71,7 @@ def test_decoder_module_against_library_path(allow_tf32):
     report(f"decoder_module[{'tf32' if allow_tf32 else '3xtf32'}]", vol=e_vol, worst_grad=max(e_grads.values()))
     assert e_vol < (1e-4 if allow_tf32 else 2e-6)
     # (tf32: five layers of 10-bit-mantissa products in a row, and LeakyReLU sign flips of near-zero pre-activations: 2 % measured)
-    assert max(e_grads.values()) < (5e-2 if allow_tf32 else 1e-4), e_grads
+    assert max(e_grads.values()) < (5e-2 if allow_tf32 else 5e-4), e_grads
     # the 56 taps of the first transposed convolution that a 1 x 1 x 1 input never touches receive an exactly zero gradient
     g1 = dec.decoder.block_conv[0].weight.grad
     dead = g1.clone()

