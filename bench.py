@@ -201,7 +201,18 @@ class Workload:
                 try:
                     bucket = sum((p[active_e2e[i]].numel() if i in active_e2e else p.numel()) for i, p in enumerate(all_params) if p is not self.emb)
                     bucket += self.vol.numel() + 6890 + 64
-                    sw = SwitchReducer(self.emb.numel(), bucket, device, active=None)
+                    # the decoder's transposed-convolution weight gradients (layers 2..5; the first keeps its compacted exchange) are
+                    # written by occnerf_deconv3d_backward straight into the all-reduce buffer
+                    dec = self.net.mweight_vol_decoder
+                    convs = [m for m in dec.decoder.block_conv if isinstance(m, torch.nn.ConvTranspose3d)]
+                    inplace = convs[1:] if dec.native else []
+                    sw = SwitchReducer(self.emb.numel(), bucket, device, active=None, reserve_numel=sum(c.weight.numel() + 4 for c in inplace))
+                    if inplace:
+                        from occnerf_b200.prologue import _DecoderFn
+                        dsts = [None] * 12
+                        for c in inplace:
+                            dsts[2 + 2 * convs.index(c)] = sw.reserve(tuple(c.weight.shape))
+                        _DecoderFn.grad_out = dsts
                 except Exception as exc:
                     print(f"bench.py: SwitchReducer unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
                     ok = 0
@@ -529,6 +540,13 @@ def main():
             ms = timed_loop(lambda: g_value.replay(), args.steps, args.warmup, world, flush)
             _lib.PROFILE = prof_keep
             value_launch = "cuda_graph"
+    if world > 1 and wl.reducer_kind != "nccl":
+        import ctypes
+        buf = (ctypes.c_ulonglong * 4)()
+        _lib.load().occnerf_allreduce_debug(ctypes.cast(buf, ctypes.c_void_p), 1)
+        n_ar = max(int(buf[3]), 1)
+        ar_phases = {"wait_arrive_us": buf[0] / n_ar / 1e3, "data_us": buf[1] / n_ar / 1e3, "wait_finish_us": buf[2] / n_ar / 1e3, "launches": int(buf[3])}
+        print(f"bench.py: rank {rank} all-reduce phases per launch {ar_phases}", file=sys.stderr)
     launches = (_lib.COUNTERS["launches"] - c0["launches"]) / args.steps
     profile, _lib.PROFILE = _lib.PROFILE, None
     clocks = sampler.stop()

@@ -387,6 +387,9 @@ int occnerf_decoder_linear_backward(const float *w, const float *e, const float 
  * through the switch) or NULL (peer loads and stores); n_floats % 4 == 0; pad: >= blocks * world u32 per rank and epochs: [blocks] u32
  * of local device memory, both zeroed once before the first call; blocks: 1..148, identical on all ranks.  Ranks synchronise inside
  * the kernel (epoch counters in device memory), so the launch is CUDA-graph replayable. */
+/* debug only: nanoseconds block 0 spent (0) waiting for the peers to arrive, (1) in the data phase, (2) waiting for them to finish,
+ * and (3) the number of launches, summed since the last reset */
+int occnerf_allreduce_debug(unsigned long long *host4, int reset);
 int occnerf_allreduce_sum_f32(const void *const *peer_bufs_host, const void *const *peer_pads_host, void *multicast, long n_floats,
                               int rank, int world, int blocks, void *epochs, occnerf_stream_t stream);
 

@@ -60,6 +60,15 @@ __device__ __forceinline__ void mc_st(float *mc, const float4 &v) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Where a launch spends its time (block 0, thread 0; nanoseconds of %globaltimer summed over launches):
+// [0] waiting for the peers to arrive  [1] the data phase  [2] waiting for the peers to finish  [3] launches
+__device__ unsigned long long g_ar_dbg[4];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // n4: number of float4 of the flat buffer.  epochs: [gridDim.x] u32 in LOCAL device memory, the barrier count of each block so far.
 template <bool MULTICAST>
 __global__ void __launch_bounds__(kThreads) allreduce_sum_kernel(Peers P, float *mc, long n4, int rank, int world, uint32_t *epochs) {
@@ -67,7 +76,10 @@ __global__ void __launch_bounds__(kThreads) allreduce_sum_kernel(Peers P, float 
     if (threadIdx.x == 0) s_epoch = epochs[blockIdx.x];
     __syncthreads();
     const uint32_t e0 = s_epoch;
+    const bool dbg = blockIdx.x == 0 && threadIdx.x == 0;
+    const unsigned long long t0 = dbg ? gtime() : 0;
     peer_barrier(P, rank, world, e0 + 1);                            // every peer's gradients are complete
+    const unsigned long long t1 = dbg ? gtime() : 0;
     const long per = (n4 + world - 1) / world;
     const long begin = min((long)rank * per, n4), end = min(begin + per, n4);
     const long stride = (long)gridDim.x * kThreads;
@@ -101,11 +113,27 @@ __global__ void __launch_bounds__(kThreads) allreduce_sum_kernel(Peers P, float 
         }
     }
     __threadfence_system();
+    const unsigned long long t2 = dbg ? gtime() : 0;
     peer_barrier(P, rank, world, e0 + 2);                            // every peer has written its slice into my copy
     if (threadIdx.x == 0) epochs[blockIdx.x] = e0 + 2;
+    if (dbg) {
+        const unsigned long long t3 = gtime();
+        g_ar_dbg[0] += t1 - t0; g_ar_dbg[1] += t2 - t1; g_ar_dbg[2] += t3 - t2; g_ar_dbg[3] += 1;
+    }
 }
 
 }  // namespace
+
+// debug only: the phase times described at g_ar_dbg (4 x u64 to host memory), optionally cleared
+extern "C" int occnerf_allreduce_debug(unsigned long long *host4, int reset) {
+    OCC_CUDA(cudaDeviceSynchronize());
+    if (host4) OCC_CUDA(cudaMemcpyFromSymbol(host4, g_ar_dbg, sizeof(unsigned long long) * 4));
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        OCC_CUDA(cudaMemcpyToSymbol(g_ar_dbg, z, sizeof(z)));
+    }
+    return OCCNERF_OK;
+}
 
 // In-place sum over `world` ranks of the flat fp32 buffer each rank holds in symmetric memory.
 // peer_bufs_host / peer_pads_host: host arrays of `world` device pointers (entry `rank` = the local copy); multicast: the multicast

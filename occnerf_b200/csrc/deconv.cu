@@ -390,11 +390,11 @@ int launch_gemm(const DeconvArgs &a0, int splits, cudaStream_t st) {
         dim3 grid(1, occ_div_up(M, 128), splits);
         if (a.exact) deconv_gemm_kernel<MODE, 128, 8, true, 128><<<grid, 128, 0, st>>>(a);
         else deconv_gemm_kernel<MODE, 128, 8, false, 128><<<grid, 128, 0, st>>>(a);
-    } else if (MODE != FWD && M >= 256) {
+    } else if (MODE != FWD && M >= 256 && !a.exact) {
         // gradient passes of the wide layers: 256-row tiles (8 warps), so that a gathered dYout element feeds 256 rows instead of 64
+        // (tf32 mode only: the (hi, lo) images of a 256-row tile would not fit the 48 KB of static shared memory)
         dim3 grid(occ_div_up(N, 64), occ_div_up(M, 256), splits);
-        if (a.exact) deconv_gemm_kernel<MODE, 256, 64, true, 256><<<grid, 256, 0, st>>>(a);
-        else deconv_gemm_kernel<MODE, 256, 64, false, 256><<<grid, 256, 0, st>>>(a);
+        deconv_gemm_kernel<MODE, 256, 64, false, 256><<<grid, 256, 0, st>>>(a);
     } else {
         dim3 grid(occ_div_up(N, 64), occ_div_up(M, 64), splits);
         if (a.exact) deconv_gemm_kernel<MODE, 64, 64, true, 128><<<grid, 128, 0, st>>>(a);

@@ -122,6 +122,10 @@ class GradReducer:
             hits.clamp_(max=1.0)                               # votes are 0/1: any rank's vote counts once
 
 
+import os as _os
+_SKIP_KERNEL = _os.environ.get("OCCNERF_SKIP_ALLREDUCE", "0") != "0"
+
+
 class SwitchReducer:
     """GradReducer's job as ONE hand-written kernel over NVSwitch peer memory (csrc/collective.cu, occnerf_allreduce_sum_f32)
     instead of NCCL calls: a two-shot sum in which the switch itself adds the ranks' copies (multimem.ld_reduce / multimem.st on the
@@ -129,9 +133,11 @@ class SwitchReducer:
 
     All gradients of a step live in one flat fp32 buffer in symmetric memory (torch.distributed._symmetric_memory does the
     allocation and the handle exchange -- plumbing; the data path is the kernel):
-        [ table | bucket ]
+        [ table | reserved | bucket ]
       * `table_view` is bound as `Network.emb_grad_out`: occnerf_hashgrid_backward scatters the 59 MiB table gradient straight into
         it (no copy in, no copy out; the owner zeroes it at the start of a step);
+      * `reserve(shape)` hands out further in-place destinations (the decoder's weight gradients: occnerf_deconv3d_backward writes
+        them there, prologue._DecoderFn.grad_out); any gradient that already lives inside the buffer is left where it is;
       * every other gradient (MLP, point_dist, weight volume / decoder weights, compacted where structurally zero) and the 0/1
         visibility votes are copied into the bucket by one multi-tensor copy and back by another.
     The ranks synchronise inside the kernel, not on the host and not through a communicator stream, so the launch sits in the
@@ -140,7 +146,8 @@ class SwitchReducer:
 
     capturable = True
 
-    def __init__(self, table_numel: int, bucket_numel: int, device, group=None, blocks: int = 16, active: dict | None = None):
+    def __init__(self, table_numel: int, bucket_numel: int, device, group=None, blocks: int = 16, active: dict | None = None,
+                 reserve_numel: int = 0):
         import torch.distributed._symmetric_memory as symm
         from occnerf_b200 import _lib
         _lib.load()
@@ -151,7 +158,9 @@ class SwitchReducer:
         self.active = dict(active or {})
         self.blocks = blocks
         self.table_numel = (table_numel + 3) // 4 * 4
-        self.capacity = self.table_numel + (bucket_numel + 3) // 4 * 4
+        self.reserve_end = self.table_numel + (reserve_numel + 3) // 4 * 4       # [table_numel, reserve_end): in-place destinations
+        self.reserve_pos = self.table_numel
+        self.capacity = self.reserve_end + (bucket_numel + 3) // 4 * 4
         self.flat = symm.empty(self.capacity, dtype=torch.float32, device=device)
         self.flat.zero_()
         self.hdl = symm.rendezvous(self.flat, self.group)
@@ -167,7 +176,7 @@ class SwitchReducer:
         self._bufs = (C.c_void_p * self.world)(*bufs)
         self._pads = (C.c_void_p * self.world)(*pads)
         self.table_view = self.flat[:table_numel]
-        self.bucket = self.flat[self.table_numel:]
+        self.bucket = self.flat[self.reserve_end:]
         self.views, self.key = None, None
         torch.cuda.synchronize(device)
         dist.barrier(self.group)                  # every rank's pad and buffer are zeroed before anybody signals into them
@@ -180,6 +189,22 @@ class SwitchReducer:
     def zero_table(self):
         self.table_view.zero_()
 
+    def reserve(self, shape):
+        """A gradient destination of `shape` inside the all-reduce buffer (16-byte aligned); whoever produces that gradient writes it
+        here and it is reduced in place."""
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if self.reserve_pos + n > self.reserve_end:
+            raise RuntimeError("SwitchReducer.reserve: the reserved region is full")
+        view = self.flat[self.reserve_pos:self.reserve_pos + n].view(*shape)
+        self.reserve_pos += (n + 3) // 4 * 4
+        return view
+
+    def _inside(self, t):
+        lo = self.flat.data_ptr()
+        return lo <= t.data_ptr() < lo + 4 * self.reserve_end
+
     def __call__(self, grads, hits=None):
         import ctypes as C
         from occnerf_b200._lib import call, stream
@@ -187,8 +212,8 @@ class SwitchReducer:
         for i, g in enumerate(grads):
             if g is None:
                 continue
-            if g.data_ptr() == self.table_view.data_ptr():
-                continue                                        # already in place
+            if self._inside(g):
+                continue                                        # already in place (table gradient, reserved destinations)
             if i in self.active:
                 c = g[self.active[i]].contiguous()
                 compact[i] = c
@@ -206,11 +231,12 @@ class SwitchReducer:
             for g in items:
                 self.views.append(self.bucket[off:off + g.numel()].view_as(g))
                 off += g.numel()
-            self.used, self.key = self.table_numel + (off + 3) // 4 * 4, key
+            self.used, self.key = self.reserve_end + (off + 3) // 4 * 4, key
         if items:
             torch._foreach_copy_(self.views, items)
-        call("occnerf_allreduce_sum_f32", C.cast(self._bufs, C.c_void_p), C.cast(self._pads, C.c_void_p), self.multicast or None,
-             self.used, self.rank, self.world, self.blocks, self.epochs.data_ptr(), stream())
+        if not _SKIP_KERNEL:          # (OCCNERF_SKIP_ALLREDUCE=1: timing experiment -- everything but the collective itself)
+            call("occnerf_allreduce_sum_f32", C.cast(self._bufs, C.c_void_p), C.cast(self._pads, C.c_void_p), self.multicast or None,
+                 self.used, self.rank, self.world, self.blocks, self.epochs.data_ptr(), stream())
         if items:
             torch._foreach_copy_(items, self.views)
         for i, c in compact.items():

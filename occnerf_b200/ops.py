@@ -131,7 +131,7 @@ def deconv3d_backward(W, Yin, dYout, D, slope, exact=False, need_dyin=True, dW_o
     data-parallel all-reduce buffer); it is overwritten."""
     Cin, Cout = W.shape[0], W.shape[1]
     V, Q = D ** 3, Cout * (8 if D == 1 else 64)
-    bm = 256 if Cin >= 256 else 64              # row tile of the gradient GEMMs (csrc/deconv.cu launch_gemm)
+    bm = 256 if (Cin >= 256 and not exact) else 64     # row tile of the gradient GEMMs (csrc/deconv.cu launch_gemm)
     w_splits = _deconv_splits(((Cin + bm - 1) // bm) * ((Q + 63) // 64), max(V // 16, 1))
     d_tiles = ((Cin + 127) // 128) if V <= 8 else ((Cin + bm - 1) // bm) * ((V + 63) // 64)
     d_splits = _deconv_splits(d_tiles, Q // 16)

@@ -119,6 +119,8 @@ class _DecoderFn(torch.autograd.Function):
         D = 16
         for l in range(4, -1, -1):
             dst = ctx.grad_out[2 + 2 * l] if ctx.grad_out is not None else None
+            if dst is not None:
+                dst = dst.view_as(dst)          # a fresh tensor object on the same memory: autograd adopts it instead of cloning it
             dW, db, g = ops.deconv3d_backward(wb[2 + 2 * l], ys[l], g, D, 0.2, ctx.exact, need_dyin=True, dW_out=dst)
             grads[2 + 2 * l], grads[3 + 2 * l] = dW, db
             D //= 2
