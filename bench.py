@@ -199,13 +199,15 @@ class Workload:
                 # symmetric-memory rendezvous is not available on this box (every rank takes the same branch)
                 ok = 1
                 try:
-                    bucket = sum((p[active_e2e[i]].numel() if i in active_e2e else p.numel()) for i, p in enumerate(all_params) if p is not self.emb)
-                    bucket += self.vol.numel() + 6890 + 64
                     # the decoder's transposed-convolution weight gradients (layers 2..5; the first keeps its compacted exchange) are
                     # written by occnerf_deconv3d_backward straight into the all-reduce buffer
                     dec = self.net.mweight_vol_decoder
                     convs = [m for m in dec.decoder.block_conv if isinstance(m, torch.nn.ConvTranspose3d)]
                     inplace = convs[1:] if dec.native else []
+                    skip = [self.emb] + [c.weight for c in inplace]
+                    bucket = sum((p[active_e2e[i]].numel() if i in active_e2e else p.numel()) for i, p in enumerate(all_params)
+                                 if not any(p is q for q in skip))
+                    bucket += self.vol.numel() + 6890 + 64
                     sw = SwitchReducer(self.emb.numel(), bucket, device, active=None, reserve_numel=sum(c.weight.numel() + 4 for c in inplace))
                     if inplace:
                         from occnerf_b200.prologue import _DecoderFn

@@ -133,7 +133,7 @@ class SwitchReducer:
 
     All gradients of a step live in one flat fp32 buffer in symmetric memory (torch.distributed._symmetric_memory does the
     allocation and the handle exchange -- plumbing; the data path is the kernel):
-        [ table | reserved | bucket ]
+        [ table | bucket | reserved ]
       * `table_view` is bound as `Network.emb_grad_out`: occnerf_hashgrid_backward scatters the 59 MiB table gradient straight into
         it (no copy in, no copy out; the owner zeroes it at the start of a step);
       * `reserve(shape)` hands out further in-place destinations (the decoder's weight gradients: occnerf_deconv3d_backward writes
@@ -156,11 +156,12 @@ class SwitchReducer:
         if self.world > 8:
             raise RuntimeError("SwitchReducer: at most 8 ranks (one NVSwitch domain)")
         self.active = dict(active or {})
+        blocks = int(_os.environ.get("OCCNERF_AR_BLOCKS", blocks))
         self.blocks = blocks
         self.table_numel = (table_numel + 3) // 4 * 4
-        self.reserve_end = self.table_numel + (reserve_numel + 3) // 4 * 4       # [table_numel, reserve_end): in-place destinations
-        self.reserve_pos = self.table_numel
-        self.capacity = self.reserve_end + (bucket_numel + 3) // 4 * 4
+        self.bucket_end = self.table_numel + (bucket_numel + 3) // 4 * 4         # [table_numel, bucket_end): the copy-in bucket
+        self.reserve_pos = self.bucket_end                                        # [bucket_end, capacity): in-place destinations
+        self.capacity = self.bucket_end + (reserve_numel + 3) // 4 * 4
         self.flat = symm.empty(self.capacity, dtype=torch.float32, device=device)
         self.flat.zero_()
         self.hdl = symm.rendezvous(self.flat, self.group)
@@ -168,6 +169,8 @@ class SwitchReducer:
         self.pad.zero_()
         self.hdl_pad = symm.rendezvous(self.pad, self.group)
         self.epochs = torch.zeros(blocks, dtype=torch.int32, device=device)
+        self.scratch = symm.empty(65536, dtype=torch.float32, device=device)          # keep-alive target (contents are garbage)
+        self.hdl_scratch = symm.rendezvous(self.scratch, self.group)
         self.multicast = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
         bufs, pads = list(self.hdl.buffer_ptrs), list(self.hdl_pad.buffer_ptrs)
         if bufs[self.rank] != self.flat.data_ptr() or pads[self.rank] != self.pad.data_ptr():
@@ -175,8 +178,10 @@ class SwitchReducer:
         import ctypes as C
         self._bufs = (C.c_void_p * self.world)(*bufs)
         self._pads = (C.c_void_p * self.world)(*pads)
+        self._scratch = (C.c_void_p * self.world)(*list(self.hdl_scratch.buffer_ptrs))
+        self._scratch_mc = int(getattr(self.hdl_scratch, "multicast_ptr", 0) or 0)
         self.table_view = self.flat[:table_numel]
-        self.bucket = self.flat[self.reserve_end:]
+        self.bucket = self.flat[self.table_numel:self.bucket_end]
         self.views, self.key = None, None
         torch.cuda.synchronize(device)
         dist.barrier(self.group)                  # every rank's pad and buffer are zeroed before anybody signals into them
@@ -189,31 +194,43 @@ class SwitchReducer:
     def zero_table(self):
         self.table_view.zero_()
 
+    def keepalive(self):
+        """A few posted stores over NVLink (occnerf_link_keepalive): call every ~1 ms of the step so that the links are awake when the
+        all-reduce starts.  `Network.link_keepalive = reducer.keepalive` makes the ray path do it after every MLP chunk."""
+        import ctypes as C
+        from occnerf_b200._lib import call, stream
+        call("occnerf_link_keepalive", C.cast(self._scratch, C.c_void_p), self._scratch_mc or None, self.scratch.numel(), self.world, stream())
+
     def reserve(self, shape):
         """A gradient destination of `shape` inside the all-reduce buffer (16-byte aligned); whoever produces that gradient writes it
         here and it is reduced in place."""
         n = 1
         for d in shape:
             n *= int(d)
-        if self.reserve_pos + n > self.reserve_end:
+        if self.reserve_pos + n > self.capacity:
             raise RuntimeError("SwitchReducer.reserve: the reserved region is full")
         view = self.flat[self.reserve_pos:self.reserve_pos + n].view(*shape)
         self.reserve_pos += (n + 3) // 4 * 4
         return view
 
     def _inside(self, t):
-        lo = self.flat.data_ptr()
-        return lo <= t.data_ptr() < lo + 4 * self.reserve_end
+        """0: not in the buffer; 1: the table gradient; 2: a reserved in-place destination."""
+        off = (t.data_ptr() - self.flat.data_ptr()) // 4
+        if 0 <= off < self.table_numel:
+            return 1
+        return 2 if self.bucket_end <= off < self.capacity else 0
 
     def __call__(self, grads, hits=None):
         import ctypes as C
         from occnerf_b200._lib import call, stream
-        compact, items = {}, []
+        compact, items, reserved_used = {}, [], False
         for i, g in enumerate(grads):
             if g is None:
                 continue
-            if self._inside(g):
-                continue                                        # already in place (table gradient, reserved destinations)
+            where = self._inside(g)
+            if where:                                           # already in place (table gradient, reserved destinations)
+                reserved_used |= where == 2
+                continue
             if i in self.active:
                 c = g[self.active[i]].contiguous()
                 compact[i] = c
@@ -222,7 +239,7 @@ class SwitchReducer:
                 items.append(g)
         if hits is not None:
             items.append(hits)
-        key = tuple((tuple(g.shape), g.dtype) for g in items)
+        key = tuple((tuple(g.shape), g.dtype) for g in items) + (reserved_used,)
         if key != self.key:
             n = sum(g.numel() for g in items)
             if n > self.bucket.numel():
@@ -231,7 +248,10 @@ class SwitchReducer:
             for g in items:
                 self.views.append(self.bucket[off:off + g.numel()].view_as(g))
                 off += g.numel()
-            self.used, self.key = self.reserve_end + (off + 3) // 4 * 4, key
+            # one contiguous prefix is reduced: up to the end of the used part of the bucket, or -- when gradients of this call live in
+            # the reserved region -- up to the end of what has been reserved
+            self.used = self.reserve_pos if reserved_used else self.table_numel + (off + 3) // 4 * 4
+            self.key = key
         if items:
             torch._foreach_copy_(self.views, items)
         if not _SKIP_KERNEL:          # (OCCNERF_SKIP_ALLREDUCE=1: timing experiment -- everything but the collective itself)

@@ -89,6 +89,101 @@ for b in (16, 32, 128):
     r2.key = ()
     res[f"switch_ms_blocks{b}"] = timed(lambda: r2([r2.table_view]))
 
+# the same launch right after 4 GB of unrelated traffic (what the training step does before it: cold L2, cold TLBs)
+big = torch.empty(1 << 30, device=dev)
+
+
+def timed_cold(fn, n=10):
+    tot = 0.0
+    for i in range(n + 2):
+        big.add_(1.0)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        if i >= 2:
+            tot += e0.elapsed_time(e1)
+    t = torch.tensor([tot / n], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+res["switch_ms_after_4GB_traffic"] = timed_cold(lambda: red([red.table_view]))
+res["nccl_ms_after_4GB_traffic"] = timed_cold(lambda: dist.all_reduce(x))
+try:
+    res["torch_multimem_ms_after_4GB_traffic"] = timed_cold(lambda: torch.ops.symm_mem.multimem_all_reduce_(red.flat[:red.used], "sum", gname))
+except Exception as exc:
+    pass
+import ctypes
+buf = (ctypes.c_ulonglong * 4)()
+from occnerf_b200 import _lib as L
+L.load().occnerf_allreduce_debug(ctypes.cast(buf, ctypes.c_void_p), 1)
+timed_cold(lambda: red([red.table_view]))
+L.load().occnerf_allreduce_debug(ctypes.cast(buf, ctypes.c_void_p), 1)
+res["cold_phases_us"] = {"wait_arrive": buf[0] / max(buf[3], 1) / 1e3, "data": buf[1] / max(buf[3], 1) / 1e3, "wait_finish": buf[2] / max(buf[3], 1) / 1e3}
+del big
+# NVLink idle between launches (the training step leaves the links idle for ~8 ms): an 8 ms matmul burst in the stream before every
+# all-reduce, no host sync and no other collective in between
+A = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
+
+
+def timed_after_compute(fn, n=10, burst=8, ping=False):
+    evs = []
+    torch.cuda.synchronize(); dist.barrier()
+    for i in range(n + 2):
+        for _ in range(burst):
+            A @ A
+            if ping:
+                red.keepalive()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs[2:]) / n], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+L.load().occnerf_allreduce_debug(ctypes.cast(buf, ctypes.c_void_p), 1)
+res["switch_ms_after_8ms_compute"] = timed_after_compute(lambda: red([red.table_view]))
+L.load().occnerf_allreduce_debug(ctypes.cast(buf, ctypes.c_void_p), 1)
+res["after_compute_phases_us"] = {"wait_arrive": buf[0] / max(buf[3], 1) / 1e3, "data": buf[1] / max(buf[3], 1) / 1e3, "wait_finish": buf[2] / max(buf[3], 1) / 1e3}
+res["nccl_ms_after_8ms_compute"] = timed_after_compute(lambda: dist.all_reduce(x))
+res["switch_ms_after_1ms_compute"] = timed_after_compute(lambda: red([red.table_view]), burst=1)
+res["switch_ms_after_8ms_compute_with_keepalive"] = timed_after_compute(lambda: red([red.table_view]), ping=True)
+res["nccl_ms_after_8ms_compute_with_keepalive"] = timed_after_compute(lambda: dist.all_reduce(x), ping=True)
+del A
+# does it matter HOW the buffer was written?  (in the training step: a memset and red.global atomics)
+idx = torch.randint(0, TABLE, (8 << 20,), device=dev)
+val = torch.randn(8 << 20, device=dev)
+
+
+def timed_after(prep, fn, n=10):
+    evs = []
+    torch.cuda.synchronize(); dist.barrier()
+    for i in range(n + 2):
+        prep()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs[2:]) / n], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+def phases():
+    L.load().occnerf_allreduce_debug(ctypes.cast(buf, ctypes.c_void_p), 1)
+    return {"wait_arrive": buf[0] / max(buf[3], 1) / 1e3, "data": buf[1] / max(buf[3], 1) / 1e3, "wait_finish": buf[2] / max(buf[3], 1) / 1e3}
+
+
+phases()
+res["switch_ms_after_memset"] = timed_after(lambda: red.flat.zero_(), lambda: red([red.table_view]))
+res["after_memset_phases_us"] = phases()
+res["switch_ms_after_atomics"] = timed_after(lambda: red.flat.index_add_(0, idx, val), lambda: red([red.table_view]))
+res["after_atomics_phases_us"] = phases()
+res["switch_ms_after_copy"] = timed_after(lambda: red.flat[:TABLE].copy_(x[:TABLE]), lambda: red([red.table_view]))
+res["after_copy_phases_us"] = phases()
+
 # CUDA-graph replay: the kernel's epochs live in device memory, so a captured launch keeps working
 fill(2)
 side = torch.cuda.Stream()
