@@ -387,10 +387,6 @@ int occnerf_decoder_linear_backward(const float *w, const float *e, const float 
  * through the switch) or NULL (peer loads and stores); n_floats % 4 == 0; pad: >= blocks * world u32 per rank and epochs: [blocks] u32
  * of local device memory, both zeroed once before the first call; blocks: 1..148, identical on all ranks.  Ranks synchronise inside
  * the kernel (epoch counters in device memory), so the launch is CUDA-graph replayable. */
-/* NVLink keep-alive: a few posted 16-byte stores into every peer's copy of a symmetric scratch buffer (contents are garbage by contract).
- * Issued every ~1 ms of a training step it keeps the links out of their idle power state, which otherwise costs the step's all-reduce
- * ~0.25 ms (measured; NCCL alike).  peer_bufs_host / multicast: the scratch buffer's peer pointers / multicast mapping (or NULL). */
-int occnerf_link_keepalive(const void *const *peer_bufs_host, void *multicast, long n_floats, int world, occnerf_stream_t stream);
 /* debug only: nanoseconds block 0 spent (0) waiting for the peers to arrive, (1) in the data phase, (2) waiting for them to finish,
  * and (3) the number of launches, summed since the last reset */
 int occnerf_allreduce_debug(unsigned long long *host4, int reset);

@@ -69,7 +69,6 @@ _SIGNATURES = {
     "occnerf_unpack_image": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "occnerf_allreduce_sum_f32": [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp],
     "occnerf_allreduce_debug": [_vp, _i],
-    "occnerf_link_keepalive": [_vp, _vp, _l, _i, _vp],
     "occnerf_deconv3d_forward": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp],
     "occnerf_deconv3d_backward": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "occnerf_decoder_linear_forward": [_vp, _vp, _vp, _i, _i, _vp, _vp],

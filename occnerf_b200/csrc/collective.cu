@@ -122,40 +122,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_sum_kernel(Peers P, float 
     }
 }
 
-// NVLink keep-alive.  Measured on the 2- and 8-GPU boxes (tools/allreduce_check.py): after ~8 ms without NVLink traffic -- one training
-// step -- the first collective pays ~0.25 ms on top of its 0.2 ms (NCCL's all-reduce just the same: 0.14 -> 0.42 ms), after 1 ms of idle
-// nothing; the in-kernel phase timers of block 0 stay at 0.19 ms, i.e. the delay sits in the links some blocks touch first (link
-// power-state exit).  A handful of posted 16-byte stores spread over 256 KB of a symmetric scratch buffer, issued every ~1 ms of the step
-// (after each MLP chunk), keeps the links awake; the kernel itself returns in microseconds because the stores are not waited for.
-__global__ void __launch_bounds__(256) keepalive_kernel(Peers P, float *mc, int world, int n4) {
-    const int i = (blockIdx.x * 256 + threadIdx.x) * 16;            // one float4 per 256 bytes
-    if (i >= n4) return;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mc) {
-        mc_st(reinterpret_cast<float *>(reinterpret_cast<float4 *>(mc) + i), z);
-    } else {
-        for (int p = 0; p < world; ++p) reinterpret_cast<float4 *>(P.buf[p])[i] = z;
-    }
-}
-
 }  // namespace
-
-// Posted stores into every peer's copy of a symmetric SCRATCH buffer (contents are garbage by contract; n_floats >= 65536 recommended):
-// keeps the NVLink links out of their idle power state between the collectives of consecutive steps.  peer_bufs_host as above
-// (the scratch buffer's peer pointers), multicast: its multicast mapping or NULL.
-extern "C" int occnerf_link_keepalive(const void *const *peer_bufs_host, void *multicast, long n_floats, int world, occnerf_stream_t stream) {
-    OCC_CHECK_ARG(peer_bufs_host && world >= 1 && world <= kMaxWorld && n_floats >= 4, "link_keepalive: bad arguments");
-    if (world == 1) return OCCNERF_OK;
-    Peers P = {};
-    for (int p = 0; p < world; ++p) {
-        OCC_CHECK_ARG(peer_bufs_host[p] && ((uintptr_t)peer_bufs_host[p] & 15) == 0, "link_keepalive: peer %d pointer null or unaligned", p);
-        P.buf[p] = (float *)peer_bufs_host[p];
-    }
-    const int n4 = (int)(n_floats / 4 > (1 << 20) ? (1 << 20) : n_floats / 4);
-    keepalive_kernel<<<occ_div_up(occ_div_up(n4, 16), 256), 256, 0, (cudaStream_t)stream>>>(P, (float *)multicast, world, n4);
-    OCC_LAUNCH_CHECK();
-    return OCCNERF_OK;
-}
 
 // debug only: the phase times described at g_ar_dbg (4 x u64 to host memory), optionally cleared
 extern "C" int occnerf_allreduce_debug(unsigned long long *host4, int reset) {

@@ -169,8 +169,6 @@ class SwitchReducer:
         self.pad.zero_()
         self.hdl_pad = symm.rendezvous(self.pad, self.group)
         self.epochs = torch.zeros(blocks, dtype=torch.int32, device=device)
-        self.scratch = symm.empty(65536, dtype=torch.float32, device=device)          # keep-alive target (contents are garbage)
-        self.hdl_scratch = symm.rendezvous(self.scratch, self.group)
         self.multicast = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
         bufs, pads = list(self.hdl.buffer_ptrs), list(self.hdl_pad.buffer_ptrs)
         if bufs[self.rank] != self.flat.data_ptr() or pads[self.rank] != self.pad.data_ptr():
@@ -178,8 +176,6 @@ class SwitchReducer:
         import ctypes as C
         self._bufs = (C.c_void_p * self.world)(*bufs)
         self._pads = (C.c_void_p * self.world)(*pads)
-        self._scratch = (C.c_void_p * self.world)(*list(self.hdl_scratch.buffer_ptrs))
-        self._scratch_mc = int(getattr(self.hdl_scratch, "multicast_ptr", 0) or 0)
         self.table_view = self.flat[:table_numel]
         self.bucket = self.flat[self.table_numel:self.bucket_end]
         self.views, self.key = None, None
@@ -193,13 +189,6 @@ class SwitchReducer:
 
     def zero_table(self):
         self.table_view.zero_()
-
-    def keepalive(self):
-        """A few posted stores over NVLink (occnerf_link_keepalive): call every ~1 ms of the step so that the links are awake when the
-        all-reduce starts.  `Network.link_keepalive = reducer.keepalive` makes the ray path do it after every MLP chunk."""
-        import ctypes as C
-        from occnerf_b200._lib import call, stream
-        call("occnerf_link_keepalive", C.cast(self._scratch, C.c_void_p), self._scratch_mc or None, self.scratch.numel(), self.world, stream())
 
     def reserve(self, shape):
         """A gradient destination of `shape` inside the all-reduce buffer (16-byte aligned); whoever produces that gradient writes it

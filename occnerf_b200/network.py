@@ -259,6 +259,10 @@ class _QueryFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_raw):
         s = ctx.state
+        if s is None:
+            # the saved buffers (and the per-call gradient buffers the chunks share) are released by the first backward pass
+            raise RuntimeError("occnerf_b200: the query node has already been differentiated once (retain_graph / a second backward "
+                               "through the same forward is not supported: run the forward again)")
         g_raw = g_raw.contiguous().float()
         sh = s["shared"]
         last = sh["pending"] == 1

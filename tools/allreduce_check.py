@@ -126,14 +126,12 @@ del big
 A = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
 
 
-def timed_after_compute(fn, n=10, burst=8, ping=False):
+def timed_after_compute(fn, n=10, burst=8):
     evs = []
     torch.cuda.synchronize(); dist.barrier()
     for i in range(n + 2):
         for _ in range(burst):
             A @ A
-            if ping:
-                red.keepalive()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record()
         evs.append((e0, e1))
@@ -149,8 +147,6 @@ L.load().occnerf_allreduce_debug(ctypes.cast(buf, ctypes.c_void_p), 1)
 res["after_compute_phases_us"] = {"wait_arrive": buf[0] / max(buf[3], 1) / 1e3, "data": buf[1] / max(buf[3], 1) / 1e3, "wait_finish": buf[2] / max(buf[3], 1) / 1e3}
 res["nccl_ms_after_8ms_compute"] = timed_after_compute(lambda: dist.all_reduce(x))
 res["switch_ms_after_1ms_compute"] = timed_after_compute(lambda: red([red.table_view]), burst=1)
-res["switch_ms_after_8ms_compute_with_keepalive"] = timed_after_compute(lambda: red([red.table_view]), ping=True)
-res["nccl_ms_after_8ms_compute_with_keepalive"] = timed_after_compute(lambda: dist.all_reduce(x), ping=True)
 del A
 # does it matter HOW the buffer was written?  (in the training step: a memset and red.global atomics)
 idx = torch.randint(0, TABLE, (8 << 20,), device=dev)
