@@ -20,6 +20,7 @@
  *   core/utils/camera_util.py:133-160,163-212 (get_rays_from_KRT, rays_intersect_3d_bbox) + the masking at
  *       core/data/occnerf/freeview.py:208-219, train.py:440-461                 -> occnerf_generate_rays
  *   run.py:39-66 (unpack_alpha_map, unpack_to_image) + core/utils/image_util.py:19-20 (to_8b_image) -> occnerf_unpack_image
+ *   core/data/occnerf/train.py:160-165,167-222,225-273 (patch selection of the training loader)    -> occnerf_sample_patches
  */
 #ifndef OCCNERF_B200_H
 #define OCCNERF_B200_H
@@ -359,6 +360,20 @@ int occnerf_generate_rays(const double *kinv_host, int k_is_f32, const double *R
 int occnerf_unpack_image(const float *rgb, const float *alpha, const int *pixel_index, int n, int H, int W,
                          const float *bgcolor_host, int fill, uint8_t *rgb8, uint8_t *alpha8, int *bad,
                          occnerf_stream_t stream);
+
+/* ---- training-patch selection (core/data/occnerf/train.py:167-222 get_patch_ray_indices, :225-273 _get_patch_ray_indices, and the
+ * gathers of :160-165 sample_patch_rays), csrc/patches.cu.  ray_mask / subject_mask / bbox_mask: [H*W] bytes (0 / non-zero).
+ * use_subject [n_patch] bytes and select_idx [n_patch] i32 (device): the caller's two random draws per patch -- the reference draws
+ * np.random.rand(1)[0] < cfg.patch.sample_subject_ratio and np.random.choice(n_candidates, size=[1], replace=False)[0], in that order.
+ * Outputs: select_inds [n_patch * patch^2] i32 (ranks in the compacted ray list; the first patch_div[n_patch] entries are valid),
+ * patch_div [n_patch + 1] i32, patch_masks [n_patch, patch, patch] bytes, xy_min / xy_max [n_patch, 2] i32 as (x, y), status [1] i32
+ * (caller-zeroed; 1 = a select_idx was outside its candidate list).  rays [n_rays, 8] -> rays_out [n_patch * patch^2, 8]: optional
+ * gather of the selected rays (both NULL to skip).  scratch: occnerf_patches_scratch_bytes(H, W, n_patch, patch) bytes. */
+long occnerf_patches_scratch_bytes(int H, int W, int n_patch, int patch);
+int occnerf_sample_patches(const uint8_t *ray_mask, const uint8_t *subject_mask, const uint8_t *bbox_mask, int H, int W, int patch,
+                           int n_patch, const uint8_t *use_subject, const int32_t *select_idx, const float *rays, float *rays_out,
+                           int32_t *select_inds, int32_t *patch_div, uint8_t *patch_masks, int32_t *xy_min, int32_t *xy_max,
+                           int32_t *status, void *scratch, occnerf_stream_t stream);
 
 /* ---- per-frame prologue: the motion-weight volume decoder (deconv_vol_decoder.py:25-33, network_util.py:12-50), csrc/deconv.cu ----
  * ConvTranspose3d(kernel 4, stride 2, padding 1), batch 1, as tf32 tensor-core GEMMs on the reference's weight layout

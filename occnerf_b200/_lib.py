@@ -69,13 +69,14 @@ _SIGNATURES = {
     "occnerf_unpack_image": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "occnerf_allreduce_sum_f32": [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp],
     "occnerf_allreduce_debug": [_vp, _i],
+    "occnerf_sample_patches": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "occnerf_deconv3d_forward": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp],
     "occnerf_deconv3d_backward": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "occnerf_decoder_linear_forward": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "occnerf_decoder_linear_backward": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
 }
 EXPORTED = sorted(list(_SIGNATURES) + ["occnerf_last_error", "occnerf_abi_version", "occnerf_mlp_packed_bytes",
-                                           "occnerf_rays_scratch_bytes", "occnerf_warp_packed_floats"])
+                                           "occnerf_rays_scratch_bytes", "occnerf_warp_packed_floats", "occnerf_patches_scratch_bytes"])
 
 GEMM_BIAS, GEMM_RELU, GEMM_ACCUM, GEMM_RELUMASK = 1, 2, 4, 8
 LAYOUT_BLC, LAYOUT_LBC = 0, 1
@@ -99,6 +100,7 @@ def load(build_if_missing: bool = True):
     lib.occnerf_abi_version.restype = _i
     lib.occnerf_mlp_packed_bytes.argtypes, lib.occnerf_mlp_packed_bytes.restype = [_i, _i], _l
     lib.occnerf_rays_scratch_bytes.argtypes, lib.occnerf_rays_scratch_bytes.restype = [_i, _i], _l
+    lib.occnerf_patches_scratch_bytes.argtypes, lib.occnerf_patches_scratch_bytes.restype = [_i, _i, _i, _i], _l
     lib.occnerf_warp_packed_floats.argtypes, lib.occnerf_warp_packed_floats.restype = [_i, _i, _i, _i], _l
     _lib = lib
     return lib
@@ -128,7 +130,7 @@ def ptr(t, dtype=None):
 
 # kernels launched per C call (for the bench's `gpu_launches` claim); entries not listed launch exactly one
 KERNELS_PER_CALL = {"occnerf_clip_adam_step": 3, "occnerf_visibility_hits": 3, "occnerf_generate_rays": 3, "occnerf_unpack_image": 2,
-                    "occnerf_deconv3d_forward": 2, "occnerf_deconv3d_backward": 3}
+                    "occnerf_deconv3d_forward": 2, "occnerf_deconv3d_backward": 3, "occnerf_sample_patches": 4}
 COUNTERS = {"calls": 0, "launches": 0}
 PROFILE = None   # set to {} to record (start_event, end_event, work) per C call on the current stream
 

@@ -657,6 +657,42 @@ def generate_rays(H, W, K, R, T, bbox_min, bbox_max, device="cuda", capacity=Non
 
 
 # ----------------------------------------------------------------------------- image assembly behind the path
+# ----------------------------------------------------------------------------- training patches (csrc/patches.cu)
+def draw_patch_randoms(n_patch, sample_subject_ratio, n_subject, n_bbox_minus_subject, rs=None):
+    """The two draws per patch exactly as the reference takes them from numpy's global RandomState (train.py:198-201, 241-242):
+    `rand(1)[0] < ratio`, then `choice(n_candidates, size=[1], replace=False)[0]`.  -> (use_subject bool [n], select_idx int [n])."""
+    rs = np.random if rs is None else rs
+    use, idx = [], []
+    for _ in range(n_patch):
+        u = bool(rs.rand(1)[0] < sample_subject_ratio)
+        n = n_subject if u else n_bbox_minus_subject
+        use.append(u)
+        idx.append(int(rs.choice(n, size=[1], replace=False)[0]))
+    return np.array(use), np.array(idx)
+
+
+def sample_patches(ray_mask, subject_mask, bbox_mask, H, W, patch_size, use_subject, select_idx, rays=None):
+    """train.py:167-273 on the device.  ray_mask / subject_mask / bbox_mask: uint8 or bool CUDA tensors with H*W elements;
+    use_subject / select_idx: the caller's draws (array-likes, see draw_patch_randoms); rays [n_rays, 8] optional.
+    -> dict(select_inds i32 [n*P*P] (first patch_div[-1] valid), patch_div i32 [n+1], patch_masks u8 [n,P,P], xy_min / xy_max i32 [n,2],
+            rays [n*P*P, 8] | None, status i32 [1])."""
+    dev = ray_mask.device
+    as_u8 = lambda t: t.reshape(-1).to(torch.uint8).contiguous()
+    rm, sm, bm = as_u8(ray_mask), as_u8(subject_mask), as_u8(bbox_mask)
+    n, P = len(use_subject), int(patch_size)
+    use_d = torch.as_tensor(np.asarray(use_subject, dtype=np.uint8), device=dev)
+    idx_d = torch.as_tensor(np.asarray(select_idx, dtype=np.int32), device=dev)
+    out = dict(select_inds=torch.empty(n * P * P, device=dev, dtype=i32), patch_div=torch.empty(n + 1, device=dev, dtype=i32),
+               patch_masks=torch.empty(n, P, P, device=dev, dtype=u8), xy_min=torch.empty(n, 2, device=dev, dtype=i32),
+               xy_max=torch.empty(n, 2, device=dev, dtype=i32), status=torch.zeros(1, device=dev, dtype=i32),
+               rays=torch.empty(n * P * P, 8, device=dev, dtype=f32) if rays is not None else None)
+    scratch = torch.empty(_lib.load().occnerf_patches_scratch_bytes(H, W, n, P), device=dev, dtype=u8)
+    call("occnerf_sample_patches", ptr(rm, u8), ptr(sm, u8), ptr(bm, u8), H, W, P, n, ptr(use_d, u8), ptr(idx_d, i32),
+         ptr(rays, f32) if rays is not None else None, ptr(out["rays"]) if rays is not None else None, ptr(out["select_inds"]),
+         ptr(out["patch_div"]), ptr(out["patch_masks"]), ptr(out["xy_min"]), ptr(out["xy_max"]), ptr(out["status"]), ptr(scratch), stream())
+    return out
+
+
 def unpack_image(rgb, alpha, pixel_index, H, W, bgcolor, out=None, fill=True):
     """run.py:39-66 (unpack_to_image / unpack_alpha_map) + image_util.py:19-20 (to_8b_image) on the device.
 
