@@ -236,8 +236,18 @@ class Workload:
         self.loss_host = torch.zeros(1).pin_memory()
 
     def loss(self, out, target, world=1):
-        # (data parallel: 1 / world folded into the loss, so that the SUM all-reduce of the gradients is their average)
-        return (0.2 * torch.mean((out["rgb"] - target) ** 2) + out["comp_loss"].mean()) * (1.0 / world)
+        """trainer.py:135-189 without the LPIPS term: 0.2 * img2mse(_unpack_imgs(rgb, ...), targets) + mean(comp_loss), value and
+        gradients by occnerf_patch_loss (csrc/loss.cu).  The six 32 x 32 patches of the synthetic frame are fully covered by rays, so the
+        unpacked images are the rays in patch order.  (data parallel: 1 / world folded into the weights, so that the SUM all-reduce of
+        the gradients is their average)"""
+        from occnerf_b200 import ops
+        if not hasattr(self, "_patch_meta"):
+            dev = out["rgb"].device
+            n_patch = RAYS_PER_STEP // 1024
+            self._patch_meta = (torch.ones(n_patch, 32, 32, device=dev, dtype=torch.uint8),
+                                torch.arange(0, RAYS_PER_STEP + 1, 1024, device=dev, dtype=torch.int32), torch.zeros(3, device=dev))
+        masks, div, bg = self._patch_meta
+        return ops.patch_loss(out["rgb"], out["comp_loss"], masks, div, bg, target.reshape(-1, 32, 32, 3), 0.2 / world, 1.0 / world)[0]
 
     def grads_to_reduce(self):
         return [p.grad for p in self.path_params if p.grad is not None] + ([self.vol.grad] if self.vol.grad is not None else [])

@@ -375,6 +375,15 @@ int occnerf_sample_patches(const uint8_t *ray_mask, const uint8_t *subject_mask,
                            int32_t *select_inds, int32_t *patch_div, uint8_t *patch_masks, int32_t *xy_min, int32_t *xy_max,
                            int32_t *status, void *scratch, occnerf_stream_t stream);
 
+/* ---- loss epilogue without the LPIPS term (core/train/trainers/occnerf/trainer.py:31-41 _unpack_imgs, :24 img2mse, :135-189 get_loss),
+ * csrc/loss.cu: value and gradients in one call.  rgb [n, 3] with n = div[N]; masks [N, P, P] bytes; div [N + 1] i32; bgcolor [3] in
+ * [0, 1]; targets [N, P, P, 3]; comp [comp_numel] or NULL.  Outputs: imgs [N, P, P, 3] or NULL (the unpacked patch images, what the
+ * perceptual loss consumes), out [4] = (w_mse * mse + w_comp * mean(comp), w_mse * mse, w_comp * mean(comp), d loss / d comp_i),
+ * g_rgb [n, 3] = d loss / d rgb.  acc: 16 bytes of scratch. */
+int occnerf_patch_loss(const float *rgb, const uint8_t *masks, const int32_t *div, const float *bgcolor, const float *targets,
+                       const float *comp, long comp_numel, int N, int P, float w_mse, float w_comp, float *imgs, float *out, float *g_rgb,
+                       void *acc, occnerf_stream_t stream);
+
 /* ---- per-frame prologue: the motion-weight volume decoder (deconv_vol_decoder.py:25-33, network_util.py:12-50), csrc/deconv.cu ----
  * ConvTranspose3d(kernel 4, stride 2, padding 1), batch 1, as tf32 tensor-core GEMMs on the reference's weight layout
  * W [Cin][Cout][4][4][4].  Activations are PRE-activations [C][D^3] (NCDHW, N = 1); the LeakyReLU(slope) between layers is applied

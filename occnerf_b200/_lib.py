@@ -69,6 +69,7 @@ _SIGNATURES = {
     "occnerf_unpack_image": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "occnerf_allreduce_sum_f32": [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp],
     "occnerf_allreduce_debug": [_vp, _i],
+    "occnerf_patch_loss": [_vp, _vp, _vp, _vp, _vp, _vp, _l, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp],
     "occnerf_sample_patches": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "occnerf_deconv3d_forward": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp],
     "occnerf_deconv3d_backward": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
@@ -130,7 +131,7 @@ def ptr(t, dtype=None):
 
 # kernels launched per C call (for the bench's `gpu_launches` claim); entries not listed launch exactly one
 KERNELS_PER_CALL = {"occnerf_clip_adam_step": 3, "occnerf_visibility_hits": 3, "occnerf_generate_rays": 3, "occnerf_unpack_image": 2,
-                    "occnerf_deconv3d_forward": 2, "occnerf_deconv3d_backward": 3, "occnerf_sample_patches": 4}
+                    "occnerf_deconv3d_forward": 2, "occnerf_deconv3d_backward": 3, "occnerf_sample_patches": 4, "occnerf_patch_loss": 3}
 COUNTERS = {"calls": 0, "launches": 0}
 PROFILE = None   # set to {} to record (start_event, end_event, work) per C call on the current stream
 

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "liboccnerf_b200.so")
-SOURCES = ["api.cu", "warp.cu", "knn.cu", "hashgrid.cu", "aggregate.cu", "vertex.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_wgrad.cu", "composite.cu", "rays.cu", "image.cu", "optim.cu", "prologue.cu", "collective.cu", "deconv.cu", "patches.cu"]
+SOURCES = ["api.cu", "warp.cu", "knn.cu", "hashgrid.cu", "aggregate.cu", "vertex.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_wgrad.cu", "composite.cu", "rays.cu", "image.cu", "optim.cu", "prologue.cu", "collective.cu", "deconv.cu", "patches.cu", "loss.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -693,6 +693,44 @@ def sample_patches(ray_mask, subject_mask, bbox_mask, H, W, patch_size, use_subj
     return out
 
 
+class _PatchLoss(torch.autograd.Function):
+    """trainer.py:31-41,24,135-189 without LPIPS: (rgb [n,3], comp_loss | None) -> (loss scalar, patch_imgs [N,P,P,3]); the gradients
+    are produced by the same call (occnerf_patch_loss)."""
+
+    @staticmethod
+    def forward(ctx, rgb, comp, masks, div, bgcolor, targets, w_mse, w_comp):
+        dev = rgb.device
+        N, P = masks.shape[0], masks.shape[1]
+        rgb_c = rgb.detach().contiguous().float()
+        comp_c = comp.detach().contiguous().float() if comp is not None else None
+        imgs = torch.empty(N, P, P, 3, device=dev, dtype=f32)
+        out = torch.empty(4, device=dev, dtype=f32)
+        g_rgb = torch.zeros_like(rgb_c)
+        acc = torch.empty(2, device=dev, dtype=torch.float64)
+        # (converted copies are held in locals until the call is enqueued: a temporary freed earlier could be handed out again and
+        #  overwritten by the next conversion kernel on the same stream)
+        masks_c, div_c = masks.to(u8).contiguous(), div.to(i32).contiguous()
+        bg_c, tg_c = bgcolor.contiguous().float(), targets.contiguous().float()
+        call("occnerf_patch_loss", ptr(rgb_c, f32), ptr(masks_c, u8), ptr(div_c, i32),
+             ptr(bg_c, f32), ptr(tg_c, f32), ptr(comp_c, f32) if comp_c is not None else None,
+             comp_c.numel() if comp_c is not None else 0, N, P, float(w_mse), float(w_comp), ptr(imgs), ptr(out), ptr(g_rgb), ptr(acc), stream())
+        ctx.save_for_backward(g_rgb, out)
+        ctx.comp_shape = tuple(comp.shape) if comp is not None else None
+        ctx.mark_non_differentiable(imgs)
+        return out[0].clone(), imgs, out[1:3].clone()
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_imgs, _g_parts):
+        g_rgb, out = ctx.saved_tensors
+        g_comp = (g_loss * out[3]).expand(ctx.comp_shape).contiguous() if ctx.comp_shape is not None else None
+        return g_rgb * g_loss, g_comp, None, None, None, None, None, None
+
+
+def patch_loss(rgb, comp_loss, patch_masks, div_indices, bgcolor, targets, w_mse=0.2, w_comp=1.0):
+    """-> (loss, patch_imgs, (w_mse * mse, w_comp * mean(comp_loss))); differentiable w.r.t. rgb and comp_loss."""
+    return _PatchLoss.apply(rgb, comp_loss, patch_masks, div_indices, bgcolor, targets, w_mse, w_comp)
+
+
 def unpack_image(rgb, alpha, pixel_index, H, W, bgcolor, out=None, fill=True):
     """run.py:39-66 (unpack_to_image / unpack_alpha_map) + image_util.py:19-20 (to_8b_image) on the device.
 
