@@ -714,16 +714,23 @@ class _PatchLoss(torch.autograd.Function):
         call("occnerf_patch_loss", ptr(rgb_c, f32), ptr(masks_c, u8), ptr(div_c, i32),
              ptr(bg_c, f32), ptr(tg_c, f32), ptr(comp_c, f32) if comp_c is not None else None,
              comp_c.numel() if comp_c is not None else 0, N, P, float(w_mse), float(w_comp), ptr(imgs), ptr(out), ptr(g_rgb), ptr(acc), stream())
-        ctx.save_for_backward(g_rgb, out)
+        ctx.save_for_backward(g_rgb, out, masks_c)
         ctx.comp_shape = tuple(comp.shape) if comp is not None else None
-        ctx.mark_non_differentiable(imgs)
-        return out[0].clone(), imgs, out[1:3].clone()
+        ctx.set_materialize_grads(False)
+        parts = out[1:3].clone()
+        ctx.mark_non_differentiable(parts)
+        return out[0].clone(), imgs, parts
 
     @staticmethod
-    def backward(ctx, g_loss, _g_imgs, _g_parts):
-        g_rgb, out = ctx.saved_tensors
-        g_comp = (g_loss * out[3]).expand(ctx.comp_shape).contiguous() if ctx.comp_shape is not None else None
-        return g_rgb * g_loss, g_comp, None, None, None, None, None, None
+    def backward(ctx, g_loss, g_imgs, _g_parts):
+        g_rgb, out, masks_c = ctx.saved_tensors
+        g = g_rgb * g_loss if g_loss is not None else torch.zeros_like(g_rgb)
+        if g_imgs is not None:              # a consumer of the unpacked images (the perceptual term): its gradient comes back through the scatter
+            g = g + g_imgs[masks_c.bool()]  # (row-major order of the hit pixels = rank order; a host sync, outside the graph-captured step)
+        g_comp = None
+        if ctx.comp_shape is not None and g_loss is not None:
+            g_comp = (g_loss * out[3]).expand(ctx.comp_shape).contiguous()
+        return g, g_comp, None, None, None, None, None, None
 
 
 def patch_loss(rgb, comp_loss, patch_masks, div_indices, bgcolor, targets, w_mse=0.2, w_comp=1.0):

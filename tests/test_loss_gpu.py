@@ -22,11 +22,21 @@ def test_reference_fixture():
     loss, imgs, parts = ops.patch_loss(rgbs, comp, torch.from_numpy(g["patch_masks"]).to(d), torch.from_numpy(g["div"]).to(d),
                                        torch.from_numpy(g["bgcolor"]).to(d), torch.from_numpy(g["targets"]).to(d), float(g["w_mse"]), float(g["w_comp"]))
     (3.0 * loss).backward()
-    assert np.array_equal(imgs.cpu().numpy(), g["patch_imgs"])
+    assert np.array_equal(imgs.detach().cpu().numpy(), g["patch_imgs"])
     assert abs(float(loss) - float(g["loss"])) < 2e-6 * abs(float(g["loss"]))
     assert np.abs(rgbs.grad.cpu().numpy() - 3.0 * g["g_rgbs"]).max() < 1e-9
     assert np.abs(comp.grad.cpu().numpy() - 3.0 * g["g_comp"]).max() < 1e-9
     assert abs(float(parts.sum()) - float(loss)) < 1e-6
+    # a consumer of the unpacked images (the perceptual term) gets its gradient back through the scatter
+    rgbs.grad = None
+    w = torch.from_numpy(g["targets"]).to(d)
+    loss2, imgs2, _ = ops.patch_loss(rgbs, None, torch.from_numpy(g["patch_masks"]).to(d), torch.from_numpy(g["div"]).to(d),
+                                     torch.from_numpy(g["bgcolor"]).to(d), torch.from_numpy(g["targets"]).to(d), 0.0, 0.0)
+    (imgs2 * w).sum().backward()
+    a = torch.from_numpy(g["rgbs"]).requires_grad_(True)
+    (L.unpack_imgs(a, torch.from_numpy(g["patch_masks"]), torch.from_numpy(g["bgcolor"]), torch.from_numpy(g["targets"]), g["div"].tolist())
+     * torch.from_numpy(g["targets"])).sum().backward()
+    assert float((rgbs.grad.cpu() - a.grad).abs().max()) < 1e-7
 
 
 def test_bench_shape_against_oracle():
