@@ -17,7 +17,11 @@
 // What did work is merging runs of equal vertices along a ray in registers: aggregate_bwd_slot_kernel below.
 // (The same idea for the FORWARD gathers -- neighbour rows cached in registers per slot, in three shapes: a warp walking
 // the run, the same with a separate attention pass, and one thread per (run, level, column chunk) with shared-memory
-// partial sums -- was 1.7-2.5x slower than the per-sample forward kernel, which already runs at 90 % of the L1 rate.)
+// partial sums -- was 1.7-2.5x slower than the per-sample forward kernel, which already runs at 90 % of the L1 rate.
+// Round 2: a bf16 copy of the table (80-byte rows, five lanes per row, six rows per warp instruction: half the gathered bytes and L1
+// wavefronts; results fp32-exact against the oracle on the rounded table) bought 4 % (0.517 -> 0.496 ms per step): the forward is
+// not limited by the gather but by the per-sample attention arithmetic (40 counter gathers, six warp reductions, exp, divisions);
+// removed again.)
 #include "common.cuh"
 
 namespace {
