@@ -306,9 +306,11 @@ int occnerf_mlp_wgrad_tc(const void *g_save, const void *act_bf16, int m, long s
  * window6_host = 6 HOST floats) is evaluated inside the kernel.  w7_host / b7_host: HOST arrays of 7 device pointers
  * (nn.Linear weights [128,105], [128,128] x3, [128,164], [128,128], [3,128] and their biases); cond_dev: the 69-value pose
  * condition on the device (folded into the first bias) or NULL (= zeros).  Buffer size: occnerf_mlp_packed_bytes(n_pass, 2). */
+/* cta_pair: as for the canonical chain (0 = cta_group::1 CTAs sharing the weight stream, 1 = cta_group::2 pairs); the same value for
+ * the packing and the forward call. */
 int occnerf_nonrigid_pack_weights(const void *const *w7_host, const void *const *b7_host, const float *cond_dev, int n_pass,
-                                  void *packed, occnerf_stream_t stream);
-int occnerf_nonrigid_forward_tc(const float *xyz, const float *window6_host, int m, const void *packed, int n_pass,
+                                  int cta_pair, void *packed, occnerf_stream_t stream);
+int occnerf_nonrigid_forward_tc(const float *xyz, const float *window6_host, int m, const void *packed, int n_pass, int cta_pair,
                                 float *out, occnerf_stream_t stream);
 
 /* ---- alpha compositing (network.py:320-348) + completeness term (network.py:486-499) ----------------

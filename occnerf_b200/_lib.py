@@ -59,8 +59,8 @@ _SIGNATURES = {
     "occnerf_mlp_debug_trace_w": [_vp],
     "occnerf_mlp_debug_max_clusters": [_i],
     "occnerf_mlp_debug_set": [_i],
-    "occnerf_nonrigid_pack_weights": [_vp, _vp, _vp, _i, _vp, _vp],
-    "occnerf_nonrigid_forward_tc": [_vp, _vp, _i, _vp, _i, _vp, _vp],
+    "occnerf_nonrigid_pack_weights": [_vp, _vp, _vp, _i, _i, _vp, _vp],
+    "occnerf_nonrigid_forward_tc": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp],
     "occnerf_mlp_wgrad_tc": [_vp, _vp, _i, _l, _vp, _vp, _vp],
     "occnerf_composite_forward": [_vp] * 5 + [_i, _i] + [_vp] * 7,
     "occnerf_composite_backward": [_vp] * 9 + [_i, _i] + [_vp] * 3,

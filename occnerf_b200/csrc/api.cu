@@ -12,4 +12,4 @@ void occnerf_set_error(const char *fmt, ...) {
 }
 
 extern "C" const char *occnerf_last_error(void) { return g_err; }
-extern "C" int occnerf_abi_version(void) { return 2; }   // 2: cta_pair argument of the tensor-core MLP entry points, packed warp kernels
+extern "C" int occnerf_abi_version(void) { return 3; }   // 2: cta_pair argument of the canonical MLP entry points, packed warp kernels; 3: of the non-rigid ones

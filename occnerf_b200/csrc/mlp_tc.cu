@@ -168,7 +168,7 @@ __global__ void pack_weights_kernel(occnerf_mlp_params P, DevLayout L, int n_pas
 
 struct NrParams { const float *w[7]; const float *b[7]; const float *cond; };   // cond: 69 floats on the device or NULL
 
-__global__ void pack_nr_kernel(NrParams P, DevLayout L, int n_pass, unsigned char *out) {
+__global__ void pack_nr_kernel(NrParams P, DevLayout L, int n_pass, int cta_pair, unsigned char *out) {
     const int l = blockIdx.y;
     const int K = nr_K(l), N = nr_N(l);
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,7 +179,7 @@ __global__ void pack_nr_kernel(NrParams P, DevLayout L, int n_pass, unsigned cha
         else if (l == 4) w = k < 164 ? P.w[4][n * 164 + k] : 0.f;                // [h128, pe36]
         else if (l == 6) w = n < 3 ? P.w[6][n * 128 + k] : 0.f;
         else w = P.w[l][n * 128 + k];
-        pack_store(out, L.w_off[l], n_pass, N, n, k, w);
+        pack_store(out, L.w_off[l], n_pass, N, n, k, w, cta_pair);
     }
     if (blockIdx.x == 0 && threadIdx.x < 256) {
         const int n = threadIdx.x;
@@ -1165,27 +1165,45 @@ __device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Sm
     float win[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) win[j] = args.nr_window[j];
-    uint32_t acc_cnt = 0;
+    uint32_t acc_cnt = 0, bl = 0;
+    const int tid = threadIdx.x;
+    // biases in shared memory one layer ahead, as in the forward chain (the per-chunk __ldg of the bias sat in front of every FADD)
+    if (tid < 256) sm.bias[tid] = __ldg(bias_all + tid);
+    epi_bar_sync();
+    // The positional encoding of a tile (16 sinf / cosf per thread) is computed ONE TILE AHEAD, while the thread would otherwise wait
+    // for accumulators: the point is loaded during layer 2, its encoding evaluated after the skip connection of layer 3 has consumed
+    // the current one.  At the head of a tile it used to sit in front of the first UMMA (~4 k issue cycles per tile).
+    float xn[3], pe0[8], pe1[8];
+    auto load_point = [&](int t) {
+        const long g = (long)t * kTileM + row;
+        const bool ok = t < num_tiles && g < args.m;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xn[c] = ok ? __ldg(args.nr_xyz + g * 3 + c) : 0.f;
+    };
+    auto encode = [&]() {
+        pe_chunk(xn, win, set, pe0);
+        pe_chunk(xn, win, set + 4, pe1);                 // (all zeros for sets 2, 3: indices >= 48)
+    };
+    load_point(blockIdx.x);
+    encode();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const long grow = (long)tile * kTileM + row;
         const bool valid = grow < args.m;
-        float x[3] = {0.f, 0.f, 0.f};
-        if (valid) { x[0] = __ldg(args.nr_xyz + grow * 3); x[1] = __ldg(args.nr_xyz + grow * 3 + 1); x[2] = __ldg(args.nr_xyz + grow * 3 + 2); }
-        // this thread's chunks of the positional encoding (chunk `set`, and chunk set+4 for sets 0 and 1), kept in registers
-        // for the skip connection
-        float pe0[8], pe1[8];
-        pe_chunk(x, win, set, pe0);
-        pe_chunk(x, win, set + 4, pe1);                  // (all zeros for sets 2, 3: indices >= 48)
-        // GEMM 0 operand A[:, 0:48) = (pe36, pad): chunks 0..5 -> A groups 0, 1
+        const float x[3] = {xn[0], xn[1], xn[2]};
+        // GEMM 0 operand A[:, 0:48) = (pe36, pad): chunks 0..5 -> A group 0
+        static_assert(kGroupCols == 64, "the non-rigid epilogue publishes 64-column groups");
         store_a8<NPASS>(sm.A, row, set, pe0);
-        if (kGroupCols == 32) publish(sm, 0);
         if (set < 2) store_a8<NPASS>(sm.A, row, set + 4, pe1);
-        publish(sm, kGroupCols == 32 ? 1 : 0);
-        for (int l = 0; l < 7; ++l, ++acc_cnt) {
+        publish(sm, 0);
+        for (int l = 0; l < 7; ++l, ++acc_cnt, ++bl) {
+            const int l_next = l + 1 == 7 ? 0 : l + 1;
+            float bias_next = 0.f;
+            if (tid < 256) bias_next = __ldg(bias_all + l_next * 256 + tid);
+            if (l == 2) load_point(tile + (int)gridDim.x);
             mbar_wait(sm.bar_acc_full, acc_cnt & 1);
             tc_fence_after();
             const uint32_t t_acc = t_lane + (uint32_t)(l & 1) * 256;
-            const float *bias = bias_all + l * 256;
+            const float *bias = sm.bias + (bl & 1) * 256;
             if (l == 6) {
                 if (set == 0) {
                     uint32_t r[8];
@@ -1193,25 +1211,25 @@ __device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Sm
                     tmem_ld_wait();
                     if (valid) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) args.nr_out[grow * 3 + c] = x[c] + (__uint_as_float(r[c]) + __ldg(bias + c));
+                        for (int c = 0; c < 3; ++c) args.nr_out[grow * 3 + c] = x[c] + (__uint_as_float(r[c]) + bias[c]);
                     }
                 }
                 tc_fence_before();
             } else {
+                const float *bias_t = bias + set * 8;
                 uint32_t ra[8], rb[8];
                 auto process = [&](int cg, const uint32_t (&r)[8]) {
-                    const int k8 = cg * 4 + set;
-                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + k8 * 8));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + k8 * 8 + 4));
+                    const float4 b0 = *reinterpret_cast<const float4 *>(bias_t + cg * 32);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(bias_t + cg * 32 + 4);
                     const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                     float v[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[i]) + bj[i], 0.f);
-                    store_a8<NPASS>(sm.A, row, k8, v);
+                    store_a8<NPASS>(sm.A, row, cg * 4 + set, v);
                     if (pub_after(cg)) publish(sm, pub_group(cg));
                 };
                 tmem_ld8_issue(t_acc + set * 8, ra);
-#pragma unroll 1
+#pragma unroll
                 for (int cg = 0; cg < 4; cg += 2) {
                     tmem_ld_wait();
                     tmem_ld8_issue(t_acc + ((cg + 1) * 4 + set) * 8, rb);
@@ -1220,13 +1238,15 @@ __device__ __forceinline__ void nr_epilogue_loop(const ChainArgs &args, const Sm
                     if (cg + 2 < 4) tmem_ld8_issue(t_acc + ((cg + 2) * 4 + set) * 8, ra);
                     process(cg + 1, rb);
                 }
-                if (l == 3) {   // skip connection: A[:, 128:176) = (pe36, pad): chunks 16..21 -> A groups 4, 5
+                if (l == 3) {   // skip connection: A[:, 128:176) = (pe36, pad): chunks 16..21 -> A group 2
                     store_a8<NPASS>(sm.A, row, 16 + set, pe0);
-                    if (kGroupCols == 32) publish(sm, 4);
                     if (set < 2) store_a8<NPASS>(sm.A, row, 20 + set, pe1);
-                    publish(sm, kGroupCols == 32 ? 5 : 2);
+                    publish(sm, 2);
+                    encode();                            // the NEXT tile's encoding (xn was loaded during layer 2)
                 }
             }
+            if (tid < 256) sm.bias[((bl + 1) & 1) * 256 + tid] = bias_next;
+            epi_bar_sync();
         }
     }
 }
@@ -1345,7 +1365,7 @@ int launch_chain(const ChainArgs &a, cudaStream_t st, int cta_pair = 0) {
         if (a.act_dtype) return cta_pair ? launch_chain_cg<NPASS, 0, 2, true>(a, st) : launch_chain_cg<NPASS, 0, 1, true>(a, st);
         return cta_pair ? launch_chain_cg<NPASS, 0, 2, false>(a, st) : launch_chain_cg<NPASS, 0, 1, false>(a, st);
     }
-    if (CHAIN != 2 && cta_pair) return launch_chain_cg<NPASS, CHAIN == 2 ? 0 : CHAIN, 2>(a, st);
+    if (cta_pair) return launch_chain_cg<NPASS, CHAIN, 2>(a, st);
     return launch_chain_cg<NPASS, CHAIN, 1>(a, st);
 }
 
@@ -1522,7 +1542,7 @@ extern "C" int occnerf_mlp_backward_tc(const float *g_raw, int m, const void *pa
 
 // ---- non-rigid motion MLP on the same chain machinery (chain 2)
 extern "C" int occnerf_nonrigid_pack_weights(const void *const *w7_host, const void *const *b7_host, const float *cond_dev, int n_pass,
-                                             void *packed, occnerf_stream_t stream) {
+                                             int cta_pair, void *packed, occnerf_stream_t stream) {
     OCC_CHECK_ARG(w7_host && b7_host && packed, "nonrigid_pack_weights: null pointer");
     OCC_CHECK_ARG(valid_pass(n_pass), "nonrigid_pack_weights: n_pass=%d (supported: 1 bf16, 2 tf32, 3 split-bf16)", n_pass);
     NrParams P;
@@ -1532,17 +1552,17 @@ extern "C" int occnerf_nonrigid_pack_weights(const void *const *w7_host, const v
         P.b[l] = (const float *)b7_host[l];
     }
     P.cond = cond_dev;
-    const PackedLayout pl = packed_layout(n_pass, 2, 0);
+    const PackedLayout pl = packed_layout(n_pass, 2, cta_pair ? 1 : 0);
     DevLayout L;
     for (int l = 0; l < kLayers; ++l) L.w_off[l] = pl.w_off[l];
     L.bias_off = pl.bias_off;
     dim3 grid(occ_div_up(176 * 128, 256), 7);
-    pack_nr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, L, n_pass, (unsigned char *)packed);
+    pack_nr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, L, n_pass, cta_pair ? 1 : 0, (unsigned char *)packed);
     OCC_LAUNCH_CHECK();
     return OCCNERF_OK;
 }
 
-extern "C" int occnerf_nonrigid_forward_tc(const float *xyz, const float *window6_host, int m, const void *packed, int n_pass,
+extern "C" int occnerf_nonrigid_forward_tc(const float *xyz, const float *window6_host, int m, const void *packed, int n_pass, int cta_pair,
                                            float *out, occnerf_stream_t stream) {
     if (m == 0) return OCCNERF_OK;
     OCC_CHECK_ARG(xyz && window6_host && packed && out && m > 0, "nonrigid_forward_tc: null pointer / m=%d", m);
@@ -1550,8 +1570,9 @@ extern "C" int occnerf_nonrigid_forward_tc(const float *xyz, const float *window
     OCC_CHECK_ARG(((uintptr_t)packed & 15) == 0, "nonrigid_forward_tc: packed must be 16-byte aligned");
     ChainArgs a = {};
     a.m = m;
-    fill_layout(a, n_pass, 2, packed);
+    fill_layout(a, n_pass, 2, packed, cta_pair ? 1 : 0);
     a.nr_xyz = xyz; a.nr_out = out;
     for (int j = 0; j < 6; ++j) a.nr_window[j] = window6_host[j];
-    return n_pass == 1 ? launch_chain<1, 2>(a, (cudaStream_t)stream) : n_pass == 2 ? launch_chain<2, 2>(a, (cudaStream_t)stream) : launch_chain<3, 2>(a, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    return n_pass == 1 ? launch_chain<1, 2>(a, st, cta_pair) : n_pass == 2 ? launch_chain<2, 2>(a, st, cta_pair) : launch_chain<3, 2>(a, st, cta_pair);
 }

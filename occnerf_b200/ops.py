@@ -547,8 +547,12 @@ def hann_pe(xyz, window, out=None):
 
 
 # ----------------------------------------------------------------------------- non-rigid MLP on tensor cores
-def nonrigid_pack(nr_w, nr_b, cond, n_pass):
+NR_PAIR = int(__import__("os").environ.get("OCCNERF_MLP_PAIR", "1")) != 0      # cta_group::2 pairs for the non-rigid chain as well
+
+
+def nonrigid_pack(nr_w, nr_b, cond, n_pass, pair=None):
     """Packed UMMA operand images of the 7 non-rigid layers (cond (1,69) or None is folded into the first bias)."""
+    pair = NR_PAIR if pair is None else pair
     dev = nr_w[0].device
     nbytes = _lib.load().occnerf_mlp_packed_bytes(n_pass, 2)
     packed = torch.empty(nbytes, device=dev, dtype=torch.uint8)
@@ -557,19 +561,20 @@ def nonrigid_pack(nr_w, nr_b, cond, n_pass):
     wp = (C.c_void_p * 7)(*[t.data_ptr() for t in ws])
     bp = (C.c_void_p * 7)(*[t.data_ptr() for t in bs])
     cond_c = cond.detach().reshape(-1).contiguous().float() if cond is not None else None
-    call("occnerf_nonrigid_pack_weights", C.cast(wp, C.c_void_p), C.cast(bp, C.c_void_p), ptr(cond_c, f32), n_pass, ptr(packed), stream())
+    call("occnerf_nonrigid_pack_weights", C.cast(wp, C.c_void_p), C.cast(bp, C.c_void_p), ptr(cond_c, f32), n_pass, int(pair), ptr(packed), stream())
     return packed
 
 
-def nonrigid_forward_tc(xyz, window, packed, n_pass, out=None):
-    """xyz (m,3) -> xyz + non-rigid offsets, through the fused tcgen05 chain (csrc/mlp_tc.cu, chain 2)."""
+def nonrigid_forward_tc(xyz, window, packed, n_pass, out=None, pair=None):
+    """xyz (m,3) -> xyz + non-rigid offsets, through the fused tcgen05 chain (csrc/mlp_tc.cu, chain 2); `pair` as given to nonrigid_pack."""
+    pair = NR_PAIR if pair is None else pair
     m = xyz.shape[0]
     if len(window) != 6:
         raise RuntimeError("the fused non-rigid chain is built for 6 frequency bands (cfg.non_rigid_motion_mlp.multires)")
     if out is None:
         out = torch.empty(m, 3, device=xyz.device, dtype=f32)
     w = (C.c_float * 6)(*window)
-    call("occnerf_nonrigid_forward_tc", ptr(xyz, f32), C.cast(w, C.c_void_p), m, ptr(packed), n_pass, ptr(out, f32), stream())
+    call("occnerf_nonrigid_forward_tc", ptr(xyz, f32), C.cast(w, C.c_void_p), m, ptr(packed), n_pass, int(pair), ptr(out, f32), stream())
     return out
 
 

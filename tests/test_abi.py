@@ -29,7 +29,7 @@ def test_header_symbols_are_exported():
 def test_abi_version_and_error_string():
     from occnerf_b200 import _lib
     lib = _lib.load()
-    assert lib.occnerf_abi_version() == 2
+    assert lib.occnerf_abi_version() == 3
     assert isinstance(lib.occnerf_last_error(), bytes)
 
 
