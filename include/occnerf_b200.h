@@ -400,6 +400,9 @@ int occnerf_deconv3d_forward(const float *W, const float *bias, const float *Yin
                              int exact, float *Yout, occnerf_stream_t stream);
 int occnerf_deconv3d_backward(const float *W, const float *Yin, const float *dYout, int Cin, int Cout, int D, float slope, int w_splits,
                               int d_splits, int accumulate_dw, int exact, float *dW, float *dbias, float *dYin, occnerf_stream_t stream);
+/* backward runs bias + weight gradient on an internal side stream, forked from and joined to `stream` inside the call (event dependencies,
+ * capturable), beside the data gradient; 0 switches that off (everything in order on `stream`).  Process-wide, default 1. */
+int occnerf_deconv_set_overlap(int on);
 /* the 256 -> 1024 linear layer in front of the stack (pre-activation out; network_util.py:25-28), batch 1, and its gradients */
 int occnerf_decoder_linear_forward(const float *w, const float *b, const float *e, int n_out, int n_in, float *y, occnerf_stream_t stream);
 int occnerf_decoder_linear_backward(const float *w, const float *e, const float *g, int n_out, int n_in, float *dw, float *db, float *de,

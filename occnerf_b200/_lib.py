@@ -73,6 +73,7 @@ _SIGNATURES = {
     "occnerf_sample_patches": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "occnerf_deconv3d_forward": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp, _vp],
     "occnerf_deconv3d_backward": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "occnerf_deconv_set_overlap": [_i],
     "occnerf_decoder_linear_forward": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "occnerf_decoder_linear_backward": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
 }
@@ -131,7 +132,7 @@ def ptr(t, dtype=None):
 
 # kernels launched per C call (for the bench's `gpu_launches` claim); entries not listed launch exactly one
 KERNELS_PER_CALL = {"occnerf_clip_adam_step": 3, "occnerf_visibility_hits": 3, "occnerf_generate_rays": 3, "occnerf_unpack_image": 2,
-                    "occnerf_deconv3d_forward": 2, "occnerf_deconv3d_backward": 3, "occnerf_sample_patches": 4, "occnerf_patch_loss": 3}
+                    "occnerf_deconv3d_forward": 2, "occnerf_deconv3d_backward": 3, "occnerf_sample_patches": 4, "occnerf_patch_loss": 3, "occnerf_deconv_set_overlap": 0}
 COUNTERS = {"calls": 0, "launches": 0}
 PROFILE = None   # set to {} to record (start_event, end_event, work) per C call on the current stream
 

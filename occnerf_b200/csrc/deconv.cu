@@ -413,6 +413,28 @@ int launch_gemm(const DeconvArgs &a0, int splits, cudaStream_t st) {
     return OCCNERF_OK;
 }
 
+// side stream of the backward entry point (one per device, created on first use, never destroyed)
+struct Side { cudaStream_t st; cudaEvent_t fork, join; };
+int g_overlap = 1;
+Side *side_stream() {
+    static Side pool[64];
+    static bool made[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { occnerf_set_error("deconv3d_backward: cudaGetDevice failed"); return nullptr; }
+    if (!made[dev]) {
+        Side s;
+        if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+            occnerf_set_error("deconv3d_backward: side stream: %s", cudaGetErrorString(cudaGetLastError()));
+            return nullptr;
+        }
+        pool[dev] = s;
+        made[dev] = true;
+    }
+    return &pool[dev];
+}
+
 bool bad_layer(int Cin, int Cout, int D) { return Cin < 1 || Cout < 1 || D < 1 || D > 64 || (D & (D - 1)) != 0 || (long)Cout * kTaps > (1 << 24); }
 
 }  // namespace
@@ -441,16 +463,40 @@ extern "C" int occnerf_deconv3d_backward(const float *W, const float *Yin, const
     OCC_CHECK_ARG(W && Yin && dYout && dW && dbias, "deconv3d_backward: null pointer");
     OCC_CHECK_ARG(!bad_layer(Cin, Cout, D), "deconv3d_backward: Cin=%d Cout=%d D=%d", Cin, Cout, D);
     const long Vo = 8L * D * D * D;
-    OCC_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Cout, (cudaStream_t)stream));
-    bias_grad_kernel<<<dim3(occ_div_up(Vo, 2048), Cout), 256, 0, (cudaStream_t)stream>>>(dYout, Cout, Vo, dbias);
+    cudaStream_t main_st = (cudaStream_t)stream, wst = main_st;
+    // The weight-gradient and the data-gradient GEMM of a layer share their inputs and neither fills the GPU (~300 CTAs of 128 - 256
+    // threads, latency-bound): with a data gradient to compute, bias + weight gradient go to a side stream forked from `stream` and
+    // joined again before the call returns (event dependencies: capturable in a CUDA graph, where they become parallel branches).
+    Side *side = nullptr;
+    if (dYin && g_overlap) {
+        side = side_stream();
+        if (!side) return OCCNERF_ECUDA;
+        OCC_CUDA(cudaEventRecord(side->fork, main_st));
+        OCC_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+        wst = side->st;
+    }
+    OCC_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Cout, wst));
+    bias_grad_kernel<<<dim3(occ_div_up(Vo, 2048), Cout), 256, 0, wst>>>(dYout, Cout, Vo, dbias);
     OCC_LAUNCH_CHECK();
     DeconvArgs a = {};
     a.W = W; a.Yin = Yin; a.dYout = dYout; a.Cin = Cin; a.Cout = Cout; a.D = D; a.slope = slope; a.exact = exact ? 1 : 0;
     a.out = dW; a.accumulate = accumulate_dw ? 1 : 0;
-    int rc = launch_gemm<WGRAD>(a, w_splits, (cudaStream_t)stream);
-    if (rc != OCCNERF_OK || !dYin) return rc;
-    a.out = dYin; a.accumulate = 0;
-    return launch_gemm<DGRAD>(a, d_splits, (cudaStream_t)stream);
+    int rc = launch_gemm<WGRAD>(a, w_splits, wst);
+    if (rc == OCCNERF_OK && dYin) {
+        a.out = dYin; a.accumulate = 0;
+        rc = launch_gemm<DGRAD>(a, d_splits, main_st);
+    }
+    if (side) {                                                       // a capturing stream must not be left forked
+        OCC_CUDA(cudaEventRecord(side->join, side->st));
+        OCC_CUDA(cudaStreamWaitEvent(main_st, side->join, 0));
+    }
+    return rc;
+}
+
+// 0: bias / weight gradient and data gradient one after the other on the caller's stream (for A/B timing); default 1
+extern "C" int occnerf_deconv_set_overlap(int on) {
+    g_overlap = on ? 1 : 0;
+    return OCCNERF_OK;
 }
 
 extern "C" int occnerf_decoder_linear_forward(const float *w, const float *b, const float *e, int n_out, int n_in, float *y, occnerf_stream_t stream) {

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -126,9 +127,17 @@ def deconv3d_forward(W, bias, Yin, D, slope, exact=False):
     return Yout
 
 
+_deconv_overlap_set = False
+
+
 def deconv3d_backward(W, Yin, dYout, D, slope, exact=False, need_dyin=True, dW_out=None):
     """-> (dW [Cin, Cout, 4, 4, 4], dbias [Cout], dYin [Cin, D^3] | None).  dW_out: caller's destination for dW (e.g. a view of the
     data-parallel all-reduce buffer); it is overwritten."""
+    global _deconv_overlap_set
+    if not _deconv_overlap_set:               # OCCNERF_DECONV_OVERLAP=0: no side stream (for A/B timing)
+        _deconv_overlap_set = True
+        if os.environ.get("OCCNERF_DECONV_OVERLAP", "1") == "0":
+            call("occnerf_deconv_set_overlap", 0)
     Cin, Cout = W.shape[0], W.shape[1]
     V, Q = D ** 3, Cout * (8 if D == 1 else 64)
     bm = 256 if (Cin >= 256 and not exact) else 64     # row tile of the gradient GEMMs (csrc/deconv.cu launch_gemm)

@@ -12,8 +12,9 @@ res = {}
 def step():
     dec.zero_grad(set_to_none=True)
     (dec(motion_weights_priors=priors) * gv).sum().backward()
-for name, native in (("library_cudnn_tf32", False), ("native_tf32", True)):
+for name, native, overlap in (("library_cudnn_tf32", False, 1), ("native_tf32_one_stream", True, 0), ("native_tf32", True, 1)):
     dec.native = native
+    _lib.call("occnerf_deconv_set_overlap", overlap)   # weight gradients on the side stream beside the data gradients
     for _ in range(3): step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
