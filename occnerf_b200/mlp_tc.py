@@ -18,6 +18,20 @@ from occnerf_b200._lib import call, stream
 
 f32, bf16 = torch.float32, torch.bfloat16
 
+# Weight gradients beside the rest of the chunk's backward pass: with `defer=True` MlpTc.backward launches occnerf_mlp_wgrad_tc on a side
+# stream (forked from the current one after the data-gradient chain) and MlpTc.finish_wgrad joins it.  The kernel is HBM-bound and holds
+# no resources the scatter kernels behind the data gradients need (hash-grid / aggregation backward: L2 atomics, no shared memory), so
+# they run on the same SMs at the same time.  OCCNERF_WGRAD_OVERLAP=0 (or WGRAD_OVERLAP = False) keeps everything on one stream.
+WGRAD_OVERLAP = os.environ.get("OCCNERF_WGRAD_OVERLAP", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _SIDE_STREAMS[key]
+
 
 class MlpTc:
     def __init__(self, n_pass: int = 3, wgrad: str = "tc", bwd_pass: int | None = None, pair: bool | None = None):
@@ -70,10 +84,12 @@ class MlpTc:
              work=M.FLOP_FWD * m)
         return {"acts": acts, "mask": mask} if save else None
 
-    def backward(self, XB, g_raw, W: M.MlpWeights, saved, shared=None, last=True):
+    def backward(self, XB, g_raw, W: M.MlpWeights, saved, shared=None, last=True, defer=False):
         """-> (gXB, list of the 20 parameter gradients | None).  With `shared` (a dict living as long as one _query_mlp
         call) the weight gradients of all its chunks accumulate in ONE dW/dB buffer -- the kernel adds into it anyway --
-        and only the chunk with last=True maps it back to the nn.Linear layout; the others return None (= zero)."""
+        and only the chunk with last=True maps it back to the nn.Linear layout; the others return None (= zero).
+        defer=True (needs `shared`): always returns (gXB, None); the weight-gradient kernel may still be running on the side stream
+        and the caller fetches the 20 gradients with finish_wgrad(shared) after the last chunk."""
         m, dev = XB.shape[0], XB.device
         acts = saved["acts"]
         stride = acts.shape[2]
@@ -85,6 +101,7 @@ class MlpTc:
         call("occnerf_mlp_backward_tc", g_raw.data_ptr(), m, packed.data_ptr(), self.bwd_pass, int(self.pair), saved["mask"].data_ptr(), gXB.data_ptr(),
              g_save.data_ptr(), stride, stream(), work=M.FLOP_FWD * m)
         if self.wgrad == "lib":
+            assert not defer, "the library weight-gradient cross-check has no deferred form"
             with _lib.region("lib:wgrad(cuBLAS bf16)+bias sums"):
                 def rows(t):     # chunk-major -> row-major [slot][row][256]
                     return t.permute(0, 2, 1, 3).reshape(10, stride, 256)[:, :m]
@@ -96,12 +113,40 @@ class MlpTc:
             dB = torch.zeros(10, 256, device=dev, dtype=f32)
             if shared is not None:
                 shared["dW"], shared["dB"] = dW, dB
+        if defer:
+            assert shared is not None, "defer=True needs the per-call `shared` dict"
+            if WGRAD_OVERLAP:
+                side, cur = _side_stream(dev), torch.cuda.current_stream()
+                side.wait_stream(cur)                                          # fork: the chain's outputs are complete for the side stream
+                with torch.cuda.stream(side):
+                    call("occnerf_mlp_wgrad_tc", g_save.data_ptr(), acts.data_ptr(), m, stride, dW.data_ptr(), dB.data_ptr(), stream(),
+                         work=M.FLOP_FWD * m)
+                # the operands stay allocated until the join: the caching allocator would otherwise hand their memory to later work
+                # of the main stream while the side stream still reads it
+                shared.setdefault("wgrad_keep", []).append((g_save, acts))
+                shared["wgrad_side"] = side
+            else:
+                call("occnerf_mlp_wgrad_tc", g_save.data_ptr(), acts.data_ptr(), m, stride, dW.data_ptr(), dB.data_ptr(), stream(),
+                     work=M.FLOP_FWD * m)
+            return gXB, None
         call("occnerf_mlp_wgrad_tc", g_save.data_ptr(), acts.data_ptr(), m, stride, dW.data_ptr(), dB.data_ptr(), stream(),
              work=M.FLOP_FWD * m)
         if shared is not None and not last:
             return gXB, None
         if shared is not None:
             shared.pop("dW"), shared.pop("dB")
+        return gXB, self._unpack_grads(dW, dB)
+
+    def finish_wgrad(self, shared):
+        """Join the side stream of the deferred weight-gradient launches of one _query_mlp call -> the 20 parameter gradients."""
+        side = shared.pop("wgrad_side", None)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        shared.pop("wgrad_keep", None)
+        return self._unpack_grads(shared.pop("dW"), shared.pop("dB"))
+
+    @staticmethod
+    def _unpack_grads(dW, dB):
         g = {}
         g["pts_w0"], g["pts_b0"] = dW[0][:, :68].contiguous(), dB[0]
         for l in (1, 2, 3):
@@ -113,7 +158,7 @@ class MlpTc:
         for l in (1, 2, 3):
             g[f"rgb_w{l}"], g[f"rgb_b{l}"] = dW[5 + l], dB[5 + l]
         g["out_w"], g["out_b"] = dW[9][:3].contiguous(), dB[9][:3].contiguous()
-        return gXB, [g[k] for k in M.MlpWeights.ORDER]
+        return [g[k] for k in M.MlpWeights.ORDER]
 
     def _wgrad_lib(self, XB, g_raw, acts, g_save):
         """Library fallback-free alternative for cross-checking the hand-written kernel: the same GEMMs through cuBLAS."""

@@ -267,9 +267,9 @@ class _QueryFn(torch.autograd.Function):
         sh = s["shared"]
         last = sh["pending"] == 1
         if hasattr(s["engine"], "bwd_pass"):      # tensor-core engine: one weight-gradient buffer for all chunks of the call
-            gXB, g_params = s["engine"].backward(s["XB"], g_raw, s["W"], s["saved"], shared=sh, last=last)
-            if g_params is None:
-                g_params = [None] * 20
+            # (the weight-gradient kernel goes to a side stream and runs beside the scatter kernels below; joined by finish_wgrad)
+            gXB, _ = s["engine"].backward(s["XB"], g_raw, s["W"], s["saved"], shared=sh, last=last, defer=True)
+            g_params = [None] * 20
         else:
             gXB, g_params = s["engine"].backward(s["XB"], g_raw, s["W"], s["saved"])
         # the chunks of one _query_mlp call scatter into ONE table-gradient buffer (and one set of privatised vertex-gradient
@@ -285,6 +285,8 @@ class _QueryFn(torch.autograd.Function):
                               s["emb_shape"][1], run_length=ops.HASH_BWD_RUN)           # samples are ordered along rays
         ops.aggregate_backward(s["knn_idx"], s["counter"], gXB.data_ptr() + 4 * M.X0_OFF, M.XB_LD, s["V"], g_priv=sh["g_priv"],
                                att_w=s["att_w"])                                         # samples are ordered along rays
+        if last and hasattr(s["engine"], "bwd_pass"):
+            g_params = s["engine"].finish_wgrad(sh)
         ctx.state = None
         sh["pending"] -= 1
         g_emb = g_feats = None

@@ -308,7 +308,13 @@ def knn_tree(queries, group_stride, tree, out=None, lane_rays=None):
 _GRID_CACHE = {}
 
 
-def build_knn_grid(base: torch.Tensor, fps, cell: float = 0.025, pad: float = 0.35, k: int = 10):
+# Edge of a candidate-grid cell (m).  Smaller cells = shorter candidate lists (the kernel's work) for more list memory: B200, 786 k
+# queries: 0.025 -> 0.50 ms, 0.0175 -> 0.41, 0.0125 -> 0.36, 0.01 -> 0.34, 0.008 -> 0.32 (gpurun_out/bench_cell_*.json; the build of
+# the two smallest takes tens of seconds).
+KNN_GRID_CELL = float(os.environ.get("OCCNERF_KNN_CELL", "0.0125"))
+
+
+def build_knn_grid(base: torch.Tensor, fps, cell: float = None, pad: float = 0.35, k: int = 10):
     """Static candidate lists for occnerf_knn_grid (include/occnerf_b200.h).  A uniform grid of `cell`-sized cells covers the
     vertex bounding box +- `pad`; for every cell (centre o, half diagonal rho) and level the list holds every point p with
         |p - o| <= d_k(o) + 2*rho + margin,     d_k(o) = distance from o to its k-th nearest point of the level.
@@ -317,6 +323,7 @@ def build_knn_grid(base: torch.Tensor, fps, cell: float = 0.025, pad: float = 0.
     margin (1e-4 + 1e-5*d) is far above fp32 rounding.  Lists are sorted by |p - o| and padded to nothing; built once per
     subject on the device (a few seconds, ~0.3 GB at the defaults)."""
     dev = base.device
+    cell = KNN_GRID_CELL if cell is None else cell
     key = (str(dev), tuple(base.shape), float(base.double().sum()), float(base.double().abs().sum()), cell, pad, k,
            tuple(int(f.shape[0]) for f in fps), tuple(int(f.long().sum()) for f in fps))
     if key in _GRID_CACHE:
