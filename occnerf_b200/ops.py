@@ -374,10 +374,20 @@ def build_knn_grid(base: torch.Tensor, fps, cell: float = None, pad: float = 0.3
     return grid
 
 
+def knn_grid_lane_rays(lane_rays: int, group_stride: int) -> int:
+    """Rays per warp actually used: with fewer samples per ray than 32 / lane_rays the depth axis cannot fill the warp, so it takes more rays
+    (group_stride = 1, flat query lists: 32 rays x 1 sample).  Powers of two <= 32, as occnerf_knn_grid requires."""
+    lane_samples = max(1, 32 // max(1, lane_rays))
+    while lane_samples > max(1, group_stride):
+        lane_samples //= 2
+    return 32 // lane_samples
+
+
 def knn_grid(queries, group_stride, grid, out=None, lane_rays=None):
     """All 4 levels x k=10 through the per-cell candidate lists -> (m,4,10) int32 vertex ids (bit-identical to knn)."""
     m = queries.shape[0]
     lane_rays = KNN_GRID_LANE_RAYS if lane_rays is None else lane_rays
+    lane_rays = knn_grid_lane_rays(lane_rays, int(group_stride))
     if out is None:
         out = torch.empty(m, 4, 10, device=queries.device, dtype=i32)
     g = grid

@@ -51,3 +51,16 @@ def test_lists_shrink_with_the_cell_size():
     fine = ops.build_knn_grid(base, fps, cell=0.04, pad=0.1)
     mean = lambda g: float(g["cell_tab"][:, 0, 1].float().mean())
     assert mean(fine) < mean(coarse)
+
+
+def test_lane_mapping_fills_the_warp():
+    """ops.knn_grid_lane_rays: rays x samples per warp is always 32, the sample axis never exceeds the ray length, powers of two only."""
+    from occnerf_b200 import ops
+    for want in (1, 2, 4, 8, 16, 32):
+        for stride in (1, 2, 3, 7, 8, 16, 31, 32, 128, 1000):
+            lr = ops.knn_grid_lane_rays(want, stride)
+            assert lr in (1, 2, 4, 8, 16, 32) and lr >= want
+            assert 32 // lr <= max(1, stride), (want, stride, lr)
+            if 32 // want <= stride:
+                assert lr == want
+    assert ops.knn_grid_lane_rays(2, 1) == 32 and ops.knn_grid_lane_rays(2, 128) == 2
