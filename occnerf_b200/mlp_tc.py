@@ -117,13 +117,17 @@ class MlpTc:
             assert shared is not None, "defer=True needs the per-call `shared` dict"
             if WGRAD_OVERLAP:
                 side, cur = _side_stream(dev), torch.cuda.current_stream()
+                keep = shared.setdefault("wgrad_keep", [])
+                if len(keep) >= 3:          # long queries (many chunks): release the operands of finished launches every few chunks
+                    cur.wait_stream(side)   # (their kernels ended during the data-gradient chain that has just been queued)
+                    keep.clear()
                 side.wait_stream(cur)                                          # fork: the chain's outputs are complete for the side stream
                 with torch.cuda.stream(side):
                     call("occnerf_mlp_wgrad_tc", g_save.data_ptr(), acts.data_ptr(), m, stride, dW.data_ptr(), dB.data_ptr(), stream(),
                          work=M.FLOP_FWD * m)
                 # the operands stay allocated until the join: the caching allocator would otherwise hand their memory to later work
                 # of the main stream while the side stream still reads it
-                shared.setdefault("wgrad_keep", []).append((g_save, acts))
+                keep.append((g_save, acts))
                 shared["wgrad_side"] = side
             else:
                 call("occnerf_mlp_wgrad_tc", g_save.data_ptr(), acts.data_ptr(), m, stride, dW.data_ptr(), dB.data_ptr(), stream(),
